@@ -1,0 +1,183 @@
+/* lite_b200.h — C ABI of the B200-native pseudo-likelihood hot path of LiTe.
+ *
+ * The reference (kien-kieu/lite) has no FFI boundary: its "operator API" for
+ * this path is the C++ class API PseudoLikDiscrete / Energy / TTessel
+ * (reference include/ttessel.h:966-1020, :1201-1240, :747-753) with host
+ * function pointers as features (:932-937).  This header is the thin C layer a
+ * binding to that API would call; include/ttessel.h (this repo) is the
+ * source-compatible C++ facade built on it.  Each entry point cites the
+ * reference member it replaces.
+ *
+ * Conventions: every call returns 0 on success, a negative LITE_E* code
+ * otherwise; lite_last_error() gives the message (thread local).  A context
+ * owns one CUDA device, one stream and (world_size > 1) one NCCL communicator;
+ * it is not thread safe, distinct contexts are independent.  All host arrays
+ * are caller owned and copied during the call.  Indices are int32, -1 = null.
+ * There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef LITE_B200_H
+#define LITE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LITE_OK 0
+#define LITE_EINVAL (-1)   /* bad argument / inconsistent tessellation      */
+#define LITE_ECUDA (-2)    /* CUDA runtime error or no device               */
+#define LITE_ENCCL (-3)    /* NCCL unavailable or failed                    */
+#define LITE_ESTATE (-4)   /* call sequence error (e.g. eval before upload) */
+#define LITE_ENOSPLIT (-5) /* pl_eval with zero dummy splits: the reference
+                              divides by stat_splits.size() (lib/ttessel.cpp:3396) */
+
+#define LITE_MAX_D 12
+
+/* Device feature ids.  The facade maps the addresses of the reference's
+ * built-in feature functions (include/ttessel.h:1384-1405) to these. */
+enum lite_feature {
+  LITE_FEAT_IS_POINT_INSIDE_WINDOW = 0,    /* vertices  lib/ttessel.cpp:4131 */
+  LITE_FEAT_EDGE_LENGTH = 1,               /* edges     :4141 (as written: boundary edges only) */
+  LITE_FEAT_SEG_NUMBER = 2,                /* segs      :4157 */
+  LITE_FEAT_IS_SEGMENT_INTERNAL = 3,       /* segs      :4172 */
+  LITE_FEAT_MINUS_IS_SEGMENT_INTERNAL = 4, /* segs      include/ttessel.h:1396 */
+  LITE_FEAT_SEGMENT_SIZE_2 = 5,            /* segs      :4424 (as written: boundary segments only) */
+  LITE_FEAT_FACE_NUMBER = 6,               /* faces     :4206 */
+  LITE_FEAT_FACE_AREA_2 = 7,               /* faces     :4215 */
+  LITE_FEAT_FACE_PERIMETER = 8,            /* faces     :4229 */
+  LITE_FEAT_FACE_SHAPE = 9,                /* faces     :4247 */
+  LITE_FEAT_FACE_SUM_OF_ANGLES = 10,       /* faces     :4285 */
+  LITE_FEAT_MIN_ANGLE = 11,                /* faces     :4348 */
+  LITE_FEAT_EDGE_LENGTH_INTERNAL = 12,     /* edges     EXTENSION, not in the reference: length of
+                                              internal edges (the evident intent of edge_length) */
+  LITE_FEAT_COUNT = 13
+};
+
+/* Flattened tessellation: the payload of LineTes_halfedge
+ * (include/ttessel.h:445-450) plus the DCEL links, in the reference's halfedge
+ * container order (TTessel::alt_length_weighted_random_halfedge depends on it,
+ * lib/ttessel.cpp:1977-1989).  Per-face halfedge lists start at outer_ccb(). */
+typedef struct lite_tess_soa {
+  int32_t n_vertices;
+  const double *vx, *vy;
+  int32_t n_halfedges;
+  const int32_t *he_src, *he_twin, *he_next, *he_face, *he_seg;
+  const int32_t *he_next_hf, *he_prev_hf; /* along-segment links, -1 = null */
+  const uint8_t *he_dir;                  /* LineTes_halfedge::get_dir()    */
+  const double *he_length;                /* LineTes_halfedge::get_length() */
+  int32_t n_faces;
+  const uint8_t *face_inside;             /* Face::data()                   */
+  const int32_t *face_he_offset, *face_he_count; /* into face_he_list; count 0 for outside faces */
+  int32_t n_face_he;
+  const int32_t *face_he_list;
+  int32_t n_segments;
+  const int32_t *seg_he_start, *seg_he_end; /* Seg::halfedges_start()/end() */
+  const int32_t *seg_n_edges;
+  const uint8_t *seg_on_boundary;
+  int32_t n_non_blocking, n_blocking;       /* TTessel private lists, container order */
+  const int32_t *non_blocking, *blocking;   /* segment ids */
+  double int_length;                        /* TTessel::get_total_internal_length() */
+} lite_tess_soa;
+
+typedef struct lite_ctx lite_ctx;
+
+const char *lite_last_error(void);
+
+/* 128-byte NCCL unique id for rank 0 to broadcast (out-of-band, e.g. through
+ * torch.distributed) before lite_ctx_create on every rank. */
+int lite_nccl_unique_id(void *out128);
+
+/* One context per process/GPU.  nccl_unique_id may be NULL when world_size==1. */
+int lite_ctx_create(lite_ctx **out, int device, int rank, int world_size,
+                    const void *nccl_unique_id);
+int lite_ctx_destroy(lite_ctx *ctx);
+int lite_ctx_sync(lite_ctx *ctx);
+/* option ids */
+#define LITE_OPT_RECORD_SPLITS 1 /* keep per-split e1,e2,p1,p2,x,angle for lite_debug_fetch */
+int lite_ctx_set_option(lite_ctx *ctx, int option, int64_t value);
+
+/* Energy::set_ttessel (lib/ttessel.cpp:2862): replicate the tessellation on the GPU. */
+int lite_tess_upload(lite_ctx *ctx, const lite_tess_soa *tess);
+
+/* Energy::add_features_* / add_theta_* (lib/ttessel.cpp:3016-3088): the d
+ * features in flattened CatVector order vertices, edges, faces, segs
+ * (lib/ttessel.cpp:2750-2761). */
+int lite_energy_set(lite_ctx *ctx, int d, const int32_t *feature_id);
+
+/* PseudoLikDiscrete::SetEnergy (lib/ttessel.cpp:3327-3348): all_merges +
+ * all_flips, their statistic variations and the two sums. */
+int lite_candidates_merges_flips(lite_ctx *ctx, int32_t *n_merges, int32_t *n_flips);
+
+/* PseudoLikDiscrete::AddGivenSplit for a list (lib/ttessel.cpp:3371-3374);
+ * split i = Split(halfedge he[i], x[i], angle[i]) (lib/ttessel.cpp:2090).
+ * The list is this rank's shard; n_global_total is the size of the whole
+ * batch over all ranks (== n when world_size == 1). */
+int lite_candidates_add_splits_given(lite_ctx *ctx, int64_t n, const int32_t *he,
+                                     const double *x, const double *angle,
+                                     int64_t n_global_total);
+
+/* PseudoLikDiscrete::AddSplits(n) (lib/ttessel.cpp:3356-3365) with the
+ * reference's global RNG replaced by a counter-based Philox4x32-10 stream:
+ * split j of the batch uses counter offset+j, whatever the number of ranks. */
+int lite_candidates_add_splits_philox(lite_ctx *ctx, int64_t n_global, uint64_t seed,
+                                      uint64_t offset);
+
+/* PseudoLikDiscrete::ClearSplits (lib/ttessel.cpp:3378-3380). */
+int lite_candidates_clear_splits(lite_ctx *ctx);
+int lite_candidates_count(lite_ctx *ctx, int64_t *n_splits_local, int64_t *n_splits_global);
+
+/* PseudoLikDiscrete::GetValue / GetGradient / GetHessian in one pass
+ * (lib/ttessel.cpp:3387-3443).  grad: d doubles, hess: d*d row-major; any of
+ * the three outputs may be NULL.  With world_size > 1 one ncclAllReduce of
+ * 1+d+d*d doubles combines the shards. */
+int lite_pl_eval(lite_ctx *ctx, const double *theta, double *lpl, double *grad, double *hess);
+
+/* Energy::statistic_variation sums kept by SetEnergy: sum_stat_merges,
+ * sum_stat_flips (d doubles each, already negated as in the reference). */
+int lite_pl_sums(lite_ctx *ctx, double *sum_stat_merges, double *sum_stat_flips);
+
+/* Config "random_lines sampling and face clipping": sample n_global lines
+ * (Philox, as add_splits_philox) and clip them against their faces without
+ * computing statistics.  mode 0: checksum only, mode 1: store e1,e2,p1,p2
+ * (readable with lite_debug_fetch).  checksum[0] = xor of (e1<<32|e2) hashes,
+ * checksum[1] = sum of e2 ids. */
+int lite_lines_sample_clip(lite_ctx *ctx, int64_t n_global, uint64_t seed, uint64_t offset,
+                           int mode, uint64_t *checksum2);
+
+/* Per-candidate outputs for parity tests.  `first`/`count` index this rank's
+ * local candidates. */
+enum lite_fetch {
+  LITE_FETCH_SPLIT_E1 = 0,    /* int32  */
+  LITE_FETCH_SPLIT_E2 = 1,    /* int32  (-1: no exit found) */
+  LITE_FETCH_SPLIT_P1 = 2,    /* double[2] */
+  LITE_FETCH_SPLIT_P2 = 3,    /* double[2] */
+  LITE_FETCH_SPLIT_X = 4,     /* double */
+  LITE_FETCH_SPLIT_ANGLE = 5, /* double */
+  LITE_FETCH_SPLIT_STAT = 6,  /* double[d]  (-statistic_variation, as stored by the reference) */
+  LITE_FETCH_MERGE_HE = 7,    /* int32 */
+  LITE_FETCH_MERGE_STAT = 8,  /* double[d] */
+  LITE_FETCH_FLIP_E1 = 9,     /* int32 */
+  LITE_FETCH_FLIP_E2 = 10,    /* int32 */
+  LITE_FETCH_FLIP_P2 = 11,    /* double[2] */
+  LITE_FETCH_FLIP_RIGHT = 12, /* int32 */
+  LITE_FETCH_FLIP_STAT = 13,  /* double[d] */
+  LITE_FETCH_SPLIT_U = 14,    /* double: the uniform behind angle = acos(1-2U) (philox path) */
+  LITE_FETCH_STATUS = 15      /* int64[4]: no-exit count, oversize-face count, ... */
+};
+int lite_debug_fetch(lite_ctx *ctx, int which, int64_t first, int64_t count, void *out);
+
+/* Timing helpers for bench.py: device time (ms, CUDA events on the context's
+ * stream) of the last add_splits / pl_eval / merges_flips kernels, and the
+ * number of kernel launches issued by the context so far. */
+int lite_last_kernel_ms(lite_ctx *ctx, float *add_splits_ms, float *pl_eval_ms,
+                        float *merges_flips_ms);
+int64_t lite_kernel_launch_count(lite_ctx *ctx);
+/* Measured DFMA throughput (TFLOP/s) of this GPU: the FP64 roofline denominator. */
+int lite_measure_fp64_peak(lite_ctx *ctx, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LITE_B200_H */

@@ -1,0 +1,303 @@
+"""ctypes binding of include/lite_b200.h.  No fallback: if ``libliteb200.so`` is
+absent or a call fails, ``LiteError`` is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+FEATURE_IDS = {
+    "is_point_inside_window": 0,
+    "edge_length": 1,
+    "seg_number": 2,
+    "is_segment_internal": 3,
+    "minus_is_segment_internal": 4,
+    "segment_size_2": 5,
+    "face_number": 6,
+    "face_area_2": 7,
+    "face_perimeter": 8,
+    "face_shape": 9,
+    "face_sum_of_angles": 10,
+    "min_angle": 11,
+    "edge_length_internal": 12,  # extension, not in the reference
+}
+
+# every symbol declared in include/lite_b200.h
+SYMBOLS = [
+    "lite_last_error", "lite_nccl_unique_id", "lite_ctx_create", "lite_ctx_destroy",
+    "lite_ctx_sync", "lite_ctx_set_option", "lite_tess_upload", "lite_energy_set",
+    "lite_candidates_merges_flips", "lite_candidates_add_splits_given",
+    "lite_candidates_add_splits_philox", "lite_candidates_clear_splits",
+    "lite_candidates_count", "lite_pl_eval", "lite_pl_sums", "lite_lines_sample_clip",
+    "lite_debug_fetch", "lite_last_kernel_ms", "lite_kernel_launch_count",
+    "lite_measure_fp64_peak",
+]
+
+FETCH = dict(SPLIT_E1=0, SPLIT_E2=1, SPLIT_P1=2, SPLIT_P2=3, SPLIT_X=4, SPLIT_ANGLE=5,
+             SPLIT_STAT=6, MERGE_HE=7, MERGE_STAT=8, FLIP_E1=9, FLIP_E2=10, FLIP_P2=11,
+             FLIP_RIGHT=12, FLIP_STAT=13, SPLIT_U=14, STATUS=15)
+
+
+class LiteError(RuntimeError):
+    pass
+
+
+class _SoA(C.Structure):
+    _fields_ = [
+        ("n_vertices", C.c_int32), ("vx", C.c_void_p), ("vy", C.c_void_p),
+        ("n_halfedges", C.c_int32),
+        ("he_src", C.c_void_p), ("he_twin", C.c_void_p), ("he_next", C.c_void_p),
+        ("he_face", C.c_void_p), ("he_seg", C.c_void_p),
+        ("he_next_hf", C.c_void_p), ("he_prev_hf", C.c_void_p),
+        ("he_dir", C.c_void_p), ("he_length", C.c_void_p),
+        ("n_faces", C.c_int32), ("face_inside", C.c_void_p),
+        ("face_he_offset", C.c_void_p), ("face_he_count", C.c_void_p),
+        ("n_face_he", C.c_int32), ("face_he_list", C.c_void_p),
+        ("n_segments", C.c_int32), ("seg_he_start", C.c_void_p), ("seg_he_end", C.c_void_p),
+        ("seg_n_edges", C.c_void_p), ("seg_on_boundary", C.c_void_p),
+        ("n_non_blocking", C.c_int32), ("n_blocking", C.c_int32),
+        ("non_blocking", C.c_void_p), ("blocking", C.c_void_p),
+        ("int_length", C.c_double),
+    ]
+
+
+_DT = dict(vx=np.float64, vy=np.float64, he_src=np.int32, he_twin=np.int32, he_next=np.int32,
+           he_face=np.int32, he_seg=np.int32, he_next_hf=np.int32, he_prev_hf=np.int32,
+           he_dir=np.uint8, he_length=np.float64, face_inside=np.uint8,
+           face_he_offset=np.int32, face_he_count=np.int32, face_he_list=np.int32,
+           seg_he_start=np.int32, seg_he_end=np.int32, seg_n_edges=np.int32,
+           seg_on_boundary=np.uint8, non_blocking=np.int32, blocking=np.int32)
+
+
+class TessSoA:
+    """Host-side flattened tessellation (dict of numpy arrays + int_length) in the
+    layout of ``lite_tess_soa``."""
+
+    def __init__(self, arrays):
+        self.a = {}
+        for k, dt in _DT.items():
+            self.a[k] = np.ascontiguousarray(arrays[k], dtype=dt)
+        self.int_length = float(arrays["int_length"])
+
+    @classmethod
+    def load(cls, path):
+        z = np.load(path)
+        return cls({k: z[k] for k in z.files})
+
+    def save(self, path):
+        np.savez_compressed(path, int_length=np.float64(self.int_length), **self.a)
+
+    def n_cells(self):
+        return int(self.a["face_inside"].sum())
+
+    def as_struct(self):
+        s = _SoA()
+        a = self.a
+        s.n_vertices = len(a["vx"])
+        s.n_halfedges = len(a["he_src"])
+        s.n_faces = len(a["face_inside"])
+        s.n_face_he = len(a["face_he_list"])
+        s.n_segments = len(a["seg_he_start"])
+        s.n_non_blocking = len(a["non_blocking"])
+        s.n_blocking = len(a["blocking"])
+        s.int_length = self.int_length
+        for k in _DT:
+            setattr(s, k, a[k].ctypes.data_as(C.c_void_p))
+        return s
+
+
+def lib_path():
+    return os.path.join(_HERE, "libliteb200.so")
+
+
+_LIB = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; raises LiteError when it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise LiteError("%s not found: build it with `make` (python -c 'import __graft_entry__ as g; g.build()'). "
+                        "There is no CPU fallback." % p)
+    L = C.CDLL(p)
+    L.lite_last_error.restype = C.c_char_p
+    L.lite_kernel_launch_count.restype = C.c_int64
+    L.lite_kernel_launch_count.argtypes = [C.c_void_p]
+    L.lite_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.lite_ctx_destroy.argtypes = [C.c_void_p]
+    L.lite_ctx_sync.argtypes = [C.c_void_p]
+    L.lite_ctx_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int64]
+    L.lite_tess_upload.argtypes = [C.c_void_p, C.POINTER(_SoA)]
+    L.lite_energy_set.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.lite_candidates_merges_flips.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.lite_candidates_add_splits_given.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_int64]
+    L.lite_candidates_add_splits_philox.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64]
+    L.lite_candidates_clear_splits.argtypes = [C.c_void_p]
+    L.lite_candidates_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.lite_pl_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lite_pl_sums.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lite_lines_sample_clip.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+    L.lite_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
+    L.lite_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.lite_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.lite_nccl_unique_id.argtypes = [C.c_void_p]
+    _LIB = L
+    return L
+
+
+def _ck(L, rc):
+    if rc != 0:
+        raise LiteError("lite_b200 error %d: %s" % (rc, L.lite_last_error().decode()))
+
+
+def nccl_unique_id():
+    L = load_library()
+    buf = (C.c_char * 128)()
+    _ck(L, L.lite_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+def shard_range(n, rank, world):
+    """Contiguous shard [r*n/G, (r+1)*n/G) — the partition used by
+    lite_candidates_add_splits_philox."""
+    j0 = (n * rank) // world
+    j1 = (n * (rank + 1)) // world
+    return j0, j1 - j0
+
+
+class Context:
+    """One GPU context (``lite_ctx``).  Method names follow the C ABI."""
+
+    def __init__(self, device=0, rank=0, world_size=1, nccl_id=None):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        idbuf = None
+        if nccl_id is not None:
+            idbuf = C.create_string_buffer(bytes(nccl_id), 128)
+        _ck(self.L, self.L.lite_ctx_create(C.byref(self.h), device, rank, world_size, idbuf))
+        self.d = 0
+        self.rank, self.world = rank, world_size
+
+    def close(self):
+        if self.h:
+            self.L.lite_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _ck(self.L, self.L.lite_ctx_sync(self.h))
+
+    def record_splits(self, on=True):
+        _ck(self.L, self.L.lite_ctx_set_option(self.h, 1, 1 if on else 0))
+
+    def tess_upload(self, soa: TessSoA):
+        s = soa.as_struct()
+        _ck(self.L, self.L.lite_tess_upload(self.h, C.byref(s)))
+        self.n_nb = len(soa.a["non_blocking"])
+        self.n_b = len(soa.a["blocking"])
+
+    def energy_set(self, features):
+        ids = np.array([FEATURE_IDS[f] if isinstance(f, str) else int(f) for f in features], dtype=np.int32)
+        _ck(self.L, self.L.lite_energy_set(self.h, len(ids), ids.ctypes.data_as(C.c_void_p)))
+        self.d = len(ids)
+
+    def merges_flips(self):
+        nm, nf = C.c_int32(), C.c_int32()
+        _ck(self.L, self.L.lite_candidates_merges_flips(self.h, C.byref(nm), C.byref(nf)))
+        return nm.value, nf.value
+
+    def add_splits_given(self, he, x, angle, n_global_total=None):
+        he = np.ascontiguousarray(he, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        angle = np.ascontiguousarray(angle, dtype=np.float64)
+        n = len(he)
+        if n_global_total is None:
+            n_global_total = n
+        _ck(self.L, self.L.lite_candidates_add_splits_given(
+            self.h, n, he.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p),
+            angle.ctypes.data_as(C.c_void_p), n_global_total))
+
+    def add_splits_philox(self, n_global, seed, offset=0):
+        _ck(self.L, self.L.lite_candidates_add_splits_philox(self.h, n_global, seed, offset))
+
+    def clear_splits(self):
+        _ck(self.L, self.L.lite_candidates_clear_splits(self.h))
+
+    def count(self):
+        a, b = C.c_int64(), C.c_int64()
+        _ck(self.L, self.L.lite_candidates_count(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def pl_eval(self, theta):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        d = self.d
+        assert len(th) == d
+        lpl = C.c_double()
+        g = np.zeros(d)
+        H = np.zeros((d, d))
+        _ck(self.L, self.L.lite_pl_eval(self.h, th.ctypes.data_as(C.c_void_p), C.byref(lpl),
+                                        g.ctypes.data_as(C.c_void_p), H.ctypes.data_as(C.c_void_p)))
+        return lpl.value, g, H
+
+    def pl_sums(self):
+        m = np.zeros(self.d)
+        f = np.zeros(self.d)
+        _ck(self.L, self.L.lite_pl_sums(self.h, m.ctypes.data_as(C.c_void_p), f.ctypes.data_as(C.c_void_p)))
+        return m, f
+
+    def lines_sample_clip(self, n_global, seed, offset=0, mode=0):
+        cs = np.zeros(2, dtype=np.uint64)
+        _ck(self.L, self.L.lite_lines_sample_clip(self.h, n_global, seed, offset, mode,
+                                                  cs.ctypes.data_as(C.c_void_p)))
+        return cs
+
+    def fetch(self, which, first=0, count=None):
+        w = FETCH[which] if isinstance(which, str) else which
+        name = which if isinstance(which, str) else {v: k for k, v in FETCH.items()}[which]
+        if name == "STATUS":
+            out = np.zeros(4, dtype=np.int64)
+            _ck(self.L, self.L.lite_debug_fetch(self.h, w, 0, 4, out.ctypes.data_as(C.c_void_p)))
+            return out
+        if count is None:
+            if name.startswith("SPLIT"):
+                count = self.count()[0] - first
+            elif name.startswith("MERGE"):
+                count = self.n_nb - first
+            else:
+                count = 2 * self.n_b - first
+        if name.endswith("_STAT"):
+            out = np.zeros((count, self.d))
+        elif name in ("SPLIT_P1", "SPLIT_P2", "FLIP_P2"):
+            out = np.zeros((count, 2))
+        elif name in ("SPLIT_X", "SPLIT_ANGLE", "SPLIT_U"):
+            out = np.zeros(count)
+        else:
+            out = np.zeros(count, dtype=np.int32)
+        if count:
+            _ck(self.L, self.L.lite_debug_fetch(self.h, w, first, count, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def last_kernel_ms(self):
+        a, b, m = C.c_float(), C.c_float(), C.c_float()
+        _ck(self.L, self.L.lite_last_kernel_ms(self.h, C.byref(a), C.byref(b), C.byref(m)))
+        return a.value, b.value, m.value
+
+    def launch_count(self):
+        return int(self.L.lite_kernel_launch_count(self.h))
+
+    def measure_fp64_peak(self):
+        t = C.c_double()
+        _ck(self.L, self.L.lite_measure_fp64_peak(self.h, C.byref(t)))
+        return t.value

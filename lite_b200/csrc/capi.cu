@@ -1,0 +1,793 @@
+// capi.cu — implementation of include/lite_b200.h (host side: context, upload,
+// kernel launches, NCCL allreduce).  No CPU fallback: every compute entry point
+// needs a CUDA device.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+// ---- minimal NCCL surface, resolved at run time (libnccl.so.2) --------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8 };
+enum { ncclSum = 0 };
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(x)                                                                         \
+  do {                                                                                \
+    cudaError_t e_ = (x);                                                             \
+    if (e_ != cudaSuccess)                                                            \
+      return fail(LITE_ECUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static int nccl_load() {
+  if (g_nccl.lib) return 0;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  void *lib = nullptr;
+  for (const char *n : names) {
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) return fail(LITE_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(lib, "ncclAllReduce");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce)
+    return fail(LITE_ENCCL, "libnccl.so.2 lacks the expected symbols");
+  g_nccl.lib = lib;
+  return 0;
+}
+
+template <typename T>
+struct DBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    if (count <= n && p) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    if (count == 0) return 0;
+    cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+    if (e != cudaSuccess) return fail(LITE_ECUDA, "cudaMalloc(%zu B): %s", count * sizeof(T), cudaGetErrorString(e));
+    n = count;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct lite_ctx {
+  int device = 0, rank = 0, world = 1;
+  cudaStream_t stream = nullptr;
+  ncclComm_t comm = nullptr;
+  bool have_tess = false, have_prog = false, have_mf = false;
+  bool record = false;
+  int64_t launches = 0;
+  // raw SoA
+  DBuf<double> vx, vy, he_length;
+  DBuf<int> he_src, he_twin, he_next, he_face, he_seg, he_next_hf, he_prev_hf;
+  DBuf<uint8_t> he_dir, face_inside, seg_bnd;
+  DBuf<int> f_off, f_cnt, f_list, seg_he_start, seg_he_end, seg_n_edges, nb_list, b_list;
+  // derived
+  DBuf<double2> pt;
+  DBuf<double> ang, len, ca, f_area, f_perim, f_sumang, f_minang, cum;
+  DBuf<uint32_t> flg;
+  DBuf<int> slot_he, slot_seg, slot_face, he_slot, cum_he, err;
+  TessDev T{};
+  int n_nb = 0, n_b = 0;
+  double int_length = 0;
+  Prog G{};
+  // splits
+  DBuf<double> stat;
+  size_t cap = 0;
+  int64_t n_local = 0, n_global = 0;
+  DBuf<int> r_e1, r_e2, in_he;
+  DBuf<double2> r_p1, r_p2;
+  DBuf<double> r_x, r_angle, r_u, in_x, in_angle;
+  size_t rcap = 0;
+  // merges / flips
+  DBuf<double> mstat, fstat, sums;  // sums: [d merges | d flips]
+  DBuf<int> m_he, fl_e1, fl_e2, fl_right;
+  DBuf<double2> fl_p2;
+  std::vector<double> h_sum_m, h_sum_f;
+  // reduce
+  DBuf<double> partials, red_out;
+  DBuf<unsigned int> counter;
+  DBuf<unsigned long long> status;  // [0] split no-exit, [1] flip no-exit, [2..3] checksum
+  double *h_pinned = nullptr;       // pinned staging for results
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float ms_split = 0, ms_eval = 0, ms_mf = 0;
+  bool ev01 = false;  // ev[0]/ev[1] have been recorded
+  std::vector<uint8_t> h_he_inside;
+  int sm_count = 148;
+};
+
+extern "C" const char *lite_last_error(void) { return g_err.c_str(); }
+
+extern "C" int lite_nccl_unique_id(void *out128) {
+  if (!out128) return fail(LITE_EINVAL, "null output");
+  int r = nccl_load();
+  if (r) return r;
+  ncclUniqueId id;
+  ncclResult_t e = g_nccl.GetUniqueId(&id);
+  if (e != 0) return fail(LITE_ENCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?");
+  memcpy(out128, &id, 128);
+  return 0;
+}
+
+extern "C" int lite_ctx_create(lite_ctx **out, int device, int rank, int world_size,
+                               const void *nccl_unique_id) {
+  if (!out) return fail(LITE_EINVAL, "null output");
+  *out = nullptr;
+  if (world_size < 1 || rank < 0 || rank >= world_size) return fail(LITE_EINVAL, "bad rank/world_size");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(LITE_ECUDA, "no CUDA device available (%s): this library has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(LITE_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  CU(cudaSetDevice(device));
+  lite_ctx *c = new lite_ctx();
+  c->device = device; c->rank = rank; c->world = world_size;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 6; i++) CU(cudaEventCreate(&c->ev[i]));
+  CU(cudaMallocHost((void **)&c->h_pinned, 4096 * sizeof(double)));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  if (c->status.alloc(8) || c->counter.alloc(4) || c->err.alloc(1)) return LITE_ECUDA;
+  CU(cudaMemsetAsync(c->status.p, 0, 8 * sizeof(unsigned long long), c->stream));
+  CU(cudaMemsetAsync(c->counter.p, 0, 4 * sizeof(unsigned int), c->stream));
+  if (world_size > 1) {
+    if (!nccl_unique_id) return fail(LITE_EINVAL, "world_size > 1 needs a NCCL unique id");
+    int r = nccl_load();
+    if (r) return r;
+    ncclUniqueId id;
+    memcpy(&id, nccl_unique_id, 128);
+    ncclResult_t ne = g_nccl.CommInitRank(&c->comm, world_size, id, rank);
+    if (ne != 0) return fail(LITE_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(ne) : "?");
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return 0;
+}
+
+extern "C" int lite_ctx_destroy(lite_ctx *c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  // DBuf members are released explicitly (no destructors: keep the struct POD-like)
+  c->vx.release(); c->vy.release(); c->he_length.release();
+  c->he_src.release(); c->he_twin.release(); c->he_next.release(); c->he_face.release();
+  c->he_seg.release(); c->he_next_hf.release(); c->he_prev_hf.release();
+  c->he_dir.release(); c->face_inside.release(); c->seg_bnd.release();
+  c->f_off.release(); c->f_cnt.release(); c->f_list.release(); c->seg_he_start.release();
+  c->seg_he_end.release(); c->seg_n_edges.release(); c->nb_list.release(); c->b_list.release();
+  c->pt.release(); c->ang.release(); c->len.release(); c->ca.release(); c->f_area.release();
+  c->f_perim.release(); c->f_sumang.release(); c->f_minang.release(); c->cum.release();
+  c->flg.release(); c->slot_he.release(); c->slot_seg.release(); c->slot_face.release();
+  c->he_slot.release(); c->cum_he.release(); c->err.release();
+  c->stat.release(); c->r_e1.release(); c->r_e2.release(); c->in_he.release();
+  c->r_p1.release(); c->r_p2.release(); c->r_x.release(); c->r_angle.release(); c->r_u.release();
+  c->in_x.release(); c->in_angle.release();
+  c->mstat.release(); c->fstat.release(); c->sums.release(); c->m_he.release();
+  c->fl_e1.release(); c->fl_e2.release(); c->fl_right.release(); c->fl_p2.release();
+  c->partials.release(); c->red_out.release(); c->counter.release(); c->status.release();
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+extern "C" int lite_ctx_sync(lite_ctx *c) {
+  if (!c) return fail(LITE_EINVAL, "null context");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int lite_ctx_set_option(lite_ctx *c, int option, int64_t value) {
+  if (!c) return fail(LITE_EINVAL, "null context");
+  if (option == LITE_OPT_RECORD_SPLITS) {
+    if (c->n_local != 0) return fail(LITE_ESTATE, "clear the splits before changing the record option");
+    c->record = value != 0;
+    return 0;
+  }
+  return fail(LITE_EINVAL, "unknown option %d", option);
+}
+
+template <typename T>
+static int up(lite_ctx *c, DBuf<T> &b, const T *src, size_t n) {
+  if (b.alloc(n ? n : 1)) return LITE_ECUDA;
+  if (n) CU(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
+extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
+  if (!c || !s) return fail(LITE_EINVAL, "null argument");
+  CU(cudaSetDevice(c->device));
+  const int nH = s->n_halfedges, nF = s->n_faces, nS = s->n_segments, nV = s->n_vertices;
+  if (nH <= 0 || nF <= 0 || nS <= 0 || nV <= 0) return fail(LITE_EINVAL, "empty tessellation");
+  // ---- export assertions (in the spirit of TTessel::is_valid, lib/ttessel.cpp:1721-1753)
+  int64_t listed = 0;
+  for (int f = 0; f < nF; f++) {
+    if (s->face_he_count[f] < 0 || s->face_he_offset[f] < 0 ||
+        s->face_he_offset[f] + s->face_he_count[f] > s->n_face_he)
+      return fail(LITE_EINVAL, "face %d: halfedge list out of range", f);
+    if (s->face_inside[f]) {
+      if (s->face_he_count[f] < 3) return fail(LITE_EINVAL, "inside face %d has %d halfedges", f, s->face_he_count[f]);
+      listed += s->face_he_count[f];
+    }
+  }
+  std::vector<double> cum;
+  std::vector<int> cum_he;
+  cum.reserve(nH); cum_he.reserve(nH);
+  c->h_he_inside.assign(nH, 0);
+  double cl = 0.0;
+  int64_t inside_he = 0;
+  for (int h = 0; h < nH; h++) {
+    int f = s->he_face[h], t = s->he_twin[h];
+    if (f < 0 || f >= nF || t < 0 || t >= nH || s->he_twin[t] != h || s->he_src[h] < 0 ||
+        s->he_src[h] >= nV || s->he_seg[h] < 0 || s->he_seg[h] >= nS)
+      return fail(LITE_EINVAL, "halfedge %d: inconsistent links", h);
+    if (!s->face_inside[f]) continue;
+    inside_he++;
+    c->h_he_inside[h] = 1;
+    cl += s->he_length[h];  // cumlen += e->get_length(), lib/ttessel.cpp:1980
+    cum.push_back(cl);
+    cum_he.push_back(h);
+  }
+  if (inside_he != listed)
+    return fail(LITE_EINVAL,
+                "%lld halfedges bound inside faces but %lld are listed on outer boundaries: faces with "
+                "holes are outside the scope of this library",
+                (long long)inside_he, (long long)listed);
+  if (!(fabs(cl - s->int_length) <= 1e-9 * fmax(1.0, fabs(cl))))
+    return fail(LITE_EINVAL, "int_length %.17g differs from the sum of inside halfedge lengths %.17g",
+                s->int_length, cl);
+  for (int i = 0; i < s->n_non_blocking; i++) {
+    int sg = s->non_blocking[i];
+    if (sg < 0 || sg >= nS || s->seg_n_edges[sg] != 1 || s->seg_on_boundary[sg])
+      return fail(LITE_EINVAL, "non-blocking segment %d must be internal with exactly one edge", sg);
+  }
+  for (int i = 0; i < s->n_blocking; i++) {
+    int sg = s->blocking[i];
+    if (sg < 0 || sg >= nS || s->seg_n_edges[sg] < 2 || s->seg_on_boundary[sg])
+      return fail(LITE_EINVAL, "blocking segment %d must be internal with at least two edges", sg);
+  }
+  // ---- copies
+  int r = 0;
+  r |= up(c, c->vx, s->vx, nV); r |= up(c, c->vy, s->vy, nV);
+  r |= up(c, c->he_src, s->he_src, nH); r |= up(c, c->he_twin, s->he_twin, nH);
+  r |= up(c, c->he_next, s->he_next, nH); r |= up(c, c->he_face, s->he_face, nH);
+  r |= up(c, c->he_seg, s->he_seg, nH); r |= up(c, c->he_next_hf, s->he_next_hf, nH);
+  r |= up(c, c->he_prev_hf, s->he_prev_hf, nH); r |= up(c, c->he_dir, s->he_dir, nH);
+  r |= up(c, c->he_length, s->he_length, nH);
+  r |= up(c, c->face_inside, s->face_inside, nF); r |= up(c, c->f_off, s->face_he_offset, nF);
+  r |= up(c, c->f_cnt, s->face_he_count, nF); r |= up(c, c->f_list, s->face_he_list, s->n_face_he);
+  r |= up(c, c->seg_he_start, s->seg_he_start, nS); r |= up(c, c->seg_he_end, s->seg_he_end, nS);
+  r |= up(c, c->seg_n_edges, s->seg_n_edges, nS); r |= up(c, c->seg_bnd, s->seg_on_boundary, nS);
+  r |= up(c, c->nb_list, s->non_blocking, s->n_non_blocking);
+  r |= up(c, c->b_list, s->blocking, s->n_blocking);
+  r |= up(c, c->cum, cum.data(), cum.size()); r |= up(c, c->cum_he, cum_he.data(), cum_he.size());
+  if (r) return LITE_ECUDA;
+  const size_t nSl = (size_t)s->n_face_he;
+  if (c->pt.alloc(nSl) || c->ang.alloc(nSl) || c->len.alloc(nSl) || c->ca.alloc(nSl) ||
+      c->flg.alloc(nSl) || c->slot_he.alloc(nSl) || c->slot_seg.alloc(nSl) ||
+      c->slot_face.alloc(nSl) || c->he_slot.alloc(nH) || c->f_area.alloc(nF) ||
+      c->f_perim.alloc(nF) || c->f_sumang.alloc(nF) || c->f_minang.alloc(nF))
+    return LITE_ECUDA;
+  CU(cudaMemsetAsync(c->he_slot.p, 0xFF, nH * sizeof(int), c->stream));
+  CU(cudaMemsetAsync(c->err.p, 0, sizeof(int), c->stream));
+  PrepArgs A{};
+  A.vx = c->vx.p; A.vy = c->vy.p; A.he_src = c->he_src.p; A.he_twin = c->he_twin.p;
+  A.he_next = c->he_next.p; A.he_face = c->he_face.p; A.he_seg = c->he_seg.p;
+  A.he_next_hf = c->he_next_hf.p; A.he_dir = c->he_dir.p; A.face_inside = c->face_inside.p;
+  A.he_length = c->he_length.p; A.face_he_offset = c->f_off.p; A.face_he_count = c->f_cnt.p;
+  A.face_he_list = c->f_list.p; A.n_faces = nF;
+  A.pt = c->pt.p; A.ang = c->ang.p; A.len = c->len.p; A.ca = c->ca.p; A.flg = c->flg.p;
+  A.slot_he = c->slot_he.p; A.slot_seg = c->slot_seg.p; A.slot_face = c->slot_face.p;
+  A.he_slot = c->he_slot.p; A.err = c->err.p;
+  TessDev &T = c->T;
+  T.n_slots = (int)nSl; T.n_faces = nF; T.n_he = nH; T.n_seg = nS;
+  T.pt = c->pt.p; T.ang = c->ang.p; T.len = c->len.p; T.ca = c->ca.p; T.flg = c->flg.p;
+  T.slot_he = c->slot_he.p; T.slot_seg = c->slot_seg.p; T.slot_face = c->slot_face.p;
+  T.he_slot = c->he_slot.p; T.he_twin = c->he_twin.p; T.he_src = c->he_src.p;
+  T.he_next_hf = c->he_next_hf.p; T.he_prev_hf = c->he_prev_hf.p;
+  T.f_off = c->f_off.p; T.f_cnt = c->f_cnt.p;
+  T.f_area = c->f_area.p; T.f_perim = c->f_perim.p; T.f_sumang = c->f_sumang.p; T.f_minang = c->f_minang.p;
+  T.seg_n_edges = c->seg_n_edges.p; T.seg_he_start = c->seg_he_start.p; T.seg_he_end = c->seg_he_end.p;
+  T.seg_bnd = c->seg_bnd.p;
+  T.cum = c->cum.p; T.cum_he = c->cum_he.p; T.n_cum = (int)cum.size(); T.total_len = cl;
+  int tb = 128, gb = (nF + tb - 1) / tb;
+  k_prep_slots<<<gb, tb, 0, c->stream>>>(A);
+  // outside faces: count 0 in the device view
+  k_prep_faces<<<gb, tb, 0, c->stream>>>(T, c->ca.p, c->f_area.p, c->f_perim.p, c->f_sumang.p, c->f_minang.p);
+  c->launches += 2;
+  int herr = 0;
+  CU(cudaMemcpyAsync(&herr, c->err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  if (herr) return fail(LITE_EINVAL, "%d face halfedge lists disagree with he_next/he_face", herr);
+  c->n_nb = s->n_non_blocking; c->n_b = s->n_blocking; c->int_length = s->int_length;
+  c->have_tess = true; c->have_mf = false;
+  c->n_local = 0; c->n_global = 0;
+  return 0;
+}
+
+static int category_of(int fid) {
+  switch (fid) {
+    case LITE_FEAT_IS_POINT_INSIDE_WINDOW: return 0;
+    case LITE_FEAT_EDGE_LENGTH: case LITE_FEAT_EDGE_LENGTH_INTERNAL: return 1;
+    case LITE_FEAT_FACE_NUMBER: case LITE_FEAT_FACE_AREA_2: case LITE_FEAT_FACE_PERIMETER:
+    case LITE_FEAT_FACE_SHAPE: case LITE_FEAT_FACE_SUM_OF_ANGLES: case LITE_FEAT_MIN_ANGLE: return 2;
+    case LITE_FEAT_SEG_NUMBER: case LITE_FEAT_IS_SEGMENT_INTERNAL:
+    case LITE_FEAT_MINUS_IS_SEGMENT_INTERNAL: case LITE_FEAT_SEGMENT_SIZE_2: return 3;
+    default: return -1;
+  }
+}
+
+extern "C" int lite_energy_set(lite_ctx *c, int d, const int32_t *fid) {
+  if (!c || !fid) return fail(LITE_EINVAL, "null argument");
+  if (d < 1 || d > LITE_MAX_D) return fail(LITE_EINVAL, "d=%d outside [1,%d]", d, LITE_MAX_D);
+  int lastcat = 0;
+  Prog G{};
+  G.d = d;
+  for (int i = 0; i < d; i++) {
+    int cat = category_of(fid[i]);
+    if (cat < 0) return fail(LITE_EINVAL, "unknown feature id %d: only the built-in feature functions run on the device", fid[i]);
+    if (cat < lastcat) return fail(LITE_EINVAL, "features must come in CatVector order vertices, edges, faces, segs");
+    lastcat = cat;
+    G.fid[i] = fid[i];
+    G.mask |= 1u << fid[i];
+  }
+  if (c->n_local != 0) return fail(LITE_ESTATE, "clear the splits before changing the energy");
+  c->G = G;
+  c->have_prog = true; c->have_mf = false;
+  return 0;
+}
+
+extern "C" int lite_candidates_merges_flips(lite_ctx *c, int32_t *n_merges, int32_t *n_flips) {
+  if (!c) return fail(LITE_EINVAL, "null context");
+  if (!c->have_tess || !c->have_prog) return fail(LITE_ESTATE, "upload a tessellation and set the energy first");
+  CU(cudaSetDevice(c->device));
+  const int d = c->G.d, nm = c->n_nb, nf = 2 * c->n_b;
+  if (c->mstat.alloc((size_t)d * (nm ? nm : 1)) || c->fstat.alloc((size_t)d * (nf ? nf : 1)) ||
+      c->sums.alloc(2 * LITE_MAX_D) || c->m_he.alloc(nm ? nm : 1) || c->fl_e1.alloc(nf ? nf : 1) ||
+      c->fl_e2.alloc(nf ? nf : 1) || c->fl_right.alloc(nf ? nf : 1) || c->fl_p2.alloc(nf ? nf : 1))
+    return LITE_ECUDA;
+  CU(cudaMemsetAsync(c->sums.p, 0, 2 * LITE_MAX_D * sizeof(double), c->stream));
+  CU(cudaEventRecord(c->ev[4], c->stream));
+  if (nm) {
+    k_merges<<<(nm + 127) / 128, 128, 0, c->stream>>>(c->T, c->G, c->nb_list.p, nm, c->mstat.p, (size_t)nm, c->m_he.p);
+    k_colsum<<<d, 256, 0, c->stream>>>(c->mstat.p, (size_t)nm, nm, c->sums.p);
+    c->launches += 2;
+  }
+  if (nf) {
+    k_flips<<<(nf + 127) / 128, 128, 0, c->stream>>>(c->T, c->G, c->b_list.p, c->n_b, c->fstat.p, (size_t)nf,
+                                                     c->fl_e1.p, c->fl_e2.p, c->fl_p2.p, c->fl_right.p,
+                                                     c->status.p + 1);
+    k_colsum<<<d, 256, 0, c->stream>>>(c->fstat.p, (size_t)nf, nf, c->sums.p + LITE_MAX_D);
+    c->launches += 2;
+  }
+  CU(cudaEventRecord(c->ev[5], c->stream));
+  CU(cudaMemcpyAsync(c->h_pinned, c->sums.p, 2 * LITE_MAX_D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  cudaEventElapsedTime(&c->ms_mf, c->ev[4], c->ev[5]);
+  c->h_sum_m.assign(c->h_pinned, c->h_pinned + d);
+  c->h_sum_f.assign(c->h_pinned + LITE_MAX_D, c->h_pinned + LITE_MAX_D + d);
+  c->have_mf = true;
+  if (n_merges) *n_merges = nm;
+  if (n_flips) *n_flips = nf;
+  return 0;
+}
+
+static int grow_splits(lite_ctx *c, int64_t add) {
+  const int d = c->G.d;
+  size_t need = (size_t)(c->n_local + add);
+  if (need > c->cap) {
+    size_t ncap = c->cap ? c->cap * 2 : 0;
+    if (ncap < need) ncap = need;
+    ncap = (ncap + 255) & ~(size_t)255;
+    DBuf<double> nb;
+    if (nb.alloc(ncap * d)) return LITE_ECUDA;
+    if (c->n_local)
+      CU(cudaMemcpy2DAsync(nb.p, ncap * sizeof(double), c->stat.p, c->cap * sizeof(double),
+                           (size_t)c->n_local * sizeof(double), d, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stat.release();
+    c->stat = nb;
+    c->cap = ncap;
+  }
+  if (c->record && need > c->rcap) {
+    size_t ncap = c->rcap ? c->rcap * 2 : 0;
+    if (ncap < need) ncap = need;
+    DBuf<int> e1, e2; DBuf<double2> p1, p2; DBuf<double> x, a, u;
+    if (e1.alloc(ncap) || e2.alloc(ncap) || p1.alloc(ncap) || p2.alloc(ncap) || x.alloc(ncap) ||
+        a.alloc(ncap) || u.alloc(ncap))
+      return LITE_ECUDA;
+    size_t n = (size_t)c->n_local;
+    if (n) {
+      CU(cudaMemcpyAsync(e1.p, c->r_e1.p, n * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+      CU(cudaMemcpyAsync(e2.p, c->r_e2.p, n * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+      CU(cudaMemcpyAsync(p1.p, c->r_p1.p, n * sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
+      CU(cudaMemcpyAsync(p2.p, c->r_p2.p, n * sizeof(double2), cudaMemcpyDeviceToDevice, c->stream));
+      CU(cudaMemcpyAsync(x.p, c->r_x.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      CU(cudaMemcpyAsync(a.p, c->r_angle.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      CU(cudaMemcpyAsync(u.p, c->r_u.p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    c->r_e1.release(); c->r_e2.release(); c->r_p1.release(); c->r_p2.release();
+    c->r_x.release(); c->r_angle.release(); c->r_u.release();
+    c->r_e1 = e1; c->r_e2 = e2; c->r_p1 = p1; c->r_p2 = p2; c->r_x = x; c->r_angle = a; c->r_u = u;
+    c->rcap = ncap;
+  }
+  return 0;
+}
+
+static int split_grid(lite_ctx *c, int64_t n) {
+  int64_t blocks = (n + 255) / 256;
+  int64_t maxb = (int64_t)c->sm_count * 16;
+  if (blocks > maxb) blocks = maxb;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+static void fill_split_args(lite_ctx *c, SplitArgs &A) {
+  A.stat = c->stat.p; A.cap = c->cap; A.base = (long)c->n_local;
+  A.r_e1 = c->r_e1.p; A.r_e2 = c->r_e2.p; A.r_p1 = c->r_p1.p; A.r_p2 = c->r_p2.p;
+  A.r_x = c->r_x.p; A.r_angle = c->r_angle.p; A.r_u = c->r_u.p;
+  A.status = c->status.p; A.checksum = c->status.p + 2;
+}
+
+extern "C" int lite_candidates_add_splits_given(lite_ctx *c, int64_t n, const int32_t *he,
+                                                const double *x, const double *angle,
+                                                int64_t n_global_total) {
+  if (!c) return fail(LITE_EINVAL, "null context");
+  if (!c->have_tess || !c->have_prog) return fail(LITE_ESTATE, "upload a tessellation and set the energy first");
+  if (n < 0 || n_global_total < n) return fail(LITE_EINVAL, "bad candidate counts");
+  CU(cudaSetDevice(c->device));
+  if (n == 0) { c->n_global += n_global_total; return 0; }
+  if (!he || !x || !angle) return fail(LITE_EINVAL, "null candidate arrays");
+  // validate the halfedge ids (they index device memory): a split starts on a
+  // halfedge bounding an inside face (lib/ttessel.cpp:1978)
+  for (int64_t i = 0; i < n; i++)
+    if (he[i] < 0 || he[i] >= c->T.n_he || !c->h_he_inside[he[i]])
+      return fail(LITE_EINVAL, "candidate %lld: halfedge id %d does not bound an inside face", (long long)i, he[i]);
+  int r = grow_splits(c, n);
+  if (r) return r;
+  if (c->in_he.alloc(n) || c->in_x.alloc(n) || c->in_angle.alloc(n)) return LITE_ECUDA;
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  CU(cudaMemcpyAsync(c->in_he.p, he, n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->in_x.p, x, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->in_angle.p, angle, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  SplitArgs A{};
+  fill_split_args(c, A);
+  A.n_local = n; A.j0 = 0; A.n_batch = n_global_total;
+  A.in_he = c->in_he.p; A.in_x = c->in_x.p; A.in_angle = c->in_angle.p;
+  int g = split_grid(c, n);
+  if (c->record) k_split<4 | 2><<<g, 256, 0, c->stream>>>(c->T, c->G, A);
+  else k_split<4><<<g, 256, 0, c->stream>>>(c->T, c->G, A);
+  c->launches += 1;
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  c->ev01 = true;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  cudaEventElapsedTime(&c->ms_split, c->ev[0], c->ev[1]);
+  c->n_local += n; c->n_global += n_global_total;
+  return 0;
+}
+
+static void shard_range(int64_t n, int rank, int world, int64_t &j0, int64_t &cnt) {
+  // contiguous shards [r*n/G, (r+1)*n/G)
+  j0 = (int64_t)(((__int128)n * rank) / world);
+  int64_t j1 = (int64_t)(((__int128)n * (rank + 1)) / world);
+  cnt = j1 - j0;
+}
+
+extern "C" int lite_candidates_add_splits_philox(lite_ctx *c, int64_t n_global, uint64_t seed,
+                                                 uint64_t offset) {
+  if (!c) return fail(LITE_EINVAL, "null context");
+  if (!c->have_tess || !c->have_prog) return fail(LITE_ESTATE, "upload a tessellation and set the energy first");
+  if (n_global < 0) return fail(LITE_EINVAL, "negative count");
+  CU(cudaSetDevice(c->device));
+  int64_t j0, n;
+  shard_range(n_global, c->rank, c->world, j0, n);
+  if (n > 0) {
+    int r = grow_splits(c, n);
+    if (r) return r;
+    SplitArgs A{};
+    fill_split_args(c, A);
+    A.n_local = n; A.j0 = j0; A.n_batch = n_global; A.seed = seed; A.ctr0 = offset;
+    int g = split_grid(c, n);
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    if (c->record) k_split<4 | 2 | 1><<<g, 256, 0, c->stream>>>(c->T, c->G, A);
+    else k_split<4 | 1><<<g, 256, 0, c->stream>>>(c->T, c->G, A);
+    c->launches += 1;
+    CU(cudaEventRecord(c->ev[1], c->stream));
+  c->ev01 = true;
+  }
+  c->n_local += n; c->n_global += n_global;
+  return 0;
+}
+
+extern "C" int lite_lines_sample_clip(lite_ctx *c, int64_t n_global, uint64_t seed, uint64_t offset,
+                                      int mode, uint64_t *checksum2) {
+  if (!c) return fail(LITE_EINVAL, "null context");
+  if (!c->have_tess) return fail(LITE_ESTATE, "upload a tessellation first");
+  if (n_global < 0 || (mode != 0 && mode != 1)) return fail(LITE_EINVAL, "bad arguments");
+  CU(cudaSetDevice(c->device));
+  int64_t j0, n;
+  shard_range(n_global, c->rank, c->world, j0, n);
+  CU(cudaMemsetAsync(c->status.p + 2, 0, 2 * sizeof(unsigned long long), c->stream));
+  if (n > 0) {
+    Prog G0{};  // no features
+    bool rec_save = c->record;
+    if (mode == 1) {
+      c->record = true;
+      if (c->n_local != 0) return fail(LITE_ESTATE, "store mode needs an empty split list");
+      int r = grow_splits(c, n);
+      c->record = rec_save;
+      if (r) return r;
+    }
+    SplitArgs A{};
+    fill_split_args(c, A);
+    A.base = 0;
+    A.n_local = n; A.j0 = j0; A.n_batch = n_global; A.seed = seed; A.ctr0 = offset;
+    int g = split_grid(c, n);
+    CU(cudaEventRecord(c->ev[0], c->stream));
+    if (mode == 1) k_split<8 | 2 | 1><<<g, 256, 0, c->stream>>>(c->T, G0, A);
+    else k_split<8 | 1><<<g, 256, 0, c->stream>>>(c->T, G0, A);
+    c->launches += 1;
+    CU(cudaEventRecord(c->ev[1], c->stream));
+  c->ev01 = true;
+  }
+  CU(cudaMemcpyAsync(c->h_pinned, c->status.p + 2, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  if (n > 0) cudaEventElapsedTime(&c->ms_split, c->ev[0], c->ev[1]);
+  if (checksum2) memcpy(checksum2, c->h_pinned, 2 * sizeof(uint64_t));
+  return 0;
+}
+
+extern "C" int lite_candidates_clear_splits(lite_ctx *c) {
+  if (!c) return fail(LITE_EINVAL, "null context");
+  c->n_local = 0; c->n_global = 0;
+  return 0;
+}
+
+extern "C" int lite_candidates_count(lite_ctx *c, int64_t *nl, int64_t *ng) {
+  if (!c) return fail(LITE_EINVAL, "null context");
+  if (nl) *nl = c->n_local;
+  if (ng) *ng = c->n_global;
+  return 0;
+}
+
+template <int D>
+static void launch_reduce(lite_ctx *c, const double *stat, size_t cap, long n, const Theta &th,
+                          int grid, double *out) {
+  k_reduce<D><<<grid, 256, 0, c->stream>>>(stat, cap, n, th, c->partials.p, c->counter.p, out);
+}
+static void reduce_dispatch(lite_ctx *c, int d, const double *stat, size_t cap, long n,
+                            const Theta &th, int grid, double *out) {
+  switch (d) {
+    case 1: launch_reduce<1>(c, stat, cap, n, th, grid, out); break;
+    case 2: launch_reduce<2>(c, stat, cap, n, th, grid, out); break;
+    case 3: launch_reduce<3>(c, stat, cap, n, th, grid, out); break;
+    case 4: launch_reduce<4>(c, stat, cap, n, th, grid, out); break;
+    case 5: launch_reduce<5>(c, stat, cap, n, th, grid, out); break;
+    case 6: launch_reduce<6>(c, stat, cap, n, th, grid, out); break;
+    case 7: launch_reduce<7>(c, stat, cap, n, th, grid, out); break;
+    case 8: launch_reduce<8>(c, stat, cap, n, th, grid, out); break;
+    case 9: launch_reduce<9>(c, stat, cap, n, th, grid, out); break;
+    case 10: launch_reduce<10>(c, stat, cap, n, th, grid, out); break;
+    case 11: launch_reduce<11>(c, stat, cap, n, th, grid, out); break;
+    case 12: launch_reduce<12>(c, stat, cap, n, th, grid, out); break;
+  }
+  c->launches += 1;
+}
+
+extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, double *grad, double *hess) {
+  if (!c || !theta) return fail(LITE_EINVAL, "null argument");
+  if (!c->have_tess || !c->have_prog) return fail(LITE_ESTATE, "upload a tessellation and set the energy first");
+  if (!c->have_mf) return fail(LITE_ESTATE, "call lite_candidates_merges_flips (SetEnergy) before evaluating");
+  if (c->n_global == 0) return fail(LITE_ENOSPLIT, "no dummy splits: the reference divides by stat_splits.size()");
+  CU(cudaSetDevice(c->device));
+  const int d = c->G.d;
+  const int NT = 1 + d + d * (d + 1) / 2;
+  Theta th{};
+  for (int i = 0; i < d; i++) th.v[i] = theta[i];
+  const int maxgrid = c->sm_count * 4;
+  if (c->partials.alloc((size_t)maxgrid * NT) || c->red_out.alloc(2 * 128)) return LITE_ECUDA;
+  CU(cudaEventRecord(c->ev[2], c->stream));
+  // splits (this rank's shard)
+  long n = (long)c->n_local;
+  int grid = (int)((n + 1023) / 1024);
+  if (grid > maxgrid) grid = maxgrid;
+  if (n > 0) reduce_dispatch(c, d, c->stat.p, c->cap, n, th, grid < 1 ? 1 : grid, c->red_out.p);
+  else CU(cudaMemsetAsync(c->red_out.p, 0, 128 * sizeof(double), c->stream));
+  // flips (replicated on every rank; cheap)
+  long nf = 2L * c->n_b;
+  if (nf > 0) {
+    int gf = (int)((nf + 1023) / 1024);
+    if (gf > maxgrid) gf = maxgrid;
+    reduce_dispatch(c, d, c->fstat.p, (size_t)nf, nf, th, gf < 1 ? 1 : gf, c->red_out.p + 128);
+  } else {
+    CU(cudaMemsetAsync(c->red_out.p + 128, 0, 128 * sizeof(double), c->stream));
+  }
+  if (c->world > 1) {
+    ncclResult_t ne = g_nccl.AllReduce(c->red_out.p, c->red_out.p, (size_t)NT, ncclFloat64, ncclSum, c->comm, c->stream);
+    if (ne != 0) return fail(LITE_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(ne) : "?");
+  }
+  CU(cudaEventRecord(c->ev[3], c->stream));
+  CU(cudaMemcpyAsync(c->h_pinned, c->red_out.p, 256 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  cudaEventElapsedTime(&c->ms_eval, c->ev[2], c->ev[3]);
+  if (c->ev01) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->ms_split = ms; }
+  const double *S = c->h_pinned, *F = c->h_pinned + 128;
+  // lib/ttessel.cpp:3396: int_length/(pi*|S|)
+  const double cn = c->int_length / (LITE_PI * (double)c->n_global);
+  const double *M = c->h_sum_m.data(), *Fl = c->h_sum_f.data();
+  if (lpl) {
+    double tm = 0, tf = 0;
+    for (int i = 0; i < d; i++) { tm += theta[i] * M[i]; tf += theta[i] * Fl[i]; }
+    double v = -tm;
+    v -= cn * S[0];
+    v -= tf;
+    v -= F[0];
+    *lpl = v;
+  }
+  if (grad)
+    for (int i = 0; i < d; i++) grad[i] = -M[i] - cn * S[1 + i] - Fl[i] - F[1 + i];
+  if (hess) {
+    int t = 1 + d;
+    for (int k = 0; k < d; k++)
+      for (int l = k; l < d; l++, t++) {
+        double v = -cn * S[t] - F[t];
+        hess[k * d + l] = v;
+        hess[l * d + k] = v;
+      }
+  }
+  return 0;
+}
+
+extern "C" int lite_pl_sums(lite_ctx *c, double *sm, double *sf) {
+  if (!c) return fail(LITE_EINVAL, "null context");
+  if (!c->have_mf) return fail(LITE_ESTATE, "call lite_candidates_merges_flips first");
+  for (int i = 0; i < c->G.d; i++) {
+    if (sm) sm[i] = c->h_sum_m[i];
+    if (sf) sf[i] = c->h_sum_f[i];
+  }
+  return 0;
+}
+
+template <typename T>
+static int fetch_plain(lite_ctx *c, const T *src, size_t have, int64_t first, int64_t count, void *out) {
+  if (first < 0 || count < 0 || (size_t)(first + count) > have) return fail(LITE_EINVAL, "fetch range out of bounds");
+  if (count == 0) return 0;
+  CU(cudaMemcpyAsync(out, src + first, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+static int fetch_stat(lite_ctx *c, const double *stat, size_t cap, size_t have, int d, int64_t first,
+                      int64_t count, double *out) {
+  if (first < 0 || count < 0 || (size_t)(first + count) > have) return fail(LITE_EINVAL, "fetch range out of bounds");
+  if (count == 0) return 0;
+  std::vector<double> tmp((size_t)count * d);
+  CU(cudaMemcpy2DAsync(tmp.data(), count * sizeof(double), stat + first, cap * sizeof(double),
+                       count * sizeof(double), d, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int64_t i = 0; i < count; i++)
+    for (int k = 0; k < d; k++) out[i * d + k] = tmp[(size_t)k * count + i];
+  return 0;
+}
+
+extern "C" int lite_debug_fetch(lite_ctx *c, int which, int64_t first, int64_t count, void *out) {
+  if (!c || !out) return fail(LITE_EINVAL, "null argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  const size_t ns = (size_t)c->n_local, nm = (size_t)c->n_nb, nf = (size_t)2 * c->n_b;
+  const bool rec = c->rcap > 0;
+  switch (which) {
+    case LITE_FETCH_SPLIT_STAT: return fetch_stat(c, c->stat.p, c->cap, ns, c->G.d, first, count, (double *)out);
+    case LITE_FETCH_MERGE_STAT:
+      if (!c->have_mf) break;
+      return fetch_stat(c, c->mstat.p, nm, nm, c->G.d, first, count, (double *)out);
+    case LITE_FETCH_FLIP_STAT:
+      if (!c->have_mf) break;
+      return fetch_stat(c, c->fstat.p, nf, nf, c->G.d, first, count, (double *)out);
+    case LITE_FETCH_MERGE_HE: if (!c->have_mf) break; return fetch_plain(c, c->m_he.p, nm, first, count, out);
+    case LITE_FETCH_FLIP_E1: if (!c->have_mf) break; return fetch_plain(c, c->fl_e1.p, nf, first, count, out);
+    case LITE_FETCH_FLIP_E2: if (!c->have_mf) break; return fetch_plain(c, c->fl_e2.p, nf, first, count, out);
+    case LITE_FETCH_FLIP_P2: if (!c->have_mf) break; return fetch_plain(c, c->fl_p2.p, nf, first, count, out);
+    case LITE_FETCH_FLIP_RIGHT: if (!c->have_mf) break; return fetch_plain(c, c->fl_right.p, nf, first, count, out);
+    case LITE_FETCH_STATUS: {
+      CU(cudaMemcpyAsync(out, c->status.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      return 0;
+    }
+    default: break;
+  }
+  if (which == LITE_FETCH_SPLIT_E1 || which == LITE_FETCH_SPLIT_E2 || which == LITE_FETCH_SPLIT_P1 ||
+      which == LITE_FETCH_SPLIT_P2 || which == LITE_FETCH_SPLIT_X || which == LITE_FETCH_SPLIT_ANGLE ||
+      which == LITE_FETCH_SPLIT_U) {
+    if (!rec) return fail(LITE_ESTATE, "per-split records need LITE_OPT_RECORD_SPLITS before adding splits");
+    size_t have = c->rcap;
+    switch (which) {
+      case LITE_FETCH_SPLIT_E1: return fetch_plain(c, c->r_e1.p, have, first, count, out);
+      case LITE_FETCH_SPLIT_E2: return fetch_plain(c, c->r_e2.p, have, first, count, out);
+      case LITE_FETCH_SPLIT_P1: return fetch_plain(c, c->r_p1.p, have, first, count, out);
+      case LITE_FETCH_SPLIT_P2: return fetch_plain(c, c->r_p2.p, have, first, count, out);
+      case LITE_FETCH_SPLIT_X: return fetch_plain(c, c->r_x.p, have, first, count, out);
+      case LITE_FETCH_SPLIT_ANGLE: return fetch_plain(c, c->r_angle.p, have, first, count, out);
+      default: return fetch_plain(c, c->r_u.p, have, first, count, out);
+    }
+  }
+  return fail(LITE_ESTATE, "nothing to fetch for selector %d (call order?)", which);
+}
+
+extern "C" int lite_last_kernel_ms(lite_ctx *c, float *a, float *b, float *m) {
+  if (!c) return fail(LITE_EINVAL, "null context");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  if (c->ev01 && cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->ms_split = ms;
+  if (a) *a = c->ms_split;
+  if (b) *b = c->ms_eval;
+  if (m) *m = c->ms_mf;
+  return 0;
+}
+
+extern "C" int64_t lite_kernel_launch_count(lite_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int lite_measure_fp64_peak(lite_ctx *c, double *tflops) {
+  if (!c || !tflops) return fail(LITE_EINVAL, "null argument");
+  CU(cudaSetDevice(c->device));
+  const int iters = 1 << 14, tb = 256, gb = c->sm_count * 8;
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    CU(cudaEventRecord(c->ev[4], c->stream));
+    k_dfma_peak<<<gb, tb, 0, c->stream>>>(c->red_out.p ? c->red_out.p : (double *)c->status.p, iters, 1.0000001, 1e-9);
+    CU(cudaEventRecord(c->ev[5], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
+    double fl = 2.0 * 8.0 * (double)iters * tb * gb;
+    double tf = fl / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  c->launches += 5;
+  *tflops = best;
+  return 0;
+}

@@ -1,0 +1,865 @@
+// kernels.cuh — sm_100a device code for the LiTe pseudo-likelihood hot path.
+//
+// Layout in HBM: the tessellation is re-indexed by *slot*: one
+// slot per halfedge bounding an inside face, faces stored contiguously in ccb
+// order starting at outer_ccb().  A split candidate reads ~6 consecutive slots
+// (double2 points, angles, lengths, corner angles) of one face; candidates are
+// emitted in halfedge order, so a warp's 32 candidates share one or two faces
+// and those loads are L1 broadcast hits.  Per-candidate statistics are stored
+// structure-of-arrays (d columns of N doubles) for coalesced writes (K2) and
+// reads (K3).
+//
+// Reference behaviour restated here (paths relative to /root/reference):
+//   Split ctor + ray_exit_face      lib/ttessel.cpp:2090-2132, :4515-4576
+//   Split/Merge/Flip modified_elements  :2135-2232, :2302-2404, :2459-2713
+//   Energy::statistic_variation     :2914-2980
+//   feature functions               :4124-4434
+//   PseudoLikDiscrete::Get*         :3387-3443
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/lite_b200.h"
+
+#define LITE_PI 3.14159265358979323846
+#define LITE_HALF_PI (LITE_PI / 2)
+
+// flag bits of a slot
+#define SF_CORNER 1u  // the source vertex of the slot is a polygon corner of its face
+#define SF_BND 2u     // the halfedge lies on the window boundary
+#define SF_DIR 4u     // LineTes_halfedge::get_dir()
+
+struct TessDev {
+  int n_slots, n_faces, n_he, n_seg;
+  // per slot
+  const double2 *pt;   // source point
+  const double *ang;   // atan2(dy,dx) of the halfedge (lib/ttessel.cpp:2095)
+  const double *len;   // LineTes_halfedge length
+  const double *ca;    // interior angle at the source vertex (corners only)
+  const uint32_t *flg; // SF_*
+  const int *slot_he, *slot_seg, *slot_face;
+  // per halfedge
+  const int *he_slot, *he_twin, *he_src, *he_next_hf, *he_prev_hf;
+  // per face
+  const int *f_off, *f_cnt;
+  const double *f_area, *f_perim, *f_sumang, *f_minang;
+  // per segment
+  const int *seg_n_edges, *seg_he_start, *seg_he_end;
+  const uint8_t *seg_bnd;
+  // length-weighted sampling (inside halfedges in container order)
+  const double *cum;
+  const int *cum_he;
+  int n_cum;
+  double total_len;
+};
+
+struct Prog {
+  int d;
+  int fid[LITE_MAX_D];
+  uint32_t mask;  // bit i set if feature id i is used
+};
+
+struct Theta {
+  double v[LITE_MAX_D];
+};
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), counter = global candidate id
+// ---------------------------------------------------------------------------
+__host__ __device__ inline void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2,
+                                             uint32_t &c3, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+  uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+  uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+  uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+
+__host__ __device__ inline void philox4x32_10(uint64_t ctr, uint32_t stream, uint64_t seed,
+                                              uint32_t out[4]) {
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = stream, c3 = 0;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__host__ __device__ inline double u53(uint32_t hi, uint32_t lo) {
+  return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double2 ldpt(const double2 *p, int i) { return __ldg(p + i); }
+__device__ __forceinline__ double cross2(double ax, double ay, double bx, double by) {
+  return ax * by - ay * bx;
+}
+__device__ __forceinline__ double wrap_pi(double d) {
+  // to (-pi, pi]
+  return d - (2 * LITE_PI) * rint(d * (1.0 / (2 * LITE_PI)));
+}
+// angle_between_vectors, lib/ttessel.cpp:4255-4268
+__device__ __forceinline__ double angle_between(double ax, double ay, double bx, double by) {
+  double n1 = ax * ax + ay * ay, n2 = bx * bx + by * by;
+  double p = ax * bx + ay * by;
+  double c = p / sqrt(n1 * n2);
+  c = fmin(1.0, fmax(-1.0, c));
+  return acos(c);
+}
+
+// ---------------------------------------------------------------------------
+// virtual polygons: a few explicit points and cyclic slot ranges of faces
+// ---------------------------------------------------------------------------
+#define VP_MAX 6
+struct VPoly {
+  int np, total;
+  int kind[VP_MAX];  // 0 point, 1 range
+  double x[VP_MAX], y[VP_MAX];
+  int cf[VP_MAX];  // corner flag of an explicit point
+  int off[VP_MAX], n[VP_MAX], s0[VP_MAX], cnt[VP_MAX];
+};
+__device__ inline void vp_init(VPoly &P) { P.np = 0; P.total = 0; }
+__device__ inline void vp_point(VPoly &P, double x, double y, int corner) {
+  int i = P.np++;
+  P.kind[i] = 0; P.x[i] = x; P.y[i] = y; P.cf[i] = corner; P.cnt[i] = 1;
+  P.total += 1;
+}
+__device__ inline void vp_range(VPoly &P, int off, int n, int s0, int cnt) {
+  if (cnt <= 0) return;
+  int i = P.np++;
+  P.kind[i] = 1; P.off[i] = off; P.n[i] = n; P.s0[i] = ((s0 % n) + n) % n; P.cnt[i] = cnt;
+  P.total += cnt;
+}
+__device__ inline void vp_get(const TessDev &T, const VPoly &P, int i, double &x, double &y,
+                              int &corner) {
+  int k = 0;
+  while (i >= P.cnt[k]) { i -= P.cnt[k]; k++; }
+  if (P.kind[k] == 0) {
+    x = P.x[k]; y = P.y[k]; corner = P.cf[k];
+  } else {
+    int s = P.s0[k] + i;
+    if (s >= P.n[k]) s -= P.n[k];
+    double2 v = ldpt(T.pt, P.off[k] + s);
+    x = v.x; y = v.y;
+    corner = (int)(T.flg[P.off[k] + s] & SF_CORNER);
+  }
+}
+
+struct FaceFeat {
+  double area, perim, sumang, minang;
+};
+// face_area_2 / face_perimeter / face_sum_of_angles / min_angle inputs of one
+// (simplified) polygon, lib/ttessel.cpp:4215-4239, :4285-4305, :4348-4367.
+// `need_ang`: compute the acos-based quantities.
+__device__ inline FaceFeat vp_features(const TessDev &T, const VPoly &P, bool need_ang) {
+  FaceFeat r;
+  int n = P.total;
+  double x0, y0; int c0;
+  vp_get(T, P, 0, x0, y0, c0);
+  double px, py; int pc;   // previous vertex (i-1)
+  vp_get(T, P, n - 1, px, py, pc);
+  double cx = x0, cy = y0; int cc = c0;  // current vertex i
+  double area2 = 0, perim = 0, sumang = 0, minang = CUDART_INF, seed = -1.0;
+  for (int i = 0; i < n; i++) {
+    double nx, ny; int nc;
+    if (i + 1 < n) vp_get(T, P, i + 1, nx, ny, nc);
+    else { nx = x0; ny = y0; nc = c0; }
+    area2 += cross2(cx - x0, cy - y0, nx - x0, ny - y0);
+    double ex = nx - cx, ey = ny - cy;
+    perim += sqrt(ex * ex + ey * ey);
+    if (need_ang && cc) {
+      double a = angle_between(px - cx, py - cy, ex, ey);
+      if (seed < 0) seed = LITE_PI - a;  // turning angle at the first corner (:4354)
+      double q = LITE_HALF_PI - a;
+      if (q >= 0) sumang += q;
+      minang = fmin(minang, a);
+    }
+    px = cx; py = cy; cx = nx; cy = ny; cc = nc;
+  }
+  r.area = 0.5 * area2;
+  r.perim = perim;
+  r.sumang = sumang;
+  r.minang = (seed >= 0) ? fmin(seed, minang) : 0.0;
+  return r;
+}
+__device__ __forceinline__ double shape_of(double perim, double area) {
+  // face_shape: perimeter/(4*pow(area^2,0.25)), lib/ttessel.cpp:4247-4249
+  return perim / (4.0 * sqrt(fabs(area)));
+}
+
+// Accumulate  sign * f(face polygon)  for every face feature of the program.
+__device__ inline void add_face_feats(const Prog &G, double *acc, double sign, const FaceFeat &F) {
+  for (int i = 0; i < G.d; i++) {
+    switch (G.fid[i]) {
+      case LITE_FEAT_FACE_NUMBER: acc[i] += sign; break;
+      case LITE_FEAT_FACE_AREA_2: acc[i] += sign * (F.area * F.area); break;
+      case LITE_FEAT_FACE_PERIMETER: acc[i] += sign * F.perim; break;
+      case LITE_FEAT_FACE_SHAPE: acc[i] += sign * shape_of(F.perim, F.area); break;
+      case LITE_FEAT_FACE_SUM_OF_ANGLES: acc[i] += sign * F.sumang; break;
+      case LITE_FEAT_MIN_ANGLE: acc[i] += sign * F.minang; break;
+      default: break;
+    }
+  }
+}
+#define MASK_FACE_ANG ((1u << LITE_FEAT_FACE_SUM_OF_ANGLES) | (1u << LITE_FEAT_MIN_ANGLE))
+#define MASK_FACE_ANY                                                                     \
+  ((1u << LITE_FEAT_FACE_NUMBER) | (1u << LITE_FEAT_FACE_AREA_2) |                        \
+   (1u << LITE_FEAT_FACE_PERIMETER) | (1u << LITE_FEAT_FACE_SHAPE) | MASK_FACE_ANG)
+#define MASK_FACE_GEOM                                                                    \
+  ((1u << LITE_FEAT_FACE_AREA_2) | (1u << LITE_FEAT_FACE_SHAPE) | (1u << LITE_FEAT_MIN_ANGLE))
+
+// ---------------------------------------------------------------------------
+// K0: per-face preparation (slot arrays + parent-face features)
+// ---------------------------------------------------------------------------
+struct PrepArgs {
+  // raw SoA on device
+  const double *vx, *vy;
+  const int *he_src, *he_twin, *he_next, *he_face, *he_seg, *he_next_hf;
+  const uint8_t *he_dir, *face_inside;
+  const double *he_length;
+  const int *face_he_offset, *face_he_count, *face_he_list;
+  int n_faces;
+  // outputs
+  double2 *pt; double *ang, *len, *ca; uint32_t *flg;
+  int *slot_he, *slot_seg, *slot_face, *he_slot;
+  double *f_area, *f_perim, *f_sumang, *f_minang;
+  int *err;  // consistency errors
+};
+
+__global__ void k_prep_slots(PrepArgs A) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= A.n_faces) return;
+  int n = A.face_he_count[f];
+  if (n == 0 || !A.face_inside[f]) return;
+  int off = A.face_he_offset[f];
+  for (int k = 0; k < n; k++) {
+    int h = A.face_he_list[off + k];
+    int hp = A.face_he_list[off + (k == 0 ? n - 1 : k - 1)];
+    int hn = A.face_he_list[off + (k + 1 == n ? 0 : k + 1)];
+    if (A.he_next[h] != hn || A.he_face[h] != f) atomicAdd(A.err, 1);
+    int vs = A.he_src[h], vt = A.he_src[hn];
+    double sx = A.vx[vs], sy = A.vy[vs], tx = A.vx[vt], ty = A.vy[vt];
+    A.pt[off + k] = make_double2(sx, sy);
+    A.ang[off + k] = atan2(ty - sy, tx - sx);
+    A.len[off + k] = A.he_length[h];
+    uint32_t fl = 0;
+    int nhf = A.he_next_hf[hp];
+    if (nhf < 0 || nhf != A.he_next[hp]) fl |= SF_CORNER;  // face2poly, lib/ttessel.cpp:4325-4327
+    if (!A.face_inside[A.he_face[A.he_twin[h]]]) fl |= SF_BND;
+    if (A.he_dir[h]) fl |= SF_DIR;
+    A.flg[off + k] = fl;
+    A.slot_he[off + k] = h;
+    A.slot_seg[off + k] = A.he_seg[h];
+    A.slot_face[off + k] = f;
+    A.he_slot[h] = off + k;
+  }
+}
+
+__global__ void k_prep_faces(TessDev T, double *ca, double *f_area, double *f_perim,
+                             double *f_sumang, double *f_minang) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= T.n_faces) return;
+  int n = T.f_cnt[f];
+  if (n == 0) return;
+  int off = T.f_off[f];
+  // corner angles at slot sources
+  for (int k = 0; k < n; k++) {
+    double a = LITE_PI;
+    if (T.flg[off + k] & SF_CORNER) {
+      double2 c = ldpt(T.pt, off + k);
+      double2 p = ldpt(T.pt, off + (k == 0 ? n - 1 : k - 1));
+      double2 q = ldpt(T.pt, off + (k + 1 == n ? 0 : k + 1));
+      a = angle_between(p.x - c.x, p.y - c.y, q.x - c.x, q.y - c.y);
+    }
+    ca[off + k] = a;
+  }
+  // face2poly order: first vertex is the target of the outer_ccb halfedge = source of slot 1
+  VPoly P; vp_init(P);
+  vp_range(P, off, n, 1, n);
+  FaceFeat F = vp_features(T, P, true);
+  f_area[f] = F.area; f_perim[f] = F.perim; f_sumang[f] = F.sumang; f_minang[f] = F.minang;
+}
+
+// ---------------------------------------------------------------------------
+// ray exit search in a hole-free face (ray_exit_face, lib/ttessel.cpp:4515-4576)
+//   line a*X + b*Y = w through the ray source p, direction (dx,dy);
+//   skip0/skip1: slots whose hit is the ray source itself (distance 0).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int ray_exit(const TessDev &T, int off, int n, double a, double b,
+                                        double w, double2 p, double dx, double dy, int skip0,
+                                        int skip1, double2 &hit) {
+  double2 V0 = ldpt(T.pt, off);
+  double s0 = fma(a, V0.x, fma(b, V0.y, -w));
+  double2 Vk = V0; double sk = s0;
+  double best = 1.7976931348623157e308;
+  int k2 = -1;
+  for (int k = 0; k < n; k++) {
+    double2 Vn; double sn;
+    if (k + 1 < n) { Vn = ldpt(T.pt, off + k + 1); sn = fma(a, Vn.x, fma(b, Vn.y, -w)); }
+    else { Vn = V0; sn = s0; }
+    if (k != skip0 && k != skip1) {
+      bool cr = (sk <= 0.0 && sn >= 0.0) || (sk >= 0.0 && sn <= 0.0);
+      if (cr && sk != sn) {
+        double sg = sk / (sk - sn);
+        double X = fma(sg, Vn.x - Vk.x, Vk.x), Y = fma(sg, Vn.y - Vk.y, Vk.y);
+        double rx = X - p.x, ry = Y - p.y;
+        if (rx * dx + ry * dy >= 0.0) {
+          double len = sqrt(rx * rx + ry * ry);
+          if (len != 0.0 && len < best) { best = len; k2 = k; hit = make_double2(X, Y); }
+        }
+      }
+    }
+    Vk = Vn; sk = sn;
+  }
+  return k2;
+}
+
+// ---------------------------------------------------------------------------
+// K1+K2: one split candidate  (Split ctor + modified_elements + statistic_variation)
+// ---------------------------------------------------------------------------
+struct SplitOut {
+  int e2;       // halfedge id, -1 if no exit was found
+  double2 p1, p2;
+};
+
+template <bool WITH_STAT>
+__device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, int h, double x,
+                                           double angle, double *st /* d, negated */,
+                                           SplitOut &o) {
+  int s1 = T.he_slot[h];
+  int f = T.slot_face[s1];
+  int off = T.f_off[f], n = T.f_cnt[f];
+  int k1 = s1 - off;
+  int k1n = (k1 + 1 == n) ? 0 : k1 + 1;
+  double2 P = ldpt(T.pt, s1), Q = ldpt(T.pt, off + k1n);
+  double ang1 = T.ang[s1];
+  // lib/ttessel.cpp:2094-2105, evaluated as the reference does (no contraction)
+  double l = ang1 + angle;
+  double a, c;
+  sincos(l, &a, &c);
+  double b = -c;
+  double u = __dadd_rn(__dmul_rn(a, P.x), __dmul_rn(b, P.y));
+  double v = __dadd_rn(__dmul_rn(a, Q.x), __dmul_rn(b, Q.y));
+  double w = __dadd_rn(u, __dmul_rn(x, __dadd_rn(v, -u)));
+  // p1 = e1 ∩ line(a,b,-w)   (:2110)
+  double sP = fma(a, P.x, fma(b, P.y, -w)), sQ = fma(a, Q.x, fma(b, Q.y, -w));
+  double t1 = sP / (sP - sQ);
+  double2 p1 = make_double2(fma(t1, Q.x - P.x, P.x), fma(t1, Q.y - P.y, P.y));
+  // ray direction (:2121-2127): Line_2(a,b,c) has direction (b,-a)
+  double dx, dy;
+  if (sQ < 0.0) { dx = b; dy = -a; } else { dx = -b; dy = a; }
+  int skip1 = (x == 0.0) ? (k1 == 0 ? n - 1 : k1 - 1) : -1;
+  double2 p2 = make_double2(0.0, 0.0);
+  int k2 = ray_exit(T, off, n, a, b, w, p1, dx, dy, k1, skip1, p2);
+  o.p1 = p1; o.p2 = p2;
+  if (k2 < 0 || !(sP != sQ)) {
+    o.e2 = -1;
+    if (WITH_STAT) for (int i = 0; i < G.d; i++) st[i] = 0.0;
+    return;
+  }
+  o.e2 = T.slot_he[off + k2];
+  if (!WITH_STAT) return;
+
+  int k2n = (k2 + 1 == n) ? 0 : k2 + 1;
+  uint32_t fl1 = T.flg[s1], fl2 = T.flg[off + k2];
+  bool bnd1 = fl1 & SF_BND, bnd2 = fl2 & SF_BND;
+  double d01x = p2.x - p1.x, d01y = p2.y - p1.y;
+  double d01 = sqrt(d01x * d01x + d01y * d01y);
+
+  // children geometry (polygon_insert_edge, :4600-4631):
+  //   C1 = [p1, p2, V(k2+1) .. V(k1)],  C2 = [p2, p1, V(k1+1) .. V(k2)]
+  double A1 = 0, A2 = 0, L1 = 0, L2 = 0, m1 = CUDART_INF, m2 = CUDART_INF;
+  if (G.mask & MASK_FACE_GEOM) {
+    int k = k1n;
+    double2 Vk = (k == k1n) ? Q : ldpt(T.pt, off + k);
+    double rx = Vk.x - p1.x, ry = Vk.y - p1.y;
+    L2 = d01 + sqrt(rx * rx + ry * ry);
+    double acc = 0;
+    while (true) {
+      if (T.flg[off + k] & SF_CORNER) m2 = fmin(m2, T.ca[off + k]);
+      if (k == k2) break;
+      int kn = (k + 1 == n) ? 0 : k + 1;
+      double2 Vn = ldpt(T.pt, off + kn);
+      double qx = Vn.x - p1.x, qy = Vn.y - p1.y;
+      acc += cross2(rx, ry, qx, qy);
+      L2 += T.len[off + k];
+      rx = qx; ry = qy; k = kn;
+    }
+    acc += cross2(rx, ry, d01x, d01y);
+    { double ex = p2.x - (rx + p1.x), ey = p2.y - (ry + p1.y); L2 += sqrt(ex * ex + ey * ey); }
+    A2 = 0.5 * acc;
+    k = k2n;
+    Vk = ldpt(T.pt, off + k);
+    rx = Vk.x - p1.x; ry = Vk.y - p1.y;
+    acc = cross2(d01x, d01y, rx, ry);
+    { double ex = Vk.x - p2.x, ey = Vk.y - p2.y; L1 = d01 + sqrt(ex * ex + ey * ey); }
+    while (true) {
+      if (T.flg[off + k] & SF_CORNER) m1 = fmin(m1, T.ca[off + k]);
+      if (k == k1) break;
+      int kn = (k + 1 == n) ? 0 : k + 1;
+      double2 Vn = ldpt(T.pt, off + kn);
+      double qx = Vn.x - p1.x, qy = Vn.y - p1.y;
+      acc += cross2(rx, ry, qx, qy);
+      L1 += T.len[off + k];
+      rx = qx; ry = qy; k = kn;
+    }
+    L1 += sqrt(rx * rx + ry * ry);
+    A1 = 0.5 * acc;
+  }
+  // new corner angles: alpha at p1 (C2 side), beta at p2 (C1 side)
+  double alpha = angle;
+  double beta = fabs(wrap_pi(T.ang[off + k2] - l - LITE_PI));
+
+  for (int i = 0; i < G.d; i++) {
+    double dv = 0.0;  // phi(after) - phi(before)
+    switch (G.fid[i]) {
+      case LITE_FEAT_IS_POINT_INSIDE_WINDOW: {
+        // add_vertices = {p1,p2} (:2143-2144); a point on an edge is strictly
+        // inside the window iff the edge is internal
+        bool in1 = !bnd1;
+        if (x == 0.0) {  // p1 == source vertex of e1
+          int kp = (k1 == 0) ? n - 1 : k1 - 1;
+          in1 = !bnd1 && !(T.flg[off + kp] & SF_BND);
+        }
+        dv = (in1 ? 1.0 : 0.0) + (bnd2 ? 0.0 : 1.0);
+      } break;
+      case LITE_FEAT_EDGE_LENGTH:
+      case LITE_FEAT_EDGE_LENGTH_INTERNAL: {
+        // -{e1,e2} +{(s1,p1),(p1,t1),(s2,p2),(p2,t2),(p1,p2)} (:2148-2164)
+        bool wantb = (G.fid[i] == LITE_FEAT_EDGE_LENGTH);
+        if (bnd1 == wantb) {
+          double ax = p1.x - P.x, ay = p1.y - P.y, bx = Q.x - p1.x, by = Q.y - p1.y;
+          double ex = Q.x - P.x, ey = Q.y - P.y;
+          dv += sqrt(ax * ax + ay * ay) + sqrt(bx * bx + by * by) - sqrt(ex * ex + ey * ey);
+        }
+        if (bnd2 == wantb) {
+          double2 S = ldpt(T.pt, off + k2), E = ldpt(T.pt, off + k2n);
+          double ax = p2.x - S.x, ay = p2.y - S.y, bx = E.x - p2.x, by = E.y - p2.y;
+          double ex = E.x - S.x, ey = E.y - S.y;
+          dv += sqrt(ax * ax + ay * ay) + sqrt(bx * bx + by * by) - sqrt(ex * ex + ey * ey);
+        }
+        if (!wantb) dv += d01;
+      } break;
+      case LITE_FEAT_SEG_NUMBER: dv = 1.0; break;
+      case LITE_FEAT_IS_SEGMENT_INTERNAL: dv = 1.0; break;
+      case LITE_FEAT_MINUS_IS_SEGMENT_INTERNAL: dv = -1.0; break;
+      case LITE_FEAT_SEGMENT_SIZE_2: {
+        // boundary segments gain one edge: (k+1)^2-k^2 (:2202-2224, :4424-4434)
+        if (bnd1) dv += 2.0 * T.seg_n_edges[T.slot_seg[s1]] + 1.0;
+        if (bnd2) dv += 2.0 * T.seg_n_edges[T.slot_seg[off + k2]] + 1.0;
+      } break;
+      case LITE_FEAT_FACE_NUMBER: dv = 1.0; break;
+      case LITE_FEAT_FACE_AREA_2: dv = -2.0 * A1 * A2; break;  // a1^2+a2^2-(a1+a2)^2
+      case LITE_FEAT_FACE_PERIMETER: dv = 2.0 * d01; break;
+      case LITE_FEAT_FACE_SHAPE:
+        dv = shape_of(L1, A1) + shape_of(L2, A2) - shape_of(T.f_perim[f], T.f_area[f]);
+        break;
+      case LITE_FEAT_FACE_SUM_OF_ANGLES:
+        // untouched corners cancel; new corners alpha, pi-alpha at p1 and beta, pi-beta at p2
+        dv = fabs(LITE_HALF_PI - alpha) + fabs(LITE_HALF_PI - beta);
+        break;
+      case LITE_FEAT_MIN_ANGLE: {
+        // C1 = [p1,p2,...]: seed pi-(pi-alpha); corners pi-alpha (p1), beta (p2)
+        double ma1 = fmin(fmin(alpha, LITE_PI - alpha), fmin(beta, m1));
+        // C2 = [p2,p1,...]: seed pi-(pi-beta); corners pi-beta (p2), alpha (p1)
+        double ma2 = fmin(fmin(beta, LITE_PI - beta), fmin(alpha, m2));
+        dv = ma1 + ma2 - T.f_minang[f];
+      } break;
+      default: break;
+    }
+    st[i] = -dv;
+  }
+}
+
+struct SplitArgs {
+  long n_local;      // candidates handled by this launch
+  long j0;           // index of the first one inside the batch
+  long n_batch;      // batch size over all ranks
+  uint64_t seed, ctr0;  // philox: counter of batch element j is ctr0 + j
+  const int *in_he; const double *in_x, *in_angle;  // given path
+  double *stat; size_t cap; long base;              // column k at stat[k*cap + base + i]
+  // optional record
+  int *r_e1, *r_e2; double2 *r_p1, *r_p2; double *r_x, *r_angle, *r_u;
+  unsigned long long *status;  // [0] no-exit count
+  unsigned long long *checksum;  // [0] xor hash, [1] sum of e2
+};
+
+// MODE bit0: philox sampling (else given list); bit1: record; bit2: statistics; bit3: checksum
+template <int MODE>
+__global__ void __launch_bounds__(256) k_split(TessDev T, Prog G, SplitArgs A) {
+  constexpr bool PHILOX = MODE & 1, RECORD = MODE & 2, STAT = MODE & 4, CHECK = MODE & 8;
+  long stride = (long)gridDim.x * blockDim.x;
+  unsigned long long cx = 0, cs = 0;
+  unsigned int bad = 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < A.n_local; i += stride) {
+    int h; double x, angle, U = 0.0;
+    if (PHILOX) {
+      long j = A.j0 + i;
+      uint32_t r[4], q[4];
+      philox4x32_10(A.ctr0 + (uint64_t)j, 0u, A.seed, r);
+      philox4x32_10(A.ctr0 + (uint64_t)j, 1u, A.seed, q);
+      x = u53(r[0], r[1]);
+      U = u53(r[2], r[3]);
+      double jit = u53(q[0], q[1]);
+      // stratified length-weighted halfedge (alt_length_weighted_random_halfedge(n),
+      // lib/ttessel.cpp:1968-1991: select sorted, first halfedge with cumlen > select)
+      double sel = ((double)j + jit) * (T.total_len / (double)A.n_batch);
+      int lo = 0, hi = T.n_cum - 1;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(T.cum + mid) > sel) hi = mid; else lo = mid + 1;
+      }
+      h = T.cum_he[lo];
+      angle = acos(1.0 - 2.0 * U);  // lib/ttessel.cpp:1792
+    } else {
+      h = A.in_he[i]; x = A.in_x[i]; angle = A.in_angle[i];
+    }
+    double st[LITE_MAX_D];
+    SplitOut o;
+    split_eval<STAT>(T, G, h, x, angle, st, o);
+    if (o.e2 < 0) bad++;
+    if (STAT) {
+#pragma unroll
+      for (int k = 0; k < LITE_MAX_D; k++)
+        if (k < G.d) A.stat[(size_t)k * A.cap + A.base + i] = st[k];
+    }
+    if (RECORD) {
+      A.r_e1[A.base + i] = h; A.r_e2[A.base + i] = o.e2;
+      A.r_p1[A.base + i] = o.p1; A.r_p2[A.base + i] = o.p2;
+      A.r_x[A.base + i] = x; A.r_angle[A.base + i] = angle; A.r_u[A.base + i] = U;
+    }
+    if (CHECK) {
+      unsigned long long key = ((unsigned long long)(unsigned)h << 32) | (unsigned)o.e2;
+      key *= 0x9E3779B97F4A7C15ull; key ^= key >> 29;
+      cx ^= key; cs += (unsigned long long)(unsigned)o.e2;
+    }
+  }
+  if (CHECK) {
+    for (int off = 16; off; off >>= 1) {
+      cx ^= __shfl_xor_sync(0xffffffffu, cx, off);
+      cs += __shfl_xor_sync(0xffffffffu, cs, off);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicXor(A.checksum, cx); atomicAdd(A.checksum + 1, cs); }
+  }
+  if (bad) atomicAdd(A.status, (unsigned long long)bad);
+}
+
+// ---------------------------------------------------------------------------
+// K4: merges  (Merge::modified_elements, lib/ttessel.cpp:2302-2404)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double plen(double2 a, double2 b) {
+  double x = b.x - a.x, y = b.y - a.y;
+  return sqrt(x * x + y * y);
+}
+
+__global__ void k_merges(TessDev T, Prog G, const int *nb_seg, int n, double *stat, size_t cap,
+                         int *out_he) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int sg = nb_seg[i];
+  int e = T.seg_he_start[sg];  // single edge, dir == true: Seg::get_halfedge_handle()
+  int t = T.he_twin[e];
+  out_he[i] = e;
+  int se = T.he_slot[e], st_ = T.he_slot[t];
+  int f1 = T.slot_face[se], f2 = T.slot_face[st_];
+  int o1 = T.f_off[f1], n1 = T.f_cnt[f1], o2 = T.f_off[f2], n2 = T.f_cnt[f2];
+  int ke = se - o1, kt = st_ - o2;
+  int ke1 = (ke + 1) % n1, kt1 = (kt + 1) % n2;  // e2() = next(e), e1() = next(twin e)
+  double2 p1 = ldpt(T.pt, se), p2 = ldpt(T.pt, st_);
+  uint32_t fe2 = T.flg[o1 + ke1], fe1 = T.flg[o2 + kt1];
+  bool bnd_e2 = fe2 & SF_BND, bnd_e1 = fe1 & SF_BND;
+  // neighbours along the blocking lines: X = tgt(next), Y = src(prev_hf(next))
+  double2 X2 = ldpt(T.pt, o1 + (ke1 + 1) % n1), X1 = ldpt(T.pt, o2 + (kt1 + 1) % n2);
+  int he2 = T.slot_he[o1 + ke1], he1 = T.slot_he[o2 + kt1];
+  int ph2 = T.he_prev_hf[he2], ph1 = T.he_prev_hf[he1];
+  // Y2 is the vertex before p2 in face(twin e), Y1 the vertex before p1 in face(e)
+  double2 Y2 = ldpt(T.pt, o2 + (kt + n2 - 1) % n2), Y1 = ldpt(T.pt, o1 + (ke + n1 - 1) % n1);
+  (void)ph2; (void)ph1;
+  double elen = plen(p1, p2);
+
+  double acc[LITE_MAX_D];
+  for (int k = 0; k < G.d; k++) acc[k] = 0.0;
+  if (G.mask & MASK_FACE_ANY) {
+    bool ang = G.mask & MASK_FACE_ANG;
+    VPoly P;
+    FaceFeat F;
+    // del: simplify(face(e)), simplify(face(twin e)) in face2poly order (:2333-2362)
+    vp_init(P); vp_range(P, o1, n1, 1, n1); F = vp_features(T, P, ang); add_face_feats(G, acc, -1.0, F);
+    vp_init(P); vp_range(P, o2, n2, 1, n2); F = vp_features(T, P, ang); add_face_feats(G, acc, -1.0, F);
+    // add: polygon_remove_edge (:4945-4966): face(e) after p2 .. p1, face(twin) after p1 .. p2
+    vp_init(P);
+    vp_range(P, o1, n1, ke + 2, n1 - 2);
+    vp_point(P, p1.x, p1.y, 0);
+    vp_range(P, o2, n2, kt + 2, n2 - 2);
+    vp_point(P, p2.x, p2.y, 0);
+    F = vp_features(T, P, ang); add_face_feats(G, acc, +1.0, F);
+  }
+  for (int k = 0; k < G.d; k++) {
+    double dv = 0.0;
+    switch (G.fid[k]) {
+      case LITE_FEAT_IS_POINT_INSIDE_WINDOW:
+        dv = -((bnd_e1 ? 0.0 : 1.0) + (bnd_e2 ? 0.0 : 1.0));
+        break;
+      case LITE_FEAT_EDGE_LENGTH:
+      case LITE_FEAT_EDGE_LENGTH_INTERNAL: {
+        bool wantb = (G.fid[k] == LITE_FEAT_EDGE_LENGTH);
+        if (!wantb) dv -= elen;
+        if (bnd_e2 == wantb) dv += plen(Y2, X2) - plen(p2, X2) - plen(Y2, p2);
+        if (bnd_e1 == wantb) dv += plen(Y1, X1) - plen(p1, X1) - plen(Y1, p1);
+      } break;
+      case LITE_FEAT_SEG_NUMBER: dv = -1.0; break;
+      case LITE_FEAT_IS_SEGMENT_INTERNAL: dv = -1.0; break;
+      case LITE_FEAT_MINUS_IS_SEGMENT_INTERNAL: dv = 1.0; break;
+      case LITE_FEAT_SEGMENT_SIZE_2: {
+        if (bnd_e1) dv -= 2.0 * T.seg_n_edges[T.slot_seg[o2 + kt1]] - 1.0;
+        if (bnd_e2) dv -= 2.0 * T.seg_n_edges[T.slot_seg[o1 + ke1]] - 1.0;
+      } break;
+      default: dv = acc[k]; break;
+    }
+    stat[(size_t)k * cap + i] = -dv;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K5: flips  (Flip ctor :2432-2454, Flip::modified_elements :2459-2713)
+// flip i < n_b : e1 = twin(halfedges_start(seg)),  i >= n_b: e1 = halfedges_end(seg)
+// ---------------------------------------------------------------------------
+__global__ void k_flips(TessDev T, Prog G, const int *b_seg, int nb, double *stat, size_t cap,
+                        int *out_e1, int *out_e2, double2 *out_p2, int *out_right,
+                        unsigned long long *status) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * nb) return;
+  int sg = b_seg[i < nb ? i : i - nb];
+  int e1 = (i < nb) ? T.he_twin[T.seg_he_start[sg]] : T.seg_he_end[sg];
+  int t1 = T.he_twin[e1];
+  int s1 = T.he_slot[e1], st1 = T.he_slot[t1];
+  int fL = T.slot_face[s1], fT = T.slot_face[st1];  // face(e1), face(twin e1)
+  int oL = T.f_off[fL], nL = T.f_cnt[fL], oT = T.f_off[fT], nT = T.f_cnt[fT];
+  int k1 = s1 - oL, kt = st1 - oT;
+  // e3: incoming halfedge at a = src(e1) that is not on e1's segment (:2435-2438)
+  int kp = (k1 + nL - 1) % nL;  // prev(e1) in face(e1), arrives at a
+  int hp = T.slot_he[oL + kp];
+  bool right = (hp != T.he_prev_hf[e1]);  // prev(e1) is e3: it comes from the left of e1
+  double2 a = ldpt(T.pt, s1), q = ldpt(T.pt, st1);
+  int oR, nR, ka;  // face the ray enters; ka = slot index (in R) whose source is a
+  double ang3;
+  if (right) {
+    ang3 = T.ang[oL + kp];
+    oR = oT; nR = nT; ka = (kt + 1) % nT;
+  } else {
+    // e3 = twin(next(twin e1)): reverse of the slot leaving a in face(twin e1)
+    ang3 = T.ang[oT + (kt + 1) % nT] + LITE_PI;
+    oR = oL; nR = nL; ka = k1;
+  }
+  double dx, dy;
+  sincos(ang3, &dy, &dx);
+  if (right) {
+    double2 s3 = ldpt(T.pt, oL + kp);  // exact direction of e3 from its endpoints
+    dx = a.x - s3.x; dy = a.y - s3.y;
+  } else {
+    double2 s3 = ldpt(T.pt, oT + (kt + 2) % nT);
+    dx = a.x - s3.x; dy = a.y - s3.y;
+  }
+  { double nrm = sqrt(dx * dx + dy * dy); dx /= nrm; dy /= nrm; }
+  double la = dy, lb = -dx, lw = la * a.x + lb * a.y;  // line through a along d
+  double2 p2 = make_double2(0, 0);
+  int k2 = ray_exit(T, oR, nR, la, lb, lw, a, dx, dy, ka, (ka + nR - 1) % nR, p2);
+  out_e1[i] = e1; out_right[i] = right ? 1 : 0; out_p2[i] = p2;
+  if (k2 < 0) {
+    out_e2[i] = -1;
+    atomicAdd(status, 1ull);
+    for (int k = 0; k < G.d; k++) stat[(size_t)k * cap + i] = 0.0;
+    return;
+  }
+  int e2 = T.slot_he[oR + k2];
+  out_e2[i] = e2;
+  int k2n = (k2 + 1) % nR;
+  // next(e1): leaves q along the blocking line; X = its target, Y = the vertex
+  // before q on the other side (source of prev_hf(next(e1)))
+  int kn1 = (k1 + 1) % nL;
+  bool bnd_n1 = T.flg[oL + kn1] & SF_BND, bnd_e2 = T.flg[oR + k2] & SF_BND;
+  double2 X = ldpt(T.pt, oL + (kn1 + 1) % nL), Y = ldpt(T.pt, oT + (kt + nT - 1) % nT);
+  double2 S2 = ldpt(T.pt, oR + k2), E2 = ldpt(T.pt, oR + k2n);
+  int vq = T.he_src[t1];
+  bool tgt_is_q = T.he_src[T.he_twin[e2]] == vq, src_is_q = T.he_src[e2] == vq;
+
+  double acc[LITE_MAX_D];
+  for (int k = 0; k < G.d; k++) acc[k] = 0.0;
+  if (G.mask & MASK_FACE_ANY) {
+    bool ang = G.mask & MASK_FACE_ANG;
+    VPoly P; FaceFeat F;
+    // deleted faces: the face of e2 first, then the other face bounded by e1 (:2644-2651)
+    if (right) {
+      vp_init(P); vp_range(P, oT, nT, 1, nT); F = vp_features(T, P, ang); add_face_feats(G, acc, -1.0, F);
+      vp_init(P); vp_range(P, oL, nL, 1, nL); F = vp_features(T, P, ang); add_face_feats(G, acc, -1.0, F);
+      // unmatched inserted face: outer2 = [p2, a, V(kt+2) .. V(k2)]
+      vp_init(P);
+      vp_point(P, p2.x, p2.y, 1); vp_point(P, a.x, a.y, 1);
+      vp_range(P, oT, nT, kt + 2, ((k2 - (kt + 1)) % nT + nT) % nT);
+      F = vp_features(T, P, ang); add_face_feats(G, acc, +1.0, F);
+      // merged face: L after q .. a(flat), p2, R V(k2+1) .. V(kt-1), q(flat)
+      vp_init(P);
+      vp_range(P, oL, nL, k1 + 2, nL - 2);
+      vp_point(P, a.x, a.y, 0); vp_point(P, p2.x, p2.y, 1);
+      vp_range(P, oT, nT, k2 + 1, ((kt - (k2 + 1)) % nT + nT) % nT);
+      vp_point(P, q.x, q.y, 0);
+      F = vp_features(T, P, ang); add_face_feats(G, acc, +1.0, F);
+    } else {
+      vp_init(P); vp_range(P, oL, nL, 1, nL); F = vp_features(T, P, ang); add_face_feats(G, acc, -1.0, F);
+      vp_init(P); vp_range(P, oT, nT, 1, nT); F = vp_features(T, P, ang); add_face_feats(G, acc, -1.0, F);
+      // unmatched inserted face: outer1 = [a, p2, V(k2+1) .. V(k1-1)]
+      vp_init(P);
+      vp_point(P, a.x, a.y, 1); vp_point(P, p2.x, p2.y, 1);
+      vp_range(P, oL, nL, k2 + 1, ((k1 - (k2 + 1)) % nL + nL) % nL);
+      F = vp_features(T, P, ang); add_face_feats(G, acc, +1.0, F);
+      // merged face: R V(k1+2) .. V(k2), p2, a(flat), L' after a .. before q, q(flat)
+      vp_init(P);
+      vp_range(P, oL, nL, k1 + 2, ((k2 - (k1 + 1)) % nL + nL) % nL);
+      vp_point(P, p2.x, p2.y, 1); vp_point(P, a.x, a.y, 0);
+      vp_range(P, oT, nT, kt + 2, nT - 2);
+      vp_point(P, q.x, q.y, 0);
+      F = vp_features(T, P, ang); add_face_feats(G, acc, +1.0, F);
+    }
+  }
+  double l_e1 = plen(a, q), l_new = plen(a, p2);
+  for (int k = 0; k < G.d; k++) {
+    double dv = 0.0;
+    switch (G.fid[k]) {
+      case LITE_FEAT_IS_POINT_INSIDE_WINDOW:
+        dv = (bnd_e2 ? 0.0 : 1.0) - (bnd_n1 ? 0.0 : 1.0);
+        break;
+      case LITE_FEAT_EDGE_LENGTH:
+      case LITE_FEAT_EDGE_LENGTH_INTERNAL: {
+        bool wantb = (G.fid[k] == LITE_FEAT_EDGE_LENGTH);
+        if (!wantb) dv += l_new - l_e1;
+        // -(q,X) -(q,Y) (:2476-2486)
+        if (bnd_n1 == wantb) dv -= plen(q, X) + plen(q, Y);
+        if (!tgt_is_q && !src_is_q) {
+          if (bnd_e2 == wantb) dv += plen(p2, E2) + plen(p2, S2) - plen(E2, S2);
+          if (bnd_n1 == wantb) dv += plen(X, Y);
+        } else if (tgt_is_q) {
+          if (bnd_e2 == wantb) dv += plen(p2, S2) + plen(p2, X);
+        } else {
+          if (bnd_e2 == wantb) dv += plen(p2, E2) + plen(p2, Y);
+        }
+      } break;
+      case LITE_FEAT_SEG_NUMBER:
+      case LITE_FEAT_IS_SEGMENT_INTERNAL:
+      case LITE_FEAT_MINUS_IS_SEGMENT_INTERNAL: dv = 0.0; break;
+      case LITE_FEAT_SEGMENT_SIZE_2: {
+        int sg2 = T.slot_seg[oR + k2], sgn = T.slot_seg[oL + kn1];
+        if (sg2 != sgn) {  // else: one segment, split and merged at once (:2696-2702)
+          if (bnd_e2) dv += 2.0 * T.seg_n_edges[sg2] + 1.0;
+          if (bnd_n1) dv -= 2.0 * T.seg_n_edges[sgn] - 1.0;
+        }
+      } break;
+      default: dv = acc[k]; break;
+    }
+    stat[(size_t)k * cap + i] = -dv;
+  }
+}
+
+// column sums of a (d x n) SoA block, deterministic (one block per column)
+__global__ void k_colsum(const double *stat, size_t cap, int n, double *out) {
+  __shared__ double sh[256];
+  int k = blockIdx.x;
+  double s = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += stat[(size_t)k * cap + i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = blockDim.x / 2; w; w >>= 1) {
+    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[k] = sh[0];
+}
+
+// ---------------------------------------------------------------------------
+// K3: theta-reduce.  One pass over the stored statistics gives
+//   S0 = sum e_i, S1_k = sum e_i p_ik, S2_kl = sum e_i p_ik p_il (k<=l),
+//   e_i = exp(theta . p_i)      (lib/ttessel.cpp:3392-3394, :3417-3419, :3435-3436)
+// warp shuffle -> block tree -> fixed-order finish by the last block.
+// ---------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ stat, size_t cap,
+                                                long n, Theta th, double *partials,
+                                                unsigned int *counter, double *out) {
+  constexpr int NT = 1 + D + D * (D + 1) / 2;
+  double acc[NT];
+#pragma unroll
+  for (int t = 0; t < NT; t++) acc[t] = 0.0;
+  long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double p[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) p[k] = __ldcs(stat + (size_t)k * cap + i);
+    double dot = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; k++) dot += th.v[k] * p[k];
+    double e = exp(dot);
+    acc[0] += e;
+    int t = 1 + D;
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+      double ek = e * p[k];
+      acc[1 + k] += ek;
+#pragma unroll
+      for (int l = k; l < D; l++) acc[t++] += ek * p[l];
+    }
+  }
+  __shared__ double sh[8][NT];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+    double v = acc[t];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[wid][t] = v;
+  }
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x < NT) {
+    double v = 0;
+    int nw = blockDim.x >> 5;
+    for (int w2 = 0; w2 < nw; w2++) v += sh[w2][threadIdx.x];
+    partials[(size_t)blockIdx.x * NT + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int prev = atomicAdd(counter, 1u);
+    last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    if (threadIdx.x < NT) {
+      double v = 0;
+      for (unsigned int b = 0; b < gridDim.x; b++)
+        v += ((volatile double *)partials)[(size_t)b * NT + threadIdx.x];
+      out[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// FP64 peak: dependent DFMA chains, 8 per thread
+// ---------------------------------------------------------------------------
+__global__ void k_dfma_peak(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+         x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 12345.678) out[0] = s;
+}

@@ -1522,6 +1522,14 @@ def edge_length(seg, t):
     return math.sqrt(float(sqdist(seg[0], seg[1])))
 
 
+def edge_length_internal(seg, t):
+    """EXTENSION (not in the reference): length of *internal* edges, the evident
+    intent of edge_length's doc comment (lib/ttessel.cpp:4137-4139)."""
+    if is_segment_internal([seg[0], seg[1]], t) > 0:
+        return math.sqrt(float(sqdist(seg[0], seg[1])))
+    return 0.0
+
+
 def seg_number(s, t):
     return 1.0
 
@@ -1618,6 +1626,7 @@ FEATURES = {
     "face_shape": (9, CAT_FACES, face_shape),
     "face_sum_of_angles": (10, CAT_FACES, face_sum_of_angles),
     "min_angle": (11, CAT_FACES, min_angle),
+    "edge_length_internal": (12, CAT_EDGES, edge_length_internal),
 }
 FEATURE_BY_ID = {v[0]: (k, v[1], v[2]) for k, v in FEATURES.items()}
 
@@ -2173,3 +2182,101 @@ def export_soa(t):
     soa["int_length"] = float(t.int_length)
     assert nH == len(soa["he_src"])
     return soa
+
+
+# ----------------------------------------------------------------------------
+# helpers for the parity tests
+# ----------------------------------------------------------------------------
+ALL12 = ["is_point_inside_window", "edge_length", "face_number", "face_area_2",
+         "face_perimeter", "face_shape", "face_sum_of_angles", "min_angle",
+         "seg_number", "is_segment_internal", "minus_is_segment_internal", "segment_size_2"]
+ACS = ["edge_length", "face_area_2", "face_sum_of_angles", "is_segment_internal"]
+
+
+def acs_theta(tau=12.0, fi1=0.05, fi2=1.0):
+    """demos/sim_acs.cpp:64-76, flattened in CatVector order edges, faces, faces, segs."""
+    return [(tau - 1) / CGAL_PI, tau ** 4 * fi1, fi2, -math.log(tau)]
+
+
+def make_energy(names, thetas=None, t=None):
+    e = Energy()
+    for i, n in enumerate(names):
+        e.add(n, 0.0 if thetas is None else thetas[i])
+    if t is not None:
+        e.set_ttessel(t)
+    return e
+
+
+def draw_split_candidates(t, n):
+    """The (halfedge, x, angle) list TTessel::split_sample(n) would build
+    (lib/ttessel.cpp:1783-1795), as indices into the SoA export order."""
+    hid = {id(h): i for i, h in enumerate(t.halfedges)}
+    es = t.alt_length_weighted_random_halfedges(n)
+    he, xs, angs = [], [], []
+    for e in es:
+        x, a = t._draw_x_angle()
+        he.append(hid[id(e)])
+        xs.append(x)
+        angs.append(a)
+    return (np.array(he, dtype=np.int32), np.array(xs, dtype=np.float64),
+            np.array(angs, dtype=np.float64))
+
+
+def eval_candidates(t, energy, he, xs, angs):
+    """Exact evaluation of a fed split list, all merges and all flips.
+    Returns a dict of numpy arrays (integer outputs + stored statistics, i.e.
+    MINUS the statistic variation as PseudoLikDiscrete keeps them)."""
+    hid = {id(h): i for i, h in enumerate(t.halfedges)}
+    d = energy.dim()
+    out = {}
+    n = len(he)
+    e2 = np.zeros(n, dtype=np.int32)
+    p1 = np.zeros((n, 2))
+    p2 = np.zeros((n, 2))
+    st = np.zeros((n, d))
+    for i in range(n):
+        s = Split(t.halfedges[int(he[i])], float(xs[i]), float(angs[i]))
+        e2[i] = hid[id(s.e2)]
+        p1[i] = [float(s.p1[0]), float(s.p1[1])]
+        p2[i] = [float(s.p2[0]), float(s.p2[1])]
+        st[i] = [-v for v in energy.statistic_variation(s)]
+    out.update(split_e2=e2, split_p1=p1, split_p2=p2, split_stat=st)
+    ms = t.all_merges()
+    out["merge_he"] = np.array([hid[id(m.e)] for m in ms], dtype=np.int32)
+    out["merge_stat"] = np.array([[-v for v in energy.statistic_variation(m)] for m in ms]).reshape(len(ms), d)
+    fs = t.all_flips()
+    out["flip_e1"] = np.array([hid[id(f.e1)] for f in fs], dtype=np.int32)
+    out["flip_e2"] = np.array([hid[id(f.e2)] for f in fs], dtype=np.int32)
+    out["flip_right"] = np.array([1 if f.right else 0 for f in fs], dtype=np.int32)
+    out["flip_p2"] = np.array([[float(f.p2[0]), float(f.p2[1])] for f in fs]).reshape(len(fs), 2)
+    out["flip_stat"] = np.array([[-v for v in energy.statistic_variation(f)] for f in fs]).reshape(len(fs), d)
+    return out
+
+
+def pl_from_stats(theta, split_stat, merge_stat, flip_stat, int_length, n_splits_global=None):
+    """lib/ttessel.cpp:3387-3443 on stored statistic arrays (sequential sums)."""
+    pl = PseudoLikDiscrete()
+
+    class _T:
+        def get_total_internal_length(self_inner):
+            return int_length
+
+    class _E:
+        def get_ttessel(self_inner):
+            return _T()
+    pl.engy = _E()
+    d = len(theta)
+    pl.stat_splits = [list(map(float, r)) for r in split_stat]
+    pl.stat_flips = [list(map(float, r)) for r in flip_stat]
+    pl.sum_stat_merges = [0.0] * d
+    for r in merge_stat:
+        pl.sum_stat_merges = [a + float(b) for a, b in zip(pl.sum_stat_merges, r)]
+    pl.sum_stat_flips = [0.0] * d
+    for r in flip_stat:
+        pl.sum_stat_flips = [a + float(b) for a, b in zip(pl.sum_stat_flips, r)]
+    if n_splits_global is not None and n_splits_global != len(pl.stat_splits):
+        k = len(pl.stat_splits) / float(n_splits_global)
+        base_c = pl._c
+        pl._c = lambda: base_c() * k
+    th = [float(x) for x in theta]
+    return pl.GetValue(th), np.array(pl.GetGradient(th)), np.array(pl.GetHessian(th))

@@ -1,0 +1,208 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the exact
+oracle's committed golden vectors (tests/golden/*.npz, made by make_golden.py)
+and against the oracle run live on device-sampled candidates.
+
+Bar: bit-exact for candidate counts, face-hit / crossed-edge indices; relative
+1e-9 for the floating-point sums (absolute floor where a statistic is pure
+rounding noise)."""
+import math
+
+import numpy as np
+import pytest
+
+from util import ATOL_STAT, RTOL, inside_cum, load_golden
+
+pytestmark = pytest.mark.gpu
+
+ALL12 = ["is_point_inside_window", "edge_length", "face_number", "face_area_2",
+         "face_perimeter", "face_shape", "face_sum_of_angles", "min_angle",
+         "seg_number", "is_segment_internal", "minus_is_segment_internal", "segment_size_2"]
+ACS = ["edge_length", "face_area_2", "face_sum_of_angles", "is_segment_internal"]
+
+
+@pytest.fixture(scope="module")
+def lite():
+    import lite_b200
+    return lite_b200
+
+
+def _ctx(lite, soa, features, record=True):
+    ctx = lite.Context(0)
+    ctx.tess_upload(lite.TessSoA(soa))
+    ctx.energy_set(features)
+    if record:
+        ctx.record_splits(True)
+    return ctx
+
+
+def _assert_stats(name, got, want, feats):
+    assert got.shape == want.shape
+    for k, f in enumerate(feats):
+        g, w = got[:, k], want[:, k]
+        tol = ATOL_STAT + RTOL * np.abs(w)
+        bad = np.nonzero(np.abs(g - w) > tol)[0]
+        assert len(bad) == 0, "%s feature %s: %d/%d candidates differ, first %d: got %r want %r" % (
+            name, f, len(bad), len(w), bad[0], g[bad[0]], w[bad[0]])
+
+
+@pytest.mark.parametrize("name", ["t11", "t100"])
+def test_golden_candidates_all12(lite, name):
+    soa, gold = load_golden(name)
+    ctx = _ctx(lite, soa, ALL12)
+    nm, nf = ctx.merges_flips()
+    assert nm == len(gold["merge_he"]) and nf == len(gold["flip_e1"])
+    ctx.add_splits_given(gold["cand_he"], gold["cand_x"], gold["cand_angle"])
+    assert ctx.count() == (len(gold["cand_he"]), len(gold["cand_he"]))
+    # integers: bit exact
+    np.testing.assert_array_equal(ctx.fetch("SPLIT_E1"), gold["cand_he"])
+    np.testing.assert_array_equal(ctx.fetch("SPLIT_E2"), gold["split_e2"])
+    np.testing.assert_array_equal(ctx.fetch("MERGE_HE"), gold["merge_he"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_E1"), gold["flip_e1"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_E2"), gold["flip_e2"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_RIGHT"), gold["flip_right"])
+    assert ctx.fetch("STATUS")[0] == 0 and ctx.fetch("STATUS")[1] == 0
+    # points
+    np.testing.assert_allclose(ctx.fetch("SPLIT_P1"), gold["split_p1"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(ctx.fetch("SPLIT_P2"), gold["split_p2"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(ctx.fetch("FLIP_P2"), gold["flip_p2"], rtol=0, atol=1e-12)
+    # statistics
+    _assert_stats("split", ctx.fetch("SPLIT_STAT"), gold["split_stat"], ALL12)
+    _assert_stats("merge", ctx.fetch("MERGE_STAT"), gold["merge_stat"], ALL12)
+    _assert_stats("flip", ctx.fetch("FLIP_STAT"), gold["flip_stat"], ALL12)
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["t11", "t100"])
+@pytest.mark.parametrize("tag,feats", [("crtt", ["minus_is_segment_internal"]), ("acs", ACS)])
+def test_golden_pl_value_gradient_hessian(lite, name, tag, feats):
+    soa, gold = load_golden(name)
+    ctx = _ctx(lite, soa, feats, record=False)
+    ctx.merges_flips()
+    ctx.add_splits_given(gold["cand_he"], gold["cand_x"], gold["cand_angle"])
+    for k in (0, 1):
+        th = gold["pl_%s_%d_theta" % (tag, k)]
+        lpl, g, H = ctx.pl_eval(th)
+        wl, wg, wH = (gold["pl_%s_%d_%s" % (tag, k, s)] for s in ("lpl", "grad", "hess"))
+        assert lpl == pytest.approx(float(wl), rel=RTOL)
+        # the edges component of the ACS energy is rounding noise: absolute floor
+        scale = np.abs(wg).max()
+        np.testing.assert_allclose(g, wg, rtol=RTOL, atol=1e-12 * max(1.0, scale))
+        np.testing.assert_allclose(H, wH, rtol=RTOL, atol=1e-12 * max(1.0, np.abs(wH).max()))
+    ctx.close()
+
+
+def test_crtt_closed_form_any_sample(lite):
+    """lpl = th*n_nb - (u/pi)e^th - 2 n_b whatever the dummy sample
+    (reference demos/pseudo_lik_inference.cpp:80-81)."""
+    soa, gold = load_golden("t100")
+    ctx = _ctx(lite, soa, ["minus_is_segment_internal"], record=False)
+    nm, nf = ctx.merges_flips()
+    ctx.add_splits_philox(100000, 0x5EED, 0)
+    u = float(soa["int_length"])
+    for th in (-0.5, 0.0, 1.7):
+        lpl, g, H = ctx.pl_eval([th])
+        assert lpl == pytest.approx(th * nm - (u / math.pi) * math.exp(th) - nf, rel=1e-12)
+        assert g[0] == pytest.approx(nm - (u / math.pi) * math.exp(th), rel=1e-12)
+        assert H[0, 0] == pytest.approx(-(u / math.pi) * math.exp(th), rel=1e-12)
+    ctx.close()
+
+
+def test_philox_sampler_matches_numpy_restatement(lite):
+    import philox_ref
+    soa, _ = load_golden("t100")
+    ctx = _ctx(lite, soa, ACS)
+    n, seed, off = 20000, 0x5EED, 12345
+    ctx.add_splits_philox(n, seed, off)
+    cum, cum_he = inside_cum(soa)
+    he, x, U = philox_ref.sample_splits(cum, cum_he, n, seed, off, 0, n)
+    np.testing.assert_array_equal(ctx.fetch("SPLIT_E1"), he)
+    np.testing.assert_array_equal(ctx.fetch("SPLIT_X"), x)
+    np.testing.assert_array_equal(ctx.fetch("SPLIT_U"), U)
+    ang = ctx.fetch("SPLIT_ANGLE")
+    np.testing.assert_allclose(ang, np.arccos(1 - 2 * U), rtol=0, atol=4e-16)
+    # halfedges come out in container order (lib/ttessel.cpp:1975-1989)
+    order = {int(h): k for k, h in enumerate(cum_he)}
+    pos = np.array([order[int(h)] for h in ctx.fetch("SPLIT_E1")])
+    assert np.all(np.diff(pos) >= 0)
+    ctx.close()
+
+
+def test_philox_candidates_against_live_oracle(lite):
+    """Device-sampled candidates re-evaluated by the exact oracle on the exact
+    tessellation (text fixture)."""
+    import lite_oracle as lo
+    import os
+    from util import GOLD
+    soa, _ = load_golden("t100")
+    window, segs = lo.parse_text(open(os.path.join(GOLD, "t100.txt")).read())
+    t = lo.ttessel_from_segments(window, segs)
+    soa2 = lo.export_soa(t)   # the oracle's own numbering of the rebuilt tessellation
+    ctx = _ctx(lite, soa2, ALL12)
+    ctx.merges_flips()
+    n = 1500
+    ctx.add_splits_philox(n, 7, 0)
+    he, x, ang = ctx.fetch("SPLIT_E1"), ctx.fetch("SPLIT_X"), ctx.fetch("SPLIT_ANGLE")
+    e = lo.make_energy(lo.ALL12, None, t)
+    res = lo.eval_candidates(t, e, he, x, ang)
+    np.testing.assert_array_equal(ctx.fetch("SPLIT_E2"), res["split_e2"])
+    _assert_stats("split", ctx.fetch("SPLIT_STAT"), res["split_stat"], ALL12)
+    _assert_stats("merge", ctx.fetch("MERGE_STAT"), res["merge_stat"], ALL12)
+    _assert_stats("flip", ctx.fetch("FLIP_STAT"), res["flip_stat"], ALL12)
+    np.testing.assert_array_equal(ctx.fetch("FLIP_E2"), res["flip_e2"])
+    ctx.close()
+
+
+def test_extension_edge_length_internal(lite):
+    import lite_oracle as lo
+    import os
+    from util import GOLD
+    window, segs = lo.parse_text(open(os.path.join(GOLD, "t11.txt")).read())
+    t = lo.ttessel_from_segments(window, segs, lo.Rng(3))
+    soa = lo.export_soa(t)
+    feats = ["edge_length_internal", "face_number"]
+    ctx = _ctx(lite, soa, feats)
+    ctx.merges_flips()
+    he, x, ang = lo.draw_split_candidates(t, 200)
+    ctx.add_splits_given(he, x, ang)
+    res = lo.eval_candidates(t, lo.make_energy(feats, None, t), he, x, ang)
+    _assert_stats("split", ctx.fetch("SPLIT_STAT"), res["split_stat"], feats)
+    _assert_stats("merge", ctx.fetch("MERGE_STAT"), res["merge_stat"], feats)
+    _assert_stats("flip", ctx.fetch("FLIP_STAT"), res["flip_stat"], feats)
+    ctx.close()
+
+
+def test_nois_growth_and_clear(lite):
+    """AddSplits appends (PLInferenceNOIS::Step, lib/ttessel.cpp:3500); ClearSplits empties."""
+    soa, gold = load_golden("t100")
+    ctx = _ctx(lite, soa, ACS, record=False)
+    ctx.merges_flips()
+    th = gold["pl_acs_1_theta"]
+    he, x, ang = gold["cand_he"], gold["cand_x"], gold["cand_angle"]
+    # add in three uneven chunks == add at once
+    for a, b in ((0, 10), (10, 5000), (5000, len(he))):
+        ctx.add_splits_given(he[a:b], x[a:b], ang[a:b])
+    lpl, g, H = ctx.pl_eval(th)
+    assert lpl == pytest.approx(float(gold["pl_acs_1_lpl"]), rel=RTOL)
+    np.testing.assert_allclose(H, gold["pl_acs_1_hess"], rtol=RTOL, atol=1e-12 * np.abs(gold["pl_acs_1_hess"]).max())
+    ctx.clear_splits()
+    assert ctx.count() == (0, 0)
+    with pytest.raises(lite.LiteError):
+        ctx.pl_eval(th)
+    ctx.close()
+
+
+def test_rejects_bad_input(lite):
+    soa, gold = load_golden("t11")
+    ctx = lite.Context(0)
+    with pytest.raises(lite.LiteError):
+        ctx.energy_set(["face_number", "is_point_inside_window"])  # not in CatVector order
+    bad = dict(soa)
+    bad["int_length"] = float(soa["int_length"]) + 1.0
+    with pytest.raises(lite.LiteError):
+        ctx.tess_upload(lite.TessSoA(bad))
+    ctx.tess_upload(lite.TessSoA(soa))
+    ctx.energy_set(ACS)
+    outside = int(np.nonzero(soa["face_inside"][soa["he_face"]] == 0)[0][0])
+    with pytest.raises(lite.LiteError):
+        ctx.add_splits_given([outside], [0.5], [1.0])
+    ctx.close()
