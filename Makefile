@@ -5,8 +5,11 @@ LIB = lite_b200/libliteb200.so
 
 all: $(LIB) oracle
 
-$(LIB): lite_b200/csrc/capi.cu lite_b200/csrc/kernels.cuh include/lite_b200.h
-	$(NVCC) $(NVFLAGS) -shared -o $@ lite_b200/csrc/capi.cu -ldl
+SRC = lite_b200/csrc/capi.cu lite_b200/csrc/host_tess.cpp lite_b200/csrc/host_capi.cpp
+HDR = lite_b200/csrc/kernels.cuh lite_b200/csrc/host_tess.h include/lite_b200.h include/lite_b200_host.h
+
+$(LIB): $(SRC) $(HDR)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRC) -ldl
 
 oracle:
 	$(MAKE) -C oracle

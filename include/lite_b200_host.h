@@ -1,0 +1,46 @@
+/* lite_b200_host.h — C entry points of the CGAL-free host model (the state
+ * behind the TTessel facade of include/ttessel.h) for callers that cannot use
+ * C++: build a T-tessellation in a polygonal window, run the CRTT chain that
+ * synthesises benchmark inputs, apply the three moves, flatten it for
+ * lite_tess_upload().  All of this is host-side, sequential bookkeeping (the
+ * reference's LineTes/TTessel layer, lib/ttessel.cpp:32-251, :606-780,
+ * :1506-1710); the pseudo-likelihood path itself only runs on the GPU. */
+#ifndef LITE_B200_HOST_H
+#define LITE_B200_HOST_H
+#include "lite_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lite_host_tess lite_host_tess;
+
+/* TTessel::insert_window(Rectangle), lib/ttessel.cpp:1544-1550 */
+int lite_host_create_rect(lite_host_tess **out, double x0, double y0, double x1, double y1);
+/* LineTes::read, lib/ttessel.cpp:1377-1441 (hole-free single-polygon windows) */
+int lite_host_create_from_text(lite_host_tess **out, const char *text);
+int lite_host_destroy(lite_host_tess *t);
+/* SMFChain(&mod,p_split,p_merge).step(n) under the CRTT energy
+ * log(tau)*minus_is_segment_internal (demos/pseudo_lik_inference.cpp:56-69).
+ * counts: proposed/accepted S, M, F (ModifCounts, include/ttessel.h:1027-1034). */
+int lite_host_crtt_run(lite_host_tess *t, double tau, uint64_t n_steps, uint64_t seed,
+                       int64_t counts6[6]);
+/* TTessel::update(Split(e,x,angle)) / update(Merge(e)) / update(Flip(e)) on
+ * halfedge ids of the last export (lib/ttessel.cpp:1580-1701). */
+int lite_host_update_split(lite_host_tess *t, int32_t he, double x, double angle);
+int lite_host_update_merge(lite_host_tess *t, int32_t nb_index);
+int lite_host_update_flip(lite_host_tess *t, int32_t b_index, int side);
+/* number of cells, non-blocking and blocking internal segments */
+int lite_host_counts(lite_host_tess *t, int32_t *n_cells, int32_t *n_nb, int32_t *n_b);
+/* consistency check in the spirit of TTessel::is_valid (lib/ttessel.cpp:1721-1753);
+ * returns 0 when valid, LITE_EINVAL with a message otherwise */
+int lite_host_check(lite_host_tess *t);
+/* Flatten; the pointers stay valid until the next call on t. */
+int lite_host_export(lite_host_tess *t, lite_tess_soa *out);
+/* LineTes::write (lib/ttessel.cpp:1348-1370), decimal doubles as n/1; returns the
+ * needed size; writes at most cap bytes */
+int64_t lite_host_write_text(lite_host_tess *t, char *buf, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -8,5 +8,7 @@ of its own and raises if the native library is missing.
 from .capi import (LiteError, Context, TessSoA, FEATURE_IDS, lib_path, load_library,
                    nccl_unique_id, shard_range)
 
-__all__ = ["LiteError", "Context", "TessSoA", "FEATURE_IDS", "lib_path", "load_library",
+from .host import HostTess, generate_crtt
+
+__all__ = ["HostTess", "generate_crtt", "LiteError", "Context", "TessSoA", "FEATURE_IDS", "lib_path", "load_library",
            "nccl_unique_id", "shard_range"]

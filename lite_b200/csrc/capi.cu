@@ -130,6 +130,8 @@ struct lite_ctx {
 };
 
 extern "C" const char *lite_last_error(void) { return g_err.c_str(); }
+// shared with host_capi.cpp
+extern "C" int lite_set_error_(int code, const char *msg) { return fail(code, "%s", msg); }
 
 extern "C" int lite_nccl_unique_id(void *out128) {
   if (!out128) return fail(LITE_EINVAL, "null output");
@@ -371,6 +373,12 @@ extern "C" int lite_energy_set(lite_ctx *c, int d, const int32_t *fid) {
     G.mask |= 1u << fid[i];
   }
   if (c->n_local != 0) return fail(LITE_ESTATE, "clear the splits before changing the energy");
+  if (c->G.d != G.d) {  // the statistic block is d columns of `cap` rows: re-dimension it
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stat.release();
+    c->cap = 0;
+  }
   c->G = G;
   c->have_prog = true; c->have_mf = false;
   return 0;

@@ -1,0 +1,755 @@
+// host_tess.cpp — see host_tess.h.
+#include "host_tess.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <random>
+#include <sstream>
+
+namespace lite {
+
+static const double kPi = 3.14159265358979323846;
+
+// ---------------------------------------------------------------------------
+// Fenwick tree over halfedge ids (length-weighted sampling in O(log n))
+// ---------------------------------------------------------------------------
+void Fenwick::resize(size_t n) {
+  if (n <= w.size()) return;
+  size_t cap = w.size() ? w.size() : 64;
+  while (cap < n) cap *= 2;
+  std::vector<double> old = w;
+  w.assign(cap, 0.0);
+  t.assign(cap + 1, 0.0);
+  for (size_t i = 0; i < old.size(); i++) w[i] = old[i];
+  for (size_t i = 0; i < cap; i++) {
+    t[i + 1] += w[i];
+    size_t j = (i + 1) + ((i + 1) & (~(i + 1) + 1));
+    if (j <= cap) t[j] += t[i + 1];
+  }
+}
+void Fenwick::set(int i, double v) {
+  double d = v - w[i];
+  if (d == 0.0) return;
+  w[i] = v;
+  for (size_t j = (size_t)i + 1; j < t.size(); j += j & (~j + 1)) t[j] += d;
+}
+double Fenwick::total() const {
+  double s = 0;
+  for (size_t j = t.size() - 1; j > 0; j -= j & (~j + 1)) s += t[j];
+  return s;
+}
+int Fenwick::find(double target) const {
+  size_t pos = 0, n = t.size() - 1;
+  size_t step = 1;
+  while (step * 2 <= n) step *= 2;
+  for (; step; step >>= 1) {
+    size_t nx = pos + step;
+    if (nx <= n && t[nx] <= target) {
+      pos = nx;
+      target -= t[nx];
+    }
+  }
+  if (pos >= n) pos = n - 1;
+  return (int)pos;
+}
+
+// ---------------------------------------------------------------------------
+// element management
+// ---------------------------------------------------------------------------
+HostTess::HostTess() {}
+
+int HostTess::new_vertex(double x, double y) {
+  int v;
+  if (!free_v.empty()) { v = free_v.back(); free_v.pop_back(); }
+  else { v = (int)vx.size(); vx.push_back(0); vy.push_back(0); v_inc.push_back(-1); v_alive.push_back(0); }
+  vx[v] = x; vy[v] = y; v_inc[v] = -1; v_alive[v] = 1;
+  return v;
+}
+void HostTess::del_vertex(int v) { v_alive[v] = 0; free_v.push_back(v); }
+
+int HostTess::new_edge_pair(int v1, int v2) {
+  int h;
+  if (!free_hp.empty()) { h = free_hp.back(); free_hp.pop_back(); }
+  else {
+    h = (int)h_src.size();
+    for (int k = 0; k < 2; k++) {
+      h_src.push_back(-1); h_next.push_back(-1); h_prev.push_back(-1); h_face.push_back(-1);
+      h_seg.push_back(-1); h_next_hf.push_back(-1); h_prev_hf.push_back(-1);
+      h_dir.push_back(0); h_alive.push_back(0); h_len.push_back(0);
+    }
+    fen.resize(h_src.size());
+  }
+  for (int k = 0; k < 2; k++) {
+    int e = h + k;
+    h_next[e] = h_prev[e] = h_face[e] = h_seg[e] = h_next_hf[e] = h_prev_hf[e] = -1;
+    h_alive[e] = 1; h_len[e] = 0; h_dir[e] = (k == 0);
+  }
+  h_src[h] = v1; h_src[h + 1] = v2;
+  return h;
+}
+void HostTess::del_edge_pair(int h) {
+  h &= ~1;
+  for (int k = 0; k < 2; k++) { h_alive[h + k] = 0; fen.set(h + k, 0.0); }
+  free_hp.push_back(h);
+}
+int HostTess::new_face(bool inside) {
+  int f;
+  if (!free_f.empty()) { f = free_f.back(); free_f.pop_back(); }
+  else { f = (int)f_he.size(); f_he.push_back(-1); f_inside.push_back(0); f_alive.push_back(0); }
+  f_he[f] = -1; f_inside[f] = inside; f_alive[f] = 1;
+  return f;
+}
+void HostTess::del_face(int f) { f_alive[f] = 0; free_f.push_back(f); }
+int HostTess::new_seg(int he, bool bnd) {
+  int s;
+  if (!free_s.empty()) { s = free_s.back(); free_s.pop_back(); }
+  else {
+    s = (int)s_he.size();
+    s_he.push_back(-1); s_nedges.push_back(0); s_pos.push_back(-1); s_bnd.push_back(0);
+    s_alive.push_back(0); s_kind.push_back(0);
+  }
+  s_he[s] = he; s_nedges[s] = 1; s_pos[s] = -1; s_bnd[s] = bnd; s_alive[s] = 1; s_kind[s] = 0;
+  return s;
+}
+void HostTess::del_seg(int s) { s_alive[s] = 0; free_s.push_back(s); }
+
+void HostTess::set_len(int h) {
+  double dx = vx[tgt(h)] - vx[h_src[h]], dy = vy[tgt(h)] - vy[h_src[h]];
+  double l = sqrt(dx * dx + dy * dy);  // LineTes_halfedge::set_length, lib/ttessel.cpp:1459
+  h_len[h] = l; h_len[h ^ 1] = l;
+}
+void HostTess::refresh_weight(int h) {
+  for (int k = 0; k < 2; k++) {
+    int e = (h & ~1) + k;
+    bool in = h_alive[e] && h_face[e] >= 0 && f_inside[h_face[e]];
+    fen.set(e, in ? h_len[e] : 0.0);
+  }
+}
+void HostTess::set_junction(int e1, int e2) {  // lib/ttessel.cpp:3909-3930
+  if (e1 >= 0) { h_next_hf[e1] = e2; h_prev_hf[e1 ^ 1] = (e2 >= 0) ? (e2 ^ 1) : -1; }
+  if (e2 >= 0) { h_prev_hf[e2] = e1; h_next_hf[e2 ^ 1] = (e1 >= 0) ? (e1 ^ 1) : -1; }
+}
+void HostTess::seg_set_handle(int s, int h) {  // Seg::set_halfedge_handle, :841-851
+  s_he[s] = h_dir[h] ? h : (h ^ 1);
+}
+int HostTess::seg_start(int s) const {
+  int e = s_he[s];
+  while (h_prev_hf[e] >= 0) e = h_prev_hf[e];
+  return e;
+}
+int HostTess::seg_end(int s) const {
+  int e = s_he[s];
+  while (h_next_hf[e] >= 0) e = h_next_hf[e];
+  return e;
+}
+int HostTess::flip_halfedge(int seg, int side) const {  // TTessel::propose_flip, :1766-1777
+  return side == 0 ? (seg_start(seg) ^ 1) : seg_end(seg);
+}
+int HostTess::degree(int v) const {
+  int h0 = v_inc[v], h = h0, n = 0;
+  do { n++; h = h_next[h] ^ 1; } while (h != h0);
+  return n;
+}
+void HostTess::list_add(int s, int kind) {
+  std::vector<int> &L = (kind == 1) ? nb_list : b_list;
+  s_kind[s] = kind; s_pos[s] = (int)L.size(); L.push_back(s);
+}
+void HostTess::list_remove(int s) {
+  int kind = s_kind[s];
+  if (!kind) return;
+  std::vector<int> &L = (kind == 1) ? nb_list : b_list;
+  int p = s_pos[s];
+  if (ordered_lists) {
+    L.erase(L.begin() + p);
+    for (size_t i = p; i < L.size(); i++) s_pos[L[i]] = (int)i;
+  } else {
+    int last = L.back();
+    L[p] = last; s_pos[last] = p; L.pop_back();
+  }
+  s_kind[s] = 0; s_pos[s] = -1;
+}
+int HostTess::n_cells() const {
+  int n = 0;
+  for (size_t f = 0; f < f_he.size(); f++) n += (f_alive[f] && f_inside[f]);
+  return n;
+}
+int HostTess::n_alive_halfedges() const {
+  int n = 0;
+  for (size_t h = 0; h < h_src.size(); h++) n += h_alive[h];
+  return n;
+}
+
+// ---------------------------------------------------------------------------
+// window (LineTes::insert_window, lib/ttessel.cpp:60-120; hole-free polygon)
+// ---------------------------------------------------------------------------
+void HostTess::insert_window_polygon(const std::vector<double> &x, const std::vector<double> &y) {
+  *this = HostTess();
+  win_x = x; win_y = y;
+  int n = (int)x.size();
+  std::vector<int> vs(n), hs(n);
+  for (int i = 0; i < n; i++) vs[i] = new_vertex(x[i], y[i]);
+  for (int i = 0; i < n; i++) hs[i] = new_edge_pair(vs[i], vs[(i + 1) % n]);
+  int fo = new_face(false), fi = new_face(true);
+  for (int i = 0; i < n; i++) {
+    int h = hs[i], hn = hs[(i + 1) % n], hp = hs[(i + n - 1) % n];
+    h_next[h] = hn; h_prev[h] = hp;
+    h_next[h ^ 1] = hp ^ 1; h_prev[h ^ 1] = hn ^ 1;
+    h_face[h] = fi; h_face[h ^ 1] = fo;
+    v_inc[vs[(i + 1) % n]] = h;
+    h_dir[h] = 1; h_dir[h ^ 1] = 0;
+    set_len(h);
+    int s = new_seg(h, true);
+    h_seg[h] = h_seg[h ^ 1] = s;
+  }
+  f_he[fi] = hs[0]; f_he[fo] = hs[0] ^ 1;
+  int_length = 0;
+  for (int i = 0; i < n; i++) { int_length += h_len[hs[i]]; refresh_weight(hs[i]); }
+}
+void HostTess::insert_window_rect(double x0, double y0, double x1, double y1) {
+  insert_window_polygon({x0, x1, x1, x0}, {y0, y0, y1, y1});
+}
+
+// ---------------------------------------------------------------------------
+// DCEL surgery
+// ---------------------------------------------------------------------------
+int HostTess::split_edge(int e, double px, double py) {  // lib/ttessel.cpp:606-655
+  int e_next_hf = h_next_hf[e];
+  int s = h_seg[e];
+  bool e_dir = h_dir[e];
+  int t = e ^ 1;
+  int b = h_src[t];
+  int v = new_vertex(px, py);
+  int e2 = new_edge_pair(v, b), t2 = e2 ^ 1;
+  h_next[e2] = h_next[e]; h_prev[h_next[e]] = e2; h_next[e] = e2; h_prev[e2] = e;
+  h_prev[t2] = h_prev[t]; h_next[h_prev[t]] = t2; h_next[t2] = t; h_prev[t] = t2;
+  h_src[t] = v;
+  h_face[e2] = h_face[e]; h_face[t2] = h_face[t];
+  v_inc[v] = e;
+  if (v_inc[b] == e) v_inc[b] = e2;
+  set_junction(e, e2);
+  set_junction(e2, e_next_hf);
+  h_dir[e] = e_dir; h_dir[t] = !e_dir; h_dir[e2] = e_dir; h_dir[t2] = !e_dir;
+  set_len(e); set_len(e2);
+  h_seg[e2] = h_seg[t2] = s;
+  s_nedges[s]++;
+  seg_set_handle(s, e);
+  refresh_weight(e); refresh_weight(e2);
+  return e;
+}
+
+int HostTess::merge_edge(int e1, int e2) {  // lib/ttessel.cpp:658-698
+  int hf_avant = h_prev_hf[e1], hf_apres = h_next_hf[e2];
+  double new_len = h_len[e1] + h_len[e2];
+  int s = h_seg[e1];
+  int v = tgt(e1), t1 = e1 ^ 1, t2 = e2 ^ 1, b = tgt(e2);
+  h_next[e1] = h_next[e2]; h_prev[h_next[e2]] = e1;
+  h_prev[t1] = h_prev[t2]; h_next[h_prev[t2]] = t1;
+  h_src[t1] = b;
+  if (v_inc[b] == e2) v_inc[b] = e1;
+  if (f_he[h_face[e2]] == e2) f_he[h_face[e2]] = e1;
+  if (f_he[h_face[t2]] == t2) f_he[h_face[t2]] = t1;
+  del_edge_pair(e2);
+  del_vertex(v);
+  set_junction(hf_avant, e1);
+  set_junction(e1, hf_apres);
+  h_len[e1] = h_len[t1] = new_len;
+  s_nedges[s]--;
+  seg_set_handle(s, e1);
+  refresh_weight(e1);
+  return e1;
+}
+
+// new edge from tgt(prev1) to tgt(prev2) inside their common face; ext_prev is
+// the halfedge whose straight continuation the new edge is (-1: new segment)
+int HostTess::add_edge(int prev1, int prev2, int ext_prev) {  // lib/ttessel.cpp:700-740
+  int v1 = tgt(prev1), v2 = tgt(prev2);
+  int f = h_face[prev1];
+  int a1 = h_next[prev1], a2 = h_next[prev2];
+  int h = new_edge_pair(v1, v2), t = h ^ 1;
+  h_next[prev1] = h; h_prev[h] = prev1; h_next[h] = a2; h_prev[a2] = h;
+  h_next[prev2] = t; h_prev[t] = prev2; h_next[t] = a1; h_prev[a1] = t;
+  int nf = new_face(true);
+  f_he[f] = t; h_face[t] = f;
+  f_he[nf] = h;
+  int e = h;
+  do { h_face[e] = nf; e = h_next[e]; } while (e != h);
+  set_len(h);
+  if (ext_prev >= 0) {
+    set_junction(ext_prev, h);
+    h_dir[h] = h_dir[ext_prev]; h_dir[t] = !h_dir[h];
+    int s = h_seg[ext_prev];
+    h_seg[h] = h_seg[t] = s;
+    s_nedges[s]++;
+  } else {
+    h_dir[h] = 1; h_dir[t] = 0;
+    int s = new_seg(h, false);
+    h_seg[h] = h_seg[t] = s;
+  }
+  // refresh weights of the halfedges that changed face
+  e = h;
+  do { refresh_weight(e); e = h_next[e]; } while (e != h);
+  refresh_weight(t);
+  return h;
+}
+
+int HostTess::remove_edge(int e) {  // lib/ttessel.cpp:743-780
+  int t = e ^ 1;
+  int f1 = h_face[e], f2 = h_face[t];
+  int p1 = h_prev[e], n1 = h_next[e], p2 = h_prev[t], n2 = h_next[t];
+  int phf = h_prev_hf[e], nhf = h_next_hf[e];
+  set_junction(phf, -1);
+  set_junction(-1, nhf);
+  int s = h_seg[e];
+  if (phf < 0 && nhf < 0) {
+    list_remove(s);
+    del_seg(s);
+  } else {
+    s_nedges[s]--;
+    seg_set_handle(s, phf >= 0 ? phf : nhf);
+  }
+  if (v_inc[tgt(e)] == e) v_inc[tgt(e)] = p2;
+  if (v_inc[h_src[e]] == t) v_inc[h_src[e]] = p1;
+  h_next[p1] = n2; h_prev[n2] = p1; h_next[p2] = n1; h_prev[n1] = p2;
+  del_edge_pair(e);
+  f_he[f1] = p1;
+  int c = p1;
+  do { h_face[c] = f1; c = h_next[c]; } while (c != p1);
+  if (f2 != f1) del_face(f2);
+  return f1;
+}
+
+void HostTess::suppress_edge(int e) {  // lib/ttessel.cpp:201-236
+  int v1 = h_src[e], v2 = tgt(e);
+  remove_edge(e);
+  for (int v : {v1, v2}) {
+    if (degree(v) == 2 && h_next_hf[v_inc[v]] >= 0) merge_edge(v_inc[v], h_next_hf[v_inc[v]]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// moves (double restatement of the reference constructors)
+// ---------------------------------------------------------------------------
+int HostTess::ray_exit(int start_he, double a, double b, double w, double px, double py,
+                       double dx, double dy, int skip0, int skip1, double &hx,
+                       double &hy) const {  // ray_exit_face, lib/ttessel.cpp:4515-4576
+  double best = 1.7976931348623157e308;
+  int res = -1;
+  int h = start_he;
+  do {
+    if (h != skip0 && h != skip1) {
+      int vs = h_src[h], vt = tgt(h);
+      double sk = fma(a, vx[vs], fma(b, vy[vs], -w)), sn = fma(a, vx[vt], fma(b, vy[vt], -w));
+      bool cr = (sk <= 0.0 && sn >= 0.0) || (sk >= 0.0 && sn <= 0.0);
+      if (cr && sk != sn) {
+        double sg = sk / (sk - sn);
+        double X = fma(sg, vx[vt] - vx[vs], vx[vs]), Y = fma(sg, vy[vt] - vy[vs], vy[vs]);
+        double rx = X - px, ry = Y - py;
+        if (rx * dx + ry * dy >= 0.0) {
+          double len = sqrt(rx * rx + ry * ry);
+          if (len != 0.0 && len < best) { best = len; res = h; hx = X; hy = Y; }
+        }
+      }
+    }
+    h = h_next[h];
+  } while (h != start_he);
+  return res;
+}
+
+SplitMove HostTess::make_split(int e, double x, double angle) const {  // lib/ttessel.cpp:2090-2132
+  SplitMove m;
+  m.e1 = e;
+  int vs = h_src[e], vt = tgt(e);
+  double sx = vx[vs], sy = vy[vs], tx = vx[vt], ty = vy[vt];
+  double e1_angle = atan2(ty - sy, tx - sx);
+  double l = e1_angle + angle;
+  double a = sin(l), b = -cos(l);
+  double u = a * sx + b * sy, v = a * tx + b * ty;
+  double w = u + x * (v - u);
+  double sP = fma(a, sx, fma(b, sy, -w)), sQ = fma(a, tx, fma(b, ty, -w));
+  if (!(sP != sQ)) return m;
+  double t1 = sP / (sP - sQ);
+  m.p1x = fma(t1, tx - sx, sx); m.p1y = fma(t1, ty - sy, sy);
+  double dx, dy;
+  if (sQ < 0.0) { dx = b; dy = -a; } else { dx = -b; dy = a; }
+  int skip1 = (x == 0.0) ? h_prev[e] : -1;
+  int e2 = ray_exit(f_he[h_face[e]], a, b, w, m.p1x, m.p1y, dx, dy, e, skip1, m.p2x, m.p2y);
+  if (e2 < 0) return m;
+  m.e2 = e2;
+  m.valid = true;
+  return m;
+}
+
+FlipMove HostTess::make_flip(int e1) const {  // lib/ttessel.cpp:2432-2454
+  FlipMove m;
+  m.e1 = e1;
+  int hp = h_prev[e1];
+  bool right = (hp != h_prev_hf[e1]);
+  int e3 = right ? hp : (h_next[e1 ^ 1] ^ 1);
+  m.e3 = e3; m.right = right;
+  int a = h_src[e1];
+  double ax = vx[a], ay = vy[a];
+  double dx = ax - vx[h_src[e3]], dy = ay - vy[h_src[e3]];
+  double nrm = sqrt(dx * dx + dy * dy);
+  dx /= nrm; dy /= nrm;
+  double la = dy, lb = -dx, lw = la * ax + lb * ay;
+  int f = right ? h_face[e1 ^ 1] : h_face[e1];
+  int skip0, skip1;
+  if (right) { skip0 = e1 ^ 1; skip1 = h_next[e1 ^ 1]; }
+  else { skip0 = e1; skip1 = h_prev[e1]; }
+  int e2 = ray_exit(f_he[f], la, lb, lw, ax, ay, dx, dy, skip0, skip1, m.p2x, m.p2y);
+  if (e2 < 0) return m;
+  m.e2 = e2;
+  m.valid = true;
+  return m;
+}
+
+int HostTess::update_split(const SplitMove &sp) {  // TTessel::update(Split), :1580-1597
+  int e1n = split_edge(sp.e1, sp.p1x, sp.p1y);
+  int e2n = split_edge(sp.e2, sp.p2x, sp.p2y);
+  int e = add_edge(e1n, e2n, -1);
+  int_length += 2 * h_len[e];
+  list_add(h_seg[e], 1);
+  int ends[2] = {h_seg[h_next[e]], h_seg[h_next[e ^ 1]]};
+  for (int s : ends) {
+    if (!s_bnd[s] && s_nedges[s] <= 2 && s_kind[s] == 1) {
+      list_remove(s);
+      list_add(s, 2);
+    }
+  }
+  return e;
+}
+
+void HostTess::update_merge(int e) {  // TTessel::update(Merge), :1604-1638
+  int s = h_seg[e];
+  list_remove(s);
+  int ends[2] = {h_seg[h_next[e]], h_seg[h_next[e ^ 1]]};
+  for (int sx : ends) {
+    if (!s_bnd[sx] && s_nedges[sx] <= 2 && s_kind[sx] == 2) {
+      list_remove(sx);
+      list_add(sx, 1);
+    }
+  }
+  double suppressed = h_len[e];
+  suppress_edge(e);
+  int_length -= 2 * suppressed;
+}
+
+int HostTess::update_flip(const FlipMove &fl) {  // TTessel::update(Flip), :1644-1701
+  int e1 = fl.e1;
+  int s1 = h_seg[e1];
+  int s1_i = h_seg[h_next[e1]];
+  int e3 = fl.e3;
+  int s2 = h_seg[e3];
+  // split_from_vertex (lib/ttessel.cpp:161-189): the halfedge arriving at a in the face of e2
+  int prev_a = fl.right ? (e1 ^ 1) : h_prev[e1];
+  int e2n = split_edge(fl.e2, fl.p2x, fl.p2y);
+  int new_e = add_edge(prev_a, e2n, e3);
+  int_length += 2 * h_len[new_e];
+  int_length -= 2 * h_len[e1];
+  int s2_i = h_seg[h_next[new_e]];
+  suppress_edge(e1);
+  if (s_nedges[s2] <= 2 && s_kind[s2] == 1) { list_remove(s2); list_add(s2, 2); }
+  if (s_nedges[s1] <= 1 && s_kind[s1] == 2) { list_remove(s1); list_add(s1, 1); }
+  if (s2_i != s1_i) {
+    if (!s_bnd[s2_i] && s_nedges[s2_i] <= 2 && s_kind[s2_i] == 1) { list_remove(s2_i); list_add(s2_i, 2); }
+    if (!s_bnd[s1_i] && s_nedges[s1_i] <= 1 && s_kind[s1_i] == 2) { list_remove(s1_i); list_add(s1_i, 1); }
+  }
+  return new_e;
+}
+
+int HostTess::sample_halfedge(double u01) const {
+  double tot = fen.total();
+  return fen.find(u01 * tot);
+}
+
+// ---------------------------------------------------------------------------
+// export
+// ---------------------------------------------------------------------------
+const lite_tess_soa *HostTess::export_soa() {
+  Export &E = ex;
+  size_t nV0 = vx.size(), nH0 = h_src.size(), nF0 = f_he.size(), nS0 = s_he.size();
+  std::vector<int> vmap(nV0, -1), hmap(nH0, -1), fmap(nF0, -1), smap(nS0, -1);
+  int nV = 0, nH = 0, nF = 0, nS = 0;
+  for (size_t i = 0; i < nV0; i++) if (v_alive[i]) vmap[i] = nV++;
+  for (size_t i = 0; i < nH0; i++) if (h_alive[i]) hmap[i] = nH++;
+  for (size_t i = 0; i < nF0; i++) if (f_alive[i]) fmap[i] = nF++;
+  for (size_t i = 0; i < nS0; i++) if (s_alive[i]) smap[i] = nS++;
+  E.vx.resize(nV); E.vy.resize(nV);
+  for (size_t i = 0; i < nV0; i++) if (v_alive[i]) { E.vx[vmap[i]] = vx[i]; E.vy[vmap[i]] = vy[i]; }
+  E.he_src.resize(nH); E.he_twin.resize(nH); E.he_next.resize(nH); E.he_face.resize(nH);
+  E.he_seg.resize(nH); E.he_next_hf.resize(nH); E.he_prev_hf.resize(nH); E.he_dir.resize(nH);
+  E.he_length.resize(nH);
+  for (size_t i = 0; i < nH0; i++) {
+    if (!h_alive[i]) continue;
+    int k = hmap[i];
+    E.he_src[k] = vmap[h_src[i]]; E.he_twin[k] = hmap[i ^ 1]; E.he_next[k] = hmap[h_next[i]];
+    E.he_face[k] = fmap[h_face[i]]; E.he_seg[k] = smap[h_seg[i]];
+    E.he_next_hf[k] = h_next_hf[i] >= 0 ? hmap[h_next_hf[i]] : -1;
+    E.he_prev_hf[k] = h_prev_hf[i] >= 0 ? hmap[h_prev_hf[i]] : -1;
+    E.he_dir[k] = h_dir[i]; E.he_length[k] = h_len[i];
+  }
+  E.face_inside.resize(nF); E.f_off.resize(nF); E.f_cnt.resize(nF); E.f_list.clear();
+  for (size_t i = 0; i < nF0; i++) {
+    if (!f_alive[i]) continue;
+    int k = fmap[i];
+    E.face_inside[k] = f_inside[i];
+    E.f_off[k] = (int)E.f_list.size();
+    int cnt = 0;
+    if (f_inside[i]) {
+      int h0 = f_he[i], h = h0;
+      do { E.f_list.push_back(hmap[h]); cnt++; h = h_next[h]; } while (h != h0);
+    }
+    E.f_cnt[k] = cnt;
+  }
+  E.seg_start.resize(nS); E.seg_end.resize(nS); E.seg_n.resize(nS); E.seg_bnd.resize(nS);
+  for (size_t i = 0; i < nS0; i++) {
+    if (!s_alive[i]) continue;
+    int k = smap[i];
+    E.seg_start[k] = hmap[seg_start((int)i)]; E.seg_end[k] = hmap[seg_end((int)i)];
+    E.seg_n[k] = s_nedges[i]; E.seg_bnd[k] = s_bnd[i];
+  }
+  E.nb.resize(nb_list.size()); E.b.resize(b_list.size());
+  for (size_t i = 0; i < nb_list.size(); i++) E.nb[i] = smap[nb_list[i]];
+  for (size_t i = 0; i < b_list.size(); i++) E.b[i] = smap[b_list[i]];
+  lite_tess_soa &S = E.soa;
+  S.n_vertices = nV; S.vx = E.vx.data(); S.vy = E.vy.data();
+  S.n_halfedges = nH; S.he_src = E.he_src.data(); S.he_twin = E.he_twin.data();
+  S.he_next = E.he_next.data(); S.he_face = E.he_face.data(); S.he_seg = E.he_seg.data();
+  S.he_next_hf = E.he_next_hf.data(); S.he_prev_hf = E.he_prev_hf.data();
+  S.he_dir = E.he_dir.data(); S.he_length = E.he_length.data();
+  S.n_faces = nF; S.face_inside = E.face_inside.data(); S.face_he_offset = E.f_off.data();
+  S.face_he_count = E.f_cnt.data(); S.n_face_he = (int)E.f_list.size(); S.face_he_list = E.f_list.data();
+  S.n_segments = nS; S.seg_he_start = E.seg_start.data(); S.seg_he_end = E.seg_end.data();
+  S.seg_n_edges = E.seg_n.data(); S.seg_on_boundary = E.seg_bnd.data();
+  S.n_non_blocking = (int)E.nb.size(); S.n_blocking = (int)E.b.size();
+  S.non_blocking = E.nb.data(); S.blocking = E.b.data();
+  // int_length as the reference keeps it (incrementally); the sum of inside
+  // halfedge lengths agrees to rounding
+  S.int_length = int_length;
+  return &S;
+}
+
+std::string HostTess::check() const {  // in the spirit of TTessel::is_valid, :1721-1753
+  char buf[256];
+  for (size_t h = 0; h < h_src.size(); h++) {
+    if (!h_alive[h]) continue;
+    if (h_prev[h_next[h]] != (int)h || h_src[h_next[h]] != tgt((int)h)) {
+      snprintf(buf, sizeof buf, "halfedge %zu: broken next/prev", h);
+      return buf;
+    }
+    if (h_face[h_next[h]] != h_face[h]) { snprintf(buf, sizeof buf, "halfedge %zu: face differs along ccb", h); return buf; }
+    int nh = h_next_hf[h];
+    if (nh >= 0 && (h_prev_hf[nh] != (int)h || h_src[nh] != tgt((int)h) || h_seg[nh] != h_seg[h])) {
+      snprintf(buf, sizeof buf, "halfedge %zu: broken segment link", h);
+      return buf;
+    }
+  }
+  for (int s : nb_list) if (s_nedges[s] != 1 || s_bnd[s]) return "non-blocking segment with != 1 edge";
+  for (int s : b_list) if (s_nedges[s] < 2 || s_bnd[s]) return "blocking segment with < 2 edges";
+  for (size_t s = 0; s < s_he.size(); s++) {
+    if (!s_alive[s]) continue;
+    int n = 1, e = seg_start((int)s);
+    while (h_next_hf[e] >= 0) { e = h_next_hf[e]; n++; }
+    if (n != s_nedges[s]) { snprintf(buf, sizeof buf, "segment %zu: edge count %d != %d", s, s_nedges[s], n); return buf; }
+    if (!s_bnd[s] && s_kind[s] != (n == 1 ? 1 : 2)) { snprintf(buf, sizeof buf, "segment %zu: wrong list", s); return buf; }
+  }
+  return "";
+}
+
+// ---------------------------------------------------------------------------
+// CRTT chain (SMFChain::step, lib/ttessel.cpp:3257-3311; Hastings ratios :3158-3252)
+// ---------------------------------------------------------------------------
+ChainCounts crtt_chain(HostTess &t, double tau, uint64_t n_steps, uint64_t seed, double p_split,
+                       double p_merge) {
+  ChainCounts cc;
+  std::mt19937_64 g(seed);
+  auto U = [&]() { return (double)(g() >> 11) * (1.0 / 9007199254740992.0); };
+  const double p_sm = p_split + p_merge;
+  bool save = t.ordered_lists;
+  t.ordered_lists = false;  // the chain draws uniformly from the lists: order is irrelevant
+  for (uint64_t it = 0; it < n_steps; it++) {
+    double r0 = U(), x = U();
+    if (r0 <= p_split) {
+      cc.c[0]++;
+      int e = t.sample_halfedge(U());
+      double xx = U(), ang = acos(1 - 2 * U());
+      SplitMove s = t.make_split(e, xx, ang);
+      if (!s.valid) continue;
+      int delta_nb = 1;
+      if (t.s_nedges[t.h_seg[s.e1]] == 1 && !t.s_bnd[t.h_seg[s.e1]]) delta_nb--;
+      if (t.s_nedges[t.h_seg[s.e2]] == 1 && !t.s_bnd[t.h_seg[s.e2]]) delta_nb--;
+      double r = p_merge / p_split;
+      r *= (1 / kPi) * t.int_length / ((double)t.nb_list.size() + delta_nb);
+      r *= tau;  // exp(-dE), dE = log(tau)*(-1)
+      if (r > 1 || x < r) { cc.c[1]++; t.update_split(s); }
+    } else if (r0 <= p_sm) {
+      cc.c[2]++;
+      if (t.nb_list.empty()) continue;
+      int s = t.nb_list[(size_t)(U() * t.nb_list.size())];
+      int e = t.s_he[s];
+      double r = p_split / p_merge;
+      r *= kPi * (double)t.nb_list.size() / (t.int_length - 2 * t.h_len[e]);
+      r /= tau;
+      if (r > 1 || x < r) { cc.c[3]++; t.update_merge(e); }
+    } else {
+      cc.c[4]++;
+      if (t.b_list.empty()) continue;
+      int s = t.b_list[(size_t)(U() * t.b_list.size())];
+      int side = U() < 0.5 ? 0 : 1;
+      FlipMove f = t.make_flip(t.flip_halfedge(s, side));
+      if (!f.valid) continue;
+      int db = 0;
+      int s_short = t.h_seg[f.e1];
+      if (t.s_nedges[s_short] == 2) db--;
+      if (t.s_nedges[t.h_seg[f.e3]] == 1) db++;
+      int i_short = t.h_seg[t.h_next[f.e1]], i_ext = t.h_seg[f.e2];
+      if (i_short != i_ext) {
+        if (t.s_nedges[i_short] == 2 && !t.s_bnd[i_short]) db--;
+        if (t.s_nedges[i_ext] == 1 && !t.s_bnd[i_ext]) db++;
+      }
+      double sb = (double)t.b_list.size();
+      double r = (sb == -db) ? sb : sb / (sb + db);
+      if (r > 1 || x < r) { cc.c[5]++; t.update_flip(f); }
+    }
+  }
+  t.ordered_lists = save;
+  return cc;
+}
+
+// ---------------------------------------------------------------------------
+// text format (LineTes::write/read, lib/ttessel.cpp:1331-1441), doubles
+// ---------------------------------------------------------------------------
+static bool parse_ratio(const std::string &tok, double &out) {
+  size_t sl = tok.find('/');
+  std::string num = tok.substr(0, sl), den = sl == std::string::npos ? "1" : tok.substr(sl + 1);
+  auto to_ld = [](const std::string &s, long double &v) {
+    if (s.empty()) return false;
+    size_t i = 0;
+    bool neg = false;
+    if (s[0] == '-' || s[0] == '+') { neg = s[0] == '-'; i = 1; }
+    if (i >= s.size()) return false;
+    v = 0;
+    for (; i < s.size(); i++) {
+      if (s[i] < '0' || s[i] > '9') return false;
+      v = v * 10.0L + (long double)(s[i] - '0');
+    }
+    if (neg) v = -v;
+    return true;
+  };
+  long double n, d;
+  if (!to_ld(num, n) || !to_ld(den, d) || d == 0) return false;
+  out = (double)(n / d);
+  return true;
+}
+
+bool read_text(HostTess &t, const std::string &text, std::string &err) {
+  std::istringstream is(text);
+  std::string line;
+  std::vector<std::vector<double>> segs;
+  bool have_window = false;
+  while (std::getline(is, line)) {
+    std::istringstream ls(line);
+    std::string tok;
+    std::vector<double> c;
+    while (ls >> tok) {
+      double v;
+      if (!parse_ratio(tok, v)) { err = "bad coordinate '" + tok + "'"; return false; }
+      c.push_back(v);
+    }
+    if (c.empty()) continue;
+    if (c.size() % 2) { err = "Uneven number of coordinates on the current line"; return false; }
+    if (c.size() > 4) {
+      if (have_window) { err = "windows made of several polygons or holes are outside the scope"; return false; }
+      std::vector<double> x, y;
+      for (size_t i = 0; i < c.size(); i += 2) { x.push_back(c[i]); y.push_back(c[i + 1]); }
+      double a = 0;
+      for (size_t i = 0; i < x.size(); i++) { size_t j = (i + 1) % x.size(); a += x[i] * y[j] - x[j] * y[i]; }
+      if (a <= 0) { err = "Invalid orientation of a domain ccb"; return false; }
+      t.insert_window_polygon(x, y);
+      have_window = true;
+    } else {
+      if (!have_window) { err = "segment before window"; return false; }
+      segs.push_back(c);
+    }
+  }
+  // insert the segments in dependency order: an end must lie on an existing edge
+  const double eps = 1e-9;
+  auto locate = [&](double px, double py, int &he, int &vert) {
+    he = -1; vert = -1;
+    for (size_t v = 0; v < t.vx.size(); v++)
+      if (t.v_alive[v] && fabs(t.vx[v] - px) <= eps && fabs(t.vy[v] - py) <= eps) { vert = (int)v; return true; }
+    for (size_t h = 0; h < t.h_src.size(); h += 2) {
+      if (!t.h_alive[h]) continue;
+      double ax = t.vx[t.h_src[h]], ay = t.vy[t.h_src[h]], bx = t.vx[t.tgt((int)h)], by = t.vy[t.tgt((int)h)];
+      double ex = bx - ax, ey = by - ay, L2 = ex * ex + ey * ey;
+      double s = ((px - ax) * ex + (py - ay) * ey) / L2;
+      if (s <= 0 || s >= 1) continue;
+      double qx = ax + s * ex - px, qy = ay + s * ey - py;
+      if (qx * qx + qy * qy <= eps * eps) { he = (int)h; return true; }
+    }
+    return false;
+  };
+  std::vector<bool> done(segs.size(), false);
+  size_t left = segs.size();
+  bool progress = true;
+  while (left && progress) {
+    progress = false;
+    for (size_t i = 0; i < segs.size(); i++) {
+      if (done[i]) continue;
+      int h1, v1, h2, v2;
+      if (!locate(segs[i][0], segs[i][1], h1, v1) || !locate(segs[i][2], segs[i][3], h2, v2)) continue;
+      if (v1 >= 0 || v2 >= 0) continue;  // T-tessellation: ends lie inside edges
+      // choose the halfedges bounding the face that contains the segment midpoint side
+      double mx = 0.5 * (segs[i][0] + segs[i][2]), my = 0.5 * (segs[i][1] + segs[i][3]);
+      auto left_of = [&](int h) {
+        double ax = t.vx[t.h_src[h]], ay = t.vy[t.h_src[h]], bx = t.vx[t.tgt(h)], by = t.vy[t.tgt(h)];
+        return (bx - ax) * (my - ay) - (by - ay) * (mx - ax) > 0;
+      };
+      int e1 = left_of(h1) ? h1 : (h1 ^ 1), e2 = left_of(h2) ? h2 : (h2 ^ 1);
+      if (t.h_face[e1] != t.h_face[e2] || !t.f_inside[t.h_face[e1]]) continue;
+      // the segment must not cross existing edges of that face (cyclic dependencies
+      // are resolved by later passes)
+      SplitMove m;
+      m.e1 = e1; m.e2 = e2; m.p1x = segs[i][0]; m.p1y = segs[i][1]; m.p2x = segs[i][2]; m.p2y = segs[i][3];
+      m.valid = true;
+      t.update_split(m);
+      done[i] = true; left--; progress = true;
+    }
+  }
+  if (left) { err = "segments cannot be inserted one by one as splits (cyclic T-dependencies)"; return false; }
+  return true;
+}
+
+// a double is m*2^e exactly: print it as the rational num/den the format wants
+static std::string exact_ratio(double v) {
+  if (v == 0.0) return "0/1";
+  int e;
+  double m = frexp(v, &e);                // v = m * 2^e, 0.5 <= |m| < 1
+  long long M = (long long)ldexp(m, 53);  // 53-bit integer mantissa
+  e -= 53;
+  while (M % 2 == 0 && e < 0) { M /= 2; e++; }
+  char buf[400];
+  if (e >= 0) snprintf(buf, sizeof buf, "%.0Lf/1", (long double)M * ldexpl(1.0L, e));
+  else snprintf(buf, sizeof buf, "%lld/%.0Lf", M, ldexpl(1.0L, -e));
+  return buf;
+}
+
+std::string write_text(const HostTess &t) {
+  std::ostringstream os;
+  for (size_t i = 0; i < t.win_x.size(); i++)
+    os << (i ? " " : "") << exact_ratio(t.win_x[i]) << " " << exact_ratio(t.win_y[i]);
+  os << "\n";
+  for (size_t s = 0; s < t.s_he.size(); s++) {
+    if (!t.s_alive[s] || t.s_bnd[s]) continue;
+    int a = t.seg_start((int)s), b = t.seg_end((int)s);
+    os << exact_ratio(t.vx[t.h_src[a]]) << " " << exact_ratio(t.vy[t.h_src[a]]) << " "
+       << exact_ratio(t.vx[t.tgt(b)]) << " " << exact_ratio(t.vy[t.tgt(b)]) << "\n";
+  }
+  return os.str();
+}
+
+}  // namespace lite

@@ -974,6 +974,7 @@ class Split:
 
     def __init__(self, e, x=0.5, angle=CGAL_PI / 2):
         self.e1 = e
+        self._x, self._angle = x, angle
         sx, sy = e.src.p
         tx, ty = e.tgt.p
         e1_angle = math.atan2(float(ty - sy), float(tx - sx))

@@ -1,0 +1,122 @@
+"""The C++ host model (lite::HostTess, the state behind the TTessel facade)
+replayed against the exact oracle on the same sequence of random splits,
+merges and flips (the reference's squared_domain scenario,
+tests/check_lite.cpp:446-542, :1031-1040)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import lite_b200
+import lite_oracle as lo
+
+pytestmark = pytest.mark.skipif(not os.path.exists(lite_b200.lib_path()), reason="libliteb200.so not built")
+
+
+def _cells_from_soa(a):
+    cells = []
+    for f in np.nonzero(a["face_inside"])[0]:
+        off, cnt = a["face_he_offset"][f], a["face_he_count"][f]
+        hs = a["face_he_list"][off:off + cnt]
+        pts = []
+        for k, h in enumerate(hs):
+            hp = hs[k - 1]
+            # corner iff the previous halfedge does not continue straight (face2poly)
+            if a["he_next_hf"][hp] < 0 or a["he_next_hf"][hp] != a["he_next"][hp]:
+                v = a["he_src"][h]
+                pts.append((round(float(a["vx"][v]), 10), round(float(a["vy"][v]), 10)))
+        k = min(range(len(pts)), key=lambda i: pts[i])
+        cells.append(tuple(pts[k:] + pts[:k]))
+    return sorted(cells)
+
+
+def _cells_from_oracle(t):
+    cells = []
+    for f in t.internal_faces():
+        pts = [(round(float(p[0]), 10), round(float(p[1]), 10)) for p in lo.face2poly(f)[0]]
+        k = min(range(len(pts)), key=lambda i: pts[i])
+        cells.append(tuple(pts[k:] + pts[:k]))
+    return sorted(cells)
+
+
+def _find_he(a, p, q, tol=1e-11):
+    sx, sy = a["vx"][a["he_src"]], a["vy"][a["he_src"]]
+    tw = a["he_twin"]
+    tx, ty = sx[tw], sy[tw]
+    m = (np.abs(sx - float(p[0])) < tol) & (np.abs(sy - float(p[1])) < tol) & \
+        (np.abs(tx - float(q[0])) < tol) & (np.abs(ty - float(q[1])) < tol)
+    idx = np.nonzero(m)[0]
+    assert len(idx) == 1
+    return int(idx[0])
+
+
+@pytest.mark.parametrize("seed", [5, 11])
+def test_replay_against_oracle(seed):
+    t = lo.TTessel(lo.Rng(seed))
+    t.insert_window_rect(0, 0, 1, 1)
+    h = lite_b200.HostTess((0, 0, 1, 1))
+    n, m = 60, 120
+    for i in range(n + m):
+        a = h.export().a
+        if i < n or i % 3 == 0:
+            mod = t.propose_split()
+            he = _find_he(a, mod.e1.src.p, mod.e1.tgt.p)
+            # recover x, angle from the oracle's draw by re-deriving them is not
+            # possible; feed the same numbers instead
+            x, ang = mod._x, mod._angle
+            h.update_split(he, x, ang)
+        elif i % 3 == 1:
+            if not t.non_blocking_segments:
+                continue
+            mod = t.propose_merge()
+            he = _find_he(a, mod.e.src.p, mod.e.tgt.p)
+            seg = a["he_seg"][he]
+            h.update_merge(int(np.nonzero(a["non_blocking"] == seg)[0][0]))
+        else:
+            if not t.blocking_segments:
+                continue
+            mod = t.propose_flip()
+            he = _find_he(a, mod.e1.src.p, mod.e1.tgt.p)
+            seg = a["he_seg"][he]
+            bi = int(np.nonzero(a["blocking"] == seg)[0][0])
+            side = 1 if a["seg_he_end"][seg] == he else 0
+            assert side == 1 or a["he_twin"][a["seg_he_start"][seg]] == he
+            h.update_flip(bi, side)
+        t.update(mod)
+        h.check()
+        cells, nnb, nb = h.counts()
+        assert (cells, nnb, nb) == (len(t.internal_faces()), len(t.non_blocking_segments),
+                                    len(t.blocking_segments))
+        if i % 10 == 0 or i == n + m - 1:
+            soa = h.export()
+            assert _cells_from_soa(soa.a) == _cells_from_oracle(t)
+            assert soa.int_length == pytest.approx(t.int_length, rel=1e-12)
+
+
+def test_generator_reaches_equilibrium_estimate():
+    """At equilibrium of the CRTT chain the closed-form PL estimate
+    log(n_nb*pi/u) (reference demos/pseudo_lik_inference.cpp:80-81) is near log(tau)."""
+    t, tau = lite_b200.generate_crtt(2000, seed=5)
+    t.check()
+    soa = t.export()
+    cells, nnb, nb = t.counts()
+    assert 0.7 * 2000 < cells < 1.4 * 2000
+    est = math.log(nnb * math.pi / soa.int_length)
+    assert abs(est - math.log(tau)) < 0.15
+    # cells = n_s+1, halfedges = 6 n_s + 8
+    ns = nnb + nb
+    assert cells == ns + 1 and len(soa.a["he_src"]) == 6 * ns + 8
+
+
+def test_text_roundtrip_and_fixture():
+    here = os.path.dirname(os.path.abspath(__file__))
+    text = open(os.path.join(here, "golden", "tessellation_data.txt")).read()
+    try:
+        h = lite_b200.HostTess(text=text)
+    except lite_b200.LiteError as e:
+        pytest.skip("fixture needs simultaneous insertion: %s" % e)
+    assert h.counts()[0] == 11
+    h.check()
+    h2 = lite_b200.HostTess(text=h.write_text())
+    assert h2.counts() == h.counts()
