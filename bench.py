@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py — pseudo-likelihood candidate moves evaluated per second.
+
+Metric (BASELINE.json): PL candidate moves evaluated/sec at 1/2/4/8 B200 next to
+the host-core CPU reference.  One candidate evaluated = sampled + clipped against
+its face + statistic delta computed + accumulated once into log-PL / gradient /
+Hessian.
+
+A *step* is one pass of the hot path over one batch:
+    SetEnergy (all merges + all flips)  ->  AddSplits(N_S) with the Philox
+    sampler (sample + clip + delta)     ->  value, gradient and Hessian at theta
+    (+ one NCCL allreduce of 1+d+d(d+1)/2 doubles when N > 1).
+
+Workloads:
+    N = 1 : config C2 — ~10^4-cell CRTT tessellation, 10^7 splits, ACS energy d=4
+    N > 1 : config C3 — ~10^5-cell tessellation, 1.25*10^7 splits per GPU
+            (10^8 at N=8), contiguous shards, weak scaling.
+
+`value`  : whole-job candidates/s, tessellation already resident in HBM.
+`e2e`    : the same through the C ABI starting from HOST buffers every step:
+           lite_tess_upload (host SoA -> device) + energy + SetEnergy + AddSplits
+           + eval, results read back to the host.
+`--impl reference` : the CPU restatement of the reference's algorithm
+           (oracle/oracle_cpu.cpp, all host threads) on a bounded sample of the
+           same workload; the reference itself needs CGAL and cannot be built
+           here.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ACS = ["edge_length", "face_area_2", "face_sum_of_angles", "is_segment_internal"]
+# demos/sim_acs.cpp:64-76 with tau=12, fi1=0.05, fi2=1, flattened in CatVector
+# order edges, faces, faces, segs
+THETA = [11.0 / math.pi, 12.0 ** 4 * 0.05, 1.0, -math.log(12.0)]
+SEED = 0x5EED
+# algorithmic work per split candidate
+F_ALG_SPLIT = 1300.0   # DP flop: K1 sample+clip 300 + K2 delta 1000
+B_ALG_SPLIT = 32.0     # bytes written: 8*d
+B_ALG_REDUCE = 32.0    # bytes read:    8*d
+F_ALG_REDUCE = 60.0
+
+
+def workload(n_gpus, args):
+    if args.cells:
+        cells = args.cells
+    else:
+        cells = 10000 if n_gpus == 1 else 100000
+    if args.splits:
+        per_gpu = args.splits
+    else:
+        per_gpu = 10_000_000 if n_gpus == 1 else 12_500_000
+    name = "C2" if (cells == 10000 and n_gpus == 1) else ("C3" if cells == 100000 else "custom")
+    return name, cells, per_gpu
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._halt.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._halt.wait(self.period)
+
+    def stop(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        med = float(np.median(self.sm)) if self.sm else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
+
+
+def soa_bytes(soa):
+    return int(sum(a.nbytes for a in soa.a.values()) + 8)
+
+
+def run_cpu_reference(args, n_gpus, rank):
+    """`--impl reference`: the reference's CPU algorithm (C++ double restatement,
+    oracle/oracle_cpu.cpp) on all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_cpu as oc
+    import lite_b200
+    name, cells, per_gpu = workload(n_gpus, args)
+    t, _tau = lite_b200.generate_crtt(cells, seed=5)
+    soa = t.export()
+    arrays = dict(soa.a)
+    arrays["int_length"] = soa.int_length
+    T = oc.Tess(arrays)
+    cores = oc.hardware_threads()
+    n_mf = T.n_nb + 2 * T.n_b
+    # bounded sample of the step's split batch: ~2 s of CPU work per step
+    sample = args.cpu_sample or max(100_000, 60_000 * cores)
+    for _ in range(args.warmup):
+        oc.pl_pass(T, ACS, THETA, max(1000, sample // 10), SEED, 0, cores)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        v, g, H = oc.pl_pass(T, ACS, THETA, sample, SEED, k * sample, cores)
+    dt = time.perf_counter() - t0
+    per_step = sample + n_mf
+    val = per_step * args.steps / dt
+    line = {
+        "impl": "reference",
+        "metric": "pl_candidate_moves_evaluated_per_sec", "value": val, "unit": "candidates/s",
+        "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %d-cell CRTT tessellation (unit square, host generator seed 5), ACS energy d=4; "
+                               "CPU arm evaluates a bounded sample of the split batch" % (name, T.s.n_faces - 1),
+                   "cells": int(T.s.n_faces - 1), "splits_per_step_sampled": int(sample),
+                   "merges": int(T.n_nb), "flips": int(2 * T.n_b), "features": ACS},
+        "cpu_baseline": {"value": val, "unit": "candidates/s", "cores": cores, "kind": "port",
+                         "sample": "%d of the step's %d splits per GPU + all %d merges/flips, per step; C++ double "
+                                   "restatement of the reference algorithm (reference needs CGAL: not buildable here)"
+                                   % (sample, per_gpu, n_mf)},
+        "e2e": {"value": val, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "lpl": v,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=0, help="override the tessellation size")
+    ap.add_argument("--splits", type=int, default=0, help="override the dummy splits per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="splits per step of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_gpus = args.gpus
+    if world > 1 and world != n_gpus:
+        n_gpus = world
+
+    if args.impl == "reference":
+        run_cpu_reference(args, n_gpus, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import lite_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(lite_b200.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().tolist())
+
+    name, cells, per_gpu = workload(n_gpus, args)
+    t, _tau = lite_b200.generate_crtt(cells, seed=5)   # deterministic: identical on every rank
+    soa = t.export()
+    n_cells = soa.n_cells()
+    n_global = per_gpu * world
+    ctx = lite_b200.Context(local_rank, rank, world, nccl_id)
+    ctx.tess_upload(soa)
+    ctx.energy_set(ACS)
+    nm, nf = ctx.merges_flips()
+    fp64_peak = ctx.measure_fp64_peak()
+    theta = np.array(THETA)
+    per_step_global = n_global + nm + nf
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    def step(k):
+        ctx.merges_flips()
+        ctx.clear_splits()
+        ctx.add_splits_philox(n_global, SEED, k * n_global)
+        return ctx.pl_eval(theta)
+
+    def step_e2e(k):
+        # everything from host buffers: tessellation SoA -> device, energy, candidates, results -> host
+        ctx.tess_upload(soa)
+        ctx.energy_set(ACS)
+        ctx.merges_flips()
+        ctx.clear_splits()
+        ctx.add_splits_philox(n_global, SEED, k * n_global)
+        return ctx.pl_eval(theta)
+
+    # ---- device-resident arm -------------------------------------------------
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    ms_split = ms_reduce = ms_mf = 0.0
+    ctx.timer_mark(0)
+    for k in range(args.steps):
+        lpl, g, H = step(args.warmup + k)
+        a, _b, m = ctx.last_kernel_ms()
+        ms_split += a
+        ms_mf += m
+        ms_reduce += ctx.last_reduce_ms()
+    ctx.timer_mark(1)
+    barrier()
+    ms_total = ctx.timer_elapsed(0, 1)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    if world > 1:
+        tt = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms_step = ms_total / args.steps
+    value = per_step_global / (ms_step * 1e-3)
+
+    # ---- end-to-end arm (host buffers every step) -------------------------------
+    for k in range(3):
+        step_e2e(k)
+    barrier()
+    ctx.timer_mark(2)
+    for k in range(args.steps):
+        step_e2e(args.warmup + k)
+    ctx.timer_mark(3)
+    barrier()
+    ms_e2e = ctx.timer_elapsed(2, 3)
+    if world > 1:
+        tt = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_e2e = float(tt.item())
+    e2e_val = per_step_global / (ms_e2e / args.steps * 1e-3)
+    d = len(ACS)
+    h2d = soa_bytes(soa) + 8 * d + 4 * d
+    d2h = 256 * 8 + 2 * 12 * 8 + 4
+
+    # ---- roofline of the dominant kernel (k_split = sample + clip + delta) -----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    split_s = ms_split / args.steps * 1e-3
+    red_s = ms_reduce / args.steps * 1e-3
+    rate_split = per_gpu / split_s
+    tf = rate_split * F_ALG_SPLIT / 1e12
+    roofline = {
+        "kernel": "k_split (Philox sample + clip + statistic delta, fused K1+K2)",
+        "bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+        "peak_source": "DFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 figure)",
+        "alg_flop_per_candidate": F_ALG_SPLIT, "alg_bytes_per_candidate": B_ALG_SPLIT,
+        "candidates_per_launch": per_gpu, "avg_launch_ms": split_s * 1e3,
+        "hbm_achieved_gbs": rate_split * B_ALG_SPLIT / 1e9,
+        "hbm_frac": rate_split * B_ALG_SPLIT / 1e9 / hbm_peak,
+        "traffic": None,
+    }
+    gbs = per_gpu * B_ALG_REDUCE / red_s / 1e9
+    roofline_reduce = {
+        "kernel": "k_reduce<4> (theta-reduce: value + gradient + Hessian in one pass, K3)",
+        "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+        "peak_source": hbm_src, "alg_bytes_per_candidate": B_ALG_REDUCE,
+        "candidates_per_launch": per_gpu, "avg_launch_ms": red_s * 1e3, "traffic": None,
+    }
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            tr = json.load(open(prof))
+            roofline["traffic"] = tr.get("k_split")
+            roofline_reduce["traffic"] = tr.get("k_reduce")
+        except Exception:
+            pass
+
+    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_cpu as oc
+        arrays = dict(soa.a)
+        arrays["int_length"] = soa.int_length
+        T = oc.Tess(arrays)
+        cores = oc.hardware_threads()
+        sample = args.cpu_sample or max(100_000, 60_000 * cores)
+        oc.pl_pass(T, ACS, THETA, sample // 10, SEED, 0, cores)
+        reps, t0 = 0, time.perf_counter()
+        while True:
+            v_cpu, _, _ = oc.pl_pass(T, ACS, THETA, sample, SEED, reps * sample, cores)
+            reps += 1
+            if time.perf_counter() - t0 > 10.0 or reps >= 20:
+                break
+        dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        oc.pl_pass(T, ACS, THETA, sample // 8, SEED, 0, 1)
+        dt1 = time.perf_counter() - t1
+        cpu = {"value": (sample + nm + nf) * reps / dt, "unit": "candidates/s", "cores": cores, "kind": "port",
+               "sample": "%d passes of %d splits (of the step's %d) + all %d merges/flips, %d threads; C++ double "
+                         "restatement of the reference algorithm (oracle/oracle_cpu.cpp)" % (
+                             reps, sample, per_gpu, nm + nf, cores),
+               "single_thread_value": (sample // 8 + nm + nf) / dt1}
+
+    if rank == 0:
+        line = {
+            "metric": "pl_candidate_moves_evaluated_per_sec", "value": value, "unit": "candidates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": "%s: PL evaluation pass of the sim_acs (ACS, d=4) energy on a %d-cell CRTT tessellation of "
+                            "the unit square (host generator seed 5): all %d merges + %d flips + %d Philox dummy splits "
+                            "per GPU, then value/gradient/Hessian at theta" % (name, n_cells, nm, nf, per_gpu),
+                "cells": n_cells, "splits_per_gpu": per_gpu, "splits_global": n_global, "merges": nm, "flips": nf,
+                "features": ACS, "theta": THETA,
+                "l2": "inputs larger than L2: the per-step statistic block is %d MB per GPU (written by k_split, read "
+                      "by k_reduce); the %0.1f MB tessellation is L2-resident by design; no flush" % (
+                          per_gpu * 32 // 1_000_000, soa_bytes(soa) / 1e6),
+                "sharding": "contiguous shards of the split batch, tessellation replicated, one NCCL allreduce of %d "
+                            "doubles per step" % (1 + d + d * (d + 1) // 2),
+            },
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "candidates/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                    "path": "lite_tess_upload(host SoA) + lite_energy_set + lite_candidates_merges_flips + "
+                            "lite_candidates_add_splits_philox + lite_pl_eval -> host lpl/grad/hess"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "roofline_reduce": roofline_reduce,
+            "kernel_ms_per_step": {"k_split": ms_split / args.steps, "k_reduce_splits": ms_reduce / args.steps,
+                                   "merges_flips": ms_mf / args.steps},
+            "fp64_peak_tflops_measured": fp64_peak,
+            "lpl": lpl,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

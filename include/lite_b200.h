@@ -174,6 +174,13 @@ int lite_debug_fetch(lite_ctx *ctx, int which, int64_t first, int64_t count, voi
 int lite_last_kernel_ms(lite_ctx *ctx, float *add_splits_ms, float *pl_eval_ms,
                         float *merges_flips_ms);
 int64_t lite_kernel_launch_count(lite_ctx *ctx);
+/* Device time (ms) of the split-statistics theta-reduce kernel of the last lite_pl_eval. */
+int lite_last_reduce_ms(lite_ctx *ctx, float *ms);
+/* CUDA-event marks on the context's stream (the stream every kernel of the
+ * context is launched on): mark slot a, do work, mark slot b, read b - a. */
+#define LITE_TIMER_SLOTS 8
+int lite_timer_mark(lite_ctx *ctx, int slot);
+int lite_timer_elapsed(lite_ctx *ctx, int slot_a, int slot_b, float *ms);
 /* Measured DFMA throughput (TFLOP/s) of this GPU: the FP64 roofline denominator. */
 int lite_measure_fp64_peak(lite_ctx *ctx, double *tflops);
 

@@ -33,7 +33,7 @@ SYMBOLS = [
     "lite_candidates_add_splits_philox", "lite_candidates_clear_splits",
     "lite_candidates_count", "lite_pl_eval", "lite_pl_sums", "lite_lines_sample_clip",
     "lite_debug_fetch", "lite_last_kernel_ms", "lite_kernel_launch_count",
-    "lite_measure_fp64_peak",
+    "lite_measure_fp64_peak", "lite_last_reduce_ms", "lite_timer_mark", "lite_timer_elapsed",
 ]
 
 FETCH = dict(SPLIT_E1=0, SPLIT_E2=1, SPLIT_P1=2, SPLIT_P2=3, SPLIT_X=4, SPLIT_ANGLE=5,
@@ -148,6 +148,9 @@ def load_library():
     L.lite_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.lite_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.lite_nccl_unique_id.argtypes = [C.c_void_p]
+    L.lite_last_reduce_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.lite_timer_mark.argtypes = [C.c_void_p, C.c_int]
+    L.lite_timer_elapsed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
     _LIB = L
     return L
 
@@ -293,6 +296,19 @@ class Context:
         a, b, m = C.c_float(), C.c_float(), C.c_float()
         _ck(self.L, self.L.lite_last_kernel_ms(self.h, C.byref(a), C.byref(b), C.byref(m)))
         return a.value, b.value, m.value
+
+    def last_reduce_ms(self):
+        t = C.c_float()
+        _ck(self.L, self.L.lite_last_reduce_ms(self.h, C.byref(t)))
+        return t.value
+
+    def timer_mark(self, slot):
+        _ck(self.L, self.L.lite_timer_mark(self.h, slot))
+
+    def timer_elapsed(self, a, b):
+        t = C.c_float()
+        _ck(self.L, self.L.lite_timer_elapsed(self.h, a, b, C.byref(t)))
+        return t.value
 
     def launch_count(self):
         return int(self.L.lite_kernel_launch_count(self.h))

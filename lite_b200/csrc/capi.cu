@@ -122,8 +122,9 @@ struct lite_ctx {
   DBuf<unsigned int> counter;
   DBuf<unsigned long long> status;  // [0] split no-exit, [1] flip no-exit, [2..3] checksum
   double *h_pinned = nullptr;       // pinned staging for results
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  float ms_split = 0, ms_eval = 0, ms_mf = 0;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t tev[LITE_TIMER_SLOTS] = {};  // user timer marks (lite_timer_mark)
+  float ms_split = 0, ms_eval = 0, ms_mf = 0, ms_reduce = 0;
   bool ev01 = false;  // ev[0]/ev[1] have been recorded
   std::vector<uint8_t> h_he_inside;
   int sm_count = 148;
@@ -159,7 +160,8 @@ extern "C" int lite_ctx_create(lite_ctx **out, int device, int rank, int world_s
   lite_ctx *c = new lite_ctx();
   c->device = device; c->rank = rank; c->world = world_size;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 6; i++) CU(cudaEventCreate(&c->ev[i]));
+  for (int i = 0; i < 8; i++) CU(cudaEventCreate(&c->ev[i]));
+  for (int i = 0; i < LITE_TIMER_SLOTS; i++) CU(cudaEventCreate(&c->tev[i]));
   CU(cudaMallocHost((void **)&c->h_pinned, 4096 * sizeof(double)));
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
@@ -186,7 +188,8 @@ extern "C" int lite_ctx_destroy(lite_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < LITE_TIMER_SLOTS; i++) if (c->tev[i]) cudaEventDestroy(c->tev[i]);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   // DBuf members are released explicitly (no destructors: keep the struct POD-like)
   c->vx.release(); c->vy.release(); c->he_length.release();
@@ -642,8 +645,10 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
   long n = (long)c->n_local;
   int grid = (int)((n + 1023) / 1024);
   if (grid > maxgrid) grid = maxgrid;
+  CU(cudaEventRecord(c->ev[6], c->stream));
   if (n > 0) reduce_dispatch(c, d, c->stat.p, c->cap, n, th, grid < 1 ? 1 : grid, c->red_out.p);
   else CU(cudaMemsetAsync(c->red_out.p, 0, 128 * sizeof(double), c->stream));
+  CU(cudaEventRecord(c->ev[7], c->stream));
   // flips (replicated on every rank; cheap)
   long nf = 2L * c->n_b;
   if (nf > 0) {
@@ -662,6 +667,7 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
   cudaEventElapsedTime(&c->ms_eval, c->ev[2], c->ev[3]);
+  cudaEventElapsedTime(&c->ms_reduce, c->ev[6], c->ev[7]);
   if (c->ev01) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->ms_split = ms; }
   const double *S = c->h_pinned, *F = c->h_pinned + 128;
   // lib/ttessel.cpp:3396: int_length/(pi*|S|)
@@ -774,6 +780,28 @@ extern "C" int lite_last_kernel_ms(lite_ctx *c, float *a, float *b, float *m) {
   if (a) *a = c->ms_split;
   if (b) *b = c->ms_eval;
   if (m) *m = c->ms_mf;
+  return 0;
+}
+
+extern "C" int lite_last_reduce_ms(lite_ctx *c, float *ms) {
+  if (!c || !ms) return fail(LITE_EINVAL, "null argument");
+  *ms = c->ms_reduce;
+  return 0;
+}
+
+extern "C" int lite_timer_mark(lite_ctx *c, int slot) {
+  if (!c || slot < 0 || slot >= LITE_TIMER_SLOTS) return fail(LITE_EINVAL, "bad timer slot");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventRecord(c->tev[slot], c->stream));
+  return 0;
+}
+
+extern "C" int lite_timer_elapsed(lite_ctx *c, int slot_a, int slot_b, float *ms) {
+  if (!c || !ms || slot_a < 0 || slot_a >= LITE_TIMER_SLOTS || slot_b < 0 || slot_b >= LITE_TIMER_SLOTS)
+    return fail(LITE_EINVAL, "bad timer slot");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(c->tev[slot_b]));
+  CU(cudaEventElapsedTime(ms, c->tev[slot_a], c->tev[slot_b]));
   return 0;
 }
 
