@@ -110,7 +110,8 @@ class TessSoA:
 
 
 def lib_path():
-    return os.path.join(_HERE, "libliteb200.so")
+    # LITE_B200_LIB selects another build of the same library (kernel tuning experiments)
+    return os.environ.get("LITE_B200_LIB") or os.path.join(_HERE, "libliteb200.so")
 
 
 _LIB = None

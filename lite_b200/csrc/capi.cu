@@ -89,6 +89,7 @@ struct lite_ctx {
   ncclComm_t comm = nullptr;
   bool have_tess = false, have_prog = false, have_mf = false;
   bool record = false;
+  bool rev = false;  // direction of the next theta-reduce pass over the split statistics
   int64_t launches = 0;
   // raw SoA
   DBuf<double> vx, vy, he_length;
@@ -97,9 +98,10 @@ struct lite_ctx {
   DBuf<int> f_off, f_cnt, f_list, seg_he_start, seg_he_end, seg_n_edges, nb_list, b_list;
   // derived
   DBuf<double2> pt;
-  DBuf<double> ang, len, ca, f_area, f_perim, f_sumang, f_minang, cum;
+  DBuf<double> ang, len, ca, f_area, f_perim, f_sumang, f_minang, cum, pre, plen, f_tot2;
+  DBuf<int2> sfo;
   DBuf<uint32_t> flg;
-  DBuf<int> slot_he, slot_seg, slot_face, he_slot, cum_he, err;
+  DBuf<int> slot_he, slot_seg, slot_face, he_slot, guide, err;
   TessDev T{};
   int n_nb = 0, n_b = 0;
   double int_length = 0;
@@ -199,9 +201,9 @@ extern "C" int lite_ctx_destroy(lite_ctx *c) {
   c->f_off.release(); c->f_cnt.release(); c->f_list.release(); c->seg_he_start.release();
   c->seg_he_end.release(); c->seg_n_edges.release(); c->nb_list.release(); c->b_list.release();
   c->pt.release(); c->ang.release(); c->len.release(); c->ca.release(); c->f_area.release();
-  c->f_perim.release(); c->f_sumang.release(); c->f_minang.release(); c->cum.release();
+  c->f_perim.release(); c->f_sumang.release(); c->f_minang.release(); c->cum.release(); c->pre.release(); c->plen.release(); c->f_tot2.release(); c->sfo.release();
   c->flg.release(); c->slot_he.release(); c->slot_seg.release(); c->slot_face.release();
-  c->he_slot.release(); c->cum_he.release(); c->err.release();
+  c->he_slot.release(); c->guide.release(); c->err.release();
   c->stat.release(); c->r_e1.release(); c->r_e2.release(); c->in_he.release();
   c->r_p1.release(); c->r_p2.release(); c->r_x.release(); c->r_angle.release(); c->r_u.release();
   c->in_x.release(); c->in_angle.release();
@@ -253,11 +255,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
       listed += s->face_he_count[f];
     }
   }
-  std::vector<double> cum;
-  std::vector<int> cum_he;
-  cum.reserve(nH); cum_he.reserve(nH);
   c->h_he_inside.assign(nH, 0);
-  double cl = 0.0;
   int64_t inside_he = 0;
   for (int h = 0; h < nH; h++) {
     int f = s->he_face[h], t = s->he_twin[h];
@@ -267,9 +265,20 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
     if (!s->face_inside[f]) continue;
     inside_he++;
     c->h_he_inside[h] = 1;
-    cl += s->he_length[h];  // cumlen += e->get_length(), lib/ttessel.cpp:1980
-    cum.push_back(cl);
-    cum_he.push_back(h);
+  }
+  // cumulative halfedge lengths of the sampler (cumlen += e->get_length(),
+  // lib/ttessel.cpp:1980), accumulated in SLOT order: faces in index order, each
+  // face in ccb order from outer_ccb().  Entry m of `cum` is slot m.
+  std::vector<double> cum((size_t)s->n_face_he, 0.0);
+  double cl = 0.0;
+  for (int f = 0; f < nF; f++) {
+    const int off = s->face_he_offset[f], cnt = s->face_he_count[f];
+    for (int k = 0; k < cnt; k++) {
+      const int h = s->face_he_list[off + k];
+      if (h < 0 || h >= nH) return fail(LITE_EINVAL, "face %d: halfedge id out of range", f);
+      if (s->face_inside[f]) cl += s->he_length[h];
+      cum[off + k] = cl;
+    }
   }
   if (inside_he != listed)
     return fail(LITE_EINVAL,
@@ -303,13 +312,26 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   r |= up(c, c->seg_n_edges, s->seg_n_edges, nS); r |= up(c, c->seg_bnd, s->seg_on_boundary, nS);
   r |= up(c, c->nb_list, s->non_blocking, s->n_non_blocking);
   r |= up(c, c->b_list, s->blocking, s->n_blocking);
-  r |= up(c, c->cum, cum.data(), cum.size()); r |= up(c, c->cum_he, cum_he.data(), cum_he.size());
+  // guide table: guide[b] = first slot m with cum[m] > b * cl / n_guide
+  int n_guide = 1;
+  while (n_guide < 2 * s->n_face_he) n_guide <<= 1;
+  std::vector<int> guide((size_t)n_guide);
+  {
+    size_t m = 0;
+    for (int b = 0; b < n_guide; b++) {
+      const double lo = (double)b * (cl / (double)n_guide);
+      while (m + 1 < cum.size() && cum[m] <= lo) m++;
+      guide[b] = (int)m;
+    }
+  }
+  r |= up(c, c->cum, cum.data(), cum.size()); r |= up(c, c->guide, guide.data(), guide.size());
   if (r) return LITE_ECUDA;
   const size_t nSl = (size_t)s->n_face_he;
   if (c->pt.alloc(nSl) || c->ang.alloc(nSl) || c->len.alloc(nSl) || c->ca.alloc(nSl) ||
       c->flg.alloc(nSl) || c->slot_he.alloc(nSl) || c->slot_seg.alloc(nSl) ||
       c->slot_face.alloc(nSl) || c->he_slot.alloc(nH) || c->f_area.alloc(nF) ||
-      c->f_perim.alloc(nF) || c->f_sumang.alloc(nF) || c->f_minang.alloc(nF))
+      c->f_perim.alloc(nF) || c->f_sumang.alloc(nF) || c->f_minang.alloc(nF) || c->pre.alloc(nSl) ||
+      c->plen.alloc(nSl) || c->f_tot2.alloc(nF) || c->sfo.alloc(nSl))
     return LITE_ECUDA;
   CU(cudaMemsetAsync(c->he_slot.p, 0xFF, nH * sizeof(int), c->stream));
   CU(cudaMemsetAsync(c->err.p, 0, sizeof(int), c->stream));
@@ -332,11 +354,14 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   T.f_area = c->f_area.p; T.f_perim = c->f_perim.p; T.f_sumang = c->f_sumang.p; T.f_minang = c->f_minang.p;
   T.seg_n_edges = c->seg_n_edges.p; T.seg_he_start = c->seg_he_start.p; T.seg_he_end = c->seg_he_end.p;
   T.seg_bnd = c->seg_bnd.p;
-  T.cum = c->cum.p; T.cum_he = c->cum_he.p; T.n_cum = (int)cum.size(); T.total_len = cl;
+  T.cum = c->cum.p; T.guide = c->guide.p; T.n_cum = (int)cum.size(); T.n_guide = n_guide;
+  T.total_len = cl; T.guide_scale = (double)n_guide / cl;
+  T.sfo = c->sfo.p; T.pre = c->pre.p; T.plen = c->plen.p; T.f_tot2 = c->f_tot2.p;
   int tb = 128, gb = (nF + tb - 1) / tb;
   k_prep_slots<<<gb, tb, 0, c->stream>>>(A);
   // outside faces: count 0 in the device view
-  k_prep_faces<<<gb, tb, 0, c->stream>>>(T, c->ca.p, c->f_area.p, c->f_perim.p, c->f_sumang.p, c->f_minang.p);
+  k_prep_faces<<<gb, tb, 0, c->stream>>>(T, c->ca.p, c->f_area.p, c->f_perim.p, c->f_sumang.p, c->f_minang.p,
+                                         c->pre.p, c->plen.p, c->f_tot2.p, c->sfo.p);
   c->launches += 2;
   int herr = 0;
   CU(cudaMemcpyAsync(&herr, c->err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -398,16 +423,13 @@ extern "C" int lite_candidates_merges_flips(lite_ctx *c, int32_t *n_merges, int3
     return LITE_ECUDA;
   CU(cudaMemsetAsync(c->sums.p, 0, 2 * LITE_MAX_D * sizeof(double), c->stream));
   CU(cudaEventRecord(c->ev[4], c->stream));
-  if (nm) {
-    k_merges<<<(nm + 127) / 128, 128, 0, c->stream>>>(c->T, c->G, c->nb_list.p, nm, c->mstat.p, (size_t)nm, c->m_he.p);
-    k_colsum<<<d, 256, 0, c->stream>>>(c->mstat.p, (size_t)nm, nm, c->sums.p);
-    c->launches += 2;
-  }
-  if (nf) {
-    k_flips<<<(nf + 127) / 128, 128, 0, c->stream>>>(c->T, c->G, c->b_list.p, c->n_b, c->fstat.p, (size_t)nf,
-                                                     c->fl_e1.p, c->fl_e2.p, c->fl_p2.p, c->fl_right.p,
-                                                     c->status.p + 1);
-    k_colsum<<<d, 256, 0, c->stream>>>(c->fstat.p, (size_t)nf, nf, c->sums.p + LITE_MAX_D);
+  if (nm + nf > 0) {
+    MFArgs A{};
+    A.nb_seg = c->nb_list.p; A.nm = nm; A.mstat = c->mstat.p; A.m_he = c->m_he.p; A.gm = (nm + 127) / 128;
+    A.b_seg = c->b_list.p; A.nb = c->n_b; A.fstat = c->fstat.p; A.f_e1 = c->fl_e1.p; A.f_e2 = c->fl_e2.p;
+    A.f_right = c->fl_right.p; A.f_p2 = c->fl_p2.p; A.status = c->status.p + 1;
+    k_merges_flips<<<A.gm + (nf + 127) / 128, 128, 0, c->stream>>>(c->T, c->G, A);
+    k_colsum2<<<dim3(d, 2), 1024, 0, c->stream>>>(c->mstat.p, nm, c->fstat.p, nf, c->sums.p);
     c->launches += 2;
   }
   CU(cudaEventRecord(c->ev[5], c->stream));
@@ -467,8 +489,8 @@ static int grow_splits(lite_ctx *c, int64_t add) {
 }
 
 static int split_grid(lite_ctx *c, int64_t n) {
-  int64_t blocks = (n + 255) / 256;
-  int64_t maxb = (int64_t)c->sm_count * 16;
+  int64_t blocks = (n + LITE_SPLIT_TB - 1) / LITE_SPLIT_TB;
+  int64_t maxb = (int64_t)c->sm_count * LITE_SPLIT_MINB * 8;
   if (blocks > maxb) blocks = maxb;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -504,11 +526,11 @@ extern "C" int lite_candidates_add_splits_given(lite_ctx *c, int64_t n, const in
   CU(cudaMemcpyAsync(c->in_angle.p, angle, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   SplitArgs A{};
   fill_split_args(c, A);
-  A.n_local = n; A.j0 = 0; A.n_batch = n_global_total;
+  A.n_local = n; A.j0 = 0; A.sel_step = 0;
   A.in_he = c->in_he.p; A.in_x = c->in_x.p; A.in_angle = c->in_angle.p;
   int g = split_grid(c, n);
-  if (c->record) k_split<4 | 2><<<g, 256, 0, c->stream>>>(c->T, c->G, A);
-  else k_split<4><<<g, 256, 0, c->stream>>>(c->T, c->G, A);
+  if (c->record) k_split<4 | 2><<<g, LITE_SPLIT_TB, 0, c->stream>>>(c->T, c->G, A);
+  else k_split<4><<<g, LITE_SPLIT_TB, 0, c->stream>>>(c->T, c->G, A);
   c->launches += 1;
   CU(cudaEventRecord(c->ev[1], c->stream));
   c->ev01 = true;
@@ -539,16 +561,17 @@ extern "C" int lite_candidates_add_splits_philox(lite_ctx *c, int64_t n_global, 
     if (r) return r;
     SplitArgs A{};
     fill_split_args(c, A);
-    A.n_local = n; A.j0 = j0; A.n_batch = n_global; A.seed = seed; A.ctr0 = offset;
+    A.n_local = n; A.j0 = j0; A.sel_step = c->T.total_len / (double)n_global; A.seed = seed; A.ctr0 = offset;
     int g = split_grid(c, n);
     CU(cudaEventRecord(c->ev[0], c->stream));
-    if (c->record) k_split<4 | 2 | 1><<<g, 256, 0, c->stream>>>(c->T, c->G, A);
-    else k_split<4 | 1><<<g, 256, 0, c->stream>>>(c->T, c->G, A);
+    if (c->record) k_split<4 | 2 | 1><<<g, LITE_SPLIT_TB, 0, c->stream>>>(c->T, c->G, A);
+    else k_split<4 | 1><<<g, LITE_SPLIT_TB, 0, c->stream>>>(c->T, c->G, A);
     c->launches += 1;
     CU(cudaEventRecord(c->ev[1], c->stream));
   c->ev01 = true;
   }
   c->n_local += n; c->n_global += n_global;
+  c->rev = false;  // k_split wrote the tail last: the next reduce starts from it
   return 0;
 }
 
@@ -574,11 +597,11 @@ extern "C" int lite_lines_sample_clip(lite_ctx *c, int64_t n_global, uint64_t se
     SplitArgs A{};
     fill_split_args(c, A);
     A.base = 0;
-    A.n_local = n; A.j0 = j0; A.n_batch = n_global; A.seed = seed; A.ctr0 = offset;
+    A.n_local = n; A.j0 = j0; A.sel_step = c->T.total_len / (double)n_global; A.seed = seed; A.ctr0 = offset;
     int g = split_grid(c, n);
     CU(cudaEventRecord(c->ev[0], c->stream));
-    if (mode == 1) k_split<8 | 2 | 1><<<g, 256, 0, c->stream>>>(c->T, G0, A);
-    else k_split<8 | 1><<<g, 256, 0, c->stream>>>(c->T, G0, A);
+    if (mode == 1) k_split<8 | 2 | 1><<<g, LITE_SPLIT_TB, 0, c->stream>>>(c->T, G0, A);
+    else k_split<8 | 1><<<g, LITE_SPLIT_TB, 0, c->stream>>>(c->T, G0, A);
     c->launches += 1;
     CU(cudaEventRecord(c->ev[1], c->stream));
   c->ev01 = true;
@@ -605,25 +628,25 @@ extern "C" int lite_candidates_count(lite_ctx *c, int64_t *nl, int64_t *ng) {
 }
 
 template <int D>
-static void launch_reduce(lite_ctx *c, const double *stat, size_t cap, long n, const Theta &th,
+static void launch_reduce(lite_ctx *c, const double *stat, size_t cap, long n, int rev, const Theta &th,
                           int grid, double *out) {
-  k_reduce<D><<<grid, 256, 0, c->stream>>>(stat, cap, n, th, c->partials.p, c->counter.p, out);
+  k_reduce<D><<<grid, 256, 0, c->stream>>>(stat, cap, n, rev, th, c->partials.p, c->counter.p, out);
 }
-static void reduce_dispatch(lite_ctx *c, int d, const double *stat, size_t cap, long n,
+static void reduce_dispatch(lite_ctx *c, int d, const double *stat, size_t cap, long n, int rev,
                             const Theta &th, int grid, double *out) {
   switch (d) {
-    case 1: launch_reduce<1>(c, stat, cap, n, th, grid, out); break;
-    case 2: launch_reduce<2>(c, stat, cap, n, th, grid, out); break;
-    case 3: launch_reduce<3>(c, stat, cap, n, th, grid, out); break;
-    case 4: launch_reduce<4>(c, stat, cap, n, th, grid, out); break;
-    case 5: launch_reduce<5>(c, stat, cap, n, th, grid, out); break;
-    case 6: launch_reduce<6>(c, stat, cap, n, th, grid, out); break;
-    case 7: launch_reduce<7>(c, stat, cap, n, th, grid, out); break;
-    case 8: launch_reduce<8>(c, stat, cap, n, th, grid, out); break;
-    case 9: launch_reduce<9>(c, stat, cap, n, th, grid, out); break;
-    case 10: launch_reduce<10>(c, stat, cap, n, th, grid, out); break;
-    case 11: launch_reduce<11>(c, stat, cap, n, th, grid, out); break;
-    case 12: launch_reduce<12>(c, stat, cap, n, th, grid, out); break;
+    case 1: launch_reduce<1>(c, stat, cap, n, rev, th, grid, out); break;
+    case 2: launch_reduce<2>(c, stat, cap, n, rev, th, grid, out); break;
+    case 3: launch_reduce<3>(c, stat, cap, n, rev, th, grid, out); break;
+    case 4: launch_reduce<4>(c, stat, cap, n, rev, th, grid, out); break;
+    case 5: launch_reduce<5>(c, stat, cap, n, rev, th, grid, out); break;
+    case 6: launch_reduce<6>(c, stat, cap, n, rev, th, grid, out); break;
+    case 7: launch_reduce<7>(c, stat, cap, n, rev, th, grid, out); break;
+    case 8: launch_reduce<8>(c, stat, cap, n, rev, th, grid, out); break;
+    case 9: launch_reduce<9>(c, stat, cap, n, rev, th, grid, out); break;
+    case 10: launch_reduce<10>(c, stat, cap, n, rev, th, grid, out); break;
+    case 11: launch_reduce<11>(c, stat, cap, n, rev, th, grid, out); break;
+    case 12: launch_reduce<12>(c, stat, cap, n, rev, th, grid, out); break;
   }
   c->launches += 1;
 }
@@ -638,15 +661,16 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
   const int NT = 1 + d + d * (d + 1) / 2;
   Theta th{};
   for (int i = 0; i < d; i++) th.v[i] = theta[i];
-  const int maxgrid = c->sm_count * 4;
+  const int maxgrid = c->sm_count * 2;
   if (c->partials.alloc((size_t)maxgrid * NT) || c->red_out.alloc(2 * 128)) return LITE_ECUDA;
   CU(cudaEventRecord(c->ev[2], c->stream));
   // splits (this rank's shard)
   long n = (long)c->n_local;
-  int grid = (int)((n + 1023) / 1024);
+  int grid = (int)((n + 2047) / 2048);
   if (grid > maxgrid) grid = maxgrid;
+  c->rev = !c->rev;  // boustrophedon: the end the previous pass (or k_split) touched last is still in L2
   CU(cudaEventRecord(c->ev[6], c->stream));
-  if (n > 0) reduce_dispatch(c, d, c->stat.p, c->cap, n, th, grid < 1 ? 1 : grid, c->red_out.p);
+  if (n > 0) reduce_dispatch(c, d, c->stat.p, c->cap, n, c->rev ? 1 : 0, th, grid < 1 ? 1 : grid, c->red_out.p);
   else CU(cudaMemsetAsync(c->red_out.p, 0, 128 * sizeof(double), c->stream));
   CU(cudaEventRecord(c->ev[7], c->stream));
   // flips (replicated on every rank; cheap)
@@ -654,7 +678,7 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
   if (nf > 0) {
     int gf = (int)((nf + 1023) / 1024);
     if (gf > maxgrid) gf = maxgrid;
-    reduce_dispatch(c, d, c->fstat.p, (size_t)nf, nf, th, gf < 1 ? 1 : gf, c->red_out.p + 128);
+    reduce_dispatch(c, d, c->fstat.p, (size_t)nf, nf, 0, th, gf < 1 ? 1 : gf, c->red_out.p + 128);
   } else {
     CU(cudaMemsetAsync(c->red_out.p + 128, 0, 128 * sizeof(double), c->stream));
   }

@@ -39,19 +39,24 @@ struct TessDev {
   const double *ca;    // interior angle at the source vertex (corners only)
   const uint32_t *flg; // SF_*
   const int *slot_he, *slot_seg, *slot_face;
+  const int2 *sfo;     // (offset, count) of the slot's face: saves the slot->face->offset chain
+  const double *pre;   // prefix shoelace sum: sum_{i<k} cross(V_i-O, V_{i+1}-O), O = first vertex of the face
+  const double *plen;  // prefix sum of the halfedge lengths inside the face
   // per halfedge
   const int *he_slot, *he_twin, *he_src, *he_next_hf, *he_prev_hf;
   // per face
   const int *f_off, *f_cnt;
   const double *f_area, *f_perim, *f_sumang, *f_minang;
+  const double *f_tot2;  // whole-face shoelace sum (twice the area) by the same prefix summation
   // per segment
   const int *seg_n_edges, *seg_he_start, *seg_he_end;
   const uint8_t *seg_bnd;
-  // length-weighted sampling (inside halfedges in container order)
+  // length-weighted sampling: cumulative halfedge lengths in SLOT order (slot m
+  // ends at cum[m]); guide[b] = first m with cum[m] > b*total_len/n_guide
   const double *cum;
-  const int *cum_he;
-  int n_cum;
-  double total_len;
+  const int *guide;
+  int n_cum, n_guide;
+  double total_len, guide_scale;  // guide_scale = n_guide/total_len
 };
 
 struct Prog {
@@ -100,6 +105,10 @@ __host__ __device__ inline double u53(uint32_t hi, uint32_t lo) {
 __device__ __forceinline__ double2 ldpt(const double2 *p, int i) { return __ldg(p + i); }
 __device__ __forceinline__ double cross2(double ax, double ay, double bx, double by) {
   return ax * by - ay * bx;
+}
+__device__ __forceinline__ double plen(double2 a, double2 b) {
+  double x = b.x - a.x, y = b.y - a.y;
+  return sqrt(x * x + y * y);
 }
 __device__ __forceinline__ double wrap_pi(double d) {
   // to (-pi, pi]
@@ -208,10 +217,21 @@ __device__ inline void add_face_feats(const Prog &G, double *acc, double sign, c
     }
   }
 }
+// features of an unmodified face of the tessellation: precomputed by k_prep_faces in
+// face2poly order, so a deleted parent face costs four loads instead of a polygon walk
+__device__ __forceinline__ FaceFeat parent_feat(const TessDev &T, int f) {
+  FaceFeat r;
+  r.area = __ldg(T.f_area + f); r.perim = __ldg(T.f_perim + f);
+  r.sumang = __ldg(T.f_sumang + f); r.minang = __ldg(T.f_minang + f);
+  return r;
+}
 #define MASK_FACE_ANG ((1u << LITE_FEAT_FACE_SUM_OF_ANGLES) | (1u << LITE_FEAT_MIN_ANGLE))
 #define MASK_FACE_ANY                                                                     \
   ((1u << LITE_FEAT_FACE_NUMBER) | (1u << LITE_FEAT_FACE_AREA_2) |                        \
    (1u << LITE_FEAT_FACE_PERIMETER) | (1u << LITE_FEAT_FACE_SHAPE) | MASK_FACE_ANG)
+#define MASK_FACE_AREA ((1u << LITE_FEAT_FACE_AREA_2) | (1u << LITE_FEAT_FACE_SHAPE))
+#define MASK_NEED_D01                                                                     \
+  ((1u << LITE_FEAT_FACE_PERIMETER) | (1u << LITE_FEAT_FACE_SHAPE) | (1u << LITE_FEAT_EDGE_LENGTH_INTERNAL))
 #define MASK_FACE_GEOM                                                                    \
   ((1u << LITE_FEAT_FACE_AREA_2) | (1u << LITE_FEAT_FACE_SHAPE) | (1u << LITE_FEAT_MIN_ANGLE))
 
@@ -263,12 +283,27 @@ __global__ void k_prep_slots(PrepArgs A) {
 }
 
 __global__ void k_prep_faces(TessDev T, double *ca, double *f_area, double *f_perim,
-                             double *f_sumang, double *f_minang) {
+                             double *f_sumang, double *f_minang, double *pre, double *plen,
+                             double *f_tot2, int2 *sfo) {
   int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= T.n_faces) return;
   int n = T.f_cnt[f];
   if (n == 0) return;
   int off = T.f_off[f];
+  {  // prefix sums used by the O(1) child-area / child-perimeter formulas of split_eval
+    double2 O = ldpt(T.pt, off), Vk = O;
+    double acc = 0, lacc = 0;
+    for (int k = 0; k < n; k++) {
+      double2 Vn = ldpt(T.pt, off + (k + 1 == n ? 0 : k + 1));
+      pre[off + k] = acc;
+      plen[off + k] = lacc;
+      sfo[off + k] = make_int2(off, n);
+      acc += cross2(Vk.x - O.x, Vk.y - O.y, Vn.x - O.x, Vn.y - O.y);
+      lacc += T.len[off + k];
+      Vk = Vn;
+    }
+    f_tot2[f] = acc;
+  }
   // corner angles at slot sources
   for (int k = 0; k < n; k++) {
     double a = LITE_PI;
@@ -321,101 +356,181 @@ __device__ __forceinline__ int ray_exit(const TessDev &T, int off, int n, double
   return k2;
 }
 
+// out-of-line copy for the rare multi-crossing case of split_eval (keeps its registers down)
+__device__ __noinline__ int ray_exit_rare(const TessDev &T, int off, int n, double a, double b,
+                                          double w, double2 p, double dx, double dy, int skip0,
+                                          int skip1, double2 &hit) {
+  return ray_exit(T, off, n, a, b, w, p, dx, dy, skip0, skip1, hit);
+}
+
 // ---------------------------------------------------------------------------
 // K1+K2: one split candidate  (Split ctor + modified_elements + statistic_variation)
+//
+// Cost model: everything after the crossed-edge search is O(1) in the face size.
+// The child areas and perimeters come from per-face prefix sums (pre/plen, built
+// once per tessellation by k_prep_faces) instead of walking the two children;
+// only min_angle still walks the parent's corners.
 // ---------------------------------------------------------------------------
 struct SplitOut {
   int e2;       // halfedge id, -1 if no exit was found
   double2 p1, p2;
 };
 
+// sum of a prefix array over slots i, i+1, .., j-1 (cyclic, empty when i == j)
+__device__ __forceinline__ double chain(const double *pre, double tot, int off, int i, int j) {
+  double a = __ldg(pre + off + j) - __ldg(pre + off + i);
+  return (j >= i) ? a : a + tot;
+}
+
 template <bool WITH_STAT>
-__device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, int h, double x,
-                                           double angle, double *st /* d, negated */,
-                                           SplitOut &o) {
-  int s1 = T.he_slot[h];
-  int f = T.slot_face[s1];
-  int off = T.f_off[f], n = T.f_cnt[f];
-  int k1 = s1 - off;
-  int k1n = (k1 + 1 == n) ? 0 : k1 + 1;
-  double2 P = ldpt(T.pt, s1), Q = ldpt(T.pt, off + k1n);
-  double ang1 = T.ang[s1];
+__device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, int s1, double x,
+                                           double angle, double *__restrict__ stat_col0,
+                                           size_t cap, SplitOut &o) {
+  const int2 fo = __ldg(T.sfo + s1);
+  const int off = fo.x, n = fo.y;
+  const int k1 = s1 - off;
+  const int k1n = (k1 + 1 == n) ? 0 : k1 + 1;
+  const double2 P = ldpt(T.pt, s1), Q = ldpt(T.pt, off + k1n);
+  const double ang1 = __ldg(T.ang + s1);
   // lib/ttessel.cpp:2094-2105, evaluated as the reference does (no contraction)
-  double l = ang1 + angle;
+  const double l = ang1 + angle;
   double a, c;
   sincos(l, &a, &c);
-  double b = -c;
-  double u = __dadd_rn(__dmul_rn(a, P.x), __dmul_rn(b, P.y));
-  double v = __dadd_rn(__dmul_rn(a, Q.x), __dmul_rn(b, Q.y));
-  double w = __dadd_rn(u, __dmul_rn(x, __dadd_rn(v, -u)));
+  const double b = -c;
+  const double u = __dadd_rn(__dmul_rn(a, P.x), __dmul_rn(b, P.y));
+  const double v = __dadd_rn(__dmul_rn(a, Q.x), __dmul_rn(b, Q.y));
+  const double w = __dadd_rn(u, __dmul_rn(x, __dadd_rn(v, -u)));
   // p1 = e1 ∩ line(a,b,-w)   (:2110)
-  double sP = fma(a, P.x, fma(b, P.y, -w)), sQ = fma(a, Q.x, fma(b, Q.y, -w));
-  double t1 = sP / (sP - sQ);
-  double2 p1 = make_double2(fma(t1, Q.x - P.x, P.x), fma(t1, Q.y - P.y, P.y));
+  const double sP = fma(a, P.x, fma(b, P.y, -w)), sQ = fma(a, Q.x, fma(b, Q.y, -w));
+  const double t1 = sP / (sP - sQ);
+  const double2 p1 = make_double2(fma(t1, Q.x - P.x, P.x), fma(t1, Q.y - P.y, P.y));
   // ray direction (:2121-2127): Line_2(a,b,c) has direction (b,-a)
   double dx, dy;
   if (sQ < 0.0) { dx = b; dy = -a; } else { dx = -b; dy = a; }
-  int skip1 = (x == 0.0) ? (k1 == 0 ? n - 1 : k1 - 1) : -1;
+  const int skip1 = (x == 0.0) ? (k1 == 0 ? n - 1 : k1 - 1) : -1;
+
+  // crossed-edge search (ray_exit_face, :4515-4576).  A vertex is classified once
+  // by the sign of its residual, so the scan is watertight.  In a convex face
+  // exactly one halfedge other than e1 crosses the line; anything else (the ray
+  // passes through a vertex) takes the general loop, which keeps the reference's
+  // first-of-equal-distances rule.
+  int cnt = 0, k2 = -1;
+  {
+    const double2 V0 = ldpt(T.pt, off);
+    const double s0 = fma(a, V0.x, fma(b, V0.y, -w));
+    double sk = s0;
+#pragma unroll 4
+    for (int k = 1; k < n; k++) {
+      const double2 Vn = ldpt(T.pt, off + k);
+      const double sn = fma(a, Vn.x, fma(b, Vn.y, -w));
+      const bool cr = ((sk <= 0.0 && sn >= 0.0) || (sk >= 0.0 && sn <= 0.0)) && sk != sn;
+      if (cr && (k - 1) != k1 && (k - 1) != skip1) { if (cnt == 0) k2 = k - 1; cnt++; }
+      sk = sn;
+    }
+    const bool cr = ((sk <= 0.0 && s0 >= 0.0) || (sk >= 0.0 && s0 <= 0.0)) && sk != s0;
+    if (cr && (n - 1) != k1 && (n - 1) != skip1) { if (cnt == 0) k2 = n - 1; cnt++; }
+  }
   double2 p2 = make_double2(0.0, 0.0);
-  int k2 = ray_exit(T, off, n, a, b, w, p1, dx, dy, k1, skip1, p2);
+  if (cnt == 1) {
+    const int k2n_ = (k2 + 1 == n) ? 0 : k2 + 1;
+    const double2 Vk = ldpt(T.pt, off + k2), Vn = ldpt(T.pt, off + k2n_);
+    const double sk = fma(a, Vk.x, fma(b, Vk.y, -w)), sn = fma(a, Vn.x, fma(b, Vn.y, -w));
+    const double sg = sk / (sk - sn);
+    const double X = fma(sg, Vn.x - Vk.x, Vk.x), Y = fma(sg, Vn.y - Vk.y, Vk.y);
+    const double rx = X - p1.x, ry = Y - p1.y;
+    if (rx * dx + ry * dy >= 0.0 && sqrt(rx * rx + ry * ry) != 0.0) p2 = make_double2(X, Y);
+    else k2 = -1;
+  } else if (cnt > 1) {
+    k2 = ray_exit_rare(T, off, n, a, b, w, p1, dx, dy, k1, skip1, p2);
+  }
   o.p1 = p1; o.p2 = p2;
   if (k2 < 0 || !(sP != sQ)) {
     o.e2 = -1;
-    if (WITH_STAT) for (int i = 0; i < G.d; i++) st[i] = 0.0;
+    if (WITH_STAT) for (int i = 0; i < G.d; i++) stat_col0[(size_t)i * cap] = 0.0;
     return;
   }
   o.e2 = T.slot_he[off + k2];
   if (!WITH_STAT) return;
 
-  int k2n = (k2 + 1 == n) ? 0 : k2 + 1;
-  uint32_t fl1 = T.flg[s1], fl2 = T.flg[off + k2];
-  bool bnd1 = fl1 & SF_BND, bnd2 = fl2 & SF_BND;
-  double d01x = p2.x - p1.x, d01y = p2.y - p1.y;
-  double d01 = sqrt(d01x * d01x + d01y * d01y);
+  const int k2n = (k2 + 1 == n) ? 0 : k2 + 1;
+  const uint32_t fl1 = __ldg(T.flg + s1), fl2 = __ldg(T.flg + off + k2);
+  const bool bnd1 = fl1 & SF_BND, bnd2 = fl2 & SF_BND;
+  const double d01x = p2.x - p1.x, d01y = p2.y - p1.y;
 
-  // children geometry (polygon_insert_edge, :4600-4631):
+  // children (polygon_insert_edge, :4600-4631):
   //   C1 = [p1, p2, V(k2+1) .. V(k1)],  C2 = [p2, p1, V(k1+1) .. V(k2)]
-  double A1 = 0, A2 = 0, L1 = 0, L2 = 0, m1 = CUDART_INF, m2 = CUDART_INF;
-  if (G.mask & MASK_FACE_GEOM) {
-    int k = k1n;
-    double2 Vk = (k == k1n) ? Q : ldpt(T.pt, off + k);
-    double rx = Vk.x - p1.x, ry = Vk.y - p1.y;
-    L2 = d01 + sqrt(rx * rx + ry * ry);
-    double acc = 0;
-    while (true) {
-      if (T.flg[off + k] & SF_CORNER) m2 = fmin(m2, T.ca[off + k]);
+  //
+  // The child with fewer parent vertices is walked from p1 (accurate however small
+  // it is: a corner cut off by the split has relative area ~x^2); the other one is
+  // the parent minus it, and its perimeter comes from the prefix sums.
+  double A1 = 0, A2 = 0, d01 = 0, L1 = 0, L2 = 0;
+  if (G.mask & MASK_NEED_D01) d01 = sqrt(d01x * d01x + d01y * d01y);
+  if (G.mask & MASK_FACE_AREA) {
+    const bool need_len = G.mask & (1u << LITE_FEAT_FACE_SHAPE);
+    int dk = k1 - k2n; if (dk < 0) dk += n;          // C1 holds dk+1 parent vertices, C2 the other n-dk-1
+    const bool walk1 = 2 * (dk + 1) <= n;
+    const double half_tot = 0.5 * __ldg(T.f_tot2 + T.slot_face[s1]);
+    const double ltot = need_len ? __ldg(T.plen + off + n - 1) + __ldg(T.len + off + n - 1) : 0.0;
+    double Aw, Lw = 0;
+    {
+      const int ks = walk1 ? k2n : k1n, ke = walk1 ? k1 : k2;
+      double2 Vk = ldpt(T.pt, off + ks);
+      double rx = Vk.x - p1.x, ry = Vk.y - p1.y;
+      double acc = walk1 ? cross2(d01x, d01y, rx, ry) : 0.0;
+      if (need_len) Lw = d01 + (walk1 ? plen(p2, Vk) : sqrt(rx * rx + ry * ry));
+      for (int k = ks; k != ke;) {
+        const int kn = (k + 1 == n) ? 0 : k + 1;
+        const double2 Vn = ldpt(T.pt, off + kn);
+        const double qx = Vn.x - p1.x, qy = Vn.y - p1.y;
+        acc += cross2(rx, ry, qx, qy);
+        if (need_len) Lw += __ldg(T.len + off + k);
+        rx = qx; ry = qy; k = kn;
+      }
+      if (!walk1) acc += cross2(rx, ry, d01x, d01y);
+      if (need_len) Lw += walk1 ? sqrt(rx * rx + ry * ry) : sqrt((rx - d01x) * (rx - d01x) + (ry - d01y) * (ry - d01y));
+      Aw = 0.5 * acc;
+    }
+    double Ao = half_tot - Aw;  // the two children tile the parent
+    if (Ao < 1e-6 * half_tot) {
+      // the many-vertex child is the sliver (micro-edges): walk it too
+      const int ks = walk1 ? k1n : k2n, ke = walk1 ? k2 : k1;
+      double2 Vk = ldpt(T.pt, off + ks);
+      double rx = Vk.x - p1.x, ry = Vk.y - p1.y;
+      double acc = walk1 ? 0.0 : cross2(d01x, d01y, rx, ry);
+      for (int k = ks; k != ke;) {
+        const int kn = (k + 1 == n) ? 0 : k + 1;
+        const double2 Vn = ldpt(T.pt, off + kn);
+        const double qx = Vn.x - p1.x, qy = Vn.y - p1.y;
+        acc += cross2(rx, ry, qx, qy);
+        rx = qx; ry = qy; k = kn;
+      }
+      if (walk1) acc += cross2(rx, ry, d01x, d01y);
+      Ao = 0.5 * acc;
+    }
+    double Lo = 0;
+    if (need_len) {
+      const double2 S2 = ldpt(T.pt, off + k2), E2 = ldpt(T.pt, off + k2n);
+      Lo = walk1 ? d01 + plen(p1, Q) + chain(T.plen, ltot, off, k1n, k2) + plen(S2, p2)
+                 : d01 + plen(p2, E2) + chain(T.plen, ltot, off, k2n, k1) + plen(P, p1);
+    }
+    A1 = walk1 ? Aw : Ao; A2 = walk1 ? Ao : Aw;
+    L1 = walk1 ? Lw : Lo; L2 = walk1 ? Lo : Lw;
+  }
+  double m1 = CUDART_INF, m2 = CUDART_INF;
+  if (G.mask & (1u << LITE_FEAT_MIN_ANGLE)) {  // parent corners inherited by each child
+    for (int k = k1n;; k = (k + 1 == n) ? 0 : k + 1) {
+      if (__ldg(T.flg + off + k) & SF_CORNER) m2 = fmin(m2, __ldg(T.ca + off + k));
       if (k == k2) break;
-      int kn = (k + 1 == n) ? 0 : k + 1;
-      double2 Vn = ldpt(T.pt, off + kn);
-      double qx = Vn.x - p1.x, qy = Vn.y - p1.y;
-      acc += cross2(rx, ry, qx, qy);
-      L2 += T.len[off + k];
-      rx = qx; ry = qy; k = kn;
     }
-    acc += cross2(rx, ry, d01x, d01y);
-    { double ex = p2.x - (rx + p1.x), ey = p2.y - (ry + p1.y); L2 += sqrt(ex * ex + ey * ey); }
-    A2 = 0.5 * acc;
-    k = k2n;
-    Vk = ldpt(T.pt, off + k);
-    rx = Vk.x - p1.x; ry = Vk.y - p1.y;
-    acc = cross2(d01x, d01y, rx, ry);
-    { double ex = Vk.x - p2.x, ey = Vk.y - p2.y; L1 = d01 + sqrt(ex * ex + ey * ey); }
-    while (true) {
-      if (T.flg[off + k] & SF_CORNER) m1 = fmin(m1, T.ca[off + k]);
+    for (int k = k2n;; k = (k + 1 == n) ? 0 : k + 1) {
+      if (__ldg(T.flg + off + k) & SF_CORNER) m1 = fmin(m1, __ldg(T.ca + off + k));
       if (k == k1) break;
-      int kn = (k + 1 == n) ? 0 : k + 1;
-      double2 Vn = ldpt(T.pt, off + kn);
-      double qx = Vn.x - p1.x, qy = Vn.y - p1.y;
-      acc += cross2(rx, ry, qx, qy);
-      L1 += T.len[off + k];
-      rx = qx; ry = qy; k = kn;
     }
-    L1 += sqrt(rx * rx + ry * ry);
-    A1 = 0.5 * acc;
   }
   // new corner angles: alpha at p1 (C2 side), beta at p2 (C1 side)
-  double alpha = angle;
-  double beta = fabs(wrap_pi(T.ang[off + k2] - l - LITE_PI));
+  const double alpha = angle;
+  double beta = 0;
+  if (G.mask & MASK_FACE_ANG) beta = fabs(wrap_pi(__ldg(T.ang + off + k2) - l - LITE_PI));
 
   for (int i = 0; i < G.d; i++) {
     double dv = 0.0;  // phi(after) - phi(before)
@@ -434,16 +549,10 @@ __device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, int 
       case LITE_FEAT_EDGE_LENGTH_INTERNAL: {
         // -{e1,e2} +{(s1,p1),(p1,t1),(s2,p2),(p2,t2),(p1,p2)} (:2148-2164)
         bool wantb = (G.fid[i] == LITE_FEAT_EDGE_LENGTH);
-        if (bnd1 == wantb) {
-          double ax = p1.x - P.x, ay = p1.y - P.y, bx = Q.x - p1.x, by = Q.y - p1.y;
-          double ex = Q.x - P.x, ey = Q.y - P.y;
-          dv += sqrt(ax * ax + ay * ay) + sqrt(bx * bx + by * by) - sqrt(ex * ex + ey * ey);
-        }
+        if (bnd1 == wantb) dv += plen(P, p1) + plen(p1, Q) - plen(P, Q);
         if (bnd2 == wantb) {
           double2 S = ldpt(T.pt, off + k2), E = ldpt(T.pt, off + k2n);
-          double ax = p2.x - S.x, ay = p2.y - S.y, bx = E.x - p2.x, by = E.y - p2.y;
-          double ex = E.x - S.x, ey = E.y - S.y;
-          dv += sqrt(ax * ax + ay * ay) + sqrt(bx * bx + by * by) - sqrt(ex * ex + ey * ey);
+          dv += plen(S, p2) + plen(p2, E) - plen(S, E);
         }
         if (!wantb) dv += d01;
       } break;
@@ -458,14 +567,16 @@ __device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, int 
       case LITE_FEAT_FACE_NUMBER: dv = 1.0; break;
       case LITE_FEAT_FACE_AREA_2: dv = -2.0 * A1 * A2; break;  // a1^2+a2^2-(a1+a2)^2
       case LITE_FEAT_FACE_PERIMETER: dv = 2.0 * d01; break;
-      case LITE_FEAT_FACE_SHAPE:
+      case LITE_FEAT_FACE_SHAPE: {
+        const int f = T.slot_face[s1];
         dv = shape_of(L1, A1) + shape_of(L2, A2) - shape_of(T.f_perim[f], T.f_area[f]);
-        break;
+      } break;
       case LITE_FEAT_FACE_SUM_OF_ANGLES:
         // untouched corners cancel; new corners alpha, pi-alpha at p1 and beta, pi-beta at p2
         dv = fabs(LITE_HALF_PI - alpha) + fabs(LITE_HALF_PI - beta);
         break;
       case LITE_FEAT_MIN_ANGLE: {
+        const int f = T.slot_face[s1];
         // C1 = [p1,p2,...]: seed pi-(pi-alpha); corners pi-alpha (p1), beta (p2)
         double ma1 = fmin(fmin(alpha, LITE_PI - alpha), fmin(beta, m1));
         // C2 = [p2,p1,...]: seed pi-(pi-beta); corners pi-beta (p2), alpha (p1)
@@ -474,14 +585,14 @@ __device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, int 
       } break;
       default: break;
     }
-    st[i] = -dv;
+    stat_col0[(size_t)i * cap] = -dv;
   }
 }
 
 struct SplitArgs {
   long n_local;      // candidates handled by this launch
   long j0;           // index of the first one inside the batch
-  long n_batch;      // batch size over all ranks
+  double sel_step;   // total_len / batch size: width of one stratum of the sampler
   uint64_t seed, ctr0;  // philox: counter of batch element j is ctr0 + j
   const int *in_he; const double *in_x, *in_angle;  // given path
   double *stat; size_t cap; long base;              // column k at stat[k*cap + base + i]
@@ -491,52 +602,58 @@ struct SplitArgs {
   unsigned long long *checksum;  // [0] xor hash, [1] sum of e2
 };
 
+// Stratified length-weighted halfedge of candidate j (the device form of
+// alt_length_weighted_random_halfedge(n), lib/ttessel.cpp:1968-1991): slot m with
+// cum[m-1] <= sel < cum[m], found from a guide table in O(1) expected loads.
+__device__ __forceinline__ int sample_slot(const TessDev &T, double sel) {
+  int b = (int)(sel * T.guide_scale);
+  b = min(max(b, 0), T.n_guide - 1);
+  int m = __ldg(T.guide + b);
+  while (m > 0 && __ldg(T.cum + m - 1) > sel) m--;
+  while (m < T.n_cum - 1 && __ldg(T.cum + m) <= sel) m++;
+  return m;
+}
+
 // MODE bit0: philox sampling (else given list); bit1: record; bit2: statistics; bit3: checksum
 template <int MODE>
-__global__ void __launch_bounds__(256) k_split(TessDev T, Prog G, SplitArgs A) {
+#ifndef LITE_SPLIT_TB
+#define LITE_SPLIT_TB 256
+#endif
+#ifndef LITE_SPLIT_MINB
+#define LITE_SPLIT_MINB 2
+#endif
+__global__ void __launch_bounds__(LITE_SPLIT_TB, LITE_SPLIT_MINB) k_split(TessDev T, Prog G, SplitArgs A) {
   constexpr bool PHILOX = MODE & 1, RECORD = MODE & 2, STAT = MODE & 4, CHECK = MODE & 8;
   long stride = (long)gridDim.x * blockDim.x;
   unsigned long long cx = 0, cs = 0;
   unsigned int bad = 0;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < A.n_local; i += stride) {
-    int h; double x, angle, U = 0.0;
+    int s1; double x, angle, U = 0.0;
     if (PHILOX) {
       long j = A.j0 + i;
-      uint32_t r[4], q[4];
+      uint32_t r[4];
       philox4x32_10(A.ctr0 + (uint64_t)j, 0u, A.seed, r);
-      philox4x32_10(A.ctr0 + (uint64_t)j, 1u, A.seed, q);
       x = u53(r[0], r[1]);
       U = u53(r[2], r[3]);
-      double jit = u53(q[0], q[1]);
-      // stratified length-weighted halfedge (alt_length_weighted_random_halfedge(n),
-      // lib/ttessel.cpp:1968-1991: select sorted, first halfedge with cumlen > select)
-      double sel = ((double)j + jit) * (T.total_len / (double)A.n_batch);
-      int lo = 0, hi = T.n_cum - 1;
-      while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (__ldg(T.cum + mid) > sel) hi = mid; else lo = mid + 1;
-      }
-      h = T.cum_he[lo];
+      // the 22 bits u53 leaves unused place the candidate inside its stratum
+      uint32_t spare = ((r[0] & 31u) << 17) | ((r[1] & 63u) << 11) | ((r[2] & 31u) << 6) | (r[3] & 63u);
+      double jit = (double)spare * (1.0 / 4194304.0);
+      double sel = ((double)j + jit) * A.sel_step;
+      s1 = sample_slot(T, sel);
       angle = acos(1.0 - 2.0 * U);  // lib/ttessel.cpp:1792
     } else {
-      h = A.in_he[i]; x = A.in_x[i]; angle = A.in_angle[i];
+      s1 = T.he_slot[A.in_he[i]]; x = A.in_x[i]; angle = A.in_angle[i];
     }
-    double st[LITE_MAX_D];
     SplitOut o;
-    split_eval<STAT>(T, G, h, x, angle, st, o);
+    split_eval<STAT>(T, G, s1, x, angle, A.stat + A.base + i, A.cap, o);
     if (o.e2 < 0) bad++;
-    if (STAT) {
-#pragma unroll
-      for (int k = 0; k < LITE_MAX_D; k++)
-        if (k < G.d) A.stat[(size_t)k * A.cap + A.base + i] = st[k];
-    }
     if (RECORD) {
-      A.r_e1[A.base + i] = h; A.r_e2[A.base + i] = o.e2;
+      A.r_e1[A.base + i] = T.slot_he[s1]; A.r_e2[A.base + i] = o.e2;
       A.r_p1[A.base + i] = o.p1; A.r_p2[A.base + i] = o.p2;
       A.r_x[A.base + i] = x; A.r_angle[A.base + i] = angle; A.r_u[A.base + i] = U;
     }
     if (CHECK) {
-      unsigned long long key = ((unsigned long long)(unsigned)h << 32) | (unsigned)o.e2;
+      unsigned long long key = ((unsigned long long)(unsigned)T.slot_he[s1] << 32) | (unsigned)o.e2;
       key *= 0x9E3779B97F4A7C15ull; key ^= key >> 29;
       cx ^= key; cs += (unsigned long long)(unsigned)o.e2;
     }
@@ -554,15 +671,9 @@ __global__ void __launch_bounds__(256) k_split(TessDev T, Prog G, SplitArgs A) {
 // ---------------------------------------------------------------------------
 // K4: merges  (Merge::modified_elements, lib/ttessel.cpp:2302-2404)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ double plen(double2 a, double2 b) {
-  double x = b.x - a.x, y = b.y - a.y;
-  return sqrt(x * x + y * y);
-}
 
-__global__ void k_merges(TessDev T, Prog G, const int *nb_seg, int n, double *stat, size_t cap,
-                         int *out_he) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ void merge_one(const TessDev &T, const Prog &G, const int *nb_seg, int i,
+                                          double *stat, size_t cap, int *out_he) {
   int sg = nb_seg[i];
   int e = T.seg_he_start[sg];  // single edge, dir == true: Seg::get_halfedge_handle()
   int t = T.he_twin[e];
@@ -591,8 +702,8 @@ __global__ void k_merges(TessDev T, Prog G, const int *nb_seg, int n, double *st
     VPoly P;
     FaceFeat F;
     // del: simplify(face(e)), simplify(face(twin e)) in face2poly order (:2333-2362)
-    vp_init(P); vp_range(P, o1, n1, 1, n1); F = vp_features(T, P, ang); add_face_feats(G, acc, -1.0, F);
-    vp_init(P); vp_range(P, o2, n2, 1, n2); F = vp_features(T, P, ang); add_face_feats(G, acc, -1.0, F);
+    add_face_feats(G, acc, -1.0, parent_feat(T, f1));
+    add_face_feats(G, acc, -1.0, parent_feat(T, f2));
     // add: polygon_remove_edge (:4945-4966): face(e) after p2 .. p1, face(twin) after p1 .. p2
     vp_init(P);
     vp_range(P, o1, n1, ke + 2, n1 - 2);
@@ -631,11 +742,9 @@ __global__ void k_merges(TessDev T, Prog G, const int *nb_seg, int n, double *st
 // K5: flips  (Flip ctor :2432-2454, Flip::modified_elements :2459-2713)
 // flip i < n_b : e1 = twin(halfedges_start(seg)),  i >= n_b: e1 = halfedges_end(seg)
 // ---------------------------------------------------------------------------
-__global__ void k_flips(TessDev T, Prog G, const int *b_seg, int nb, double *stat, size_t cap,
-                        int *out_e1, int *out_e2, double2 *out_p2, int *out_right,
-                        unsigned long long *status) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * nb) return;
+__device__ __forceinline__ void flip_one(const TessDev &T, const Prog &G, const int *b_seg, int nb, int i,
+                                         double *stat, size_t cap, int *out_e1, int *out_e2,
+                                         double2 *out_p2, int *out_right, unsigned long long *status) {
   int sg = b_seg[i < nb ? i : i - nb];
   int e1 = (i < nb) ? T.he_twin[T.seg_he_start[sg]] : T.seg_he_end[sg];
   int t1 = T.he_twin[e1];
@@ -697,8 +806,8 @@ __global__ void k_flips(TessDev T, Prog G, const int *b_seg, int nb, double *sta
     VPoly P; FaceFeat F;
     // deleted faces: the face of e2 first, then the other face bounded by e1 (:2644-2651)
     if (right) {
-      vp_init(P); vp_range(P, oT, nT, 1, nT); F = vp_features(T, P, ang); add_face_feats(G, acc, -1.0, F);
-      vp_init(P); vp_range(P, oL, nL, 1, nL); F = vp_features(T, P, ang); add_face_feats(G, acc, -1.0, F);
+      add_face_feats(G, acc, -1.0, parent_feat(T, fT));
+      add_face_feats(G, acc, -1.0, parent_feat(T, fL));
       // unmatched inserted face: outer2 = [p2, a, V(kt+2) .. V(k2)]
       vp_init(P);
       vp_point(P, p2.x, p2.y, 1); vp_point(P, a.x, a.y, 1);
@@ -712,8 +821,8 @@ __global__ void k_flips(TessDev T, Prog G, const int *b_seg, int nb, double *sta
       vp_point(P, q.x, q.y, 0);
       F = vp_features(T, P, ang); add_face_feats(G, acc, +1.0, F);
     } else {
-      vp_init(P); vp_range(P, oL, nL, 1, nL); F = vp_features(T, P, ang); add_face_feats(G, acc, -1.0, F);
-      vp_init(P); vp_range(P, oT, nT, 1, nT); F = vp_features(T, P, ang); add_face_feats(G, acc, -1.0, F);
+      add_face_feats(G, acc, -1.0, parent_feat(T, fL));
+      add_face_feats(G, acc, -1.0, parent_feat(T, fT));
       // unmatched inserted face: outer1 = [a, p2, V(k2+1) .. V(k1-1)]
       vp_init(P);
       vp_point(P, a.x, a.y, 1); vp_point(P, p2.x, p2.y, 1);
@@ -767,18 +876,39 @@ __global__ void k_flips(TessDev T, Prog G, const int *b_seg, int nb, double *sta
 }
 
 // column sums of a (d x n) SoA block, deterministic (one block per column)
-__global__ void k_colsum(const double *stat, size_t cap, int n, double *out) {
-  __shared__ double sh[256];
-  int k = blockIdx.x;
+// all merges and all flips in one launch: blocks [0, gm) take the merges, the rest the flips
+struct MFArgs {
+  const int *nb_seg; int nm; double *mstat; int *m_he; int gm;
+  const int *b_seg; int nb; double *fstat; int *f_e1, *f_e2, *f_right; double2 *f_p2;
+  unsigned long long *status;
+};
+__global__ void __launch_bounds__(128) k_merges_flips(TessDev T, Prog G, MFArgs A) {
+  if ((int)blockIdx.x < A.gm) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < A.nm) merge_one(T, G, A.nb_seg, i, A.mstat, (size_t)A.nm, A.m_he);
+  } else {
+    int i = (blockIdx.x - A.gm) * blockDim.x + threadIdx.x;
+    if (i < 2 * A.nb) flip_one(T, G, A.b_seg, A.nb, i, A.fstat, (size_t)(2 * A.nb), A.f_e1, A.f_e2, A.f_p2, A.f_right, A.status);
+  }
+}
+
+// column sums of the merge (blockIdx.y == 0) and flip (== 1) statistic blocks,
+// deterministic: one block per column, fixed tree
+__global__ void __launch_bounds__(1024) k_colsum2(const double *mstat, int nm, const double *fstat, int nf,
+                                                  double *out /* [2][LITE_MAX_D] */) {
+  __shared__ double sh[1024];
+  const int k = blockIdx.x;
+  const double *stat = blockIdx.y ? fstat : mstat;
+  const int n = blockIdx.y ? nf : nm;
   double s = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s += stat[(size_t)k * cap + i];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += stat[(size_t)k * n + i];
   sh[threadIdx.x] = s;
   __syncthreads();
   for (int w = blockDim.x / 2; w; w >>= 1) {
     if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[k] = sh[0];
+  if (threadIdx.x == 0) out[blockIdx.y * LITE_MAX_D + k] = sh[0];
 }
 
 // ---------------------------------------------------------------------------
@@ -787,32 +917,81 @@ __global__ void k_colsum(const double *stat, size_t cap, int n, double *out) {
 //   e_i = exp(theta . p_i)      (lib/ttessel.cpp:3392-3394, :3417-3419, :3435-3436)
 // warp shuffle -> block tree -> fixed-order finish by the last block.
 // ---------------------------------------------------------------------------
+template <int D, int NT>
+__device__ __forceinline__ void reduce_one(const Theta &th, const double (&p)[D], double (&acc)[NT]) {
+  double dot = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; k++) dot += th.v[k] * p[k];
+  double e = exp(dot);
+  acc[0] += e;
+  int t = 1 + D;
+#pragma unroll
+  for (int k = 0; k < D; k++) {
+    double ek = e * p[k];
+    acc[1 + k] += ek;
+#pragma unroll
+    for (int l = k; l < D; l++) acc[t++] += ek * p[l];
+  }
+}
+
+// Each thread streams two candidates per 16-byte load and keeps two such loads
+// per column in flight (64*D bytes per thread), which is what it takes to cover
+// the HBM latency-bandwidth product with 2 x 256 threads per SM.  `rev` walks the
+// block from its end: right after k_split, and on every other evaluation of a
+// Newton loop, the tail of the statistic block is still in the 126 MB L2.
 template <int D>
 __global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ stat, size_t cap,
-                                                long n, Theta th, double *partials,
+                                                long n, int rev, Theta th, double *partials,
                                                 unsigned int *counter, double *out) {
   constexpr int NT = 1 + D + D * (D + 1) / 2;
   double acc[NT];
 #pragma unroll
   for (int t = 0; t < NT; t++) acc[t] = 0.0;
-  long stride = (long)gridDim.x * blockDim.x;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    double p[D];
-#pragma unroll
-    for (int k = 0; k < D; k++) p[k] = __ldcs(stat + (size_t)k * cap + i);
-    double dot = 0.0;
-#pragma unroll
-    for (int k = 0; k < D; k++) dot += th.v[k] * p[k];
-    double e = exp(dot);
-    acc[0] += e;
-    int t = 1 + D;
+  const long stride = (long)gridDim.x * blockDim.x;
+  const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long npair = n >> 1;
+  long i = gtid;
+  // two loads per column in flight only while the accumulators leave room for them
+  for (; D <= 6 && i + stride < npair; i += 2 * stride) {
+    const long ia = rev ? npair - 1 - i : i, ib = rev ? npair - 1 - (i + stride) : i + stride;
+    double2 va[D], vb[D];
 #pragma unroll
     for (int k = 0; k < D; k++) {
-      double ek = e * p[k];
-      acc[1 + k] += ek;
-#pragma unroll
-      for (int l = k; l < D; l++) acc[t++] += ek * p[l];
+      va[k] = __ldcs((const double2 *)(stat + (size_t)k * cap) + ia);
+      vb[k] = __ldcs((const double2 *)(stat + (size_t)k * cap) + ib);
     }
+    double p[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) p[k] = va[k].x;
+    reduce_one<D, NT>(th, p, acc);
+#pragma unroll
+    for (int k = 0; k < D; k++) p[k] = va[k].y;
+    reduce_one<D, NT>(th, p, acc);
+#pragma unroll
+    for (int k = 0; k < D; k++) p[k] = vb[k].x;
+    reduce_one<D, NT>(th, p, acc);
+#pragma unroll
+    for (int k = 0; k < D; k++) p[k] = vb[k].y;
+    reduce_one<D, NT>(th, p, acc);
+  }
+  for (; i < npair; i += stride) {
+    const long ia = rev ? npair - 1 - i : i;
+    double2 va[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) va[k] = __ldcs((const double2 *)(stat + (size_t)k * cap) + ia);
+    double p[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) p[k] = va[k].x;
+    reduce_one<D, NT>(th, p, acc);
+#pragma unroll
+    for (int k = 0; k < D; k++) p[k] = va[k].y;
+    reduce_one<D, NT>(th, p, acc);
+  }
+  if ((n & 1) && gtid == 0) {  // odd tail
+    double p[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) p[k] = stat[(size_t)k * cap + n - 1];
+    reduce_one<D, NT>(th, p, acc);
   }
   __shared__ double sh[8][NT];
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

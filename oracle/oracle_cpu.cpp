@@ -730,21 +730,25 @@ int oracle_sample_splits(const lite_tess_soa *s, int64_t n_batch, uint64_t seed,
   std::vector<double> cum;
   std::vector<int> cum_he;
   double cl = 0;
-  for (int h = 0; h < s->n_halfedges; h++)
-    if (s->face_inside[s->he_face[h]]) {
+  // slot order: faces in index order, each in ccb order from outer_ccb()
+  for (int f = 0; f < s->n_faces; f++) {
+    if (!s->face_inside[f]) continue;
+    for (int k = 0; k < s->face_he_count[f]; k++) {
+      int h = s->face_he_list[s->face_he_offset[f] + k];
       cl += s->he_length[h];  // cumlen += e->get_length(), lib/ttessel.cpp:1980
       cum.push_back(cl);
       cum_he.push_back(h);
     }
+  }
   if (cum.empty()) { g_err = "no inside halfedge"; return -1; }
   parallel_for(n, nthreads, [&](int64_t a, int64_t b, int) {
     for (int64_t i = a; i < b; i++) {
       uint64_t j = (uint64_t)(j0 + i);
-      uint32_t r[4], q[4];
+      uint32_t r[4];
       philox4x32_10(ctr0 + j, 0u, seed, r);
-      philox4x32_10(ctr0 + j, 1u, seed, q);
       x[i] = u53(r[0], r[1]);
-      double U = u53(r[2], r[3]), jit = u53(q[0], q[1]);
+      uint32_t spare = ((r[0] & 31u) << 17) | ((r[1] & 63u) << 11) | ((r[2] & 31u) << 6) | (r[3] & 63u);
+      double U = u53(r[2], r[3]), jit = (double)spare * (1.0 / 4194304.0);
       double sel = ((double)j + jit) * (cl / (double)n_batch);
       size_t k = std::upper_bound(cum.begin(), cum.end(), sel) - cum.begin();  // first cum > sel
       if (k >= cum.size()) k = cum.size() - 1;

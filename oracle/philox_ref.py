@@ -40,8 +40,11 @@ def u53(hi, lo):
 
 def sample_splits(cum, cum_he, n_batch, seed, ctr0, j0, n):
     """Candidates j0 .. j0+n-1 of a batch of n_batch: returns (he, x, U).
-    cum / cum_he: cumulative lengths of the inside halfedges in container order
-    and their ids (built as lite_tess_upload does)."""
+    cum / cum_he: cumulative lengths of the inside halfedges in SLOT order (faces in
+    index order, each in ccb order from outer_ccb) and their ids, built as
+    lite_tess_upload does (tests/util.py:inside_cum).  One Philox call per
+    candidate: words 0-1 -> x, words 2-3 -> U (53 bits each); the 22 bits those
+    leave unused place the candidate inside its stratum of width total/n_batch."""
     j = np.arange(j0, j0 + n, dtype=np.uint64)
     ctr = np.uint64(ctr0) + j
     lo = (ctr & MASK).astype(np.uint32)
@@ -49,10 +52,11 @@ def sample_splits(cum, cum_he, n_batch, seed, ctr0, j0, n):
     z = np.zeros(n, dtype=np.uint32)
     k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
     r = philox4x32_10(lo, hi, z, z, k0, k1)
-    q = philox4x32_10(lo, hi, z + np.uint32(1), z, k0, k1)
     x = u53(r[0], r[1])
     U = u53(r[2], r[3])
-    jit = u53(q[0], q[1])
+    spare = (((r[0] & np.uint32(31)) << np.uint32(17)) | ((r[1] & np.uint32(63)) << np.uint32(11))
+             | ((r[2] & np.uint32(31)) << np.uint32(6)) | (r[3] & np.uint32(63)))
+    jit = spare.astype(np.float64) * (1.0 / 4194304.0)
     sel = (j.astype(np.float64) + jit) * (cum[-1] / float(n_batch))
     idx = np.searchsorted(cum, sel, side="right")  # first m with cum[m] > sel
     idx = np.minimum(idx, len(cum) - 1)

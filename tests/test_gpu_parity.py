@@ -120,7 +120,8 @@ def test_philox_sampler_matches_numpy_restatement(lite):
     np.testing.assert_array_equal(ctx.fetch("SPLIT_U"), U)
     ang = ctx.fetch("SPLIT_ANGLE")
     np.testing.assert_allclose(ang, np.arccos(1 - 2 * U), rtol=0, atol=1e-15)  # device acos: <= 2 ulp
-    # halfedges come out in container order (lib/ttessel.cpp:1975-1989)
+    # halfedges come out in sampler (slot) order, as split_sample's come out in container order
+    # (lib/ttessel.cpp:1975-1989)
     order = {int(h): k for k, h in enumerate(cum_he)}
     pos = np.array([order[int(h)] for h in ctx.fetch("SPLIT_E1")])
     assert np.all(np.diff(pos) >= 0)

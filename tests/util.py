@@ -22,13 +22,17 @@ def load_golden(name):
 
 
 def inside_cum(soa):
-    """cum / cum_he exactly as lite_tess_upload builds them."""
-    inside = soa["face_inside"][soa["he_face"]].astype(bool)
-    ids = np.nonzero(inside)[0].astype(np.int32)
-    cum = np.zeros(len(ids))
-    c = 0.0
+    """cum / cum_he exactly as lite_tess_upload builds them: inside halfedges in
+    slot order (faces in index order, each in ccb order from outer_ccb())."""
     lens = soa["he_length"]
-    for k, h in enumerate(ids):
-        c += float(lens[h])
-        cum[k] = c
-    return cum, ids
+    ids, cum = [], []
+    c = 0.0
+    for f in range(len(soa["face_inside"])):
+        if not soa["face_inside"][f]:
+            continue
+        off, cnt = int(soa["face_he_offset"][f]), int(soa["face_he_count"][f])
+        for h in soa["face_he_list"][off:off + cnt]:
+            c += float(lens[h])
+            cum.append(c)
+            ids.append(int(h))
+    return np.array(cum), np.array(ids, dtype=np.int32)
