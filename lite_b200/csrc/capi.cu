@@ -98,7 +98,7 @@ struct lite_ctx {
   DBuf<int> f_off, f_cnt, f_list, seg_he_start, seg_he_end, seg_n_edges, nb_list, b_list;
   // derived
   DBuf<double2> pt;
-  DBuf<double> ang, len, ca, f_area, f_perim, f_sumang, f_minang, cum, pre, plen, f_tot2;
+  DBuf<double> ang, len, ca, f_area, f_perim, f_sumang, f_minang, cum, pre, plen, f_tot2, stot2;
   DBuf<int2> sfo;
   DBuf<uint32_t> flg;
   DBuf<int> slot_he, slot_seg, slot_face, he_slot, guide, err;
@@ -201,7 +201,7 @@ extern "C" int lite_ctx_destroy(lite_ctx *c) {
   c->f_off.release(); c->f_cnt.release(); c->f_list.release(); c->seg_he_start.release();
   c->seg_he_end.release(); c->seg_n_edges.release(); c->nb_list.release(); c->b_list.release();
   c->pt.release(); c->ang.release(); c->len.release(); c->ca.release(); c->f_area.release();
-  c->f_perim.release(); c->f_sumang.release(); c->f_minang.release(); c->cum.release(); c->pre.release(); c->plen.release(); c->f_tot2.release(); c->sfo.release();
+  c->f_perim.release(); c->f_sumang.release(); c->f_minang.release(); c->cum.release(); c->pre.release(); c->plen.release(); c->f_tot2.release(); c->stot2.release(); c->sfo.release();
   c->flg.release(); c->slot_he.release(); c->slot_seg.release(); c->slot_face.release();
   c->he_slot.release(); c->guide.release(); c->err.release();
   c->stat.release(); c->r_e1.release(); c->r_e2.release(); c->in_he.release();
@@ -331,7 +331,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
       c->flg.alloc(nSl) || c->slot_he.alloc(nSl) || c->slot_seg.alloc(nSl) ||
       c->slot_face.alloc(nSl) || c->he_slot.alloc(nH) || c->f_area.alloc(nF) ||
       c->f_perim.alloc(nF) || c->f_sumang.alloc(nF) || c->f_minang.alloc(nF) || c->pre.alloc(nSl) ||
-      c->plen.alloc(nSl) || c->f_tot2.alloc(nF) || c->sfo.alloc(nSl))
+      c->plen.alloc(nSl) || c->f_tot2.alloc(nF) || c->sfo.alloc(nSl) || c->stot2.alloc(nSl))
     return LITE_ECUDA;
   CU(cudaMemsetAsync(c->he_slot.p, 0xFF, nH * sizeof(int), c->stream));
   CU(cudaMemsetAsync(c->err.p, 0, sizeof(int), c->stream));
@@ -356,12 +356,12 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   T.seg_bnd = c->seg_bnd.p;
   T.cum = c->cum.p; T.guide = c->guide.p; T.n_cum = (int)cum.size(); T.n_guide = n_guide;
   T.total_len = cl; T.guide_scale = (double)n_guide / cl;
-  T.sfo = c->sfo.p; T.pre = c->pre.p; T.plen = c->plen.p; T.f_tot2 = c->f_tot2.p;
+  T.sfo = c->sfo.p; T.pre = c->pre.p; T.plen = c->plen.p; T.f_tot2 = c->f_tot2.p; T.stot2 = c->stot2.p;
   int tb = 128, gb = (nF + tb - 1) / tb;
   k_prep_slots<<<gb, tb, 0, c->stream>>>(A);
   // outside faces: count 0 in the device view
   k_prep_faces<<<gb, tb, 0, c->stream>>>(T, c->ca.p, c->f_area.p, c->f_perim.p, c->f_sumang.p, c->f_minang.p,
-                                         c->pre.p, c->plen.p, c->f_tot2.p, c->sfo.p);
+                                         c->pre.p, c->plen.p, c->f_tot2.p, c->sfo.p, c->stot2.p);
   c->launches += 2;
   int herr = 0;
   CU(cudaMemcpyAsync(&herr, c->err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -489,11 +489,24 @@ static int grow_splits(lite_ctx *c, int64_t add) {
 }
 
 static int split_grid(lite_ctx *c, int64_t n) {
+  // one resident wave: every warp then owns one contiguous run of candidates
   int64_t blocks = (n + LITE_SPLIT_TB - 1) / LITE_SPLIT_TB;
-  int64_t maxb = (int64_t)c->sm_count * LITE_SPLIT_MINB * 8;
+  int64_t maxb = (int64_t)c->sm_count * LITE_SPLIT_MINB;
   if (blocks > maxb) blocks = maxb;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
+}
+
+static bool prog_is_acs(const Prog &G) {
+  return G.d == 4 && G.fid[0] == LITE_FEAT_EDGE_LENGTH && G.fid[1] == LITE_FEAT_FACE_AREA_2 &&
+         G.fid[2] == LITE_FEAT_FACE_SUM_OF_ANGLES && G.fid[3] == LITE_FEAT_IS_SEGMENT_INTERNAL;
+}
+// the sim_acs energy gets the compile-time program, everything else the run-time one
+template <int MODE>
+static void launch_split(lite_ctx *c, const Prog &G, const SplitArgs &A, int grid) {
+  if ((MODE & 4) && prog_is_acs(G)) k_split<MODE, ProgACS><<<grid, LITE_SPLIT_TB, 0, c->stream>>>(c->T, G, A);
+  else k_split<MODE, ProgDyn><<<grid, LITE_SPLIT_TB, 0, c->stream>>>(c->T, G, A);
+  c->launches += 1;
 }
 
 static void fill_split_args(lite_ctx *c, SplitArgs &A) {
@@ -529,9 +542,8 @@ extern "C" int lite_candidates_add_splits_given(lite_ctx *c, int64_t n, const in
   A.n_local = n; A.j0 = 0; A.sel_step = 0;
   A.in_he = c->in_he.p; A.in_x = c->in_x.p; A.in_angle = c->in_angle.p;
   int g = split_grid(c, n);
-  if (c->record) k_split<4 | 2><<<g, LITE_SPLIT_TB, 0, c->stream>>>(c->T, c->G, A);
-  else k_split<4><<<g, LITE_SPLIT_TB, 0, c->stream>>>(c->T, c->G, A);
-  c->launches += 1;
+  if (c->record) launch_split<4 | 2>(c, c->G, A, g);
+  else launch_split<4>(c, c->G, A, g);
   CU(cudaEventRecord(c->ev[1], c->stream));
   c->ev01 = true;
   CU(cudaStreamSynchronize(c->stream));
@@ -564,9 +576,8 @@ extern "C" int lite_candidates_add_splits_philox(lite_ctx *c, int64_t n_global, 
     A.n_local = n; A.j0 = j0; A.sel_step = c->T.total_len / (double)n_global; A.seed = seed; A.ctr0 = offset;
     int g = split_grid(c, n);
     CU(cudaEventRecord(c->ev[0], c->stream));
-    if (c->record) k_split<4 | 2 | 1><<<g, LITE_SPLIT_TB, 0, c->stream>>>(c->T, c->G, A);
-    else k_split<4 | 1><<<g, LITE_SPLIT_TB, 0, c->stream>>>(c->T, c->G, A);
-    c->launches += 1;
+    if (c->record) launch_split<4 | 2 | 1>(c, c->G, A, g);
+    else launch_split<4 | 1>(c, c->G, A, g);
     CU(cudaEventRecord(c->ev[1], c->stream));
   c->ev01 = true;
   }
@@ -600,9 +611,8 @@ extern "C" int lite_lines_sample_clip(lite_ctx *c, int64_t n_global, uint64_t se
     A.n_local = n; A.j0 = j0; A.sel_step = c->T.total_len / (double)n_global; A.seed = seed; A.ctr0 = offset;
     int g = split_grid(c, n);
     CU(cudaEventRecord(c->ev[0], c->stream));
-    if (mode == 1) k_split<8 | 2 | 1><<<g, LITE_SPLIT_TB, 0, c->stream>>>(c->T, G0, A);
-    else k_split<8 | 1><<<g, LITE_SPLIT_TB, 0, c->stream>>>(c->T, G0, A);
-    c->launches += 1;
+    if (mode == 1) launch_split<8 | 2 | 1>(c, G0, A, g);
+    else launch_split<8 | 1>(c, G0, A, g);
     CU(cudaEventRecord(c->ev[1], c->stream));
   c->ev01 = true;
   }

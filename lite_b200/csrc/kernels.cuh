@@ -48,6 +48,7 @@ struct TessDev {
   const int *f_off, *f_cnt;
   const double *f_area, *f_perim, *f_sumang, *f_minang;
   const double *f_tot2;  // whole-face shoelace sum (twice the area) by the same prefix summation
+  const double *stot2;   // the same, copied to every slot of the face
   // per segment
   const int *seg_n_edges, *seg_he_start, *seg_he_end;
   const uint8_t *seg_bnd;
@@ -284,7 +285,7 @@ __global__ void k_prep_slots(PrepArgs A) {
 
 __global__ void k_prep_faces(TessDev T, double *ca, double *f_area, double *f_perim,
                              double *f_sumang, double *f_minang, double *pre, double *plen,
-                             double *f_tot2, int2 *sfo) {
+                             double *f_tot2, int2 *sfo, double *stot2) {
   int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= T.n_faces) return;
   int n = T.f_cnt[f];
@@ -303,6 +304,7 @@ __global__ void k_prep_faces(TessDev T, double *ca, double *f_area, double *f_pe
       Vk = Vn;
     }
     f_tot2[f] = acc;
+    for (int k = 0; k < n; k++) stot2[off + k] = acc;
   }
   // corner angles at slot sources
   for (int k = 0; k < n; k++) {
@@ -356,24 +358,45 @@ __device__ __forceinline__ int ray_exit(const TessDev &T, int off, int n, double
   return k2;
 }
 
-// out-of-line copy for the rare multi-crossing case of split_eval (keeps its registers down)
-__device__ __noinline__ int ray_exit_rare(const TessDev &T, int off, int n, double a, double b,
-                                          double w, double2 p, double dx, double dy, int skip0,
-                                          int skip1, double2 &hit) {
-  return ray_exit(T, off, n, a, b, w, p, dx, dy, skip0, skip1, hit);
-}
-
 // ---------------------------------------------------------------------------
 // K1+K2: one split candidate  (Split ctor + modified_elements + statistic_variation)
 //
-// Cost model: everything after the crossed-edge search is O(1) in the face size.
-// The child areas and perimeters come from per-face prefix sums (pre/plen, built
-// once per tessellation by k_prep_faces) instead of walking the two children;
-// only min_angle still walks the parent's corners.
+// Cost model.  Candidates reach the kernel sorted by slot (the sampler is
+// stratified along the cumulative halfedge length), and a warp owns a contiguous
+// run of them, so the lanes of a warp sit on the same halfedge of the same face
+// and each lane meets a new slot only every few iterations: the slot's data
+// (SlotData) stay in registers in between and the sampler needs no memory access.
+// After the crossed-edge search the work is O(min(child sizes)): the child with
+// fewer parent vertices is walked from p1, the other is the parent minus it.
+// The feature program is a template policy: ProgDyn reads it from the kernel
+// argument (any registered energy), ProgACS is the sim_acs energy folded at
+// compile time; both run the same code.
 // ---------------------------------------------------------------------------
 struct SplitOut {
   int e2;       // halfedge id, -1 if no exit was found
   double2 p1, p2;
+};
+
+struct ProgDyn {
+  static constexpr bool kStatic = false;
+  __device__ static __forceinline__ uint32_t mask(const Prog &G) { return G.mask; }
+  __device__ static __forceinline__ int d(const Prog &G) { return G.d; }
+  __device__ static __forceinline__ int fid(const Prog &G, int i) { return G.fid[i]; }
+};
+// demos/sim_acs.cpp:64-76 in CatVector order: edges edge_length, faces face_area_2,
+// faces face_sum_of_angles, segs is_segment_internal
+struct ProgACS {
+  static constexpr bool kStatic = true;
+  __device__ static __forceinline__ constexpr uint32_t mask(const Prog &) {
+    return (1u << LITE_FEAT_EDGE_LENGTH) | (1u << LITE_FEAT_FACE_AREA_2) |
+           (1u << LITE_FEAT_FACE_SUM_OF_ANGLES) | (1u << LITE_FEAT_IS_SEGMENT_INTERNAL);
+  }
+  __device__ static __forceinline__ constexpr int d(const Prog &) { return 4; }
+  __device__ static __forceinline__ constexpr int fid(const Prog &, int i) {
+    return i == 0 ? LITE_FEAT_EDGE_LENGTH
+                  : i == 1 ? LITE_FEAT_FACE_AREA_2
+                           : i == 2 ? LITE_FEAT_FACE_SUM_OF_ANGLES : LITE_FEAT_IS_SEGMENT_INTERNAL;
+  }
 };
 
 // sum of a prefix array over slots i, i+1, .., j-1 (cyclic, empty when i == j)
@@ -382,18 +405,55 @@ __device__ __forceinline__ double chain(const double *pre, double tot, int off, 
   return (j >= i) ? a : a + tot;
 }
 
-template <bool WITH_STAT>
-__device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, int s1, double x,
+// what a candidate needs from the halfedge it starts on
+struct SlotData {
+  int off, n, k1;     // face slot range, position of the halfedge in it
+  double2 P, Q;       // source and target of the halfedge
+  double ang1;        // atan2 of its direction
+  double half_tot;    // area of its face (shoelace, prefix summation)
+  uint32_t fl1;       // SF_* of the slot
+};
+__device__ __forceinline__ SlotData load_slot(const TessDev &T, int s1) {
+  SlotData S;
+  const int2 fo = __ldg(T.sfo + s1);
+  S.off = fo.x; S.n = fo.y; S.k1 = s1 - fo.x;
+  S.P = ldpt(T.pt, s1);
+  S.Q = ldpt(T.pt, fo.x + ((S.k1 + 1 == fo.y) ? 0 : S.k1 + 1));
+  S.ang1 = __ldg(T.ang + s1);
+  S.half_tot = 0.5 * __ldg(T.stot2 + s1);
+  S.fl1 = __ldg(T.flg + s1);
+  return S;
+}
+
+// out of line on purpose: only taken for the few candidates that start or end on a
+// window-boundary edge (edge_length as written) or when the feature is registered
+__device__ __noinline__ double edge_cut_delta(double ax, double ay, double mx, double my, double bx,
+                                              double by) {
+  // |a-m| + |m-b| - |a-b| for a point m on the edge (a,b)
+  return sqrt((mx - ax) * (mx - ax) + (my - ay) * (my - ay)) +
+         sqrt((bx - mx) * (bx - mx) + (by - my) * (by - my)) -
+         sqrt((bx - ax) * (bx - ax) + (by - ay) * (by - ay));
+}
+// min over the parent's corner angles at slots ks .. ke (cyclic, inclusive)
+__device__ __noinline__ double corner_min(const uint32_t *flg, const double *ca, int off, int n, int ks,
+                                          int ke) {
+  double m = CUDART_INF;
+  for (int k = ks;; k = (k + 1 == n) ? 0 : k + 1) {
+    if (__ldg(flg + off + k) & SF_CORNER) m = fmin(m, __ldg(ca + off + k));
+    if (k == ke) break;
+  }
+  return m;
+}
+
+template <bool WITH_STAT, class PG>
+__device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, const SlotData &S, double x,
                                            double angle, double *__restrict__ stat_col0,
                                            size_t cap, SplitOut &o) {
-  const int2 fo = __ldg(T.sfo + s1);
-  const int off = fo.x, n = fo.y;
-  const int k1 = s1 - off;
+  const int off = S.off, n = S.n, k1 = S.k1;
   const int k1n = (k1 + 1 == n) ? 0 : k1 + 1;
-  const double2 P = ldpt(T.pt, s1), Q = ldpt(T.pt, off + k1n);
-  const double ang1 = __ldg(T.ang + s1);
+  const double2 P = S.P, Q = S.Q;
   // lib/ttessel.cpp:2094-2105, evaluated as the reference does (no contraction)
-  const double l = ang1 + angle;
+  const double l = S.ang1 + angle;
   double a, c;
   sincos(l, &a, &c);
   const double b = -c;
@@ -410,10 +470,10 @@ __device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, int 
   const int skip1 = (x == 0.0) ? (k1 == 0 ? n - 1 : k1 - 1) : -1;
 
   // crossed-edge search (ray_exit_face, :4515-4576).  A vertex is classified once
-  // by the sign of its residual, so the scan is watertight.  In a convex face
-  // exactly one halfedge other than e1 crosses the line; anything else (the ray
-  // passes through a vertex) takes the general loop, which keeps the reference's
-  // first-of-equal-distances rule.
+  // by the sign of its residual s = a*X + b*Y - w, so the scan is watertight; a
+  // halfedge crosses the line when its end residuals have opposite signs or one is
+  // zero (s_k * s_{k+1} <= 0, not both zero).  In a convex face exactly one
+  // halfedge other than e1 does, unless the line passes through a vertex.
   int cnt = 0, k2 = -1;
   {
     const double2 V0 = ldpt(T.pt, off);
@@ -423,53 +483,69 @@ __device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, int 
     for (int k = 1; k < n; k++) {
       const double2 Vn = ldpt(T.pt, off + k);
       const double sn = fma(a, Vn.x, fma(b, Vn.y, -w));
-      const bool cr = ((sk <= 0.0 && sn >= 0.0) || (sk >= 0.0 && sn <= 0.0)) && sk != sn;
-      if (cr && (k - 1) != k1 && (k - 1) != skip1) { if (cnt == 0) k2 = k - 1; cnt++; }
+      if (sk * sn <= 0.0 && sk != sn && (k - 1) != k1 && (k - 1) != skip1) { if (cnt == 0) k2 = k - 1; cnt++; }
       sk = sn;
     }
-    const bool cr = ((sk <= 0.0 && s0 >= 0.0) || (sk >= 0.0 && s0 <= 0.0)) && sk != s0;
-    if (cr && (n - 1) != k1 && (n - 1) != skip1) { if (cnt == 0) k2 = n - 1; cnt++; }
+    if (sk * s0 <= 0.0 && sk != s0 && (n - 1) != k1 && (n - 1) != skip1) { if (cnt == 0) k2 = n - 1; cnt++; }
   }
   double2 p2 = make_double2(0.0, 0.0);
-  if (cnt == 1) {
-    const int k2n_ = (k2 + 1 == n) ? 0 : k2 + 1;
-    const double2 Vk = ldpt(T.pt, off + k2), Vn = ldpt(T.pt, off + k2n_);
-    const double sk = fma(a, Vk.x, fma(b, Vk.y, -w)), sn = fma(a, Vn.x, fma(b, Vn.y, -w));
-    const double sg = sk / (sk - sn);
-    const double X = fma(sg, Vn.x - Vk.x, Vk.x), Y = fma(sg, Vn.y - Vk.y, Vk.y);
-    const double rx = X - p1.x, ry = Y - p1.y;
-    if (rx * dx + ry * dy >= 0.0 && sqrt(rx * rx + ry * ry) != 0.0) p2 = make_double2(X, Y);
-    else k2 = -1;
-  } else if (cnt > 1) {
-    k2 = ray_exit_rare(T, off, n, a, b, w, p1, dx, dy, k1, skip1, p2);
+  if (cnt >= 1) {
+    // nearest forward hit among the crossing halfedges, first wins ties (:4563); cnt is 1
+    // unless the line passes through a vertex, so this loop runs once
+    double best = 1.7976931348623157e308;
+    int kb = -1;
+    for (int k = k2, left = cnt;;) {
+      const int kn = (k + 1 == n) ? 0 : k + 1;
+      const double2 Vk = ldpt(T.pt, off + k), Vn = ldpt(T.pt, off + kn);
+      const double sk = fma(a, Vk.x, fma(b, Vk.y, -w)), sn = fma(a, Vn.x, fma(b, Vn.y, -w));
+      const double sg = sk / (sk - sn);
+      const double X = fma(sg, Vn.x - Vk.x, Vk.x), Y = fma(sg, Vn.y - Vk.y, Vk.y);
+      const double rx = X - p1.x, ry = Y - p1.y;
+      if (rx * dx + ry * dy >= 0.0) {
+        const double len = sqrt(rx * rx + ry * ry);
+        if (len != 0.0 && len < best) { best = len; kb = k; p2 = make_double2(X, Y); }
+      }
+      if (--left == 0) break;
+      for (;;) {  // next crossing halfedge after k
+        k++;
+        if (k == k1 || k == skip1) continue;
+        const int kn2 = (k + 1 == n) ? 0 : k + 1;
+        const double2 A_ = ldpt(T.pt, off + k), B_ = ldpt(T.pt, off + kn2);
+        const double sa = fma(a, A_.x, fma(b, A_.y, -w)), sb = fma(a, B_.x, fma(b, B_.y, -w));
+        if (sa * sb <= 0.0 && sa != sb) break;
+      }
+    }
+    k2 = kb;
   }
   o.p1 = p1; o.p2 = p2;
+  const int D = PG::d(G);
+  const uint32_t M = PG::mask(G);
   if (k2 < 0 || !(sP != sQ)) {
     o.e2 = -1;
-    if (WITH_STAT) for (int i = 0; i < G.d; i++) stat_col0[(size_t)i * cap] = 0.0;
+    if (WITH_STAT) for (int i = 0; i < D; i++) stat_col0[(size_t)i * cap] = 0.0;
     return;
   }
-  o.e2 = T.slot_he[off + k2];
+  o.e2 = __ldg(T.slot_he + off + k2);
   if (!WITH_STAT) return;
 
+  const int s1 = off + k1;
   const int k2n = (k2 + 1 == n) ? 0 : k2 + 1;
-  const uint32_t fl1 = __ldg(T.flg + s1), fl2 = __ldg(T.flg + off + k2);
-  const bool bnd1 = fl1 & SF_BND, bnd2 = fl2 & SF_BND;
+  const uint32_t fl2 = __ldg(T.flg + off + k2);
+  const bool bnd1 = S.fl1 & SF_BND, bnd2 = fl2 & SF_BND;
   const double d01x = p2.x - p1.x, d01y = p2.y - p1.y;
 
   // children (polygon_insert_edge, :4600-4631):
   //   C1 = [p1, p2, V(k2+1) .. V(k1)],  C2 = [p2, p1, V(k1+1) .. V(k2)]
-  //
   // The child with fewer parent vertices is walked from p1 (accurate however small
   // it is: a corner cut off by the split has relative area ~x^2); the other one is
   // the parent minus it, and its perimeter comes from the prefix sums.
   double A1 = 0, A2 = 0, d01 = 0, L1 = 0, L2 = 0;
-  if (G.mask & MASK_NEED_D01) d01 = sqrt(d01x * d01x + d01y * d01y);
-  if (G.mask & MASK_FACE_AREA) {
-    const bool need_len = G.mask & (1u << LITE_FEAT_FACE_SHAPE);
+  if (M & MASK_NEED_D01) d01 = sqrt(d01x * d01x + d01y * d01y);
+  if (M & MASK_FACE_AREA) {
+    const bool need_len = M & (1u << LITE_FEAT_FACE_SHAPE);
     int dk = k1 - k2n; if (dk < 0) dk += n;          // C1 holds dk+1 parent vertices, C2 the other n-dk-1
     const bool walk1 = 2 * (dk + 1) <= n;
-    const double half_tot = 0.5 * __ldg(T.f_tot2 + T.slot_face[s1]);
+    const double half_tot = S.half_tot;
     const double ltot = need_len ? __ldg(T.plen + off + n - 1) + __ldg(T.len + off + n - 1) : 0.0;
     double Aw, Lw = 0;
     {
@@ -516,73 +592,79 @@ __device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, int 
     A1 = walk1 ? Aw : Ao; A2 = walk1 ? Ao : Aw;
     L1 = walk1 ? Lw : Lo; L2 = walk1 ? Lo : Lw;
   }
-  double m1 = CUDART_INF, m2 = CUDART_INF;
-  if (G.mask & (1u << LITE_FEAT_MIN_ANGLE)) {  // parent corners inherited by each child
-    for (int k = k1n;; k = (k + 1 == n) ? 0 : k + 1) {
-      if (__ldg(T.flg + off + k) & SF_CORNER) m2 = fmin(m2, __ldg(T.ca + off + k));
-      if (k == k2) break;
-    }
-    for (int k = k2n;; k = (k + 1 == n) ? 0 : k + 1) {
-      if (__ldg(T.flg + off + k) & SF_CORNER) m1 = fmin(m1, __ldg(T.ca + off + k));
-      if (k == k1) break;
-    }
-  }
   // new corner angles: alpha at p1 (C2 side), beta at p2 (C1 side)
   const double alpha = angle;
   double beta = 0;
-  if (G.mask & MASK_FACE_ANG) beta = fabs(wrap_pi(__ldg(T.ang + off + k2) - l - LITE_PI));
+  if (M & MASK_FACE_ANG) beta = fabs(wrap_pi(__ldg(T.ang + off + k2) - l - LITE_PI));
 
-  for (int i = 0; i < G.d; i++) {
+  // Every feature value is computed under a branch on the (uniform) program mask,
+  // so that a program pays only for the features it registers; the final loop just
+  // routes the values to their columns.
+  double v_edge_b = 0, v_edge_i = 0, v_inside = 0, v_segsize = 0, v_shape = 0, v_minang = 0;
+  if (M & (1u << LITE_FEAT_IS_POINT_INSIDE_WINDOW)) {
+    // add_vertices = {p1,p2} (:2143-2144); a point on an edge is strictly inside the
+    // window iff the edge is internal
+    bool in1 = !bnd1;
+    if (x == 0.0) {  // p1 == source vertex of e1
+      int kp = (k1 == 0) ? n - 1 : k1 - 1;
+      in1 = !bnd1 && !(T.flg[off + kp] & SF_BND);
+    }
+    v_inside = (in1 ? 1.0 : 0.0) + (bnd2 ? 0.0 : 1.0);
+  }
+  if (M & ((1u << LITE_FEAT_EDGE_LENGTH) | (1u << LITE_FEAT_EDGE_LENGTH_INTERNAL))) {
+    // -{e1,e2} +{(s1,p1),(p1,t1),(s2,p2),(p2,t2),(p1,p2)} (:2148-2164): the two halves of
+    // a cut edge minus the edge, as the reference sums them (rounding noise, not 0).
+    // edge_length as written only sees window-boundary edges: a rare branch.
+    const bool wi = M & (1u << LITE_FEAT_EDGE_LENGTH_INTERNAL);
+    double c1 = 0, c2 = 0;
+    if (bnd1 || wi) c1 = edge_cut_delta(P.x, P.y, p1.x, p1.y, Q.x, Q.y);
+    if (bnd2 || wi) {
+      const double2 S2 = ldpt(T.pt, off + k2), E2 = ldpt(T.pt, off + k2n);
+      c2 = edge_cut_delta(S2.x, S2.y, p2.x, p2.y, E2.x, E2.y);
+    }
+    v_edge_b = (bnd1 ? c1 : 0.0) + (bnd2 ? c2 : 0.0);
+    v_edge_i = (bnd1 ? 0.0 : c1) + (bnd2 ? 0.0 : c2) + d01;
+  }
+  if (M & (1u << LITE_FEAT_SEGMENT_SIZE_2)) {
+    // boundary segments gain one edge: (k+1)^2-k^2 (:2202-2224, :4424-4434)
+    if (bnd1) v_segsize += 2.0 * T.seg_n_edges[T.slot_seg[s1]] + 1.0;
+    if (bnd2) v_segsize += 2.0 * T.seg_n_edges[T.slot_seg[off + k2]] + 1.0;
+  }
+  if (M & (1u << LITE_FEAT_FACE_SHAPE)) {
+    const int f = T.slot_face[s1];
+    v_shape = shape_of(L1, A1) + shape_of(L2, A2) - shape_of(T.f_perim[f], T.f_area[f]);
+  }
+  if (M & (1u << LITE_FEAT_MIN_ANGLE)) {
+    const int f = T.slot_face[s1];
+    const double m2 = corner_min(T.flg, T.ca, off, n, k1n, k2);  // parent corners inherited by C2
+    const double m1 = corner_min(T.flg, T.ca, off, n, k2n, k1);  // ... by C1
+    // C1 = [p1,p2,...]: seed pi-(pi-alpha); corners pi-alpha (p1), beta (p2)
+    double ma1 = fmin(fmin(alpha, LITE_PI - alpha), fmin(beta, m1));
+    // C2 = [p2,p1,...]: seed pi-(pi-beta); corners pi-beta (p2), alpha (p1)
+    double ma2 = fmin(fmin(beta, LITE_PI - beta), fmin(alpha, m2));
+    v_minang = ma1 + ma2 - T.f_minang[f];
+  }
+#pragma unroll
+  for (int i = 0; i < (PG::kStatic ? PG::d(G) : LITE_MAX_D); i++) {
+    if (!PG::kStatic && i >= D) break;
     double dv = 0.0;  // phi(after) - phi(before)
-    switch (G.fid[i]) {
-      case LITE_FEAT_IS_POINT_INSIDE_WINDOW: {
-        // add_vertices = {p1,p2} (:2143-2144); a point on an edge is strictly
-        // inside the window iff the edge is internal
-        bool in1 = !bnd1;
-        if (x == 0.0) {  // p1 == source vertex of e1
-          int kp = (k1 == 0) ? n - 1 : k1 - 1;
-          in1 = !bnd1 && !(T.flg[off + kp] & SF_BND);
-        }
-        dv = (in1 ? 1.0 : 0.0) + (bnd2 ? 0.0 : 1.0);
-      } break;
-      case LITE_FEAT_EDGE_LENGTH:
-      case LITE_FEAT_EDGE_LENGTH_INTERNAL: {
-        // -{e1,e2} +{(s1,p1),(p1,t1),(s2,p2),(p2,t2),(p1,p2)} (:2148-2164)
-        bool wantb = (G.fid[i] == LITE_FEAT_EDGE_LENGTH);
-        if (bnd1 == wantb) dv += plen(P, p1) + plen(p1, Q) - plen(P, Q);
-        if (bnd2 == wantb) {
-          double2 S = ldpt(T.pt, off + k2), E = ldpt(T.pt, off + k2n);
-          dv += plen(S, p2) + plen(p2, E) - plen(S, E);
-        }
-        if (!wantb) dv += d01;
-      } break;
+    switch (PG::fid(G, i)) {
+      case LITE_FEAT_IS_POINT_INSIDE_WINDOW: dv = v_inside; break;
+      case LITE_FEAT_EDGE_LENGTH: dv = v_edge_b; break;
+      case LITE_FEAT_EDGE_LENGTH_INTERNAL: dv = v_edge_i; break;
       case LITE_FEAT_SEG_NUMBER: dv = 1.0; break;
       case LITE_FEAT_IS_SEGMENT_INTERNAL: dv = 1.0; break;
       case LITE_FEAT_MINUS_IS_SEGMENT_INTERNAL: dv = -1.0; break;
-      case LITE_FEAT_SEGMENT_SIZE_2: {
-        // boundary segments gain one edge: (k+1)^2-k^2 (:2202-2224, :4424-4434)
-        if (bnd1) dv += 2.0 * T.seg_n_edges[T.slot_seg[s1]] + 1.0;
-        if (bnd2) dv += 2.0 * T.seg_n_edges[T.slot_seg[off + k2]] + 1.0;
-      } break;
+      case LITE_FEAT_SEGMENT_SIZE_2: dv = v_segsize; break;
       case LITE_FEAT_FACE_NUMBER: dv = 1.0; break;
       case LITE_FEAT_FACE_AREA_2: dv = -2.0 * A1 * A2; break;  // a1^2+a2^2-(a1+a2)^2
       case LITE_FEAT_FACE_PERIMETER: dv = 2.0 * d01; break;
-      case LITE_FEAT_FACE_SHAPE: {
-        const int f = T.slot_face[s1];
-        dv = shape_of(L1, A1) + shape_of(L2, A2) - shape_of(T.f_perim[f], T.f_area[f]);
-      } break;
+      case LITE_FEAT_FACE_SHAPE: dv = v_shape; break;
       case LITE_FEAT_FACE_SUM_OF_ANGLES:
         // untouched corners cancel; new corners alpha, pi-alpha at p1 and beta, pi-beta at p2
         dv = fabs(LITE_HALF_PI - alpha) + fabs(LITE_HALF_PI - beta);
         break;
-      case LITE_FEAT_MIN_ANGLE: {
-        const int f = T.slot_face[s1];
-        // C1 = [p1,p2,...]: seed pi-(pi-alpha); corners pi-alpha (p1), beta (p2)
-        double ma1 = fmin(fmin(alpha, LITE_PI - alpha), fmin(beta, m1));
-        // C2 = [p2,p1,...]: seed pi-(pi-beta); corners pi-beta (p2), alpha (p1)
-        double ma2 = fmin(fmin(beta, LITE_PI - beta), fmin(alpha, m2));
-        dv = ma1 + ma2 - T.f_minang[f];
-      } break;
+      case LITE_FEAT_MIN_ANGLE: dv = v_minang; break;
       default: break;
     }
     stat_col0[(size_t)i * cap] = -dv;
@@ -604,7 +686,8 @@ struct SplitArgs {
 
 // Stratified length-weighted halfedge of candidate j (the device form of
 // alt_length_weighted_random_halfedge(n), lib/ttessel.cpp:1968-1991): slot m with
-// cum[m-1] <= sel < cum[m], found from a guide table in O(1) expected loads.
+// cum[m-1] <= sel < cum[m] (last slot if sel is beyond), found from a guide table
+// in O(1) expected loads.
 __device__ __forceinline__ int sample_slot(const TessDev &T, double sel) {
   int b = (int)(sel * T.guide_scale);
   b = min(max(b, 0), T.n_guide - 1);
@@ -614,48 +697,64 @@ __device__ __forceinline__ int sample_slot(const TessDev &T, double sel) {
   return m;
 }
 
-// MODE bit0: philox sampling (else given list); bit1: record; bit2: statistics; bit3: checksum
-template <int MODE>
 #ifndef LITE_SPLIT_TB
-#define LITE_SPLIT_TB 256
+#define LITE_SPLIT_TB 128
 #endif
 #ifndef LITE_SPLIT_MINB
-#define LITE_SPLIT_MINB 2
+#define LITE_SPLIT_MINB 6
 #endif
+// MODE bit0: philox sampling (else given list); bit1: record; bit2: statistics; bit3: checksum
+template <int MODE, class PG>
 __global__ void __launch_bounds__(LITE_SPLIT_TB, LITE_SPLIT_MINB) k_split(TessDev T, Prog G, SplitArgs A) {
   constexpr bool PHILOX = MODE & 1, RECORD = MODE & 2, STAT = MODE & 4, CHECK = MODE & 8;
-  long stride = (long)gridDim.x * blockDim.x;
+  // each warp owns a contiguous run of candidates, 32 per iteration
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long n_warps = ((long)gridDim.x * blockDim.x) >> 5;
+  long per = (A.n_local + n_warps - 1) / n_warps;
+  per = (per + 31) & ~31L;
+  const long beg = warp * per;
+  const long end = min(beg + per, A.n_local);
   unsigned long long cx = 0, cs = 0;
   unsigned int bad = 0;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < A.n_local; i += stride) {
-    int s1; double x, angle, U = 0.0;
+  int m = -1;          // current slot of this lane (philox path)
+  double cum_hi = 0;   // cum[m]
+  SlotData S;
+  for (long i = beg + lane; i < end; i += 32) {
+    double x, angle, U = 0.0;
     if (PHILOX) {
-      long j = A.j0 + i;
+      const long j = A.j0 + i;
       uint32_t r[4];
       philox4x32_10(A.ctr0 + (uint64_t)j, 0u, A.seed, r);
       x = u53(r[0], r[1]);
       U = u53(r[2], r[3]);
       // the 22 bits u53 leaves unused place the candidate inside its stratum
-      uint32_t spare = ((r[0] & 31u) << 17) | ((r[1] & 63u) << 11) | ((r[2] & 31u) << 6) | (r[3] & 63u);
-      double jit = (double)spare * (1.0 / 4194304.0);
-      double sel = ((double)j + jit) * A.sel_step;
-      s1 = sample_slot(T, sel);
+      const uint32_t spare = ((r[0] & 31u) << 17) | ((r[1] & 63u) << 11) | ((r[2] & 31u) << 6) | (r[3] & 63u);
+      const double sel = ((double)j + (double)spare * (1.0 / 4194304.0)) * A.sel_step;
+      // sel grows along the lane's run, so the slot only moves forward
+      int m_new = m;
+      if (m < 0) m_new = sample_slot(T, sel);
+      else while (m_new < T.n_cum - 1 && sel >= cum_hi) cum_hi = __ldg(T.cum + ++m_new);
+      if (m_new != m) { m = m_new; cum_hi = __ldg(T.cum + m); S = load_slot(T, m); }
       angle = acos(1.0 - 2.0 * U);  // lib/ttessel.cpp:1792
     } else {
-      s1 = T.he_slot[A.in_he[i]]; x = A.in_x[i]; angle = A.in_angle[i];
+      S = load_slot(T, __ldg(T.he_slot + A.in_he[i])); x = A.in_x[i]; angle = A.in_angle[i];
     }
     SplitOut o;
-    split_eval<STAT>(T, G, s1, x, angle, A.stat + A.base + i, A.cap, o);
+    split_eval<STAT, PG>(T, G, S, x, angle, A.stat + A.base + i, A.cap, o);
     if (o.e2 < 0) bad++;
-    if (RECORD) {
-      A.r_e1[A.base + i] = T.slot_he[s1]; A.r_e2[A.base + i] = o.e2;
-      A.r_p1[A.base + i] = o.p1; A.r_p2[A.base + i] = o.p2;
-      A.r_x[A.base + i] = x; A.r_angle[A.base + i] = angle; A.r_u[A.base + i] = U;
-    }
-    if (CHECK) {
-      unsigned long long key = ((unsigned long long)(unsigned)T.slot_he[s1] << 32) | (unsigned)o.e2;
-      key *= 0x9E3779B97F4A7C15ull; key ^= key >> 29;
-      cx ^= key; cs += (unsigned long long)(unsigned)o.e2;
+    if (RECORD || CHECK) {
+      const int h = __ldg(T.slot_he + S.off + S.k1);
+      if (RECORD) {
+        A.r_e1[A.base + i] = h; A.r_e2[A.base + i] = o.e2;
+        A.r_p1[A.base + i] = o.p1; A.r_p2[A.base + i] = o.p2;
+        A.r_x[A.base + i] = x; A.r_angle[A.base + i] = angle; A.r_u[A.base + i] = U;
+      }
+      if (CHECK) {
+        unsigned long long key = ((unsigned long long)(unsigned)h << 32) | (unsigned)o.e2;
+        key *= 0x9E3779B97F4A7C15ull; key ^= key >> 29;
+        cx ^= key; cs += (unsigned long long)(unsigned)o.e2;
+      }
     }
   }
   if (CHECK) {
@@ -663,7 +762,7 @@ __global__ void __launch_bounds__(LITE_SPLIT_TB, LITE_SPLIT_MINB) k_split(TessDe
       cx ^= __shfl_xor_sync(0xffffffffu, cx, off);
       cs += __shfl_xor_sync(0xffffffffu, cs, off);
     }
-    if ((threadIdx.x & 31) == 0) { atomicXor(A.checksum, cx); atomicAdd(A.checksum + 1, cs); }
+    if (lane == 0) { atomicXor(A.checksum, cx); atomicAdd(A.checksum + 1, cs); }
   }
   if (bad) atomicAdd(A.status, (unsigned long long)bad);
 }
