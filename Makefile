@@ -1,6 +1,6 @@
 # Builds the C-ABI shared library (CUDA, sm_100a) and the CPU oracle.
 NVCC ?= nvcc
-NVFLAGS = -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC
+NVFLAGS = -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -pthread
 LIB = lite_b200/libliteb200.so
 
 all: $(LIB) oracle

@@ -66,7 +66,7 @@ def workload(n_gpus, args):
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.sm, self.reasons, self.max_mhz = [], set(), None
@@ -169,8 +169,8 @@ def run_cpu_reference(args, n_gpus, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=int, default=0, help="override the tessellation size")
     ap.add_argument("--splits", type=int, default=0, help="override the dummy splits per GPU per step")

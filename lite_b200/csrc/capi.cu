@@ -6,9 +6,12 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -70,9 +73,11 @@ template <typename T>
 struct DBuf {
   T *p = nullptr;
   size_t n = 0;
+  bool view = false;  // points into the upload arena, not owned
   int alloc(size_t count) {
-    if (count <= n && p) return 0;
-    if (p) cudaFree(p);
+    if (count <= n && p && !view) return 0;
+    if (p && !view) cudaFree(p);
+    view = false;
     p = nullptr; n = 0;
     if (count == 0) return 0;
     cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
@@ -80,15 +85,27 @@ struct DBuf {
     n = count;
     return 0;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p && !view) cudaFree(p); p = nullptr; n = 0; view = false; }
 };
+
+// One device block + one pinned host block for everything lite_tess_upload copies:
+// the host arrays are packed into the pinned block and cross PCIe in a single copy.
+struct Arena {
+  char *d = nullptr, *h = nullptr;
+  size_t cap = 0, used = 0;
+};
+static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 struct lite_ctx {
   int device = 0, rank = 0, world = 1;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;   // merges+flips run here, beside the split kernel
+  cudaEvent_t ev_fork = nullptr, ev_mf = nullptr;
+  bool mf_inflight = false;         // stream must wait for ev_mf before using the flip statistics
   ncclComm_t comm = nullptr;
   bool have_tess = false, have_prog = false, have_mf = false;
   bool record = false;
+  bool mf_pending = false;  // sums of the last merges_flips still in flight
   bool rev = false;  // direction of the next theta-reduce pass over the split statistics
   int64_t launches = 0;
   // raw SoA
@@ -102,6 +119,9 @@ struct lite_ctx {
   DBuf<int2> sfo;
   DBuf<uint32_t> flg;
   DBuf<int> slot_he, slot_seg, slot_face, he_slot, guide, err;
+  Arena arena;
+  struct PackJob { char *dst; const void *src; size_t bytes; };
+  std::vector<PackJob> pack_jobs;  // host->pinned copies of one upload, run on a few threads
   TessDev T{};
   int n_nb = 0, n_b = 0;
   double int_length = 0;
@@ -162,6 +182,9 @@ extern "C" int lite_ctx_create(lite_ctx **out, int device, int rank, int world_s
   lite_ctx *c = new lite_ctx();
   c->device = device; c->rank = rank; c->world = world_size;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_mf, cudaEventDisableTiming));
   for (int i = 0; i < 8; i++) CU(cudaEventCreate(&c->ev[i]));
   for (int i = 0; i < LITE_TIMER_SLOTS; i++) CU(cudaEventCreate(&c->tev[i]));
   CU(cudaMallocHost((void **)&c->h_pinned, 4096 * sizeof(double)));
@@ -189,6 +212,7 @@ extern "C" int lite_ctx_destroy(lite_ctx *c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->stream2) cudaStreamSynchronize(c->stream2);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < LITE_TIMER_SLOTS; i++) if (c->tev[i]) cudaEventDestroy(c->tev[i]);
@@ -210,6 +234,11 @@ extern "C" int lite_ctx_destroy(lite_ctx *c) {
   c->mstat.release(); c->fstat.release(); c->sums.release(); c->m_he.release();
   c->fl_e1.release(); c->fl_e2.release(); c->fl_right.release(); c->fl_p2.release();
   c->partials.release(); c->red_out.release(); c->counter.release(); c->status.release();
+  if (c->arena.d) cudaFree(c->arena.d);
+  if (c->arena.h) cudaFreeHost(c->arena.h);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_mf) cudaEventDestroy(c->ev_mf);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -219,6 +248,7 @@ extern "C" int lite_ctx_sync(lite_ctx *c) {
   if (!c) return fail(LITE_EINVAL, "null context");
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->stream2));
   return 0;
 }
 
@@ -232,15 +262,43 @@ extern "C" int lite_ctx_set_option(lite_ctx *c, int option, int64_t value) {
   return fail(LITE_EINVAL, "unknown option %d", option);
 }
 
+// stage one host array into the arena; the single H2D copy happens afterwards
 template <typename T>
 static int up(lite_ctx *c, DBuf<T> &b, const T *src, size_t n) {
-  if (b.alloc(n ? n : 1)) return LITE_ECUDA;
-  if (n) CU(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  Arena &A = c->arena;
+  const size_t bytes = (n ? n : 1) * sizeof(T);
+  if (A.used + align256(bytes) > A.cap) return fail(LITE_ESTATE, "upload arena overflow");
+  if (!b.view) b.release();
+  if (n) c->pack_jobs.push_back({A.h + A.used, (const void *)src, n * sizeof(T)});
+  b.p = (T *)(A.d + A.used); b.n = n ? n : 1; b.view = true;
+  A.used += align256(bytes);
+  return 0;
+}
+static int arena_reserve(lite_ctx *c, size_t need) {
+  Arena &A = c->arena;
+  A.used = 0;
+  if (need <= A.cap) return 0;
+  CU(cudaStreamSynchronize(c->stream));
+  if (A.d) cudaFree(A.d);
+  if (A.h) cudaFreeHost(A.h);
+  A.d = A.h = nullptr; A.cap = 0;
+  const size_t cap = need + need / 4;
+  CU(cudaMalloc((void **)&A.d, cap));
+  CU(cudaMallocHost((void **)&A.h, cap));
+  A.cap = cap;
   return 0;
 }
 
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static const bool g_trace = getenv("LITE_B200_TRACE") != nullptr;
+
 extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   if (!c || !s) return fail(LITE_EINVAL, "null argument");
+  if (c->mf_inflight) { cudaStreamSynchronize(c->stream2); c->mf_inflight = false; }
+  const double t0 = now_ms();
+  double t1 = t0, t2 = t0, t3 = t0, t4 = t0;
   CU(cudaSetDevice(c->device));
   const int nH = s->n_halfedges, nF = s->n_faces, nS = s->n_segments, nV = s->n_vertices;
   if (nH <= 0 || nF <= 0 || nS <= 0 || nV <= 0) return fail(LITE_EINVAL, "empty tessellation");
@@ -298,7 +356,21 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
     if (sg < 0 || sg >= nS || s->seg_n_edges[sg] < 2 || s->seg_on_boundary[sg])
       return fail(LITE_EINVAL, "blocking segment %d must be internal with at least two edges", sg);
   }
-  // ---- copies
+  t1 = now_ms();
+  // ---- copies: everything is packed into one pinned block and sent in one transfer
+  int n_guide = 1;
+  while (n_guide < 2 * s->n_face_he) n_guide <<= 1;
+  {
+    size_t need = 0;
+    need += 2 * align256((size_t)nV * 8);
+    need += 8 * align256((size_t)nH * 4) + align256((size_t)nH) + align256((size_t)nH * 8);
+    need += align256((size_t)nF) + 2 * align256((size_t)nF * 4) + align256((size_t)s->n_face_he * 4);
+    need += 3 * align256((size_t)nS * 4) + align256((size_t)nS);
+    need += align256((size_t)(s->n_non_blocking + 1) * 4) + align256((size_t)(s->n_blocking + 1) * 4);
+    need += align256((size_t)s->n_face_he * 8) + 64 * 256;
+    int ra = arena_reserve(c, need);
+    if (ra) return ra;
+  }
   int r = 0;
   r |= up(c, c->vx, s->vx, nV); r |= up(c, c->vy, s->vy, nV);
   r |= up(c, c->he_src, s->he_src, nH); r |= up(c, c->he_twin, s->he_twin, nH);
@@ -312,20 +384,22 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   r |= up(c, c->seg_n_edges, s->seg_n_edges, nS); r |= up(c, c->seg_bnd, s->seg_on_boundary, nS);
   r |= up(c, c->nb_list, s->non_blocking, s->n_non_blocking);
   r |= up(c, c->b_list, s->blocking, s->n_blocking);
-  // guide table: guide[b] = first slot m with cum[m] > b * cl / n_guide
-  int n_guide = 1;
-  while (n_guide < 2 * s->n_face_he) n_guide <<= 1;
-  std::vector<int> guide((size_t)n_guide);
-  {
-    size_t m = 0;
-    for (int b = 0; b < n_guide; b++) {
-      const double lo = (double)b * (cl / (double)n_guide);
-      while (m + 1 < cum.size() && cum[m] <= lo) m++;
-      guide[b] = (int)m;
-    }
+  r |= up(c, c->cum, cum.data(), cum.size());
+  if (c->guide.alloc((size_t)n_guide)) return LITE_ECUDA;
+  if (r) return r;
+  {  // pack the host arrays into the pinned block (memory-bound: a few threads help)
+    const int nt = 4;
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++)
+      th.emplace_back([c, t, nt] {
+        for (size_t k = t; k < c->pack_jobs.size(); k += nt) memcpy(c->pack_jobs[k].dst, c->pack_jobs[k].src, c->pack_jobs[k].bytes);
+      });
+    for (size_t k = 0; k < c->pack_jobs.size(); k += nt) memcpy(c->pack_jobs[k].dst, c->pack_jobs[k].src, c->pack_jobs[k].bytes);
+    for (auto &x : th) x.join();
+    c->pack_jobs.clear();
   }
-  r |= up(c, c->cum, cum.data(), cum.size()); r |= up(c, c->guide, guide.data(), guide.size());
-  if (r) return LITE_ECUDA;
+  t2 = now_ms();
+  CU(cudaMemcpyAsync(c->arena.d, c->arena.h, c->arena.used, cudaMemcpyHostToDevice, c->stream));
   const size_t nSl = (size_t)s->n_face_he;
   if (c->pt.alloc(nSl) || c->ang.alloc(nSl) || c->len.alloc(nSl) || c->ca.alloc(nSl) ||
       c->flg.alloc(nSl) || c->slot_he.alloc(nSl) || c->slot_seg.alloc(nSl) ||
@@ -358,18 +432,24 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   T.total_len = cl; T.guide_scale = (double)n_guide / cl;
   T.sfo = c->sfo.p; T.pre = c->pre.p; T.plen = c->plen.p; T.f_tot2 = c->f_tot2.p; T.stot2 = c->stot2.p;
   int tb = 128, gb = (nF + tb - 1) / tb;
+  k_build_guide<<<(n_guide + 255) / 256, 256, 0, c->stream>>>(c->cum.p, (int)cum.size(), cl / (double)n_guide, n_guide, c->guide.p);
   k_prep_slots<<<gb, tb, 0, c->stream>>>(A);
   // outside faces: count 0 in the device view
   k_prep_faces<<<gb, tb, 0, c->stream>>>(T, c->ca.p, c->f_area.p, c->f_perim.p, c->f_sumang.p, c->f_minang.p,
                                          c->pre.p, c->plen.p, c->f_tot2.p, c->sfo.p, c->stot2.p);
-  c->launches += 2;
+  c->launches += 3;
+  t3 = now_ms();
   int herr = 0;
   CU(cudaMemcpyAsync(&herr, c->err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
+  t4 = now_ms();
+  if (g_trace)
+    fprintf(stderr, "[lite_b200] tess_upload: checks %.3f ms, pack %.3f ms, enqueue %.3f ms, device wait %.3f ms (%zu bytes)\n",
+            t1 - t0, t2 - t1, t3 - t2, t4 - t3, c->arena.used);
   if (herr) return fail(LITE_EINVAL, "%d face halfedge lists disagree with he_next/he_face", herr);
   c->n_nb = s->n_non_blocking; c->n_b = s->n_blocking; c->int_length = s->int_length;
-  c->have_tess = true; c->have_mf = false;
+  c->have_tess = true; c->have_mf = false; c->mf_pending = false;
   c->n_local = 0; c->n_global = 0;
   return 0;
 }
@@ -401,6 +481,7 @@ extern "C" int lite_energy_set(lite_ctx *c, int d, const int32_t *fid) {
     G.mask |= 1u << fid[i];
   }
   if (c->n_local != 0) return fail(LITE_ESTATE, "clear the splits before changing the energy");
+  if (c->mf_inflight) { cudaStreamSynchronize(c->stream2); c->mf_inflight = false; }
   if (c->G.d != G.d) {  // the statistic block is d columns of `cap` rows: re-dimension it
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
@@ -408,8 +489,18 @@ extern "C" int lite_energy_set(lite_ctx *c, int d, const int32_t *fid) {
     c->cap = 0;
   }
   c->G = G;
-  c->have_prog = true; c->have_mf = false;
+  c->have_prog = true; c->have_mf = false; c->mf_pending = false;
   return 0;
+}
+
+// after a stream synchronisation: pick up the merge/flip sums copied by merges_flips
+static void finalize_mf(lite_ctx *c) {
+  if (!c->mf_pending) return;
+  const int d = c->G.d;
+  c->h_sum_m.assign(c->h_pinned + 512, c->h_pinned + 512 + d);
+  c->h_sum_f.assign(c->h_pinned + 512 + LITE_MAX_D, c->h_pinned + 512 + LITE_MAX_D + d);
+  cudaEventElapsedTime(&c->ms_mf, c->ev[4], c->ev[5]);
+  c->mf_pending = false;
 }
 
 extern "C" int lite_candidates_merges_flips(lite_ctx *c, int32_t *n_merges, int32_t *n_flips) {
@@ -421,24 +512,27 @@ extern "C" int lite_candidates_merges_flips(lite_ctx *c, int32_t *n_merges, int3
       c->sums.alloc(2 * LITE_MAX_D) || c->m_he.alloc(nm ? nm : 1) || c->fl_e1.alloc(nf ? nf : 1) ||
       c->fl_e2.alloc(nf ? nf : 1) || c->fl_right.alloc(nf ? nf : 1) || c->fl_p2.alloc(nf ? nf : 1))
     return LITE_ECUDA;
-  CU(cudaMemsetAsync(c->sums.p, 0, 2 * LITE_MAX_D * sizeof(double), c->stream));
-  CU(cudaEventRecord(c->ev[4], c->stream));
+  // fork: the merge/flip kernels are independent of the split kernel and run beside it
+  if (c->mf_inflight) CU(cudaStreamSynchronize(c->stream2));
+  CU(cudaEventRecord(c->ev_fork, c->stream));
+  CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+  CU(cudaMemsetAsync(c->sums.p, 0, 2 * LITE_MAX_D * sizeof(double), c->stream2));
+  CU(cudaEventRecord(c->ev[4], c->stream2));
   if (nm + nf > 0) {
     MFArgs A{};
     A.nb_seg = c->nb_list.p; A.nm = nm; A.mstat = c->mstat.p; A.m_he = c->m_he.p; A.gm = (nm + 127) / 128;
     A.b_seg = c->b_list.p; A.nb = c->n_b; A.fstat = c->fstat.p; A.f_e1 = c->fl_e1.p; A.f_e2 = c->fl_e2.p;
     A.f_right = c->fl_right.p; A.f_p2 = c->fl_p2.p; A.status = c->status.p + 1;
-    k_merges_flips<<<A.gm + (nf + 127) / 128, 128, 0, c->stream>>>(c->T, c->G, A);
-    k_colsum2<<<dim3(d, 2), 1024, 0, c->stream>>>(c->mstat.p, nm, c->fstat.p, nf, c->sums.p);
+    k_merges_flips<<<A.gm + (nf + 127) / 128, 128, 0, c->stream2>>>(c->T, c->G, A);
+    k_colsum2<<<dim3(d, 2), 1024, 0, c->stream2>>>(c->mstat.p, nm, c->fstat.p, nf, c->sums.p);
     c->launches += 2;
   }
-  CU(cudaEventRecord(c->ev[5], c->stream));
-  CU(cudaMemcpyAsync(c->h_pinned, c->sums.p, 2 * LITE_MAX_D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  CU(cudaGetLastError());
-  cudaEventElapsedTime(&c->ms_mf, c->ev[4], c->ev[5]);
-  c->h_sum_m.assign(c->h_pinned, c->h_pinned + d);
-  c->h_sum_f.assign(c->h_pinned + LITE_MAX_D, c->h_pinned + LITE_MAX_D + d);
+  CU(cudaEventRecord(c->ev[5], c->stream2));
+  // the two sums come back with the next synchronisation (lite_pl_eval / lite_pl_sums):
+  // SetEnergy itself does not stall the stream
+  CU(cudaMemcpyAsync(c->h_pinned + 512, c->sums.p, 2 * LITE_MAX_D * sizeof(double), cudaMemcpyDeviceToHost, c->stream2));
+  CU(cudaEventRecord(c->ev_mf, c->stream2));
+  c->mf_pending = true; c->mf_inflight = true;
   c->have_mf = true;
   if (n_merges) *n_merges = nm;
   if (n_flips) *n_flips = nf;
@@ -504,6 +598,7 @@ static bool prog_is_acs(const Prog &G) {
 // the sim_acs energy gets the compile-time program, everything else the run-time one
 template <int MODE>
 static void launch_split(lite_ctx *c, const Prog &G, const SplitArgs &A, int grid) {
+  cudaMemsetAsync(A.ticket, 0, sizeof(unsigned long long), c->stream);
   if ((MODE & 4) && prog_is_acs(G)) k_split<MODE, ProgACS><<<grid, LITE_SPLIT_TB, 0, c->stream>>>(c->T, G, A);
   else k_split<MODE, ProgDyn><<<grid, LITE_SPLIT_TB, 0, c->stream>>>(c->T, G, A);
   c->launches += 1;
@@ -513,7 +608,7 @@ static void fill_split_args(lite_ctx *c, SplitArgs &A) {
   A.stat = c->stat.p; A.cap = c->cap; A.base = (long)c->n_local;
   A.r_e1 = c->r_e1.p; A.r_e2 = c->r_e2.p; A.r_p1 = c->r_p1.p; A.r_p2 = c->r_p2.p;
   A.r_x = c->r_x.p; A.r_angle = c->r_angle.p; A.r_u = c->r_u.p;
-  A.status = c->status.p; A.checksum = c->status.p + 2;
+  A.status = c->status.p; A.checksum = c->status.p + 2; A.ticket = c->status.p + 4;
 }
 
 extern "C" int lite_candidates_add_splits_given(lite_ctx *c, int64_t n, const int32_t *he,
@@ -673,6 +768,7 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
   for (int i = 0; i < d; i++) th.v[i] = theta[i];
   const int maxgrid = c->sm_count * 2;
   if (c->partials.alloc((size_t)maxgrid * NT) || c->red_out.alloc(2 * 128)) return LITE_ECUDA;
+  if (c->mf_inflight) CU(cudaStreamWaitEvent(c->stream, c->ev_mf, 0));  // join the merge/flip stream
   CU(cudaEventRecord(c->ev[2], c->stream));
   // splits (this rank's shard)
   long n = (long)c->n_local;
@@ -700,6 +796,8 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
   CU(cudaMemcpyAsync(c->h_pinned, c->red_out.p, 256 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
+  c->mf_inflight = false;
+  finalize_mf(c);
   cudaEventElapsedTime(&c->ms_eval, c->ev[2], c->ev[3]);
   cudaEventElapsedTime(&c->ms_reduce, c->ev[6], c->ev[7]);
   if (c->ev01) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->ms_split = ms; }
@@ -733,6 +831,11 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
 extern "C" int lite_pl_sums(lite_ctx *c, double *sm, double *sf) {
   if (!c) return fail(LITE_EINVAL, "null context");
   if (!c->have_mf) return fail(LITE_ESTATE, "call lite_candidates_merges_flips first");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->stream2));
+  c->mf_inflight = false;
+  finalize_mf(c);
   for (int i = 0; i < c->G.d; i++) {
     if (sm) sm[i] = c->h_sum_m[i];
     if (sf) sf[i] = c->h_sum_f[i];
@@ -765,6 +868,9 @@ extern "C" int lite_debug_fetch(lite_ctx *c, int which, int64_t first, int64_t c
   if (!c || !out) return fail(LITE_EINVAL, "null argument");
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->stream2));
+  c->mf_inflight = false;
+  finalize_mf(c);
   const size_t ns = (size_t)c->n_local, nm = (size_t)c->n_nb, nf = (size_t)2 * c->n_b;
   const bool rec = c->rcap > 0;
   switch (which) {
@@ -809,6 +915,9 @@ extern "C" int lite_last_kernel_ms(lite_ctx *c, float *a, float *b, float *m) {
   if (!c) return fail(LITE_EINVAL, "null context");
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->stream2));
+  c->mf_inflight = false;
+  finalize_mf(c);
   float ms = 0;
   if (c->ev01 && cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->ms_split = ms;
   if (a) *a = c->ms_split;

@@ -324,6 +324,19 @@ __global__ void k_prep_faces(TessDev T, double *ca, double *f_area, double *f_pe
   f_area[f] = F.area; f_perim[f] = F.perim; f_sumang[f] = F.sumang; f_minang[f] = F.minang;
 }
 
+// guide table of the sampler: guide[b] = first slot m with cum[m] > b * step, clamped
+__global__ void k_build_guide(const double *cum, int n_cum, double step, int n_guide, int *guide) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_guide) return;
+  const double lo = (double)b * step;
+  int l = 0, h = n_cum - 1;
+  while (l < h) {
+    int mid = (l + h) >> 1;
+    if (__ldg(cum + mid) > lo) h = mid; else l = mid + 1;
+  }
+  guide[b] = l;
+}
+
 // ---------------------------------------------------------------------------
 // ray exit search in a hole-free face (ray_exit_face, lib/ttessel.cpp:4515-4576)
 //   line a*X + b*Y = w through the ray source p, direction (dx,dy);
@@ -682,6 +695,7 @@ struct SplitArgs {
   int *r_e1, *r_e2; double2 *r_p1, *r_p2; double *r_x, *r_angle, *r_u;
   unsigned long long *status;  // [0] no-exit count
   unsigned long long *checksum;  // [0] xor hash, [1] sum of e2
+  unsigned long long *ticket;  // run scheduler of this launch (zeroed before it)
 };
 
 // Stratified length-weighted halfedge of candidate j (the device form of
@@ -707,19 +721,31 @@ __device__ __forceinline__ int sample_slot(const TessDev &T, double sel) {
 template <int MODE, class PG>
 __global__ void __launch_bounds__(LITE_SPLIT_TB, LITE_SPLIT_MINB) k_split(TessDev T, Prog G, SplitArgs A) {
   constexpr bool PHILOX = MODE & 1, RECORD = MODE & 2, STAT = MODE & 4, CHECK = MODE & 8;
-  // each warp owns a contiguous run of candidates, 32 per iteration
+  // Guided self-scheduling: a warp takes contiguous runs of candidates (32 per
+  // iteration) from a ticket counter; run lengths halve from n/(2*warps) down to 128,
+  // so the slot cache pays off on the long early runs and the short late ones even
+  // out the finish whatever the residency of the blocks.
   const int lane = threadIdx.x & 31;
-  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long n_warps = ((long)gridDim.x * blockDim.x) >> 5;
-  long per = (A.n_local + n_warps - 1) / n_warps;
-  per = (per + 31) & ~31L;
-  const long beg = warp * per;
-  const long end = min(beg + per, A.n_local);
+  long run0 = (A.n_local + 2 * n_warps - 1) / (2 * n_warps);
+  run0 = max((run0 + 31) & ~31L, 128L);
   unsigned long long cx = 0, cs = 0;
   unsigned int bad = 0;
   int m = -1;          // current slot of this lane (philox path)
   double cum_hi = 0;   // cum[m]
   SlotData S;
+  for (;;) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(A.ticket, 1ULL);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    long beg = 0, len = run0;
+    while (t >= (unsigned long long)n_warps && len > 128) {  // skip whole levels of the schedule
+      beg += n_warps * len; t -= n_warps; len = max(((len >> 1) + 31) & ~31L, 128L);
+    }
+    beg += (long)t * len;
+    if (beg >= A.n_local) break;
+    const long end = min(beg + len, A.n_local);
+    m = -1;
   for (long i = beg + lane; i < end; i += 32) {
     double x, angle, U = 0.0;
     if (PHILOX) {
@@ -756,6 +782,7 @@ __global__ void __launch_bounds__(LITE_SPLIT_TB, LITE_SPLIT_MINB) k_split(TessDe
         cx ^= key; cs += (unsigned long long)(unsigned)o.e2;
       }
     }
+  }
   }
   if (CHECK) {
     for (int off = 16; off; off >>= 1) {
@@ -1016,6 +1043,18 @@ __global__ void __launch_bounds__(1024) k_colsum2(const double *mstat, int nm, c
 //   e_i = exp(theta . p_i)      (lib/ttessel.cpp:3392-3394, :3417-3419, :3435-3436)
 // warp shuffle -> block tree -> fixed-order finish by the last block.
 // ---------------------------------------------------------------------------
+#ifndef LITE_REDUCE_LD
+#define LITE_REDUCE_LD 0
+#endif
+__device__ __forceinline__ double2 ld_stat2(const double2 *p) {
+#if LITE_REDUCE_LD == 0
+  return __ldcs(p);   // streaming: evict first
+#elif LITE_REDUCE_LD == 1
+  return __ldg(p);    // normal caching: the tail of a pass can stay in L2 for the next one
+#else
+  return __ldlu(p);
+#endif
+}
 template <int D, int NT>
 __device__ __forceinline__ void reduce_one(const Theta &th, const double (&p)[D], double (&acc)[NT]) {
   double dot = 0.0;
@@ -1056,8 +1095,8 @@ __global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ stat,
     double2 va[D], vb[D];
 #pragma unroll
     for (int k = 0; k < D; k++) {
-      va[k] = __ldcs((const double2 *)(stat + (size_t)k * cap) + ia);
-      vb[k] = __ldcs((const double2 *)(stat + (size_t)k * cap) + ib);
+      va[k] = ld_stat2((const double2 *)(stat + (size_t)k * cap) + ia);
+      vb[k] = ld_stat2((const double2 *)(stat + (size_t)k * cap) + ib);
     }
     double p[D];
 #pragma unroll
@@ -1077,7 +1116,7 @@ __global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ stat,
     const long ia = rev ? npair - 1 - i : i;
     double2 va[D];
 #pragma unroll
-    for (int k = 0; k < D; k++) va[k] = __ldcs((const double2 *)(stat + (size_t)k * cap) + ia);
+    for (int k = 0; k < D; k++) va[k] = ld_stat2((const double2 *)(stat + (size_t)k * cap) + ia);
     double p[D];
 #pragma unroll
     for (int k = 0; k < D; k++) p[k] = va[k].x;
@@ -1117,12 +1156,15 @@ __global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ stat,
   }
   __syncthreads();
   if (last) {
+    // fixed-order finish: warp w sums output t = w, w+8, ..; its lanes stride over the
+    // blocks' partials and a shuffle tree combines them (same order every run)
     __threadfence();
-    if (threadIdx.x < NT) {
+    for (int t = wid; t < NT; t += (blockDim.x >> 5)) {
       double v = 0;
-      for (unsigned int b = 0; b < gridDim.x; b++)
-        v += ((volatile double *)partials)[(size_t)b * NT + threadIdx.x];
-      out[threadIdx.x] = v;
+      for (unsigned int b = lane; b < gridDim.x; b += 32) v += __ldcg(partials + (size_t)b * NT + t);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) out[t] = v;
     }
     if (threadIdx.x == 0) *counter = 0;
   }
