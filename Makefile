@@ -3,10 +3,10 @@ NVCC ?= nvcc
 NVFLAGS = -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -pthread
 LIB = lite_b200/libliteb200.so
 
-all: $(LIB) oracle
+all: $(LIB) oracle tests/cpp/test_facade
 
-SRC = lite_b200/csrc/capi.cu lite_b200/csrc/host_tess.cpp lite_b200/csrc/host_capi.cpp
-HDR = lite_b200/csrc/kernels.cuh lite_b200/csrc/host_tess.h include/lite_b200.h include/lite_b200_host.h
+SRC = lite_b200/csrc/capi.cu lite_b200/csrc/host_tess.cpp lite_b200/csrc/host_capi.cpp lite_b200/csrc/facade.cpp
+HDR = lite_b200/csrc/kernels.cuh lite_b200/csrc/host_tess.h include/lite_b200.h include/lite_b200_host.h include/ttessel.h
 
 $(LIB): $(SRC) $(HDR)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRC) -ldl
@@ -19,3 +19,7 @@ clean:
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean
+
+# C++ tests of the facade (run by tests/test_facade_cpp.py)
+tests/cpp/test_facade: tests/cpp/test_facade.cpp include/ttessel.h $(LIB)
+	g++ -O1 -std=c++17 -Iinclude -o $@ tests/cpp/test_facade.cpp -Llite_b200 -lliteb200 -Wl,-rpath,'$$ORIGIN/../../lite_b200' -pthread

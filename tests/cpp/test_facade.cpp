@@ -1,0 +1,342 @@
+// Tests of the C++ facade (include/ttessel.h), written after the reference's own
+// Boost.Test suite (reference tests/check_lite.cpp): scripted known answers for
+// the Split constructor, the face-prediction property of modified_elements()
+// against update() on seeded random split/merge/flip sequences (`squared_domain`,
+// tests/check_lite.cpp:1031-1040 with driver :446-542), plus what the reference
+// never tests: statistic_variation, the pseudo-likelihood and its Newton fit.
+//   test_facade cpu   host-only part (no CUDA device needed)
+//   test_facade gpu   device part (Energy / PseudoLikDiscrete / PLInferenceNOIS)
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <fstream>
+#include <sstream>
+
+#include "ttessel.h"
+
+static int g_fail = 0;
+#define CHECK(c)                                                                  \
+  do {                                                                            \
+    if (!(c)) { printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #c); g_fail++; }   \
+  } while (0)
+#define CHECK_CLOSE(a, b, tol)                                                                     \
+  do {                                                                                             \
+    double a_ = (a), b_ = (b);                                                                     \
+    if (!(fabs(a_ - b_) <= (tol) * (1.0 + fabs(b_)))) {                                             \
+      printf("FAIL %s:%d  %s = %.17g vs %s = %.17g\n", __FILE__, __LINE__, #a, a_, #b, b_); g_fail++; \
+    }                                                                                              \
+  } while (0)
+
+// tests/check_lite.cpp:230-290: points equal to 1e-6 %, polygons equal up to rotation
+static bool close_pt(const Point2 &p, const Point2 &q) {
+  double s = 1e-8 * (1.0 + fabs(q.x()) + fabs(q.y()));
+  return fabs(p.x() - q.x()) <= s && fabs(p.y() - q.y()) <= s;
+}
+static bool close_poly(const Polygon &a, const Polygon &b) {
+  if (a.size() != b.size()) return false;
+  Size n = a.size();
+  for (Size r = 0; r < n; r++) {
+    bool ok = true;
+    for (Size i = 0; i < n && ok; i++) ok = close_pt(a[i], b[(i + r) % n]);
+    if (ok) return true;
+  }
+  return false;
+}
+static bool remove_one(HPolygons &set, const HPolygon &p) {
+  for (Size i = 0; i < set.size(); i++)
+    if (close_poly(set[i].outer_boundary(), p.outer_boundary())) { set.erase(set.begin() + i); return true; }
+  return false;
+}
+// prediction_is_right<> (tests/check_lite.cpp:339-397): faces removed / added by update()
+// are exactly modified_elements().del_faces / add_faces
+template <class Mod>
+static bool prediction_is_right(TTessel &t, Mod m) {
+  ModList pred = m.modified_elements();
+  HPolygons before = t.all_faces();
+  t.update(m);
+  HPolygons after = t.all_faces();
+  HPolygons removed = before, added = after;  // set differences
+  for (Size i = 0; i < after.size(); i++) remove_one(removed, after[i]);
+  for (Size i = 0; i < before.size(); i++) remove_one(added, before[i]);
+  bool ok = removed.size() == pred.del_faces.size() && added.size() == pred.add_faces.size();
+  for (Size i = 0; ok && i < pred.del_faces.size(); i++) ok = remove_one(removed, pred.del_faces[i]);
+  for (Size i = 0; ok && i < pred.add_faces.size(); i++) ok = remove_one(added, pred.add_faces[i]);
+  return ok && t.is_valid();
+}
+
+static void test_split_constructor() {
+  // unit square, bottom edge (0,0)->(1,0), x = 1/4, angle pi/2: the split is the vertical x = 1/4
+  TTessel t;
+  t.insert_window(Rectangle(Point2(0, 0), Point2(1, 1)));
+  std::vector<LineTes::Halfedge_handle> hs = t.halfedges();
+  LineTes::Halfedge_handle e;
+  for (Size i = 0; i < hs.size(); i++)
+    if (hs[i]->face()->data() && hs[i]->source()->point() == Point2(0, 0) && hs[i]->target()->point() == Point2(1, 0)) e = hs[i];
+  CHECK(!e.is_null());
+  TTessel::Split s(e, 0.25, CGAL_PI / 2);
+  CHECK(s.is_valid());
+  CHECK(close_pt(s.get_p1(), Point2(0.25, 0)));
+  CHECK(close_pt(s.get_p2(), Point2(0.25, 1)));
+  CHECK(s.get_e2()->source()->point() == Point2(1, 1) && s.get_e2()->target()->point() == Point2(0, 1));
+  ModList m = s.modified_elements();
+  CHECK(m.add_vertices.size() == 2 && m.del_edges.size() == 2 && m.add_edges.size() == 5);
+  CHECK(m.del_faces.size() == 1 && m.add_faces.size() == 2 && m.del_segs.size() == 2 && m.add_segs.size() == 3);
+  CHECK_CLOSE(fabs(m.add_faces[0].outer_boundary().area()) + fabs(m.add_faces[1].outer_boundary().area()), 1.0, 1e-14);
+  t.update(s);
+  CHECK(t.number_of_non_blocking_segments() == 1 && t.number_of_blocking_segments() == 0);
+  CHECK_CLOSE(t.get_total_internal_length(), 4 + 2 * 1.0, 1e-14);
+  CHECK(t.is_valid());
+}
+
+static void test_squared_domain(unsigned seed, int n_split, int n_mixed) {
+  rnd = new CGAL::Random(seed);
+  TTessel t;
+  t.insert_window(Rectangle(Point2(0, 0), Point2(1, 1)));
+  int ok_s = 0, ok_m = 0, ok_f = 0, n_s = 0, n_m = 0, n_f = 0;
+  for (int i = 0; i < n_split; i++) { n_s++; ok_s += prediction_is_right(t, t.propose_split()); }
+  for (int i = 0; i < n_mixed; i++) {
+    int ty = rnd->get_int(0, 3);
+    if (ty == 0) { n_s++; ok_s += prediction_is_right(t, t.propose_split()); }
+    else if (ty == 1 && t.number_of_non_blocking_segments() > 0) { n_m++; ok_m += prediction_is_right(t, t.propose_merge()); }
+    else if (ty == 2 && t.number_of_blocking_segments() > 0) {
+      TTessel::Flip f = t.propose_flip();
+      if (f.get_e2().is_null()) continue;
+      n_f++; ok_f += prediction_is_right(t, f);
+    }
+  }
+  printf("squared_domain seed %u: splits %d/%d merges %d/%d flips %d/%d, %zu cells\n", seed, ok_s, n_s, ok_m, n_m,
+         ok_f, n_f, t.all_faces().size());
+  CHECK(ok_s == n_s); CHECK(ok_m == n_m); CHECK(ok_f == n_f);
+  CHECK(n_m > 0 && n_f > 0);
+  delete rnd; rnd = 0;
+}
+
+static void test_text_roundtrip(const char *fixture) {
+  std::ifstream in(fixture);
+  CHECK(in.good());
+  TTessel t;
+  t.read(in);
+  CHECK(t.is_valid());
+  CHECK(t.all_faces().size() == 11);  // the reference's 11-cell fixture
+  std::stringstream out;
+  t.write(out);
+  TTessel u;
+  u.read(out);
+  CHECK(u.all_faces().size() == 11);
+  CHECK_CLOSE(u.get_total_internal_length(), t.get_total_internal_length(), 1e-13);
+  CHECK(u.number_of_blocking_segments() == t.number_of_blocking_segments());
+}
+
+static void test_catvector_and_energy_registry() {
+  CatVector a, b;
+  a.edges.push_back(1); a.faces.push_back(2); a.faces.push_back(3); a.segs.push_back(4);
+  b = 2.0 * a;
+  CHECK(sum(a + b) == 30 && sum(b - a) == 10 && sum(a * b) == 2 * (1 + 4 + 9 + 16));
+  CatMatrix o = outer(a, a);
+  FMatrix fo = asFMatrix(o);
+  CHECK(fo.size() == 4 && fo[1][2] == 6 && fo[3][3] == 16);
+  FVector x(4); x[0] = 9; x[1] = 8; x[2] = 7; x[3] = 6;
+  fill(a, x);
+  CHECK(a.edges[0] == 9 && a.faces[1] == 7 && a.segs[0] == 6);
+  Energy e;
+  e.add_theta_segs(1.0); e.add_features_segs(minus_is_segment_internal);
+  e.add_theta_faces(0.5); e.add_features_faces(face_area_2);
+  std::vector<int32_t> p = e.device_program();
+  CHECK(p.size() == 2 && p[0] == LITE_FEAT_FACE_AREA_2 && p[1] == LITE_FEAT_MINUS_IS_SEGMENT_INTERNAL);
+  Energy bad;
+  bad.add_theta_faces(1.0);
+  bool threw = false;
+  try { bad.device_program(); } catch (const std::logic_error &) { threw = true; }
+  CHECK(threw);  // #theta != #features (UB in the reference, lib/ttessel.cpp:2925-2929)
+}
+
+static double user_feature(HPolygon, TTessel *) { return 42.0; }
+static void test_unknown_feature_is_refused() {
+  Energy e;
+  e.add_theta_faces(1.0); e.add_features_faces(user_feature);
+  bool threw = false;
+  try { e.device_program(); } catch (const std::invalid_argument &) { threw = true; }
+  CHECK(threw);  // no CPU fallback for user feature functions
+}
+
+static void test_host_features() {
+  TTessel t;
+  t.insert_window(Rectangle(Point2(0, 0), Point2(1, 1)));
+  CHECK(is_point_inside_window(Point2(0.5, 0.5), &t) == 1.0 && is_point_inside_window(Point2(0, 0.5), &t) == 0.0);
+  std::vector<Point2> s; s.push_back(Point2(0, 0.2)); s.push_back(Point2(0, 0.7));
+  CHECK(is_segment_internal(s, &t) == 0.0);
+  s[1] = Point2(1, 0.7);
+  CHECK(is_segment_internal(s, &t) == 1.0);
+  CHECK_CLOSE(edge_length(Segment(Point2(0, 0.2), Point2(0, 0.7)), &t), 0.5, 1e-15);  // boundary edge: length (as written)
+  CHECK(edge_length(Segment(Point2(0.1, 0.2), Point2(0.1, 0.7)), &t) == 0.0);   // internal edge: 0 (as written)
+  HPolygons f = t.all_faces();
+  CHECK(f.size() == 1);
+  CHECK_CLOSE(face_area_2(f[0], &t), 1.0, 1e-15);
+  CHECK_CLOSE(face_perimeter(f[0], &t), 4.0, 1e-15);
+  CHECK_CLOSE(face_sum_of_angles(f[0], &t), 0.0, 1e-15);
+  CHECK_CLOSE(min_angle(f[0], &t), CGAL_PI / 2, 1e-15);
+}
+
+// ---- device part -----------------------------------------------------------
+// Energy::statistic_variation on the GPU == sum f(added) - sum f(removed) over the
+// host's modified_elements() with the host feature functions (lib/ttessel.cpp:2914-2980)
+static CatVector host_statistic_variation(Energy &e, TTessel::Modification &m) {
+  ModList ml = m.modified_elements();
+  const Features &F = e.get_features();
+  TTessel *t = e.get_ttessel();
+  CatVector r;
+  for (Size i = 0; i < F.vertices.size(); i++) {
+    double v = 0;
+    for (Size k = 0; k < ml.del_vertices.size(); k++) v -= F.vertices[i](ml.del_vertices[k], t);
+    for (Size k = 0; k < ml.add_vertices.size(); k++) v += F.vertices[i](ml.add_vertices[k], t);
+    r.vertices.push_back(v);
+  }
+  for (Size i = 0; i < F.edges.size(); i++) {
+    double v = 0;
+    for (Size k = 0; k < ml.del_edges.size(); k++) v -= F.edges[i](ml.del_edges[k], t);
+    for (Size k = 0; k < ml.add_edges.size(); k++) v += F.edges[i](ml.add_edges[k], t);
+    r.edges.push_back(v);
+  }
+  for (Size i = 0; i < F.faces.size(); i++) {
+    double v = 0;
+    for (Size k = 0; k < ml.del_faces.size(); k++) v -= F.faces[i](ml.del_faces[k], t);
+    for (Size k = 0; k < ml.add_faces.size(); k++) v += F.faces[i](ml.add_faces[k], t);
+    r.faces.push_back(v);
+  }
+  for (Size i = 0; i < F.segs.size(); i++) {
+    double v = 0;
+    for (Size k = 0; k < ml.del_segs.size(); k++) v -= F.segs[i](ml.del_segs[k], t);
+    for (Size k = 0; k < ml.add_segs.size(); k++) v += F.segs[i](ml.add_segs[k], t);
+    r.segs.push_back(v);
+  }
+  return r;
+}
+static void check_vec(const CatVector &got, const CatVector &want, const char *what) {
+  std::vector<double> g = asVectorOfDoubles(got), w = asVectorOfDoubles(want);
+  CHECK(g.size() == w.size());
+  for (Size i = 0; i < g.size() && i < w.size(); i++)
+    if (!(fabs(g[i] - w[i]) <= 1e-12 + 1e-9 * fabs(w[i]))) {
+      printf("FAIL %s component %zu: device %.17g host %.17g\n", what, i, g[i], w[i]);
+      g_fail++;
+    }
+}
+
+static void test_device_statistic_variation() {
+  rnd = new CGAL::Random(7);
+  TTessel t;
+  t.insert_window(Rectangle(Point2(0, 0), Point2(1, 1)));
+  t.simulate_crtt(3.0, 4000, 11);
+  CHECK(t.is_valid());
+  Energy e;  // all twelve built-in features, CatVector order
+  e.add_theta_vertices(0.3); e.add_features_vertices(is_point_inside_window);
+  e.add_theta_edges(0.2); e.add_features_edges(edge_length);
+  double (*ff[])(HPolygon, TTessel *) = {face_number, face_area_2, face_perimeter, face_shape, face_sum_of_angles, min_angle};
+  for (int i = 0; i < 6; i++) { e.add_theta_faces(0.1 * (i + 1)); e.add_features_faces(ff[i]); }
+  double (*sf[])(std::vector<Point2>, TTessel *) = {seg_number, is_segment_internal, minus_is_segment_internal, segment_size_2};
+  for (int i = 0; i < 4; i++) { e.add_theta_segs(0.05 * (i + 1)); e.add_features_segs(sf[i]); }
+  e.set_ttessel(&t);
+  TTessel::Split_list ss = t.split_sample(60);
+  for (Size i = 0; i < ss.size(); i++) {
+    if (!ss[i].is_valid()) continue;
+    check_vec(e.statistic_variation(ss[i]), host_statistic_variation(e, ss[i]), "split");
+  }
+  TTessel::Merge_list ms = t.all_merges();
+  for (Size i = 0; i < ms.size(); i++) check_vec(e.statistic_variation(ms[i]), host_statistic_variation(e, ms[i]), "merge");
+  TTessel::Flip_list fs = t.all_flips();
+  for (Size i = 0; i < fs.size(); i++) check_vec(e.statistic_variation(fs[i]), host_statistic_variation(e, fs[i]), "flip");
+  printf("statistic_variation: %zu splits, %zu merges, %zu flips checked against the host element lists\n", ss.size(),
+         ms.size(), fs.size());
+  // energy bookkeeping of the chain: value tracks set_ttessel's from-scratch value
+  SMFChain smf(&e, 0.33, 0.33);
+  double v0 = e.get_value();
+  ModifCounts c = smf.step(60);
+  double tracked = e.get_value();
+  e.set_ttessel(&t);
+  CHECK(c.proposed_S + c.proposed_M + c.proposed_F == 60);
+  CHECK_CLOSE(tracked, e.get_value(), 1e-9);
+  (void)v0;
+  delete rnd; rnd = 0;
+}
+
+static void test_crtt_newton_fit() {
+  // demos/pseudo_lik_inference.cpp:56-81 realised with PLInferenceNOIS: the estimate must
+  // reach the closed form log(n_nb*pi/u) whatever the dummy sample
+  rnd = new CGAL::Random(5);
+  TTessel t;
+  t.insert_window(Rectangle(Point2(0, 0), Point2(1, 1)));
+  t.simulate_crtt(3.0, 6000, 5);
+  Energy fit;
+  fit.add_theta_segs(0.0);
+  fit.add_features_segs(minus_is_segment_internal);
+  fit.set_ttessel(&t);
+  PLInferenceNOIS pl(&fit, true, 1.0);
+  unsigned it = pl.Run(1e-10, 50);
+  double exact = log(t.number_of_non_blocking_segments() * CGAL_PI / t.get_total_internal_length());
+  printf("CRTT fit: %u iterations, estimate %.12f, exact %.12f\n", it, pl.GetEstimate().segs[0], exact);
+  CHECK_CLOSE(pl.GetEstimate().segs[0], exact, 1e-8);
+  CHECK(pl.GetEstimates().size() == it + 1 && pl.GetValues().size() == it + 1);
+  // value / gradient / Hessian at the optimum: gradient 0, Hessian -(u/pi) e^theta
+  CatVector th = pl.GetEstimate();
+  CHECK(fabs(pl.GetGradient(th).segs[0]) < 1e-6);
+  CHECK_CLOSE(pl.GetHessian(th).segs[0].segs[0], -(t.get_total_internal_length() / CGAL_PI) * exp(th.segs[0]), 1e-10);
+  delete rnd; rnd = 0;
+}
+
+static void test_acs_eval_and_given_splits() {
+  rnd = new CGAL::Random(3);
+  TTessel t;
+  t.insert_window(Rectangle(Point2(0, 0), Point2(1, 1)));
+  t.simulate_crtt(3.0, 4000, 3);
+  const double tau = 12, fi1 = 0.05, fi2 = 1.0;  // demos/sim_acs.cpp:64-76
+  Energy eng;
+  eng.add_theta_segs(-log(tau)); eng.add_features_segs(is_segment_internal);
+  eng.add_theta_edges((tau - 1) / CGAL_PI); eng.add_features_edges(edge_length);
+  eng.add_features_faces(face_area_2); eng.add_theta_faces(tau * tau * tau * tau * fi1);
+  eng.add_features_faces(face_sum_of_angles); eng.add_theta_faces(fi2);
+  eng.set_ttessel(&t);
+  PseudoLikDiscrete pl(&eng);
+  TTessel::Split_list ss = t.split_sample(300);
+  // the same value from the per-candidate statistics, summed as lib/ttessel.cpp:3387-3404
+  CatVector th = eng.get_theta();
+  double S = 0;
+  Size n = 0;
+  for (Size i = 0; i < ss.size(); i++) {
+    if (!ss[i].is_valid()) continue;
+    pl.AddGivenSplit(ss[i]);
+    S += exp(sum(th * (-1.0 * eng.statistic_variation(ss[i]))));
+    n++;
+  }
+  CHECK(pl.NumberOfSplits() == n);
+  double lpl = 0, F = 0;
+  TTessel::Merge_list ms = t.all_merges();
+  for (Size i = 0; i < ms.size(); i++) lpl += eng.variation(ms[i]);   // -theta.M with M = -sum variation
+  TTessel::Flip_list fs = t.all_flips();
+  for (Size i = 0; i < fs.size(); i++) { double v = eng.variation(fs[i]); lpl += v; F += exp(-v); }
+  lpl -= t.get_total_internal_length() / (CGAL_PI * n) * S + F;
+  CHECK_CLOSE(pl.GetValue(th), lpl, 1e-9);
+  pl.ClearSplits();
+  bool threw = false;
+  try { pl.GetValue(th); } catch (const std::exception &) { threw = true; }
+  CHECK(threw);  // no dummy split: the reference divides by zero (lib/ttessel.cpp:3396)
+  delete rnd; rnd = 0;
+}
+
+int main(int argc, char **argv) {
+  const char *mode = argc > 1 ? argv[1] : "cpu";
+  if (!strcmp(mode, "cpu")) {
+    test_split_constructor();
+    test_squared_domain(5, 100, 50);     // tests/check_lite.cpp:1031-1040
+    test_squared_domain(11, 40, 400);
+    test_text_roundtrip(argc > 2 ? argv[2] : "tests/golden/tessellation_data.txt");
+    test_catvector_and_energy_registry();
+    test_unknown_feature_is_refused();
+    test_host_features();
+  } else {
+    test_device_statistic_variation();
+    test_crtt_newton_fit();
+    test_acs_eval_and_given_splits();
+  }
+  printf(g_fail ? "%d FAILED\n" : "all passed\n", g_fail);
+  return g_fail ? 1 : 0;
+}
