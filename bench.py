@@ -12,9 +12,11 @@ A *step* is one pass of the hot path over one batch:
     (+ one NCCL allreduce of 1+d+d(d+1)/2 doubles when N > 1).
 
 Workloads:
-    N = 1 : config C2 — ~10^4-cell CRTT tessellation, 10^7 splits, ACS energy d=4
-    N > 1 : config C3 — ~10^5-cell tessellation, 1.25*10^7 splits per GPU
-            (10^8 at N=8), contiguous shards, weak scaling.
+    default     : config C2 — ~10^4-cell CRTT tessellation, ACS energy d=4, 10^7
+                  dummy splits PER GPU (weak scaling: N GPUs evaluate N*10^7 splits
+                  of the same tessellation in contiguous shards).
+    --workload c3 : config C3 — ~10^5-cell tessellation, 1.25*10^7 splits per GPU
+                  (10^8 at N=8), the north star's multi-GPU sizing.
 
 `value`  : whole-job candidates/s, tessellation already resident in HBM.
 `e2e`    : the same through the C ABI starting from HOST buffers every step:
@@ -51,15 +53,10 @@ F_ALG_REDUCE = 60.0
 
 
 def workload(n_gpus, args):
-    if args.cells:
-        cells = args.cells
-    else:
-        cells = 10000 if n_gpus == 1 else 100000
-    if args.splits:
-        per_gpu = args.splits
-    else:
-        per_gpu = 10_000_000 if n_gpus == 1 else 12_500_000
-    name = "C2" if (cells == 10000 and n_gpus == 1) else ("C3" if cells == 100000 else "custom")
+    c3 = args.workload == "c3"
+    cells = args.cells or (100000 if c3 else 10000)
+    per_gpu = args.splits or (12_500_000 if c3 else 10_000_000)
+    name = "custom" if (args.cells or args.splits) else ("C3" if c3 else "C2")
     return name, cells, per_gpu
 
 
@@ -172,6 +169,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
     ap.add_argument("--cells", type=int, default=0, help="override the tessellation size")
     ap.add_argument("--splits", type=int, default=0, help="override the dummy splits per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=0, help="splits per step of the CPU baseline sample")
@@ -202,6 +200,7 @@ def main():
     nccl_id = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
