@@ -823,7 +823,33 @@ __device__ __forceinline__ void merge_one(const TessDev &T, const Prog &G, const
 
   double acc[LITE_MAX_D];
   for (int k = 0; k < G.d; k++) acc[k] = 0.0;
-  if (G.mask & MASK_FACE_ANY) {
+  if ((G.mask & MASK_FACE_ANY) && !(G.mask & (1u << LITE_FEAT_MIN_ANGLE))) {
+    // Closed forms from the parents' precomputed features.  The merged face is
+    // face(e) + face(twin e) with p1, p2 flat (:4945-4966): areas add, the perimeter
+    // loses e twice, every other corner keeps its angle, so only the four corners at
+    // p1 and p2 leave the sum of angles.
+    const FaceFeat F1 = parent_feat(T, f1), F2 = parent_feat(T, f2);
+    double gone = 0;
+    if (G.mask & (1u << LITE_FEAT_FACE_SUM_OF_ANGLES)) {
+      const int cs[4] = {o1 + ke, o1 + ke1, o2 + kt, o2 + kt1};
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+        if (T.flg[cs[c]] & SF_CORNER) gone += fmax(0.0, LITE_HALF_PI - T.ca[cs[c]]);
+    }
+    for (int k = 0; k < G.d; k++) {
+      switch (G.fid[k]) {
+        case LITE_FEAT_FACE_NUMBER: acc[k] = -1.0; break;
+        case LITE_FEAT_FACE_AREA_2: acc[k] = 2.0 * F1.area * F2.area; break;  // (a1+a2)^2-a1^2-a2^2
+        case LITE_FEAT_FACE_PERIMETER: acc[k] = -2.0 * elen; break;
+        case LITE_FEAT_FACE_SHAPE:
+          acc[k] = shape_of(F1.perim + F2.perim - 2.0 * elen, F1.area + F2.area) - shape_of(F1.perim, F1.area) -
+                   shape_of(F2.perim, F2.area);
+          break;
+        case LITE_FEAT_FACE_SUM_OF_ANGLES: acc[k] = -gone; break;
+        default: break;
+      }
+    }
+  } else if (G.mask & MASK_FACE_ANY) {
     bool ang = G.mask & MASK_FACE_ANG;
     VPoly P;
     FaceFeat F;
@@ -927,7 +953,87 @@ __device__ __forceinline__ void flip_one(const TessDev &T, const Prog &G, const 
 
   double acc[LITE_MAX_D];
   for (int k = 0; k < G.d; k++) acc[k] = 0.0;
-  if (G.mask & MASK_FACE_ANY) {
+  const double l_e1 = plen(a, q), l_new = plen(a, p2);
+  if ((G.mask & MASK_FACE_ANY) && !(G.mask & (1u << LITE_FEAT_MIN_ANGLE))) {
+    // Closed forms.  R = the face the ray enters, L = the other face
+    // of e1.  The chord (a,p2) cuts R into R1 (the part bounded by e1) and R2; the
+    // flip gives -{R, L} +{R2, R1 u L} (:2515-2655).  Areas and perimeters follow
+    // from those of R, L (precomputed) and of ONE of the two parts, walked from a
+    // (the one with fewer vertices).  In the sum of angles only three vertices move:
+    // a keeps its corner (it passes from L to R2), q loses its two corners delta and
+    // pi-delta, p2 gains beta and pi-beta.
+    const int fR = right ? fT : fL, fO = right ? fL : fT;
+    const FaceFeat FR = parent_feat(T, fR), FO = parent_feat(T, fO);
+    const bool need_len = G.mask & (1u << LITE_FEAT_FACE_SHAPE);
+    double r1 = 0, pr1 = 0;  // area and perimeter of R1
+    if (G.mask & MASK_FACE_AREA) {
+      // left part  [a, p2, V(k2n) .. V(ka-1)]  and right part  [a, V(ka+1) .. V(k2), p2]
+      int cl = ka - 1 - k2n; cl = ((cl % nR) + nR) % nR + 1;
+      const bool walk_left = 2 * cl <= nR - 1;
+      const double px = p2.x - a.x, py = p2.y - a.y;
+      double Aw, Lw = 0;
+      {
+        const int ks = walk_left ? k2n : (ka + 1) % nR, ke_ = walk_left ? (ka + nR - 1) % nR : k2;
+        double2 Vk = ldpt(T.pt, oR + ks);
+        double rx = Vk.x - a.x, ry = Vk.y - a.y;
+        double acc2 = walk_left ? cross2(px, py, rx, ry) : 0.0;
+        if (need_len) Lw = l_new + (walk_left ? plen(p2, Vk) : T.len[oR + ka]);
+        for (int k = ks; k != ke_;) {
+          const int kn = (k + 1 == nR) ? 0 : k + 1;
+          const double2 Vn = ldpt(T.pt, oR + kn);
+          const double qx = Vn.x - a.x, qy = Vn.y - a.y;
+          acc2 += cross2(rx, ry, qx, qy);
+          if (need_len) Lw += T.len[oR + k];
+          rx = qx; ry = qy; k = kn;
+        }
+        if (!walk_left) acc2 += cross2(rx, ry, px, py);
+        if (need_len) Lw += walk_left ? T.len[oR + ke_] : sqrt((rx - px) * (rx - px) + (ry - py) * (ry - py));
+        Aw = 0.5 * acc2;
+      }
+      double Ao = FR.area - Aw;
+      if (Ao < 1e-6 * FR.area) {  // the unwalked part is a sliver: walk it as well
+        const int ks = walk_left ? (ka + 1) % nR : k2n, ke_ = walk_left ? k2 : (ka + nR - 1) % nR;
+        double2 Vk = ldpt(T.pt, oR + ks);
+        double rx = Vk.x - a.x, ry = Vk.y - a.y;
+        double acc2 = walk_left ? 0.0 : cross2(px, py, rx, ry);
+        for (int k = ks; k != ke_;) {
+          const int kn = (k + 1 == nR) ? 0 : k + 1;
+          const double2 Vn = ldpt(T.pt, oR + kn);
+          const double qx = Vn.x - a.x, qy = Vn.y - a.y;
+          acc2 += cross2(rx, ry, qx, qy);
+          rx = qx; ry = qy; k = kn;
+        }
+        if (walk_left) acc2 += cross2(rx, ry, px, py);
+        Ao = 0.5 * acc2;
+      }
+      const double Lo = FR.perim + 2.0 * l_new - Lw;  // the two parts share the chord
+      // R1 is the left part when the ray went to the right of e1 (it holds twin(e1): q -> a)
+      const bool r1_is_walked = (walk_left == right);
+      r1 = r1_is_walked ? Aw : Ao;
+      pr1 = r1_is_walked ? Lw : Lo;
+    }
+    double d_sumang = 0;
+    if (G.mask & (1u << LITE_FEAT_FACE_SUM_OF_ANGLES)) {
+      const int sq = right ? oL + (k1 + 1) % nL : oT + kt;  // slot of L whose source is q
+      const double delta = (T.flg[sq] & SF_CORNER) ? T.ca[sq] : LITE_PI;
+      const double beta = fabs(wrap_pi(T.ang[oR + k2] - ang3 - LITE_PI));
+      d_sumang = fabs(LITE_HALF_PI - beta) - fabs(LITE_HALF_PI - delta);
+    }
+    for (int k = 0; k < G.d; k++) {
+      switch (G.fid[k]) {
+        case LITE_FEAT_FACE_NUMBER: acc[k] = 0.0; break;
+        // a(R2)^2 + a(R1 u L)^2 - a(R)^2 - a(L)^2 with a(R2) = a(R) - r1, a(R1 u L) = a(L) + r1
+        case LITE_FEAT_FACE_AREA_2: acc[k] = 2.0 * r1 * (FO.area - FR.area + r1); break;
+        case LITE_FEAT_FACE_PERIMETER: acc[k] = 2.0 * (l_new - l_e1); break;
+        case LITE_FEAT_FACE_SHAPE:
+          acc[k] = shape_of(FR.perim + 2.0 * l_new - pr1, FR.area - r1) + shape_of(FO.perim + pr1 - 2.0 * l_e1, FO.area + r1) -
+                   shape_of(FR.perim, FR.area) - shape_of(FO.perim, FO.area);
+          break;
+        case LITE_FEAT_FACE_SUM_OF_ANGLES: acc[k] = d_sumang; break;
+        default: break;
+      }
+    }
+  } else if (G.mask & MASK_FACE_ANY) {
     bool ang = G.mask & MASK_FACE_ANG;
     VPoly P; FaceFeat F;
     // deleted faces: the face of e2 first, then the other face bounded by e1 (:2644-2651)
@@ -963,7 +1069,6 @@ __device__ __forceinline__ void flip_one(const TessDev &T, const Prog &G, const 
       F = vp_features(T, P, ang); add_face_feats(G, acc, +1.0, F);
     }
   }
-  double l_e1 = plen(a, q), l_new = plen(a, p2);
   for (int k = 0; k < G.d; k++) {
     double dv = 0.0;
     switch (G.fid[k]) {

@@ -73,6 +73,22 @@ def test_golden_candidates_all12(lite, name):
 
 
 @pytest.mark.parametrize("name", ["t11", "t100"])
+def test_golden_candidates_without_min_angle(lite, name):
+    """Without min_angle the merge and flip kernels take their closed-form path (areas,
+    perimeters and angles from the parents' precomputed features); same golden columns."""
+    soa, gold = load_golden(name)
+    feats = [f for f in ALL12 if f != "min_angle"]
+    cols = [ALL12.index(f) for f in feats]
+    ctx = _ctx(lite, soa, feats)
+    ctx.merges_flips()
+    ctx.add_splits_given(gold["cand_he"], gold["cand_x"], gold["cand_angle"])
+    _assert_stats("split", ctx.fetch("SPLIT_STAT"), gold["split_stat"][:, cols], feats)
+    _assert_stats("merge", ctx.fetch("MERGE_STAT"), gold["merge_stat"][:, cols], feats)
+    _assert_stats("flip", ctx.fetch("FLIP_STAT"), gold["flip_stat"][:, cols], feats)
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["t11", "t100"])
 @pytest.mark.parametrize("tag,feats", [("crtt", ["minus_is_segment_internal"]), ("acs", ACS)])
 def test_golden_pl_value_gradient_hessian(lite, name, tag, feats):
     soa, gold = load_golden(name)
