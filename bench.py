@@ -323,6 +323,11 @@ def main():
             tr = json.load(open(prof))
             roofline["traffic"] = tr.get("k_split")
             roofline_reduce["traffic"] = tr.get("k_reduce")
+            fx = tr.get("k_split_dp_flop_per_candidate_executed")
+            if fx:   # what the kernel actually executes (ncu), next to the nominal SURVEY figure
+                roofline["executed_flop_per_candidate"] = fx
+                roofline["executed_tflops"] = rate_split * fx / 1e12
+                roofline["executed_frac"] = rate_split * fx / 1e12 / fp64_peak
         except Exception:
             pass
 

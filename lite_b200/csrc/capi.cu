@@ -149,6 +149,9 @@ struct lite_ctx {
   float ms_split = 0, ms_eval = 0, ms_mf = 0, ms_reduce = 0;
   bool ev01 = false;  // ev[0]/ev[1] have been recorded
   std::vector<uint8_t> h_he_inside;
+  std::vector<double> h_cum;        // cumulative slot lengths of the last upload (host copy)
+  cudaEvent_t ev_upload = nullptr;  // the H2D copy of the last upload has left the pinned block
+  bool upload_inflight = false;
   int sm_count = 148;
 };
 
@@ -184,6 +187,7 @@ extern "C" int lite_ctx_create(lite_ctx **out, int device, int rank, int world_s
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_upload, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_mf, cudaEventDisableTiming));
   for (int i = 0; i < 8; i++) CU(cudaEventCreate(&c->ev[i]));
   for (int i = 0; i < LITE_TIMER_SLOTS; i++) CU(cudaEventCreate(&c->tev[i]));
@@ -237,6 +241,7 @@ extern "C" int lite_ctx_destroy(lite_ctx *c) {
   if (c->arena.d) cudaFree(c->arena.d);
   if (c->arena.h) cudaFreeHost(c->arena.h);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_upload) cudaEventDestroy(c->ev_upload);
   if (c->ev_mf) cudaEventDestroy(c->ev_mf);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
@@ -282,6 +287,7 @@ static int arena_reserve(lite_ctx *c, size_t need) {
   if (A.d) cudaFree(A.d);
   if (A.h) cudaFreeHost(A.h);
   A.d = A.h = nullptr; A.cap = 0;
+  c->have_tess = false;  // the previous tessellation lived in the freed block
   const size_t cap = need + need / 4;
   CU(cudaMalloc((void **)&A.d, cap));
   CU(cudaMallocHost((void **)&A.h, cap));
@@ -301,7 +307,49 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   double t1 = t0, t2 = t0, t3 = t0, t4 = t0;
   CU(cudaSetDevice(c->device));
   const int nH = s->n_halfedges, nF = s->n_faces, nS = s->n_segments, nV = s->n_vertices;
-  if (nH <= 0 || nF <= 0 || nS <= 0 || nV <= 0) return fail(LITE_EINVAL, "empty tessellation");
+  if (nH <= 0 || nF <= 0 || nS <= 0 || nV <= 0 || s->n_face_he <= 0 || s->n_non_blocking < 0 || s->n_blocking < 0)
+    return fail(LITE_EINVAL, "empty tessellation or negative counts");
+  // ---- copies: everything is packed into one pinned block and sent in one transfer
+  int n_guide = 1;
+  while (n_guide < 2 * s->n_face_he) n_guide <<= 1;
+  {
+    size_t need = 0;
+    need += 2 * align256((size_t)nV * 8);
+    need += 8 * align256((size_t)nH * 4) + align256((size_t)nH) + align256((size_t)nH * 8);
+    need += align256((size_t)nF) + 2 * align256((size_t)nF * 4) + align256((size_t)s->n_face_he * 4);
+    need += 3 * align256((size_t)nS * 4) + align256((size_t)nS);
+    need += align256((size_t)(s->n_non_blocking + 1) * 4) + align256((size_t)(s->n_blocking + 1) * 4);
+    need += align256((size_t)s->n_face_he * 8) + 64 * 256;
+    int ra = arena_reserve(c, need);
+    if (ra) return ra;
+  }
+  if (c->upload_inflight) { CU(cudaEventSynchronize(c->ev_upload)); c->upload_inflight = false; }
+  c->pack_jobs.clear();
+  int r = 0;
+  r |= up(c, c->vx, s->vx, nV); r |= up(c, c->vy, s->vy, nV);
+  r |= up(c, c->he_src, s->he_src, nH); r |= up(c, c->he_twin, s->he_twin, nH);
+  r |= up(c, c->he_next, s->he_next, nH); r |= up(c, c->he_face, s->he_face, nH);
+  r |= up(c, c->he_seg, s->he_seg, nH); r |= up(c, c->he_next_hf, s->he_next_hf, nH);
+  r |= up(c, c->he_prev_hf, s->he_prev_hf, nH); r |= up(c, c->he_dir, s->he_dir, nH);
+  r |= up(c, c->he_length, s->he_length, nH);
+  r |= up(c, c->face_inside, s->face_inside, nF); r |= up(c, c->f_off, s->face_he_offset, nF);
+  r |= up(c, c->f_cnt, s->face_he_count, nF); r |= up(c, c->f_list, s->face_he_list, s->n_face_he);
+  r |= up(c, c->seg_he_start, s->seg_he_start, nS); r |= up(c, c->seg_he_end, s->seg_he_end, nS);
+  r |= up(c, c->seg_n_edges, s->seg_n_edges, nS); r |= up(c, c->seg_bnd, s->seg_on_boundary, nS);
+  r |= up(c, c->nb_list, s->non_blocking, s->n_non_blocking);
+  r |= up(c, c->b_list, s->blocking, s->n_blocking);
+  if (r) return r;
+  // helper threads pack the raw arrays into the pinned block while this thread validates
+  // the links and accumulates the sampler's cumulative lengths
+  std::vector<std::thread> packers;
+  {
+    const int nt = 3;
+    for (int t = 0; t < nt; t++)
+      packers.emplace_back([c, t, nt] {
+        for (size_t k = t; k < c->pack_jobs.size(); k += nt) memcpy(c->pack_jobs[k].dst, c->pack_jobs[k].src, c->pack_jobs[k].bytes);
+      });
+  }
+  struct Joiner { std::vector<std::thread> &v; ~Joiner() { for (auto &x : v) if (x.joinable()) x.join(); } } joiner{packers};
   // ---- export assertions (in the spirit of TTessel::is_valid, lib/ttessel.cpp:1721-1753)
   int64_t listed = 0;
   for (int f = 0; f < nF; f++) {
@@ -327,13 +375,18 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   // cumulative halfedge lengths of the sampler (cumlen += e->get_length(),
   // lib/ttessel.cpp:1980), accumulated in SLOT order: faces in index order, each
   // face in ccb order from outer_ccb().  Entry m of `cum` is slot m.
-  std::vector<double> cum((size_t)s->n_face_he, 0.0);
+  std::vector<double> &cum = c->h_cum;
+  cum.assign((size_t)s->n_face_he, 0.0);
   double cl = 0.0;
   for (int f = 0; f < nF; f++) {
     const int off = s->face_he_offset[f], cnt = s->face_he_count[f];
     for (int k = 0; k < cnt; k++) {
       const int h = s->face_he_list[off + k];
       if (h < 0 || h >= nH) return fail(LITE_EINVAL, "face %d: halfedge id out of range", f);
+      // the list is the ccb of the face: consecutive entries are linked by next()
+      if (s->face_inside[f] &&
+          (s->he_face[h] != f || s->he_next[h] != s->face_he_list[off + (k + 1 == cnt ? 0 : k + 1)]))
+        return fail(LITE_EINVAL, "face %d: halfedge list disagrees with he_next/he_face at position %d", f, k);
       if (s->face_inside[f]) cl += s->he_length[h];
       cum[off + k] = cl;
     }
@@ -357,49 +410,17 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
       return fail(LITE_EINVAL, "blocking segment %d must be internal with at least two edges", sg);
   }
   t1 = now_ms();
-  // ---- copies: everything is packed into one pinned block and sent in one transfer
-  int n_guide = 1;
-  while (n_guide < 2 * s->n_face_he) n_guide <<= 1;
-  {
-    size_t need = 0;
-    need += 2 * align256((size_t)nV * 8);
-    need += 8 * align256((size_t)nH * 4) + align256((size_t)nH) + align256((size_t)nH * 8);
-    need += align256((size_t)nF) + 2 * align256((size_t)nF * 4) + align256((size_t)s->n_face_he * 4);
-    need += 3 * align256((size_t)nS * 4) + align256((size_t)nS);
-    need += align256((size_t)(s->n_non_blocking + 1) * 4) + align256((size_t)(s->n_blocking + 1) * 4);
-    need += align256((size_t)s->n_face_he * 8) + 64 * 256;
-    int ra = arena_reserve(c, need);
-    if (ra) return ra;
-  }
-  int r = 0;
-  r |= up(c, c->vx, s->vx, nV); r |= up(c, c->vy, s->vy, nV);
-  r |= up(c, c->he_src, s->he_src, nH); r |= up(c, c->he_twin, s->he_twin, nH);
-  r |= up(c, c->he_next, s->he_next, nH); r |= up(c, c->he_face, s->he_face, nH);
-  r |= up(c, c->he_seg, s->he_seg, nH); r |= up(c, c->he_next_hf, s->he_next_hf, nH);
-  r |= up(c, c->he_prev_hf, s->he_prev_hf, nH); r |= up(c, c->he_dir, s->he_dir, nH);
-  r |= up(c, c->he_length, s->he_length, nH);
-  r |= up(c, c->face_inside, s->face_inside, nF); r |= up(c, c->f_off, s->face_he_offset, nF);
-  r |= up(c, c->f_cnt, s->face_he_count, nF); r |= up(c, c->f_list, s->face_he_list, s->n_face_he);
-  r |= up(c, c->seg_he_start, s->seg_he_start, nS); r |= up(c, c->seg_he_end, s->seg_he_end, nS);
-  r |= up(c, c->seg_n_edges, s->seg_n_edges, nS); r |= up(c, c->seg_bnd, s->seg_on_boundary, nS);
-  r |= up(c, c->nb_list, s->non_blocking, s->n_non_blocking);
-  r |= up(c, c->b_list, s->blocking, s->n_blocking);
+  for (auto &x : packers) x.join();
+  c->pack_jobs.clear();
   r |= up(c, c->cum, cum.data(), cum.size());
   if (c->guide.alloc((size_t)n_guide)) return LITE_ECUDA;
   if (r) return r;
-  {  // pack the host arrays into the pinned block (memory-bound: a few threads help)
-    const int nt = 4;
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; t++)
-      th.emplace_back([c, t, nt] {
-        for (size_t k = t; k < c->pack_jobs.size(); k += nt) memcpy(c->pack_jobs[k].dst, c->pack_jobs[k].src, c->pack_jobs[k].bytes);
-      });
-    for (size_t k = 0; k < c->pack_jobs.size(); k += nt) memcpy(c->pack_jobs[k].dst, c->pack_jobs[k].src, c->pack_jobs[k].bytes);
-    for (auto &x : th) x.join();
-    c->pack_jobs.clear();
-  }
+  for (size_t k = 0; k < c->pack_jobs.size(); k++) memcpy(c->pack_jobs[k].dst, c->pack_jobs[k].src, c->pack_jobs[k].bytes);
+  c->pack_jobs.clear();
   t2 = now_ms();
   CU(cudaMemcpyAsync(c->arena.d, c->arena.h, c->arena.used, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaEventRecord(c->ev_upload, c->stream));
+  c->upload_inflight = true;
   const size_t nSl = (size_t)s->n_face_he;
   if (c->pt.alloc(nSl) || c->ang.alloc(nSl) || c->len.alloc(nSl) || c->ca.alloc(nSl) ||
       c->flg.alloc(nSl) || c->slot_he.alloc(nSl) || c->slot_seg.alloc(nSl) ||
@@ -439,15 +460,13 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
                                          c->pre.p, c->plen.p, c->f_tot2.p, c->sfo.p, c->stot2.p);
   c->launches += 3;
   t3 = now_ms();
-  int herr = 0;
-  CU(cudaMemcpyAsync(&herr, c->err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  // no synchronisation: the link checks were done on the host above, the copy and the
+  // preparation kernels run behind the caller's next calls on the same stream
   CU(cudaGetLastError());
   t4 = now_ms();
   if (g_trace)
     fprintf(stderr, "[lite_b200] tess_upload: checks %.3f ms, pack %.3f ms, enqueue %.3f ms, device wait %.3f ms (%zu bytes)\n",
             t1 - t0, t2 - t1, t3 - t2, t4 - t3, c->arena.used);
-  if (herr) return fail(LITE_EINVAL, "%d face halfedge lists disagree with he_next/he_face", herr);
   c->n_nb = s->n_non_blocking; c->n_b = s->n_blocking; c->int_length = s->int_length;
   c->have_tess = true; c->have_mf = false; c->mf_pending = false;
   c->n_local = 0; c->n_global = 0;

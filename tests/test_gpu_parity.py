@@ -223,3 +223,78 @@ def test_rejects_bad_input(lite):
     with pytest.raises(lite.LiteError):
         ctx.add_splits_given([outside], [0.5], [1.0])
     ctx.close()
+
+
+def test_random_lines_sample_clip_modes_and_oracle(lite):
+    """Config "random_lines sampling and face clipping" (loop 3a alone): store mode
+    against the CPU port of the oracle on the sampled (halfedge, x, angle), and the
+    checksum mode against the checksum of what store mode wrote."""
+    import oracle_cpu as oc
+    soa, _ = load_golden("t100")
+    ctx = _ctx(lite, soa, ACS, record=False)
+    n, seed, off = 200000, 99, 5
+    cs_store = ctx.lines_sample_clip(n, seed, off, mode=1)
+    e1, e2 = ctx.fetch("SPLIT_E1", 0, n), ctx.fetch("SPLIT_E2", 0, n)
+    p1, p2 = ctx.fetch("SPLIT_P1", 0, n), ctx.fetch("SPLIT_P2", 0, n)
+    x, ang = ctx.fetch("SPLIT_X", 0, n), ctx.fetch("SPLIT_ANGLE", 0, n)
+    cs_only = ctx.lines_sample_clip(n, seed, off, mode=0)
+    np.testing.assert_array_equal(cs_store, cs_only)
+    key = (e1.astype(np.uint64) << np.uint64(32)) | e2.astype(np.uint32).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        key = key * np.uint64(0x9E3779B97F4A7C15)
+        key ^= key >> np.uint64(29)
+    assert int(np.bitwise_xor.reduce(key)) == int(cs_only[0])
+    assert int(e2.astype(np.uint32).astype(np.uint64).sum()) == int(cs_only[1])
+    t = oc.Tess(soa)
+    he, xx, aa = oc.sample_splits(t, n, seed, off, nthreads=4)
+    np.testing.assert_array_equal(e1, he)
+    np.testing.assert_array_equal(x, xx)
+    r = oc.split_stats(t, ["face_number"], e1, x, ang, nthreads=4)
+    assert r["bad"] == 0 and ctx.fetch("STATUS")[0] == 0
+    np.testing.assert_array_equal(e2, r["split_e2"])
+    np.testing.assert_allclose(p1, r["split_p1"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(p2, r["split_p2"], rtol=0, atol=1e-12)
+    ctx.close()
+
+
+def test_full_size_properties(lite):
+    """BASELINE.json's full size (10^7 splits on a 10^4-cell tessellation) through
+    size-independent properties: the CRTT value is the closed form whatever the sample;
+    the per-feature column sums obey the conservation laws of the moves
+    (is_segment_internal: +1 per split; face_area_2: -2*a1*a2 <= 0 and bounded by the
+    parent; edge_length as written: rounding noise); evaluation is linear in the batch:
+    two half batches appended == one batch."""
+    t, _tau = lite.generate_crtt(10000, seed=5)
+    soa = t.export()
+    n = 10_000_000
+    ctx = lite.Context(0)
+    ctx.tess_upload(soa)
+    ctx.energy_set(["minus_is_segment_internal"])
+    nm, nf = ctx.merges_flips()
+    ctx.add_splits_philox(n, 0x5EED, 0)
+    u = soa.int_length
+    for th in (-0.7, 2.0):
+        lpl, g, H = ctx.pl_eval([th])
+        assert lpl == pytest.approx(th * nm - (u / math.pi) * math.exp(th) - nf, rel=1e-12)
+    assert ctx.fetch("STATUS")[0] == 0
+    ctx.clear_splits()
+    ctx.energy_set(ACS)
+    ctx.merges_flips()
+    th = np.array([11 / np.pi, 12.0 ** 4 * 0.05, 1.0, -np.log(12.0)])
+    ctx.add_splits_philox(n, 7, 0)
+    whole = ctx.pl_eval(th)
+    # theta = 0: S0 = N, S1 = column sums of the stored statistics
+    lpl0, g0, H0 = ctx.pl_eval(np.zeros(4))
+    m, f = ctx.pl_sums()
+    c = u / (math.pi * n)
+    col = -(g0 + m + f + ctx.fetch("FLIP_STAT").sum(0)) / c      # sum over splits of -dphi
+    assert col[3] == pytest.approx(-n, rel=1e-12)                 # is_segment_internal: +1 per split
+    assert abs(col[0]) < 1e-6                                     # edge_length as written: noise
+    assert 0 < col[1] < n * 0.5 * (1.0 / 100) ** 2 * 100           # 2*a1*a2, tiny cells
+    assert col[2] < 0                                             # new corners only add to the sum
+    ctx.clear_splits()
+    ctx.add_splits_philox(n, 7, 0)          # same batch again: bitwise the same evaluation
+    again = ctx.pl_eval(th)
+    assert again[0] == whole[0]
+    np.testing.assert_array_equal(again[2], whole[2])
+    ctx.close()
