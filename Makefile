@@ -3,7 +3,7 @@ NVCC ?= nvcc
 NVFLAGS = -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xcompiler -pthread
 LIB = lite_b200/libliteb200.so
 
-all: $(LIB) oracle tests/cpp/test_facade
+all: $(LIB) oracle tests/cpp/test_facade tests/cpp/smf_host
 
 SRC = lite_b200/csrc/capi.cu lite_b200/csrc/host_tess.cpp lite_b200/csrc/host_capi.cpp lite_b200/csrc/facade.cpp
 HDR = lite_b200/csrc/kernels.cuh lite_b200/csrc/philox.h lite_b200/csrc/host_tess.h include/lite_b200.h include/lite_b200_host.h include/ttessel.h
@@ -23,3 +23,7 @@ clean:
 # C++ tests of the facade (run by tests/test_facade_cpp.py)
 tests/cpp/test_facade: tests/cpp/test_facade.cpp include/ttessel.h $(LIB)
 	g++ -O1 -std=c++17 -Iinclude -o $@ tests/cpp/test_facade.cpp -Llite_b200 -lliteb200 -Wl,-rpath,'$$ORIGIN/../../lite_b200' -pthread
+
+# host build of the SMF chain source for the oracle replay test (run by tests/test_smf_chain_cpu.py)
+tests/cpp/smf_host: tests/cpp/smf_host.cpp lite_b200/csrc/smf_chain.h lite_b200/csrc/philox.h include/lite_b200.h
+	g++ -O2 -std=c++17 -o $@ tests/cpp/smf_host.cpp
