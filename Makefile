@@ -6,7 +6,7 @@ LIB = lite_b200/libliteb200.so
 all: $(LIB) oracle tests/cpp/test_facade tests/cpp/smf_host
 
 SRC = lite_b200/csrc/capi.cu lite_b200/csrc/host_tess.cpp lite_b200/csrc/host_capi.cpp lite_b200/csrc/facade.cpp
-HDR = lite_b200/csrc/kernels.cuh lite_b200/csrc/philox.h lite_b200/csrc/host_tess.h include/lite_b200.h include/lite_b200_host.h include/ttessel.h
+HDR = lite_b200/csrc/kernels.cuh lite_b200/csrc/philox.h lite_b200/csrc/smf_chain.h lite_b200/csrc/smf_ensemble.cuh lite_b200/csrc/host_tess.h include/lite_b200.h include/lite_b200_host.h include/ttessel.h
 
 $(LIB): $(SRC) $(HDR)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRC) -ldl

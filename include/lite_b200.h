@@ -33,6 +33,8 @@ extern "C" {
 #define LITE_ENOSPLIT (-5) /* pl_eval with zero dummy splits: the reference
                               divides by stat_splits.size() (lib/ttessel.cpp:3396) */
 
+#define LITE_ECAPACITY (-6) /* an SMF chain outgrew the capacity the ensemble was created with */
+
 #define LITE_MAX_D 12
 
 /* Device feature ids.  The facade maps the addresses of the reference's
@@ -183,6 +185,53 @@ int lite_timer_mark(lite_ctx *ctx, int slot);
 int lite_timer_elapsed(lite_ctx *ctx, int slot_a, int slot_b, float *ms);
 /* Measured DFMA throughput (TFLOP/s) of this GPU: the FP64 roofline denominator. */
 int lite_measure_fp64_peak(lite_ctx *ctx, double *tflops);
+
+/* ------------------------------------------------------------------------
+ * Ensemble of independent SMF chains (BASELINE.json config 5).  The reference
+ * simulates ONE chain per process: SMFChain(&energy, p_split, p_merge).step(n)
+ * (lib/ttessel.cpp:3121-3311) on a TTessel that starts as the empty window, and
+ * applications/checkACS.cpp runs it once per seed, writing a row of statistics
+ * every `nipl` proposals.  Here chain i of the ensemble is one GPU thread with
+ * its own tessellation in device memory; its random numbers are the Philox4x32-10
+ * stream (seed, global chain id, proposal index), so its trajectory does not
+ * depend on the number of ranks.  Chains [r*n/G, (r+1)*n/G) live on rank r; no
+ * collective is involved.
+ * ------------------------------------------------------------------------ */
+struct lite_host_tess; /* include/lite_b200_host.h */
+
+/* TTessel::insert_window(Rectangle) (lib/ttessel.cpp:1544-1550) for every chain.
+ * max_segments: capacity in internal segments per chain (<= 10896); a chain that
+ * would exceed it stops and lite_smf_run returns LITE_ECAPACITY. */
+int lite_smf_create(lite_ctx *ctx, int64_t n_chains_global, int32_t max_segments, double x0,
+                    double y0, double x1, double y1, uint64_t seed);
+int lite_smf_destroy(lite_ctx *ctx);
+/* Energy::add_features_* / add_theta_* + SMFChain::SMFChain(e, p_split, p_merge)
+ * (lib/ttessel.cpp:3016-3088, :3121-3127): d device feature ids with their theta. */
+int lite_smf_set_model(lite_ctx *ctx, int d, const int32_t *feature_id, const double *theta,
+                       double p_split, double p_merge);
+#define LITE_SMF_COLS 12
+/* n_samples x SMFChain::step(steps_per_sample) on every local chain.  rows_out (may
+ * be NULL): n_samples x LITE_SMF_COLS x n_local doubles, the columns of
+ * applications/checkACS.cpp:136-148 after each batch: l(T), n(T), n_bl, n_nbl,
+ * m(T), proposed/accepted S, M, F of that batch, then the energy accumulated
+ * since creation (Energy::add_value, lib/ttessel.cpp:3284). */
+int lite_smf_run(lite_ctx *ctx, int32_t n_samples, int64_t steps_per_sample, double *rows_out);
+/* The same columns for the current state (counts: since the last batch started);
+ * validate != 0 also runs the consistency check of TTessel::is_valid
+ * (lib/ttessel.cpp:1721-1753) on every chain. */
+int lite_smf_stats(lite_ctx *ctx, double *rows_out, int32_t validate);
+/* Parity hook: advance ONE local chain by n_steps proposals, recording each one
+ * (layout: smf::TraceRec, 23 doubles; tests/smf_replay.py). */
+int lite_smf_trace(lite_ctx *ctx, int64_t chain_local, int64_t n_steps, void *trace_out,
+                   int64_t *n_done);
+/* Copy one chain's tessellation into a host model (lite_host_export gives the
+ * lite_tess_soa to upload for a pseudo-likelihood fit, lite_host_write_text the
+ * reference's text format). */
+int lite_smf_export(lite_ctx *ctx, int64_t chain_local, struct lite_host_tess **out);
+int lite_smf_count(lite_ctx *ctx, int64_t *n_local, int64_t *n_global, int64_t *first_global,
+                   int64_t *bytes_per_chain);
+/* Device time (ms) of the last lite_smf_run kernel. */
+int lite_smf_last_ms(lite_ctx *ctx, float *ms);
 
 #ifdef __cplusplus
 }

@@ -34,7 +34,12 @@ SYMBOLS = [
     "lite_candidates_count", "lite_pl_eval", "lite_pl_sums", "lite_lines_sample_clip",
     "lite_debug_fetch", "lite_last_kernel_ms", "lite_kernel_launch_count",
     "lite_measure_fp64_peak", "lite_last_reduce_ms", "lite_timer_mark", "lite_timer_elapsed",
+    "lite_smf_create", "lite_smf_destroy", "lite_smf_set_model", "lite_smf_run", "lite_smf_stats",
+    "lite_smf_trace", "lite_smf_export", "lite_smf_count", "lite_smf_last_ms",
 ]
+
+# columns of lite_smf_run / lite_smf_stats (applications/checkACS.cpp:136-148 + energy)
+SMF_COLS = ["l", "n", "n_bl", "n_nbl", "m", "prop_S", "acc_S", "prop_M", "acc_M", "prop_F", "acc_F", "energy"]
 
 FETCH = dict(SPLIT_E1=0, SPLIT_E2=1, SPLIT_P1=2, SPLIT_P2=3, SPLIT_X=4, SPLIT_ANGLE=5,
              SPLIT_STAT=6, MERGE_HE=7, MERGE_STAT=8, FLIP_E1=9, FLIP_E2=10, FLIP_P2=11,
@@ -152,6 +157,17 @@ def load_library():
     L.lite_last_reduce_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.lite_timer_mark.argtypes = [C.c_void_p, C.c_int]
     L.lite_timer_elapsed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    L.lite_smf_create.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                  C.c_double, C.c_uint64]
+    L.lite_smf_destroy.argtypes = [C.c_void_p]
+    L.lite_smf_set_model.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
+    L.lite_smf_run.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
+    L.lite_smf_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.lite_smf_trace.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(C.c_int64)]
+    L.lite_smf_export.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+    L.lite_smf_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                 C.POINTER(C.c_int64)]
+    L.lite_smf_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     _LIB = L
     return L
 
@@ -317,4 +333,58 @@ class Context:
     def measure_fp64_peak(self):
         t = C.c_double()
         _ck(self.L, self.L.lite_measure_fp64_peak(self.h, C.byref(t)))
+        return t.value
+
+    # ---- ensemble of SMF chains (BASELINE.json config 5) ----
+    def smf_create(self, n_chains_global, max_segments, rect=(0.0, 0.0, 1.0, 1.0), seed=5):
+        _ck(self.L, self.L.lite_smf_create(self.h, int(n_chains_global), int(max_segments),
+                                           *map(float, rect), int(seed)))
+
+    def smf_destroy(self):
+        _ck(self.L, self.L.lite_smf_destroy(self.h))
+
+    def smf_set_model(self, features, theta, p_split=0.33, p_merge=0.33):
+        ids = np.array([FEATURE_IDS[f] if isinstance(f, str) else int(f) for f in features], dtype=np.int32)
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        assert len(th) == len(ids)
+        _ck(self.L, self.L.lite_smf_set_model(self.h, len(ids), ids.ctypes.data_as(C.c_void_p),
+                                              th.ctypes.data_as(C.c_void_p), float(p_split), float(p_merge)))
+
+    def smf_count(self):
+        a, b, f, sz = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        _ck(self.L, self.L.lite_smf_count(self.h, C.byref(a), C.byref(b), C.byref(f), C.byref(sz)))
+        return a.value, b.value, f.value, sz.value
+
+    def smf_run(self, n_samples, steps_per_sample, rows=True):
+        """Returns an array [n_samples, 12, n_local] (columns SMF_COLS) or None."""
+        out = None
+        if rows:
+            out = np.zeros((int(n_samples), len(SMF_COLS), self.smf_count()[0]))
+        _ck(self.L, self.L.lite_smf_run(self.h, int(n_samples), int(steps_per_sample),
+                                        out.ctypes.data_as(C.c_void_p) if rows else None))
+        return out
+
+    def smf_stats(self, validate=False):
+        out = np.zeros((len(SMF_COLS), self.smf_count()[0]))
+        _ck(self.L, self.L.lite_smf_stats(self.h, out.ctypes.data_as(C.c_void_p), 1 if validate else 0))
+        return out
+
+    def smf_trace(self, chain_local, n_steps):
+        """Advance one chain by n_steps proposals; returns the raw trace (23 doubles per step)."""
+        out = np.zeros((int(n_steps), 23))
+        done = C.c_int64()
+        _ck(self.L, self.L.lite_smf_trace(self.h, int(chain_local), int(n_steps), out.ctypes.data_as(C.c_void_p),
+                                          C.byref(done)))
+        return out[:done.value]
+
+    def smf_export(self, chain_local):
+        """One chain's tessellation as a host model (lite_b200.HostTess)."""
+        from .host import HostTess
+        h = C.c_void_p()
+        _ck(self.L, self.L.lite_smf_export(self.h, int(chain_local), C.byref(h)))
+        return HostTess(handle=h)
+
+    def smf_last_ms(self):
+        t = C.c_float()
+        _ck(self.L, self.L.lite_smf_last_ms(self.h, C.byref(t)))
         return t.value

@@ -96,8 +96,11 @@ struct Arena {
 };
 static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
+struct SmfState;  // ensemble of SMF chains, smf_ensemble.cuh
+
 struct lite_ctx {
   int device = 0, rank = 0, world = 1;
+  SmfState *smf = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;   // merges+flips run here, beside the split kernel
   cudaEvent_t ev_fork = nullptr, ev_mf = nullptr;
@@ -212,10 +215,13 @@ extern "C" int lite_ctx_create(lite_ctx **out, int device, int rank, int world_s
   return 0;
 }
 
+static void smf_release(lite_ctx *c);
+
 extern "C" int lite_ctx_destroy(lite_ctx *c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  smf_release(c);
   if (c->stream2) cudaStreamSynchronize(c->stream2);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -989,3 +995,5 @@ extern "C" int lite_measure_fp64_peak(lite_ctx *c, double *tflops) {
   *tflops = best;
   return 0;
 }
+
+#include "smf_ensemble.cuh"

@@ -5,6 +5,7 @@
 
 #include "../../include/lite_b200_host.h"
 #include "host_tess.h"
+#include "smf_chain.h"
 
 extern "C" int lite_set_error_(int code, const char *msg);  // defined in capi.cu
 
@@ -113,4 +114,57 @@ extern "C" int64_t lite_host_write_text(lite_host_tess *h, char *buf, int64_t ca
     buf[n] = 0;
   }
   return (int64_t)s.size() + 1;
+}
+
+// One SMF chain brought back from the GPU (lite_smf_export, capi.cu) -> host model.
+// Ids are kept; elements on the chain's free lists stay dead.
+extern "C" int lite_smf_blob_to_host_(char *blob, int cap, lite_host_tess **out) {
+  smf::Chain c;
+  smf::bind(c, blob, cap);
+  smf::load(c);
+  if (c.H.cap != cap) return lite_set_error_(LITE_EINVAL, "chain block does not match the ensemble capacity");
+  lite_host_tess *h = new lite_host_tess();
+  lite::HostTess &t = h->t;
+  const int nV = c.H.n_v, nH = 2 * c.H.n_p, nF = c.H.n_f, nS = c.H.n_s;
+  t.vx.assign(nV, 0.0); t.vy.assign(nV, 0.0); t.v_inc.assign(nV, -1); t.v_alive.assign(nV, 0);
+  t.h_src.assign(nH, -1); t.h_next.assign(nH, -1); t.h_prev.assign(nH, -1); t.h_face.assign(nH, -1);
+  t.h_seg.assign(nH, -1); t.h_next_hf.assign(nH, -1); t.h_prev_hf.assign(nH, -1);
+  t.h_dir.assign(nH, 0); t.h_alive.assign(nH, 0); t.h_len.assign(nH, 0.0);
+  t.f_he.assign(nF, -1); t.f_inside.assign(nF, 0); t.f_alive.assign(nF, 0);
+  t.s_he.assign(nS, -1); t.s_nedges.assign(nS, 0); t.s_pos.assign(nS, -1); t.s_bnd.assign(nS, 0);
+  t.s_alive.assign(nS, 0); t.s_kind.assign(nS, 0);
+  for (int e = 0; e < nH; e++) {
+    if (c.he[e & ~1].src == smf::NIL) continue;
+    t.h_alive[e] = 1;
+    t.h_src[e] = smf::h_src(c, e); t.h_next[e] = smf::h_next(c, e); t.h_prev[e] = smf::h_prev(c, e);
+    t.h_face[e] = smf::h_face(c, e); t.h_seg[e] = smf::h_seg(c, e);
+    t.h_next_hf[e] = smf::h_nhf(c, e); t.h_prev_hf[e] = smf::h_phf(c, e);
+    t.h_dir[e] = smf::h_dir(c, e); t.h_len[e] = smf::h_len(c, e);
+    const int v = t.h_src[e], f = t.h_face[e], s = t.h_seg[e];
+    t.v_alive[v] = 1; t.vx[v] = c.vtx[v].x; t.vy[v] = c.vtx[v].y;
+    t.f_alive[f] = 1; t.f_inside[f] = (f != 0); t.f_he[f] = c.f_he[f];
+    t.s_alive[s] = 1;
+  }
+  for (int e = 0; e < nH; e++) if (t.h_alive[e]) t.v_inc[t.h_src[e ^ 1]] = e;
+  for (int s = 0; s < nS; s++) {
+    if (!t.s_alive[s]) continue;
+    t.s_he[s] = c.seg[s].he; t.s_nedges[s] = c.seg[s].nedges; t.s_bnd[s] = smf::seg_bnd(s);
+    t.s_kind[s] = (uint8_t)c.seg[s].kind;
+    t.s_pos[s] = (c.seg[s].kind == 1 || c.seg[s].kind == 2) ? (int)c.seg[s].pos : -1;
+  }
+  t.nb_list.assign(c.nb_list, c.nb_list + c.H.n_nb);
+  t.b_list.assign(c.b_list, c.b_list + c.H.n_b);
+  t.int_length = c.H.int_length;
+  // the window: the four corner vertices are ids 0..3 and never die
+  t.win_x = {c.vtx[0].x, c.vtx[1].x, c.vtx[2].x, c.vtx[3].x};
+  t.win_y = {c.vtx[0].y, c.vtx[1].y, c.vtx[2].y, c.vtx[3].y};
+  t.finish_import();
+  std::string err = t.check();
+  if (!err.empty()) {
+    delete h;
+    return lite_set_error_(LITE_EINVAL, ("exported chain is inconsistent: " + err).c_str());
+  }
+  remember_ids(h);
+  *out = h;
+  return 0;
 }

@@ -461,6 +461,17 @@ int HostTess::update_flip(const FlipMove &fl) {  // TTessel::update(Flip), :1644
   return new_e;
 }
 
+void HostTess::finish_import() {
+  free_v.clear(); free_hp.clear(); free_f.clear(); free_s.clear();
+  for (int v = (int)vx.size() - 1; v >= 0; v--) if (!v_alive[v]) free_v.push_back(v);
+  for (int h = (int)h_src.size() - 2; h >= 0; h -= 2) if (!h_alive[h]) free_hp.push_back(h);
+  for (int f = (int)f_he.size() - 1; f >= 0; f--) if (!f_alive[f]) free_f.push_back(f);
+  for (int s = (int)s_he.size() - 1; s >= 0; s--) if (!s_alive[s]) free_s.push_back(s);
+  fen = Fenwick();
+  fen.resize(h_src.size());
+  for (size_t h = 0; h < h_src.size(); h += 2) if (h_alive[h]) refresh_weight((int)h);
+}
+
 int HostTess::sample_halfedge(double u01) const {
   double tot = fen.total();
   return fen.find(u01 * tot);

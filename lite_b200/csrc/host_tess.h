@@ -84,6 +84,10 @@ class HostTess {
   int sample_halfedge(double u01) const;  // u01 in [0,1)
   double weight_total() const { return fen.total(); }
 
+  // after the public arrays have been filled from outside (an SMF chain brought back
+  // from the GPU): rebuild the free lists and the sampling tree from the alive flags
+  void finish_import();
+
   // export; the returned struct points into buffers owned by this object
   const lite_tess_soa *export_soa();
   std::string check() const;  // empty if consistent

@@ -694,8 +694,8 @@ LITE_HD inline double shape_of(double perim, double area) {  // face_shape, :424
 }
 
 #define SMF_BIT(f) (1u << (f))
-static const uint32_t MASK_FACE_ANG = SMF_BIT(LITE_FEAT_FACE_SUM_OF_ANGLES) | SMF_BIT(LITE_FEAT_MIN_ANGLE);
-static const uint32_t MASK_FACE_WALK = SMF_BIT(LITE_FEAT_FACE_AREA_2) | SMF_BIT(LITE_FEAT_FACE_SHAPE) | MASK_FACE_ANG;
+static const uint32_t kMaskFaceAng = SMF_BIT(LITE_FEAT_FACE_SUM_OF_ANGLES) | SMF_BIT(LITE_FEAT_MIN_ANGLE);
+static const uint32_t kMaskFaceWalk = SMF_BIT(LITE_FEAT_FACE_AREA_2) | SMF_BIT(LITE_FEAT_FACE_SHAPE) | kMaskFaceAng;
 
 LITE_HD inline void add_face_feats(const Energy &G, double *acc, double sign, const FaceFeat &F) {
   for (int i = 0; i < G.d; i++) {
@@ -722,8 +722,8 @@ LITE_HD inline void split_variation(const Chain &c, const Energy &G, const Split
   const double d01 = dist(m.p1, m.p2);
   double acc[LITE_MAX_D];
   for (int i = 0; i < G.d; i++) acc[i] = 0.0;
-  if (G.mask & MASK_FACE_WALK) {
-    const bool ang = (G.mask & MASK_FACE_ANG) != 0;
+  if (G.mask & kMaskFaceWalk) {
+    const bool ang = (G.mask & kMaskFaceAng) != 0;
     // children (polygon_insert_edge, :4600-4631):
     //   C1 = [p1, p2, tgt(e2) .. src(e1)],  C2 = [p2, p1, tgt(e1) .. src(e2)]
     Poly Pl;
@@ -791,8 +791,8 @@ LITE_HD inline void merge_variation(const Chain &c, const Energy &G, int e, doub
   const double elen = dist(p1, p2);
   double acc[LITE_MAX_D];
   for (int i = 0; i < G.d; i++) acc[i] = 0.0;
-  if (G.mask & MASK_FACE_WALK) {
-    const bool ang = (G.mask & MASK_FACE_ANG) != 0;
+  if (G.mask & kMaskFaceWalk) {
+    const bool ang = (G.mask & kMaskFaceAng) != 0;
     add_face_feats(G, acc, -1.0, face_feat(c, h_face(c, e), ang));
     add_face_feats(G, acc, -1.0, face_feat(c, h_face(c, t), ang));
     // polygon_remove_edge (:4945-4966): face(e) after p2 up to p1 (flat), then
@@ -844,8 +844,8 @@ LITE_HD inline void flip_variation(const Chain &c, const Energy &G, const FlipMo
   const double l_e1 = dist(a, q), l_new = dist(a, p2);
   double acc[LITE_MAX_D];
   for (int i = 0; i < G.d; i++) acc[i] = 0.0;
-  if (G.mask & MASK_FACE_WALK) {
-    const bool ang = (G.mask & MASK_FACE_ANG) != 0;
+  if (G.mask & kMaskFaceWalk) {
+    const bool ang = (G.mask & kMaskFaceAng) != 0;
     const int fL = h_face(c, e1), fT = h_face(c, t1);
     Poly Pl;
     if (right) {

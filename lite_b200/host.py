@@ -46,10 +46,12 @@ def _lib():
 class HostTess:
     """A dynamic T-tessellation on the host (C++ ``lite::HostTess``)."""
 
-    def __init__(self, rect=(0.0, 0.0, 1.0, 1.0), text=None):
+    def __init__(self, rect=(0.0, 0.0, 1.0, 1.0), text=None, handle=None):
         self.L = _lib()
         self.h = C.c_void_p()
-        if text is not None:
+        if handle is not None:
+            self.h = handle  # takes ownership (lite_smf_export)
+        elif text is not None:
             _ck(self.L, self.L.lite_host_create_from_text(C.byref(self.h), text.encode()))
         else:
             _ck(self.L, self.L.lite_host_create_rect(C.byref(self.h), *map(float, rect)))
