@@ -120,12 +120,14 @@ extern "C" int64_t lite_host_write_text(lite_host_tess *h, char *buf, int64_t ca
 // Ids are kept; elements on the chain's free lists stay dead.
 extern "C" int lite_smf_blob_to_host_(char *blob, int cap, lite_host_tess **out) {
   smf::Chain c;
+  smf::Header H;
+  c.H = &H;
   smf::bind(c, blob, cap);
   smf::load(c);
-  if (c.H.cap != cap) return lite_set_error_(LITE_EINVAL, "chain block does not match the ensemble capacity");
+  if (c.H->cap != cap) return lite_set_error_(LITE_EINVAL, "chain block does not match the ensemble capacity");
   lite_host_tess *h = new lite_host_tess();
   lite::HostTess &t = h->t;
-  const int nV = c.H.n_v, nH = 2 * c.H.n_p, nF = c.H.n_f, nS = c.H.n_s;
+  const int nV = c.H->n_v, nH = 2 * c.H->n_p, nF = c.H->n_f, nS = c.H->n_s;
   t.vx.assign(nV, 0.0); t.vy.assign(nV, 0.0); t.v_inc.assign(nV, -1); t.v_alive.assign(nV, 0);
   t.h_src.assign(nH, -1); t.h_next.assign(nH, -1); t.h_prev.assign(nH, -1); t.h_face.assign(nH, -1);
   t.h_seg.assign(nH, -1); t.h_next_hf.assign(nH, -1); t.h_prev_hf.assign(nH, -1);
@@ -152,9 +154,9 @@ extern "C" int lite_smf_blob_to_host_(char *blob, int cap, lite_host_tess **out)
     t.s_kind[s] = (uint8_t)c.seg[s].kind;
     t.s_pos[s] = (c.seg[s].kind == 1 || c.seg[s].kind == 2) ? (int)c.seg[s].pos : -1;
   }
-  t.nb_list.assign(c.nb_list, c.nb_list + c.H.n_nb);
-  t.b_list.assign(c.b_list, c.b_list + c.H.n_b);
-  t.int_length = c.H.int_length;
+  t.nb_list.assign(c.nb_list, c.nb_list + c.H->n_nb);
+  t.b_list.assign(c.b_list, c.b_list + c.H->n_b);
+  t.int_length = c.H->int_length;
   // the window: the four corner vertices are ids 0..3 and never die
   t.win_x = {c.vtx[0].x, c.vtx[1].x, c.vtx[2].x, c.vtx[3].x};
   t.win_y = {c.vtx[0].y, c.vtx[1].y, c.vtx[2].y, c.vtx[3].y};

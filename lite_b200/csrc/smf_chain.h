@@ -30,6 +30,16 @@
 #include "../../include/lite_b200.h"
 #include "philox.h"
 
+// The heavy steps of a proposal stay out of line on the device: inlined into one
+// kernel body they need 255 registers and still spill; as calls the kernel fits 64-128
+// registers, which is what decides how many chains a SM keeps in flight (the kernel is
+// bound by the latency of dependent loads, not by issue slots: profiles/r1_k_smf_run.txt).
+#ifdef __CUDACC__
+#define SMF_FN __host__ __device__ __noinline__
+#else
+#define SMF_FN inline
+#endif
+
 namespace smf {
 
 typedef uint16_t idx;
@@ -74,8 +84,8 @@ struct Pt {
 };
 
 struct Chain {
-  Header H;  // working copy; load()/store() move it from/to the block
-  Header *Hm;
+  Header *H;   // working copy (shared memory in the kernel); load()/store() move it from/to the block
+  Header *Hm;  // its home at the start of the chain's block
   Pt *vtx;
   HE *he;
   double *w, *bsum;
@@ -108,8 +118,8 @@ LITE_HD inline void bind(Chain &c, char *base, int cap) {
   c.nb_list = (idx *)p; p += align_up((size_t)cap * sizeof(idx), 16);
   c.b_list = (idx *)p;
 }
-LITE_HD inline void load(Chain &c) { c.H = *c.Hm; }
-LITE_HD inline void store(Chain &c) { *c.Hm = c.H; }
+LITE_HD inline void load(Chain &c) { *c.H = *c.Hm; }
+LITE_HD inline void store(Chain &c) { *c.Hm = *c.H; }
 
 // ---------------------------------------------------------------------------
 // field access
@@ -160,16 +170,39 @@ LITE_HD inline double cross2(double ax, double ay, double bx, double by) { retur
 // ---------------------------------------------------------------------------
 // sampling weights
 // ---------------------------------------------------------------------------
-LITE_HD inline void refresh_block(Chain &c, int p) {
-  const int b = p / WBLOCK;
-  const double *w = c.w + b * WBLOCK;
-  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-  for (int k = 0; k < WBLOCK; k += 4) { s0 += w[k]; s1 += w[k + 1]; s2 += w[k + 2]; s3 += w[k + 3]; }
-  c.bsum[b] = (s0 + s1) + (s2 + s3);
+// A block sum is recomputed from its 32 weights whenever one of them changes: exact,
+// and measured faster on B200 than the incremental update `bsum += new - old`
+// (-DSMF_INCREMENTAL_BSUM; 2.3e8 vs 1.3e8 chain-steps/s at 65536 chains,
+// gpurun_out/smf_ab1.log).  Every REFRESH_PERIOD proposals all sums are rebuilt, which
+// only matters for the incremental variant (bounds its rounding drift).
+static const int REFRESH_PERIOD = 1024;
+LITE_HD inline void refresh_all_blocks(Chain &c) {
+  const int nb = (c.H->n_p + WBLOCK - 1) / WBLOCK;
+  for (int b = 0; b < nb; b++) {
+    const double *w = c.w + b * WBLOCK;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int k = 0; k < WBLOCK; k += 4) { s0 += w[k]; s1 += w[k + 1]; s2 += w[k + 2]; s3 += w[k + 3]; }
+    c.bsum[b] = (s0 + s1) + (s2 + s3);
+  }
+}
+LITE_HD inline void set_pair_weight(Chain &c, int p, double wnew) {
+  const double wold = c.w[p];
+  c.w[p] = wnew;
+#ifndef SMF_INCREMENTAL_BSUM
+  (void)wold;
+  {
+    const int b = p / WBLOCK;
+    const double *w = c.w + b * WBLOCK;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int k = 0; k < WBLOCK; k += 4) { s0 += w[k]; s1 += w[k + 1]; s2 += w[k + 2]; s3 += w[k + 3]; }
+    c.bsum[b] = (s0 + s1) + (s2 + s3);
+  }
+#else
+  c.bsum[p / WBLOCK] += wnew - wold;
+#endif
 }
 LITE_HD inline void set_weight(Chain &c, int h, double len) {
-  c.w[h >> 1] = h_bnd(c, h) ? len : 2.0 * len;
-  refresh_block(c, h >> 1);
+  set_pair_weight(c, h >> 1, h_bnd(c, h) ? len : 2.0 * len);
 }
 // LineTes_halfedge::set_length, lib/ttessel.cpp:1459
 LITE_HD inline void set_len(Chain &c, int h) { set_weight(c, h, dist(P_src(c, h), P_tgt(c, h))); }
@@ -179,24 +212,24 @@ LITE_HD inline void set_len(Chain &c, int h) { set_weight(c, h, dist(P_src(c, h)
 // ---------------------------------------------------------------------------
 LITE_HD inline int new_vertex(Chain &c, double x, double y) {
   int v;
-  if (c.H.free_v >= 0) { v = c.H.free_v; c.H.free_v = (int)c.vtx[v].y; }
+  if (c.H->free_v >= 0) { v = c.H->free_v; c.H->free_v = (int)c.vtx[v].y; }
   else {
-    if (c.H.n_v >= 2 * c.H.cap) { c.H.status = ST_CAPACITY; return -1; }
-    v = c.H.n_v++;
+    if (c.H->n_v >= 2 * c.H->cap) { c.H->status = ST_CAPACITY; return -1; }
+    v = c.H->n_v++;
   }
   c.vtx[v].x = x; c.vtx[v].y = y;
   return v;
 }
 LITE_HD inline void del_vertex(Chain &c, int v) {
-  c.vtx[v].x = NAN; c.vtx[v].y = (double)c.H.free_v;
-  c.H.free_v = v;
+  c.vtx[v].x = NAN; c.vtx[v].y = (double)c.H->free_v;
+  c.H->free_v = v;
 }
 LITE_HD inline int new_pair(Chain &c, int v1, int v2) {
   int p;
-  if (c.H.free_p >= 0) { p = c.H.free_p; int nx = c.he[2 * p].next; c.H.free_p = (nx == NIL) ? -1 : nx; }
+  if (c.H->free_p >= 0) { p = c.H->free_p; int nx = c.he[2 * p].next; c.H->free_p = (nx == NIL) ? -1 : nx; }
   else {
-    if (c.H.n_p >= 3 * c.H.cap) { c.H.status = ST_CAPACITY; return -1; }
-    p = c.H.n_p++;
+    if (c.H->n_p >= 3 * c.H->cap) { c.H->status = ST_CAPACITY; return -1; }
+    p = c.H->n_p++;
   }
   HE r;
   r.next = r.prev = r.face = r.nhf = r.phf = (idx)NIL; r.pad = 0; r.segd = 0x7FFF;
@@ -206,57 +239,56 @@ LITE_HD inline int new_pair(Chain &c, int v1, int v2) {
 }
 LITE_HD inline void del_pair(Chain &c, int h) {
   const int p = h >> 1;
-  c.w[p] = 0.0;
-  refresh_block(c, p);
+  set_pair_weight(c, p, 0.0);
   c.he[2 * p].src = (idx)NIL; c.he[2 * p + 1].src = (idx)NIL;
-  c.he[2 * p].next = (idx)(c.H.free_p < 0 ? NIL : c.H.free_p);
-  c.H.free_p = p;
+  c.he[2 * p].next = (idx)(c.H->free_p < 0 ? NIL : c.H->free_p);
+  c.H->free_p = p;
 }
 LITE_HD inline int new_face(Chain &c) {
   int f;
-  if (c.H.free_f >= 0) { f = c.H.free_f; int nx = c.f_he[f]; c.H.free_f = (nx == NIL) ? -1 : nx; }
+  if (c.H->free_f >= 0) { f = c.H->free_f; int nx = c.f_he[f]; c.H->free_f = (nx == NIL) ? -1 : nx; }
   else {
-    if (c.H.n_f >= c.H.cap + 1) { c.H.status = ST_CAPACITY; return -1; }
-    f = c.H.n_f++;
+    if (c.H->n_f >= c.H->cap + 1) { c.H->status = ST_CAPACITY; return -1; }
+    f = c.H->n_f++;
   }
   c.f_he[f] = (idx)NIL;
   return f;
 }
 LITE_HD inline void del_face(Chain &c, int f) {
-  c.f_he[f] = (idx)(c.H.free_f < 0 ? NIL : c.H.free_f);
-  c.H.free_f = f;
+  c.f_he[f] = (idx)(c.H->free_f < 0 ? NIL : c.H->free_f);
+  c.H->free_f = f;
 }
 LITE_HD inline int new_seg(Chain &c, int he) {
   int s;
-  if (c.H.free_s >= 0) { s = c.H.free_s; int nx = c.seg[s].he; c.H.free_s = (nx == NIL) ? -1 : nx; }
+  if (c.H->free_s >= 0) { s = c.H->free_s; int nx = c.seg[s].he; c.H->free_s = (nx == NIL) ? -1 : nx; }
   else {
-    if (c.H.n_s >= c.H.cap) { c.H.status = ST_CAPACITY; return -1; }
-    s = c.H.n_s++;
+    if (c.H->n_s >= c.H->cap) { c.H->status = ST_CAPACITY; return -1; }
+    s = c.H->n_s++;
   }
   SegRec r; r.he = (idx)he; r.nedges = 1; r.pos = (idx)NIL; r.kind = 0;
   c.seg[s] = r;
-  c.H.n_seg++;
+  c.H->n_seg++;
   return s;
 }
 LITE_HD inline void del_seg(Chain &c, int s) {
   c.seg[s].kind = (idx)NIL;
-  c.seg[s].he = (idx)(c.H.free_s < 0 ? NIL : c.H.free_s);
-  c.H.free_s = s;
-  c.H.n_seg--;
+  c.seg[s].he = (idx)(c.H->free_s < 0 ? NIL : c.H->free_s);
+  c.H->free_s = s;
+  c.H->n_seg--;
 }
 
 // blocking / non-blocking lists (include/ttessel.h:784-785).  The chain draws
 // uniformly from them, so removal may reorder (swap with the last element).
 LITE_HD inline void list_add(Chain &c, int s, int kind) {
   c.seg[s].kind = (idx)kind;
-  if (kind == 1) { c.seg[s].pos = (idx)c.H.n_nb; c.nb_list[c.H.n_nb++] = (idx)s; }
-  else { c.seg[s].pos = (idx)c.H.n_b; c.b_list[c.H.n_b++] = (idx)s; }
+  if (kind == 1) { c.seg[s].pos = (idx)c.H->n_nb; c.nb_list[c.H->n_nb++] = (idx)s; }
+  else { c.seg[s].pos = (idx)c.H->n_b; c.b_list[c.H->n_b++] = (idx)s; }
 }
 LITE_HD inline void list_remove(Chain &c, int s) {
   const int kind = c.seg[s].kind;
   if (kind != 1 && kind != 2) return;
   idx *L = (kind == 1) ? c.nb_list : c.b_list;
-  int &n = (kind == 1) ? c.H.n_nb : c.H.n_b;
+  int &n = (kind == 1) ? c.H->n_nb : c.H->n_b;
   const int p = c.seg[s].pos;
   const int last = L[n - 1];
   L[p] = (idx)last; c.seg[last].pos = (idx)p;
@@ -286,7 +318,7 @@ LITE_HD inline int seg_end(const Chain &c, int s) {
 // window (LineTes::insert_window, lib/ttessel.cpp:60-120; rectangle)
 // ---------------------------------------------------------------------------
 LITE_HD inline void init_window(Chain &c, int cap, double x0, double y0, double x1, double y1) {
-  Header &H = c.H;
+  Header &H = *c.H;
   H.cap = cap;
   H.n_v = H.n_p = H.n_f = H.n_s = 0;
   H.free_v = H.free_p = H.free_f = H.free_s = -1;
@@ -452,7 +484,7 @@ struct FlipMove {
 
 // ray_exit_face, lib/ttessel.cpp:4515-4576 on the ccb of a hole-free face: nearest
 // forward hit of the line a*X+b*Y=w from p along (dx,dy); strict minimum, first wins
-LITE_HD inline int ray_exit(const Chain &c, int start_he, double a, double b, double w, Pt p, double dx,
+SMF_FN int ray_exit(const Chain &c, int start_he, double a, double b, double w, Pt p, double dx,
                             double dy, int skip0, int skip1, Pt &hit) {
   double best = 1.7976931348623157e308;
   int res = -1;
@@ -481,7 +513,7 @@ LITE_HD inline int ray_exit(const Chain &c, int start_he, double a, double b, do
 }
 
 // Split::Split(e,x,angle), lib/ttessel.cpp:2090-2132
-LITE_HD inline SplitMove make_split(const Chain &c, int e, double x, double angle) {
+SMF_FN SplitMove make_split(const Chain &c, int e, double x, double angle) {
   SplitMove m;
   m.e1 = e; m.e2 = -1; m.x = x; m.angle = angle; m.valid = false;
   m.p1.x = m.p1.y = m.p2.x = m.p2.y = 0;
@@ -506,7 +538,7 @@ LITE_HD inline SplitMove make_split(const Chain &c, int e, double x, double angl
 
 // Flip::Flip(e1), lib/ttessel.cpp:2432-2454: a = src(e1) is where another segment (the
 // one of e3) ends on e1's segment; the flip removes e1 and prolongs e3 beyond a
-LITE_HD inline FlipMove make_flip(const Chain &c, int e1) {
+SMF_FN FlipMove make_flip(const Chain &c, int e1) {
   FlipMove m;
   m.e1 = e1; m.e2 = -1; m.valid = false; m.p2.x = m.p2.y = 0;
   const int hp = h_prev(c, e1);
@@ -528,11 +560,11 @@ LITE_HD inline FlipMove make_flip(const Chain &c, int e1) {
 }
 
 // TTessel::update(Split), lib/ttessel.cpp:1580-1597
-LITE_HD inline int update_split(Chain &c, const SplitMove &sp) {
+SMF_FN int update_split(Chain &c, const SplitMove &sp) {
   const int e1n = split_edge(c, sp.e1, sp.p1.x, sp.p1.y);
   const int e2n = split_edge(c, sp.e2, sp.p2.x, sp.p2.y);
   const int e = add_edge(c, e1n, e2n, -1);
-  c.H.int_length += 2 * h_len(c, e);
+  c.H->int_length += 2 * h_len(c, e);
   list_add(c, h_seg(c, e), 1);
   const int ends[2] = {h_seg(c, h_next(c, e)), h_seg(c, h_next(c, e ^ 1))};
   for (int k = 0; k < 2; k++) {
@@ -542,7 +574,7 @@ LITE_HD inline int update_split(Chain &c, const SplitMove &sp) {
   return e;
 }
 // TTessel::update(Merge), lib/ttessel.cpp:1604-1638
-LITE_HD inline void update_merge(Chain &c, int e) {
+SMF_FN void update_merge(Chain &c, int e) {
   const int s = h_seg(c, e);
   list_remove(c, s);
   const int ends[2] = {h_seg(c, h_next(c, e)), h_seg(c, h_next(c, e ^ 1))};
@@ -552,10 +584,10 @@ LITE_HD inline void update_merge(Chain &c, int e) {
   }
   const double suppressed = h_len(c, e);
   suppress_edge(c, e);
-  c.H.int_length -= 2 * suppressed;
+  c.H->int_length -= 2 * suppressed;
 }
 // TTessel::update(Flip), lib/ttessel.cpp:1644-1701
-LITE_HD inline int update_flip(Chain &c, const FlipMove &fl) {
+SMF_FN int update_flip(Chain &c, const FlipMove &fl) {
   const int e1 = fl.e1;
   const int s1 = h_seg(c, e1);
   const int s1_i = h_seg(c, h_next(c, e1));
@@ -565,8 +597,8 @@ LITE_HD inline int update_flip(Chain &c, const FlipMove &fl) {
   const int prev_a = fl.right ? (e1 ^ 1) : h_prev(c, e1);
   const int e2n = split_edge(c, fl.e2, fl.p2.x, fl.p2.y);
   const int new_e = add_edge(c, prev_a, e2n, e3);
-  c.H.int_length += 2 * h_len(c, new_e);
-  c.H.int_length -= 2 * h_len(c, e1);
+  c.H->int_length += 2 * h_len(c, new_e);
+  c.H->int_length -= 2 * h_len(c, e1);
   const int s2_i = h_seg(c, h_next(c, new_e));
   suppress_edge(c, e1);
   if (c.seg[s2].nedges <= 2 && c.seg[s2].kind == 1) { list_remove(c, s2); list_add(c, s2, 2); }
@@ -581,8 +613,12 @@ LITE_HD inline int update_flip(Chain &c, const FlipMove &fl) {
 // TTessel::length_weighted_random_halfedge (lib/ttessel.cpp:1948-1966) by two-level
 // sums: u01 in [0,1) -> a halfedge bounding an inside face, with probability
 // proportional to its length
-LITE_HD inline int sample_halfedge(const Chain &c, double u01) {
-  const int nb = (c.H.n_p + WBLOCK - 1) / WBLOCK;
+SMF_FN int sample_halfedge(const Chain &c, double u01) {
+  // First pass: the total, with every load independent of the others, so the misses
+  // of the whole array overlap; the early-exit scan below then runs out of L1.  (Taking
+  // int_length as the total and scanning once exposes one miss after the other: measured
+  // 8% slower, gpurun_out/smf_ab2.log.)
+  const int nb = (c.H->n_p + WBLOCK - 1) / WBLOCK;
   double total = 0;
   for (int b = 0; b < nb; b++) total += c.bsum[b];
   const double target = u01 * total;
@@ -607,6 +643,11 @@ LITE_HD inline int sample_halfedge(const Chain &c, double u01) {
   }
   if (p < 0) { p = last_p; r = 0; }
   p += b * WBLOCK;
+  if (p < b * WBLOCK) {
+    // the block is empty and its sum is rounding residue: take the first live pair
+    for (p = 0; p < c.H->n_p && !(c.w[p] > 0); p++) {}
+    r = 0;
+  }
   const int h = 2 * p;
   if (h_bnd(c, h)) return (h_face(c, h) != 0) ? h : (h ^ 1);
   return (r >= 0.5 * c.w[p]) ? (h ^ 1) : h;
@@ -682,7 +723,7 @@ LITE_HD inline void poly_walk(const Chain &c, Poly &P, int from, int to, bool to
   }
 }
 // an unmodified face in face2poly order: the first vertex is the target of outer_ccb()
-LITE_HD inline FaceFeat face_feat(const Chain &c, int f, bool need_ang) {
+SMF_FN FaceFeat face_feat(const Chain &c, int f, bool need_ang) {
   Poly P; poly_begin(P, need_ang);
   const int h0 = h_next(c, c.f_he[f]);
   int h = h0;
@@ -715,7 +756,7 @@ LITE_HD inline double edge_cut_delta(Pt a, Pt m, Pt b) { return dist(a, m) + dis
 // statistic variations  phi(after) - phi(before), one value per registered feature
 // ---------------------------------------------------------------------------
 // Split::modified_elements, lib/ttessel.cpp:2135-2232
-LITE_HD inline void split_variation(const Chain &c, const Energy &G, const SplitMove &m, double *dv) {
+SMF_FN void split_variation(const Chain &c, const Energy &G, const SplitMove &m, double *dv) {
   const int e1 = m.e1, e2 = m.e2;
   const bool bnd1 = h_bnd(c, e1), bnd2 = h_bnd(c, e2);
   const Pt P = P_src(c, e1), Q = P_tgt(c, e1), S2 = P_src(c, e2), E2 = P_tgt(c, e2);
@@ -781,7 +822,7 @@ LITE_HD inline void split_variation(const Chain &c, const Energy &G, const Split
 
 // Merge::modified_elements, lib/ttessel.cpp:2302-2404; e = the only edge of a
 // non-blocking segment
-LITE_HD inline void merge_variation(const Chain &c, const Energy &G, int e, double *dv) {
+SMF_FN void merge_variation(const Chain &c, const Energy &G, int e, double *dv) {
   const int t = e ^ 1;
   const int e2h = h_next(c, e), e1h = h_next(c, t);  // Merge::e2(), Merge::e1()
   const bool bnd_e2 = h_bnd(c, e2h), bnd_e1 = h_bnd(c, e1h);
@@ -831,7 +872,7 @@ LITE_HD inline void merge_variation(const Chain &c, const Energy &G, int e, doub
 }
 
 // Flip::modified_elements, lib/ttessel.cpp:2459-2713
-LITE_HD inline void flip_variation(const Chain &c, const Energy &G, const FlipMove &m, double *dv) {
+SMF_FN void flip_variation(const Chain &c, const Energy &G, const FlipMove &m, double *dv) {
   const int e1 = m.e1, t1 = e1 ^ 1, e2 = m.e2;
   const bool right = m.right;
   const Pt a = P_src(c, e1), q = P_src(c, t1), p2 = m.p2;
@@ -959,8 +1000,11 @@ struct ChainParams {
 
 // Returns false if the chain cannot go on (capacity exhausted / broken state).
 LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, const StepRng &R, TraceRec *tr) {
-  if (c.H.status != ST_OK) return false;
-  const uint64_t t = c.H.step;
+  if (c.H->status != ST_OK) return false;
+  const uint64_t t = c.H->step;
+#ifdef SMF_INCREMENTAL_BSUM
+  if ((t & (REFRESH_PERIOD - 1)) == REFRESH_PERIOD - 1) refresh_all_blocks(c);
+#endif
   uint32_t r4[4];
   draw4(R, t, 0, r4);
   const double r0 = u53(r4[0], r4[1]);  // SMFChain::propose_modif_type, :3143-3151
@@ -973,9 +1017,9 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
     tr->e2s[0] = tr->e2s[1] = tr->e2t[0] = tr->e2t[1] = 0;
   }
   if (r0 <= cp.p_split) {
-    c.H.counts[0]++;
+    c.H->counts[0]++;
     if (tr) tr->type = 0;
-    if (c.H.n_seg + 1 > c.H.cap) { c.H.status = ST_CAPACITY; return false; }
+    if (c.H->n_seg + 1 > c.H->cap) { c.H->status = ST_CAPACITY; return false; }
     draw4(R, t, 1, r4);
     const int e = sample_halfedge(c, u53(r4[0], r4[1]));
     const double xs = u53(r4[2], r4[3]);
@@ -994,7 +1038,7 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
       if (c.seg[sa].nedges == 1 && !seg_bnd(sa)) delta_nb--;
       if (c.seg[sb].nedges == 1 && !seg_bnd(sb)) delta_nb--;
       double r = cp.p_merge / cp.p_split;
-      r *= (1 / kPi) * c.H.int_length / (c.H.n_nb + delta_nb);
+      r *= (1 / kPi) * c.H->int_length / (c.H->n_nb + delta_nb);
       split_variation(c, G, s, dv);
       const double ev = dot_theta(G, dv);
       r *= exp(-ev);
@@ -1005,20 +1049,20 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
         tr->p1[0] = s.p1.x; tr->p1[1] = s.p1.y; tr->p2[0] = s.p2.x; tr->p2[1] = s.p2.y;
         tr->r = r; tr->e_var = ev; tr->status = acc ? 2 : 1;
       }
-      if (acc) { c.H.counts[1]++; update_split(c, s); c.H.energy += ev; }
+      if (acc) { c.H->counts[1]++; update_split(c, s); c.H->energy += ev; }
     }
   } else if (r0 <= cp.p_split + cp.p_merge) {
-    c.H.counts[2]++;
+    c.H->counts[2]++;
     if (tr) tr->type = 1;
-    if (c.H.n_nb > 0) {
+    if (c.H->n_nb > 0) {
       draw4(R, t, 1, r4);
-      int n = (int)(u53(r4[0], r4[1]) * c.H.n_nb);  // TTessel::propose_merge, :1761
-      if (n >= c.H.n_nb) n = c.H.n_nb - 1;
+      int n = (int)(u53(r4[0], r4[1]) * c.H->n_nb);  // TTessel::propose_merge, :1761
+      if (n >= c.H->n_nb) n = c.H->n_nb - 1;
       const int sg = c.nb_list[n];
       const int e = c.seg[sg].he;
       // SMFChain::Hasting_ratio(Merge), :3184-3193
       double r = cp.p_split / cp.p_merge;
-      r *= kPi * c.H.n_nb / (c.H.int_length - 2 * h_len(c, e));
+      r *= kPi * c.H->n_nb / (c.H->int_length - 2 * h_len(c, e));
       merge_variation(c, G, e, dv);
       const double ev = dot_theta(G, dv);
       r *= exp(-ev);
@@ -1028,15 +1072,15 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
         tr->e1s[0] = A.x; tr->e1s[1] = A.y; tr->e1t[0] = B.x; tr->e1t[1] = B.y;
         tr->r = r; tr->e_var = ev; tr->status = acc ? 2 : 1;
       }
-      if (acc) { c.H.counts[3]++; update_merge(c, e); c.H.energy += ev; }
+      if (acc) { c.H->counts[3]++; update_merge(c, e); c.H->energy += ev; }
     }
   } else {
-    c.H.counts[4]++;
+    c.H->counts[4]++;
     if (tr) tr->type = 2;
-    if (c.H.n_b > 0) {
+    if (c.H->n_b > 0) {
       draw4(R, t, 1, r4);
-      int n = (int)(u53(r4[0], r4[1]) * c.H.n_b);  // TTessel::propose_flip, :1766-1777
-      if (n >= c.H.n_b) n = c.H.n_b - 1;
+      int n = (int)(u53(r4[0], r4[1]) * c.H->n_b);  // TTessel::propose_flip, :1766-1777
+      if (n >= c.H->n_b) n = c.H->n_b - 1;
       const int sg = c.b_list[n];
       const int side = (u53(r4[2], r4[3]) < 0.5) ? 0 : 1;
       const int e1 = side == 0 ? (seg_start(c, sg) ^ 1) : seg_end(c, sg);
@@ -1057,8 +1101,8 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
           if (c.seg[i_short].nedges == 2 && !seg_bnd(i_short)) db--;
           if (c.seg[i_ext].nedges == 1 && !seg_bnd(i_ext)) db++;
         }
-        const double sb = (double)c.H.n_b;
-        double r = (c.H.n_b == -db) ? sb : sb / (sb + db);
+        const double sb = (double)c.H->n_b;
+        double r = (c.H->n_b == -db) ? sb : sb / (sb + db);
         flip_variation(c, G, f, dv);
         const double ev = dot_theta(G, dv);
         r *= exp(-ev);
@@ -1069,15 +1113,15 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
           tr->p2[0] = f.p2.x; tr->p2[1] = f.p2.y;
           tr->r = r; tr->e_var = ev; tr->status = acc ? 2 : 1;
         }
-        if (acc) { c.H.counts[5]++; update_flip(c, f); c.H.energy += ev; }
+        if (acc) { c.H->counts[5]++; update_flip(c, f); c.H->energy += ev; }
       }
     }
   }
-  c.H.step = t + 1;
+  c.H->step = t + 1;
   if (tr) {
-    tr->n_seg = c.H.n_seg - 4; tr->n_nb = c.H.n_nb; tr->n_b = c.H.n_b; tr->int_length = c.H.int_length;
+    tr->n_seg = c.H->n_seg - 4; tr->n_nb = c.H->n_nb; tr->n_b = c.H->n_b; tr->int_length = c.H->int_length;
   }
-  return c.H.status == ST_OK;
+  return c.H->status == ST_OK;
 }
 
 // the columns applications/checkACS.cpp:136-148 writes after each batch of steps
@@ -1085,20 +1129,20 @@ static const int N_STAT_COLS = 12;
 LITE_HD inline void stat_row(const Chain &c, double *row, size_t stride) {
   int bnd_edges = 0;
   for (int s = 0; s < 4; s++) bnd_edges += c.seg[s].nedges;
-  const int n_int = c.H.n_seg - 4;
-  row[0 * stride] = (c.H.int_length - c.H.perimeter) / 2;  // l(T)
+  const int n_int = c.H->n_seg - 4;
+  row[0 * stride] = (c.H->int_length - c.H->perimeter) / 2;  // l(T)
   row[1 * stride] = n_int;                                 // n(T)
-  row[2 * stride] = c.H.n_b;                               // n_bl(T)
-  row[3 * stride] = c.H.n_nb;                              // n_nbl(T)
+  row[2 * stride] = c.H->n_b;                               // n_bl(T)
+  row[3 * stride] = c.H->n_nb;                              // n_nbl(T)
   row[4 * stride] = (2 * n_int + 4) - bnd_edges;           // m(T): number_of_internal_vertices, :4105-4115
-  for (int k = 0; k < 6; k++) row[(5 + k) * stride] = (double)c.H.counts[k];
-  row[11 * stride] = c.H.energy;
+  for (int k = 0; k < 6; k++) row[(5 + k) * stride] = (double)c.H->counts[k];
+  row[11 * stride] = c.H->energy;
 }
 
 // consistency check in the spirit of TTessel::is_valid (:1721-1753); 0 = valid
 LITE_HD inline int check(const Chain &c) {
   int live_pairs = 0;
-  for (int p = 0; p < c.H.n_p; p++) {
+  for (int p = 0; p < c.H->n_p; p++) {
     if (c.he[2 * p].src == NIL) { if (c.w[p] != 0.0) return 1; continue; }
     live_pairs++;
     for (int k = 0; k < 2; k++) {
@@ -1113,12 +1157,12 @@ LITE_HD inline int check(const Chain &c) {
     const double l = dist(P_src(c, 2 * p), P_tgt(c, 2 * p));
     if (fabs(h_len(c, 2 * p) - l) > 1e-9) return 6;
   }
-  const int n_int = c.H.n_seg - 4;
+  const int n_int = c.H->n_seg - 4;
   if (live_pairs != 3 * n_int + 4) return 7;
-  if (c.H.n_nb + c.H.n_b != n_int) return 8;
-  for (int i = 0; i < c.H.n_nb; i++) { const int s = c.nb_list[i]; if (c.seg[s].nedges != 1 || c.seg[s].kind != 1 || c.seg[s].pos != i) return 9; }
-  for (int i = 0; i < c.H.n_b; i++) { const int s = c.b_list[i]; if (c.seg[s].nedges < 2 || c.seg[s].kind != 2 || c.seg[s].pos != i) return 10; }
-  for (int s = 0; s < c.H.n_s; s++) {
+  if (c.H->n_nb + c.H->n_b != n_int) return 8;
+  for (int i = 0; i < c.H->n_nb; i++) { const int s = c.nb_list[i]; if (c.seg[s].nedges != 1 || c.seg[s].kind != 1 || c.seg[s].pos != i) return 9; }
+  for (int i = 0; i < c.H->n_b; i++) { const int s = c.b_list[i]; if (c.seg[s].nedges < 2 || c.seg[s].kind != 2 || c.seg[s].pos != i) return 10; }
+  for (int s = 0; s < c.H->n_s; s++) {
     if (c.seg[s].kind == NIL) continue;
     int n = 1, e = seg_start(c, s);
     if (h_seg(c, e) != s) return 11;
@@ -1126,8 +1170,13 @@ LITE_HD inline int check(const Chain &c) {
     if (n != c.seg[s].nedges) return 12;
   }
   double tot = 0;
-  for (int b = 0; b < (c.H.n_p + WBLOCK - 1) / WBLOCK; b++) tot += c.bsum[b];
-  if (fabs(tot - c.H.int_length) > 1e-9 * (1 + tot)) return 13;
+  for (int b = 0; b < (c.H->n_p + WBLOCK - 1) / WBLOCK; b++) tot += c.bsum[b];
+  if (fabs(tot - c.H->int_length) > 1e-9 * (1 + tot)) return 13;
+  for (int b = 0; b < (c.H->n_p + WBLOCK - 1) / WBLOCK; b++) {
+    double s = 0;
+    for (int k = 0; k < WBLOCK; k++) s += c.w[b * WBLOCK + k];
+    if (fabs(s - c.bsum[b]) > 1e-11) return 14;
+  }
   return 0;
 }
 

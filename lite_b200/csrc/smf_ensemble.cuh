@@ -32,7 +32,9 @@ __global__ void __launch_bounds__(LITE_SMF_TB) k_smf_init(char *blob, size_t str
                                                           double y0, double x1, double y1) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  smf::Header h_loc;
   smf::Chain c;
+  c.H = &h_loc;
   smf::bind(c, blob + (size_t)i * stride, cap);
   smf::init_window(c, cap, x0, y0, x1, y1);
   smf::store(c);
@@ -42,31 +44,51 @@ __global__ void __launch_bounds__(LITE_SMF_TB) k_smf_init(char *blob, size_t str
 // writes the checkACS columns (applications/checkACS.cpp:136-148) of its state,
 // with the proposal / acceptance counts of that batch (SMFChain::step returns the
 // counts of one call, lib/ttessel.cpp:3257-3311).
-__global__ void __launch_bounds__(LITE_SMF_TB) k_smf_run(char *blob, size_t stride, int cap, int n, uint64_t first,
-                                                         smf::Energy G, smf::ChainParams cp, uint64_t seed,
-                                                         int n_samples, long steps, double *rows, int *bad) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+//
+// The kernel is bound by the latency of dependent loads (a DCEL is pointer chasing),
+// so what matters is how many chains are in flight.  MINB blocks of 64 threads per SM
+// fix the register budget (4 -> 255 registers, 8 -> 128, 16 -> 64); lpc_shift lets only
+// every (1 << lpc_shift)-th thread take a chain (an experiment knob: spreading the chains
+// over more warps measured slower than packing them, see lite_smf_run).
+template <int MINB>
+__global__ void __launch_bounds__(LITE_SMF_TB, MINB) k_smf_run(char *blob, size_t stride, int cap, int n, uint64_t first,
+                                                               smf::Energy G_arg, smf::ChainParams cp, uint64_t seed,
+                                                               int n_samples, long steps, double *rows, int *bad,
+                                                               int lpc_shift) {
+  // the energy is read through a reference by the out-of-line steps: one copy per block
+  // in shared memory instead of one per thread in local memory
+  __shared__ smf::Energy sh_G;
+  if (threadIdx.x == 0) sh_G = G_arg;
+  __syncthreads();
+  const smf::Energy &G = sh_G;
+  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt & ((1L << lpc_shift) - 1)) return;
+  const long i = gt >> lpc_shift;
   if (i >= n) return;
   smf::Chain c;
+  smf::Header h_loc;  // working copy of the header (shared memory measured no faster)
+  c.H = &h_loc;
   smf::bind(c, blob + (size_t)i * stride, cap);
   smf::load(c);
   smf::StepRng R;
   R.seed = seed; R.chain = first + (uint64_t)i;
   for (int s = 0; s < n_samples; s++) {
-    for (int k = 0; k < 6; k++) c.H.counts[k] = 0;
+    for (int k = 0; k < 6; k++) c.H->counts[k] = 0;
     for (long t = 0; t < steps; t++)
       if (!smf::smf_step(c, G, cp, R, nullptr)) break;
     if (rows) smf::stat_row(c, rows + (size_t)s * smf::N_STAT_COLS * n + i, (size_t)n);
   }
-  if (c.H.status == smf::ST_CAPACITY) atomicAdd(bad, 1);
-  else if (c.H.status != smf::ST_OK) atomicAdd(bad + 1, 1);
+  if (c.H->status == smf::ST_CAPACITY) atomicAdd(bad, 1);
+  else if (c.H->status != smf::ST_OK) atomicAdd(bad + 1, 1);
   smf::store(c);
 }
 
 // one chain, every proposal recorded (parity tests)
 __global__ void k_smf_trace(char *blob, size_t stride, int cap, int i, uint64_t first, smf::Energy G,
                             smf::ChainParams cp, uint64_t seed, long steps, smf::TraceRec *out, int *done) {
+  smf::Header h_loc;
   smf::Chain c;
+  c.H = &h_loc;
   smf::bind(c, blob + (size_t)i * stride, cap);
   smf::load(c);
   smf::StepRng R;
@@ -82,7 +104,9 @@ __global__ void __launch_bounds__(LITE_SMF_TB) k_smf_stats(char *blob, size_t st
                                                            int *check_fail) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  smf::Header h_loc;
   smf::Chain c;
+  c.H = &h_loc;
   smf::bind(c, blob + (size_t)i * stride, cap);
   smf::load(c);
   smf::stat_row(c, rows + i, (size_t)n);
@@ -192,9 +216,29 @@ extern "C" int lite_smf_run(lite_ctx *c, int32_t n_samples, int64_t steps_per_sa
   }
   CU(cudaEventRecord(c->ev[6], c->stream));
   if (n > 0) {
-    k_smf_run<<<(n + LITE_SMF_TB - 1) / LITE_SMF_TB, LITE_SMF_TB, 0, c->stream>>>(
-        S->blob, S->stride, S->cap, n, (uint64_t)S->first, S->G, S->cp, S->seed, n_samples, (long)steps_per_sample,
-        rows_out ? S->rows : nullptr, S->bad);
+    // Launch shape, measured on B200 (gpurun_out/smf_sweep1.log, smf_ab2.log, smf_ab3.log).
+    // The kernel is bound by the latency of dependent loads, so: (1) chains are packed 32
+    // to a warp (the diverged lanes of a warp overlap their misses: 32 chains per warp cost
+    // 1.8x one chain per warp); (2) an ensemble that fits the GPU at 255 registers per
+    // thread runs the unconstrained build in one-warp blocks spread over all SMs (6.5e7
+    // vs 5.3e7 chain-steps/s at 8192 chains); (3) a larger one runs at 128 registers so
+    // that 512 chains per SM are resident (2.3e8 at 65536 chains; 64 registers: 2.0e8).
+    static const char *env_minb = getenv("LITE_SMF_MINB"), *env_lpc = getenv("LITE_SMF_LPC");
+    int shift = 0;
+    if (env_lpc) while ((1 << (shift + 1)) <= atoi(env_lpc) && shift < 5) shift++;
+    const long threads = (long)n << shift;
+    int minb = (threads <= (long)c->sm_count * 4 * LITE_SMF_TB) ? 4 : 8;
+    if (env_minb) minb = atoi(env_minb);
+    const int tb = (minb <= 4) ? 32 : LITE_SMF_TB;
+    const unsigned grid = (unsigned)((threads + tb - 1) / tb);
+    double *rows = rows_out ? S->rows : nullptr;
+#define SMF_LAUNCH(M)                                                                                             \
+  k_smf_run<M><<<grid, tb, 0, c->stream>>>(S->blob, S->stride, S->cap, n, (uint64_t)S->first, S->G, S->cp, S->seed, \
+                                           n_samples, (long)steps_per_sample, rows, S->bad, shift)
+    if (minb <= 4) SMF_LAUNCH(4);
+    else if (minb <= 8) SMF_LAUNCH(8);
+    else SMF_LAUNCH(16);
+#undef SMF_LAUNCH
     c->launches++;
     CU(cudaGetLastError());
   }

@@ -32,6 +32,8 @@ int main(int argc, char **argv) {
   std::vector<char> blob(smf::chain_bytes(cap) + 256);
   char *base = (char *)(((uintptr_t)blob.data() + 255) & ~(uintptr_t)255);
   smf::Chain c;
+  smf::Header H;
+  c.H = &H;
   smf::bind(c, base, cap);
   smf::init_window(c, cap, 0.0, 0.0, 1.0, 1.0);
   std::vector<smf::TraceRec> tr((size_t)n_steps);
@@ -48,7 +50,7 @@ int main(int argc, char **argv) {
   fclose(f);
   double row[smf::N_STAT_COLS];
   smf::stat_row(c, row, 1);
-  printf("steps %ld status %d", done, c.H.status);
+  printf("steps %ld status %d", done, c.H->status);
   for (int k = 0; k < smf::N_STAT_COLS; k++) printf(" %.17g", row[k]);
   printf("\n");
   return 0;
