@@ -17,6 +17,10 @@ Workloads:
                   of the same tessellation in contiguous shards).
     --workload c3 : config C3 — ~10^5-cell tessellation, 1.25*10^7 splits per GPU
                   (10^8 at N=8), the north star's multi-GPU sizing.
+    --workload c5 : config C5 — ensemble of independent SMF chains under the checkACS
+                  energy (applications/checkACS.cpp, tau=6), 8192 chains per GPU (65536 at
+                  N=8); a step is one checkACS batch of 250 proposals on every chain and the
+                  metric is chain-steps/s.  No collective.
 
 `value`  : whole-job candidates/s, tessellation already resident in HBM.
 `e2e`    : the same through the C ABI starting from HOST buffers every step:
@@ -117,11 +121,181 @@ def soa_bytes(soa):
     return int(sum(a.nbytes for a in soa.a.values()) + 8)
 
 
+SMF_TAU = 6.0                      # applications/checkACS.cpp:29
+SMF_FEATURES = ["is_segment_internal", "edge_length"]
+SMF_THETA = [-math.log(SMF_TAU), (SMF_TAU - 1) / math.pi]   # :113-117
+SMF_NIPL = 250                     # proposals per batch (demos/sim_acs.cpp:21)
+SMF_BURN = 20000                   # proposals before timing: the chain starts from the empty window
+SMF_CAP = 1020                     # capacity in internal segments (equilibrium ~600 at tau=6)
+# What one proposal has to move: the sampler's sums ((n_pairs/32 + 32) doubles,
+# ~700 B at 600 segments), the rings of one or two faces (6 halfedges x 32 B each), the segment
+# records and list slots (~64 B); an accepted move writes 2-3 new edge pairs, 1-2 vertices and
+# relinks ~8 neighbours (~400 B).
+B_ALG_SMF = 1500.0
+
+
+def oracle_chain_rate(budget_s):
+    """Exact-arithmetic oracle chain (oracle/lite_oracle.py SMFChain) from the empty
+    window for about budget_s seconds: proposals per second on one core."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lite_oracle as lo
+    t = lo.TTessel(lo.Rng(5))
+    t.insert_window_rect(0, 0, 1, 1)
+    eng = lo.make_energy(SMF_FEATURES, SMF_THETA, t)
+    chain = lo.SMFChain(eng, 0.33, 0.33)
+    done, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        chain.step(25)
+        done += 25
+    dt = time.perf_counter() - t0
+    return done / dt, done, len(t.all_segments) - 4
+
+
+def run_smf(args, rank, local_rank, world, nccl_id, dist, torch):
+    """Workload C5: ensemble of SMF chains; one step = SMF_NIPL proposals on every chain."""
+    import lite_b200
+    per_gpu = args.chains or 8192
+    n_global = per_gpu * world
+    ctx = lite_b200.Context(local_rank, rank, world, nccl_id)
+    ctx.smf_create(n_global, SMF_CAP, seed=5)
+    ctx.smf_set_model(SMF_FEATURES, SMF_THETA, 0.33, 0.33)
+    n_local = ctx.smf_count()[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    ctx.smf_run(1, SMF_BURN, rows=False)          # untimed burn-in to the stationary size
+    for _ in range(args.warmup):
+        ctx.smf_run(1, SMF_NIPL, rows=False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    ms_kernel = 0.0
+    ctx.timer_mark(0)
+    for _ in range(args.steps):
+        ctx.smf_run(1, SMF_NIPL, rows=False)
+        ms_kernel += ctx.smf_last_ms()
+    ctx.timer_mark(1)
+    barrier()
+    ms_total = ctx.timer_elapsed(0, 1)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    # end to end: model set from host values and the batch's statistics rows read back, every step
+    barrier()
+    ctx.timer_mark(2)
+    for _ in range(args.steps):
+        ctx.smf_set_model(SMF_FEATURES, SMF_THETA, 0.33, 0.33)
+        rows = ctx.smf_run(1, SMF_NIPL, rows=True)
+    ctx.timer_mark(3)
+    barrier()
+    ms_e2e = ctx.timer_elapsed(2, 3)
+    if world > 1:
+        tt = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(tt[0].item()), float(tt[1].item())
+    final = ctx.smf_stats(validate=True)
+    per_step = n_global * SMF_NIPL
+    value = per_step / (ms_total / args.steps * 1e-3)
+    e2e_val = per_step / (ms_e2e / args.steps * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    k_s = ms_kernel / args.steps * 1e-3
+    gbs = n_local * SMF_NIPL * B_ALG_SMF / k_s / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            per = json.load(open(prof)).get("k_smf_run_bytes_per_chain_step")
+            if per:
+                traffic = per * n_local * SMF_NIPL
+        except Exception:
+            pass
+    roofline = {
+        "kernel": "k_smf_run (one thread per chain: propose + Hastings ratio + update on a 16-bit DCEL in HBM)",
+        "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+        "peak_source": hbm_src, "alg_bytes_per_chain_step": B_ALG_SMF,
+        "chain_steps_per_launch": n_local * SMF_NIPL, "avg_launch_ms": k_s * 1e3, "traffic": traffic,
+        "note": "latency bound (dependent loads of a pointer structure), not bandwidth bound: see profiles/",
+    }
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, done, nseg = oracle_chain_rate(10.0)
+        cpu = {"value": rate, "unit": "chain-steps/s", "cores": 1, "kind": "port",
+               "sample": "the first %d proposals of ONE chain from the empty window (it reaches %d segments; the "
+                         "timed GPU chains hold ~600), exact rational arithmetic as the CGAL reference "
+                         "(oracle/lite_oracle.py), single thread as the reference" % (done, nseg)}
+    if rank == 0:
+        col = {n: i for i, n in enumerate(lite_b200.SMF_COLS)}
+        line = {
+            "metric": "smf_chain_steps_per_sec", "value": value, "unit": "chain-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": "C5: %d independent SMF chains per GPU (%d in all) in the unit square under the checkACS "
+                            "energy (is_segment_internal theta=-log 6, edge_length theta=5/pi, p_split=p_merge=0.33), "
+                            "%d burn-in proposals from the empty window, then one step = one checkACS batch of %d "
+                            "proposals on every chain" % (per_gpu, n_global, SMF_BURN, SMF_NIPL),
+                "chains_per_gpu": per_gpu, "chains_global": n_global, "proposals_per_step_per_chain": SMF_NIPL,
+                "mean_segments": float(final[col["n"]].mean()), "max_segments_capacity": SMF_CAP,
+                "l2": "inputs larger than L2: the chains' tessellations take %d MB per GPU, touched at random; no flush"
+                      % (ctx.smf_count()[3] * n_local // 1_000_000),
+                "sharding": "chains [r*n/G, (r+1)*n/G) on rank r, Philox stream keyed by the global chain id, "
+                            "no collective",
+            },
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "chain-steps/s", "h2d_bytes_per_step": 12 * len(SMF_THETA) + 16,
+                    "d2h_bytes_per_step": int(rows.nbytes), "ms_per_step": ms_e2e / args.steps,
+                    "path": "lite_smf_set_model(host theta) + lite_smf_run -> host rows (12 columns per chain)"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    ctx.close()
+
+
+def run_cpu_reference_smf(args, n_gpus, rank):
+    """`--impl reference --workload c5`: the exact oracle chain on one core, bounded sample per step."""
+    if rank != 0:
+        return
+    rates = []
+    t0 = time.perf_counter()
+    for _ in range(args.warmup + args.steps):
+        rate, done, nseg = oracle_chain_rate(2.0)
+        rates.append(rate)
+    rates = rates[args.warmup:]
+    val = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": "smf_chain_steps_per_sec", "value": val, "unit": "chain-steps/s",
+        "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 2000.0,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C5: one SMF chain under the checkACS energy from the empty window, exact arithmetic "
+                               "(the reference is single-threaded; it needs CGAL and cannot be built here)",
+                   "proposals_sampled_per_step": int(done)},
+        "cpu_baseline": {"value": val, "unit": "chain-steps/s", "cores": 1, "kind": "port",
+                         "sample": "2 s of one chain from the empty window per step (%d proposals, %d segments)" % (done, nseg)},
+        "e2e": {"value": val, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def run_cpu_reference(args, n_gpus, rank):
     """`--impl reference`: the reference's CPU algorithm (C++ double restatement,
     oracle/oracle_cpu.cpp) on all host threads, bounded sample per step."""
     if rank != 0:
         return
+    if args.workload == "c5":
+        return run_cpu_reference_smf(args, n_gpus, rank)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_cpu as oc
     import lite_b200
@@ -169,7 +343,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"])
+    ap.add_argument("--chains", type=int, default=0, help="c5: chains per GPU (default 8192)")
     ap.add_argument("--cells", type=int, default=0, help="override the tessellation size")
     ap.add_argument("--splits", type=int, default=0, help="override the dummy splits per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=0, help="splits per step of the CPU baseline sample")
@@ -207,6 +382,12 @@ def main():
             idt = torch.tensor(list(lite_b200.nccl_unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(idt, 0)
         nccl_id = bytes(idt.cpu().tolist())
+
+    if args.workload == "c5":
+        run_smf(args, rank, local_rank, world, nccl_id, dist, torch)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     name, cells, per_gpu = workload(n_gpus, args)
     t, _tau = lite_b200.generate_crtt(cells, seed=5)   # deterministic: identical on every rank
