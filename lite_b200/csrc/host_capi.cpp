@@ -127,8 +127,7 @@ extern "C" int lite_smf_blob_to_host_(char *blob, int cap, lite_host_tess **out)
   if (c.H->cap != cap) return lite_set_error_(LITE_EINVAL, "chain block does not match the ensemble capacity");
   lite_host_tess *h = new lite_host_tess();
   lite::HostTess &t = h->t;
-  const int nV = c.H->n_v, nH = 2 * c.H->n_p, nF = c.H->n_f, nS = c.H->n_s;
-  t.vx.assign(nV, 0.0); t.vy.assign(nV, 0.0); t.v_inc.assign(nV, -1); t.v_alive.assign(nV, 0);
+  const int nH = 2 * c.H->n_p, nF = c.H->n_f, nS = c.H->n_s;
   t.h_src.assign(nH, -1); t.h_next.assign(nH, -1); t.h_prev.assign(nH, -1); t.h_face.assign(nH, -1);
   t.h_seg.assign(nH, -1); t.h_next_hf.assign(nH, -1); t.h_prev_hf.assign(nH, -1);
   t.h_dir.assign(nH, 0); t.h_alive.assign(nH, 0); t.h_len.assign(nH, 0.0);
@@ -136,18 +135,30 @@ extern "C" int lite_smf_blob_to_host_(char *blob, int cap, lite_host_tess **out)
   t.s_he.assign(nS, -1); t.s_nedges.assign(nS, 0); t.s_pos.assign(nS, -1); t.s_bnd.assign(nS, 0);
   t.s_alive.assign(nS, 0); t.s_kind.assign(nS, 0);
   for (int e = 0; e < nH; e++) {
-    if (c.he[e & ~1].src == smf::NIL) continue;
+    if (!smf::pair_alive(c, e >> 1)) continue;
     t.h_alive[e] = 1;
-    t.h_src[e] = smf::h_src(c, e); t.h_next[e] = smf::h_next(c, e); t.h_prev[e] = smf::h_prev(c, e);
+    t.h_next[e] = smf::h_next(c, e); t.h_prev[e] = smf::h_prev(c, e);
     t.h_face[e] = smf::h_face(c, e); t.h_seg[e] = smf::h_seg(c, e);
     t.h_next_hf[e] = smf::h_nhf(c, e); t.h_prev_hf[e] = smf::h_phf(c, e);
     t.h_dir[e] = smf::h_dir(c, e); t.h_len[e] = smf::h_len(c, e);
-    const int v = t.h_src[e], f = t.h_face[e], s = t.h_seg[e];
-    t.v_alive[v] = 1; t.vx[v] = c.vtx[v].x; t.vy[v] = c.vtx[v].y;
+    const int f = t.h_face[e], s = t.h_seg[e];
     t.f_alive[f] = 1; t.f_inside[f] = (f != 0); t.f_he[f] = c.f_he[f];
     t.s_alive[s] = 1;
   }
-  for (int e = 0; e < nH; e++) if (t.h_alive[e]) t.v_inc[t.h_src[e ^ 1]] = e;
+  // The chain stores a vertex as the source point of each halfedge leaving it: give the
+  // halfedges around one vertex (h -> twin(prev(h))) one id.  The window corners come
+  // first (ids 0..3, halfedges 0, 2, 4, 6 leave them), as in insert_window.
+  t.vx.clear(); t.vy.clear(); t.v_inc.clear(); t.v_alive.clear();
+  for (int pass = 0; pass < 2; pass++) {
+    for (int e = 0; e < nH; e += (pass == 0 ? 2 : 1)) {
+      if (pass == 0 && e >= 8) break;
+      if (!t.h_alive[e] || t.h_src[e] >= 0) continue;
+      const int v = (int)t.vx.size();
+      t.vx.push_back(c.he[e].x); t.vy.push_back(c.he[e].y); t.v_inc.push_back(e ^ 1); t.v_alive.push_back(1);
+      int k = e;
+      do { t.h_src[k] = v; k = t.h_prev[k] ^ 1; } while (k != e && t.h_alive[k] && t.h_src[k] < 0);
+    }
+  }
   for (int s = 0; s < nS; s++) {
     if (!t.s_alive[s]) continue;
     t.s_he[s] = c.seg[s].he; t.s_nedges[s] = c.seg[s].nedges; t.s_bnd[s] = smf::seg_bnd(s);
@@ -158,8 +169,8 @@ extern "C" int lite_smf_blob_to_host_(char *blob, int cap, lite_host_tess **out)
   t.b_list.assign(c.b_list, c.b_list + c.H->n_b);
   t.int_length = c.H->int_length;
   // the window: the four corner vertices are ids 0..3 and never die
-  t.win_x = {c.vtx[0].x, c.vtx[1].x, c.vtx[2].x, c.vtx[3].x};
-  t.win_y = {c.vtx[0].y, c.vtx[1].y, c.vtx[2].y, c.vtx[3].y};
+  t.win_x = {t.vx[0], t.vx[1], t.vx[2], t.vx[3]};
+  t.win_y = {t.vy[0], t.vy[1], t.vy[2], t.vy[3]};
   t.finish_import();
   std::string err = t.check();
   if (!err.empty()) {

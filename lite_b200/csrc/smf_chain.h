@@ -14,9 +14,14 @@
 //   Energy::statistic_variation / variation   :2914-3012, features :4124-4434
 //
 // Layout of one chain (a contiguous block of chain_bytes(cap) bytes, cap = capacity
-// in segments, the four window sides included).  Indices are 16 bit: a halfedge
-// record is 16 bytes, so following a DCEL link is one 16-byte load.
-//   Header | vtx double2[2cap] | he HE[6cap] | w double[3cap] | bsum double[3cap/32]
+// in segments, the four window sides included).  Indices are 16 bit and a halfedge
+// record carries its own source point: 32 bytes = one memory sector, an edge (both
+// twins, hence both end points and all links) = one aligned 64-byte line.  There is
+// no vertex array: walking a face costs one dependent miss per halfedge instead of
+// two (record, then vertex), and the chain is bound by exactly those misses
+// (profiles/r1_k_smf_run.txt).  A vertex of degree 3 is stored three times; vertices
+// never move, so the copies are bit-identical.
+//   Header | he HE[6cap] | w double[3cap] | bsum double[3cap/32]
 //          | seg SegRec[cap] | f_he u16[cap+1] | nb_list u16[cap] | b_list u16[cap]
 // Halfedges are allocated in pairs (twin(h) = h^1); face 0 is the outside face;
 // segments 0..3 are the window sides.  w[p] is the sampling weight of edge pair p
@@ -48,8 +53,10 @@ static const int WBLOCK = 32;
 static const double kPi = 3.14159265358979323846;
 static const double kHalfPi = kPi / 2;
 
-struct alignas(16) HE {
-  idx src, next, prev, face, segd /* seg | dir << 15 */, nhf, phf, pad;
+struct alignas(32) HE {
+  double x, y;  // source point
+  idx next, prev, face, segd /* seg | dir << 15; 0xFFFF = dead pair */, nhf, phf;
+  uint32_t pad;
 };
 struct alignas(8) SegRec {
   idx he, nedges, pos, kind;  // kind: 0 none (window side), 1 non-blocking, 2 blocking, NIL dead
@@ -59,12 +66,12 @@ enum Status { ST_OK = 0, ST_CAPACITY = 1, ST_BROKEN = 2 };
 
 struct alignas(16) Header {
   int32_t cap;
-  int32_t n_v, n_p, n_f, n_s;              // high-water marks of the four id spaces
-  int32_t free_v, free_p, free_f, free_s;  // heads of the intrusive free lists, -1 = empty
+  int32_t n_p, n_f, n_s;              // high-water marks of the id spaces (edge pairs, faces, segments)
+  int32_t free_p, free_f, free_s;     // heads of the intrusive free lists, -1 = empty
   int32_t n_nb, n_b;                       // sizes of the non-blocking / blocking lists
   int32_t n_seg;                           // live segments, window sides included
   int32_t status;
-  int32_t pad0;
+  int32_t pad0[3];
   double int_length;                       // TTessel::int_length (include/ttessel.h:786)
   double perimeter;                        // of the window
   double energy;                           // Energy::value, updated on acceptance (:3284)
@@ -86,7 +93,6 @@ struct Pt {
 struct Chain {
   Header *H;   // working copy (shared memory in the kernel); load()/store() move it from/to the block
   Header *Hm;  // its home at the start of the chain's block
-  Pt *vtx;
   HE *he;
   double *w, *bsum;
   SegRec *seg;
@@ -97,7 +103,6 @@ LITE_HD inline size_t align_up(size_t b, size_t a) { return (b + a - 1) / a * a;
 LITE_HD inline int n_blocks_cap(int cap) { return (3 * cap + WBLOCK - 1) / WBLOCK; }
 LITE_HD inline size_t chain_bytes(int cap) {
   size_t b = align_up(sizeof(Header), 128);
-  b += (size_t)2 * cap * sizeof(Pt);
   b += (size_t)6 * cap * sizeof(HE);
   b += (size_t)n_blocks_cap(cap) * WBLOCK * sizeof(double);
   b += align_up((size_t)n_blocks_cap(cap) * sizeof(double), 16);
@@ -109,7 +114,6 @@ LITE_HD inline size_t chain_bytes(int cap) {
 LITE_HD inline void bind(Chain &c, char *base, int cap) {
   char *p = base;
   c.Hm = (Header *)p; p += align_up(sizeof(Header), 128);
-  c.vtx = (Pt *)p; p += (size_t)2 * cap * sizeof(Pt);
   c.he = (HE *)p; p += (size_t)6 * cap * sizeof(HE);
   c.w = (double *)p; p += (size_t)n_blocks_cap(cap) * WBLOCK * sizeof(double);
   c.bsum = (double *)p; p += align_up((size_t)n_blocks_cap(cap) * sizeof(double), 16);
@@ -124,8 +128,6 @@ LITE_HD inline void store(Chain &c) { *c.Hm = *c.H; }
 // ---------------------------------------------------------------------------
 // field access
 // ---------------------------------------------------------------------------
-LITE_HD inline int h_src(const Chain &c, int h) { return c.he[h].src; }
-LITE_HD inline int h_tgt(const Chain &c, int h) { return c.he[h ^ 1].src; }
 LITE_HD inline int h_next(const Chain &c, int h) { return c.he[h].next; }
 LITE_HD inline int h_prev(const Chain &c, int h) { return c.he[h].prev; }
 LITE_HD inline int h_face(const Chain &c, int h) { return c.he[h].face; }
@@ -135,8 +137,11 @@ LITE_HD inline int h_nhf(const Chain &c, int h) { int v = c.he[h].nhf; return v 
 LITE_HD inline int h_phf(const Chain &c, int h) { int v = c.he[h].phf; return v == NIL ? -1 : v; }
 LITE_HD inline void set_segdir(Chain &c, int h, int s, bool dir) { c.he[h].segd = (idx)(s | (dir ? 0x8000 : 0)); }
 LITE_HD inline void set_dir(Chain &c, int h, bool dir) { c.he[h].segd = (idx)((c.he[h].segd & 0x7FFF) | (dir ? 0x8000 : 0)); }
-LITE_HD inline Pt P_src(const Chain &c, int h) { return c.vtx[c.he[h].src]; }
-LITE_HD inline Pt P_tgt(const Chain &c, int h) { return c.vtx[c.he[h ^ 1].src]; }
+LITE_HD inline Pt P_src(const Chain &c, int h) { Pt p; p.x = c.he[h].x; p.y = c.he[h].y; return p; }
+LITE_HD inline Pt P_tgt(const Chain &c, int h) { return P_src(c, h ^ 1); }
+LITE_HD inline void set_src(Chain &c, int h, Pt p) { c.he[h].x = p.x; c.he[h].y = p.y; }
+LITE_HD inline bool same_pt(Pt a, Pt b) { return a.x == b.x && a.y == b.y; }
+LITE_HD inline bool pair_alive(const Chain &c, int p) { return c.he[2 * p].segd != 0xFFFF; }
 LITE_HD inline bool seg_bnd(int s) { return s < 4; }
 LITE_HD inline bool h_bnd(const Chain &c, int h) { return h_seg(c, h) < 4; }
 LITE_HD inline double h_len(const Chain &c, int h) {
@@ -210,21 +215,7 @@ LITE_HD inline void set_len(Chain &c, int h) { set_weight(c, h, dist(P_src(c, h)
 // ---------------------------------------------------------------------------
 // element management (ids of removed elements are recycled, last freed first)
 // ---------------------------------------------------------------------------
-LITE_HD inline int new_vertex(Chain &c, double x, double y) {
-  int v;
-  if (c.H->free_v >= 0) { v = c.H->free_v; c.H->free_v = (int)c.vtx[v].y; }
-  else {
-    if (c.H->n_v >= 2 * c.H->cap) { c.H->status = ST_CAPACITY; return -1; }
-    v = c.H->n_v++;
-  }
-  c.vtx[v].x = x; c.vtx[v].y = y;
-  return v;
-}
-LITE_HD inline void del_vertex(Chain &c, int v) {
-  c.vtx[v].x = NAN; c.vtx[v].y = (double)c.H->free_v;
-  c.H->free_v = v;
-}
-LITE_HD inline int new_pair(Chain &c, int v1, int v2) {
+LITE_HD inline int new_pair(Chain &c, Pt v1, Pt v2) {
   int p;
   if (c.H->free_p >= 0) { p = c.H->free_p; int nx = c.he[2 * p].next; c.H->free_p = (nx == NIL) ? -1 : nx; }
   else {
@@ -233,14 +224,14 @@ LITE_HD inline int new_pair(Chain &c, int v1, int v2) {
   }
   HE r;
   r.next = r.prev = r.face = r.nhf = r.phf = (idx)NIL; r.pad = 0; r.segd = 0x7FFF;
-  r.src = (idx)v1; c.he[2 * p] = r;
-  r.src = (idx)v2; c.he[2 * p + 1] = r;
+  r.x = v1.x; r.y = v1.y; c.he[2 * p] = r;
+  r.x = v2.x; r.y = v2.y; c.he[2 * p + 1] = r;
   return 2 * p;
 }
 LITE_HD inline void del_pair(Chain &c, int h) {
   const int p = h >> 1;
   set_pair_weight(c, p, 0.0);
-  c.he[2 * p].src = (idx)NIL; c.he[2 * p + 1].src = (idx)NIL;
+  c.he[2 * p].segd = 0xFFFF; c.he[2 * p + 1].segd = 0xFFFF;
   c.he[2 * p].next = (idx)(c.H->free_p < 0 ? NIL : c.H->free_p);
   c.H->free_p = p;
 }
@@ -320,18 +311,19 @@ LITE_HD inline int seg_end(const Chain &c, int s) {
 LITE_HD inline void init_window(Chain &c, int cap, double x0, double y0, double x1, double y1) {
   Header &H = *c.H;
   H.cap = cap;
-  H.n_v = H.n_p = H.n_f = H.n_s = 0;
-  H.free_v = H.free_p = H.free_f = H.free_s = -1;
-  H.n_nb = H.n_b = 0; H.n_seg = 0; H.status = ST_OK; H.pad0 = 0;
+  H.n_p = H.n_f = H.n_s = 0;
+  H.free_p = H.free_f = H.free_s = -1;
+  H.n_nb = H.n_b = 0; H.n_seg = 0; H.status = ST_OK; H.pad0[0] = H.pad0[1] = H.pad0[2] = 0;
   H.int_length = 0; H.energy = 0; H.step = 0;
   for (int k = 0; k < 6; k++) H.counts[k] = 0;
   const int nb = n_blocks_cap(cap);
   for (int i = 0; i < nb * WBLOCK; i++) c.w[i] = 0.0;
   for (int i = 0; i < nb; i++) c.bsum[i] = 0.0;
   const double xs[4] = {x0, x1, x1, x0}, ys[4] = {y0, y0, y1, y1};
-  int vs[4], hs[4];
-  for (int i = 0; i < 4; i++) vs[i] = new_vertex(c, xs[i], ys[i]);
-  for (int i = 0; i < 4; i++) hs[i] = new_pair(c, vs[i], vs[(i + 1) & 3]);
+  Pt vs[4];
+  int hs[4];
+  for (int i = 0; i < 4; i++) { vs[i].x = xs[i]; vs[i].y = ys[i]; }
+  for (int i = 0; i < 4; i++) hs[i] = new_pair(c, vs[i], vs[(i + 1) & 3]);  // pairs 0..3: the window sides
   const int fo = new_face(c), fi = new_face(c);  // 0 = outside, 1 = the window
   for (int i = 0; i < 4; i++) {
     const int h = hs[i], hn = hs[(i + 1) & 3], hp = hs[(i + 3) & 3];
@@ -358,13 +350,13 @@ LITE_HD inline int split_edge(Chain &c, int e, double px, double py) {
   const int s = h_seg(c, e);
   const bool e_dir = h_dir(c, e);
   const int t = e ^ 1;
-  const int b = h_src(c, t);
-  const int v = new_vertex(c, px, py);
+  const Pt b = P_src(c, t);
+  Pt v; v.x = px; v.y = py;
   const int e2 = new_pair(c, v, b), t2 = e2 ^ 1;
   const int en = h_next(c, e), tp = h_prev(c, t);
   c.he[e2].next = (idx)en; c.he[en].prev = (idx)e2; c.he[e].next = (idx)e2; c.he[e2].prev = (idx)e;
   c.he[t2].prev = (idx)tp; c.he[tp].next = (idx)t2; c.he[t2].next = (idx)t; c.he[t].prev = (idx)t2;
-  c.he[t].src = (idx)v;
+  set_src(c, t, v);
   c.he[e2].face = c.he[e].face; c.he[t2].face = c.he[t].face;
   set_junction(c, e, e2);
   set_junction(c, e2, e_nhf);
@@ -381,16 +373,16 @@ LITE_HD inline int merge_edge(Chain &c, int e1, int e2) {
   const int hf_before = h_phf(c, e1), hf_after = h_nhf(c, e2);
   const double new_len = h_len(c, e1) + h_len(c, e2);
   const int s = h_seg(c, e1);
-  const int v = h_tgt(c, e1), t1 = e1 ^ 1, t2 = e2 ^ 1, b = h_tgt(c, e2);
+  const int t1 = e1 ^ 1, t2 = e2 ^ 1;
+  const Pt b = P_tgt(c, e2);
   const int e2n = h_next(c, e2), t2p = h_prev(c, t2);
   c.he[e1].next = (idx)e2n; c.he[e2n].prev = (idx)e1;
   c.he[t1].prev = (idx)t2p; c.he[t2p].next = (idx)t1;
-  c.he[t1].src = (idx)b;
+  set_src(c, t1, b);
   const int fe = h_face(c, e2), ft = h_face(c, t2);
   if (c.f_he[fe] == (idx)e2) c.f_he[fe] = (idx)e1;
   if (c.f_he[ft] == (idx)t2) c.f_he[ft] = (idx)t1;
   del_pair(c, e2);
-  del_vertex(c, v);
   set_junction(c, hf_before, e1);
   set_junction(c, e1, hf_after);
   set_weight(c, e1, new_len);
@@ -403,7 +395,7 @@ LITE_HD inline int merge_edge(Chain &c, int e1, int e2) {
 // inside their common face; ext_prev is the halfedge whose straight continuation the
 // new edge is (-1: it starts a new segment)
 LITE_HD inline int add_edge(Chain &c, int prev1, int prev2, int ext_prev) {
-  const int v1 = h_tgt(c, prev1), v2 = h_tgt(c, prev2);
+  const Pt v1 = P_tgt(c, prev1), v2 = P_tgt(c, prev2);
   const int f = h_face(c, prev1);
   const int a1 = h_next(c, prev1), a2 = h_next(c, prev2);
   const int h = new_pair(c, v1, v2), t = h ^ 1;
@@ -447,9 +439,14 @@ LITE_HD inline void remove_edge(Chain &c, int e) {
   c.he[p1].next = (idx)n2; c.he[n2].prev = (idx)p1; c.he[p2].next = (idx)n1; c.he[n1].prev = (idx)p2;
   del_pair(c, e);
   c.f_he[f1] = (idx)p1;
-  int k = p1;
-  do { c.he[k].face = (idx)f1; k = h_next(c, k); } while (k != p1);
-  if (f2 != f1) del_face(c, f2);
+  if (f2 != f1) {
+    // only the halfedges that bounded f2 change face: n2 .. p2 on the merged ccb
+    for (int k = n2;; k = h_next(c, k)) {
+      c.he[k].face = (idx)f1;
+      if (k == p2) break;
+    }
+    del_face(c, f2);
+  }
 }
 
 // LineTes::suppress_edge, lib/ttessel.cpp:201-236: remove the edge, then dissolve its
@@ -880,8 +877,7 @@ SMF_FN void flip_variation(const Chain &c, const Energy &G, const FlipMove &m, d
   const bool bnd_n1 = h_bnd(c, n1), bnd_e2 = h_bnd(c, e2);
   const Pt X = P_tgt(c, n1), Y = P_src(c, h_prev(c, t1));
   const Pt S2 = P_src(c, e2), E2 = P_tgt(c, e2);
-  const int vq = h_src(c, t1);
-  const bool tgt_is_q = h_tgt(c, e2) == vq, src_is_q = h_src(c, e2) == vq;
+  const bool tgt_is_q = same_pt(E2, q), src_is_q = same_pt(S2, q);  // copies of a vertex are bit-identical
   const double l_e1 = dist(a, q), l_new = dist(a, p2);
   double acc[LITE_MAX_D];
   for (int i = 0; i < G.d; i++) acc[i] = 0.0;
@@ -1143,15 +1139,15 @@ LITE_HD inline void stat_row(const Chain &c, double *row, size_t stride) {
 LITE_HD inline int check(const Chain &c) {
   int live_pairs = 0;
   for (int p = 0; p < c.H->n_p; p++) {
-    if (c.he[2 * p].src == NIL) { if (c.w[p] != 0.0) return 1; continue; }
+    if (!pair_alive(c, p)) { if (c.w[p] != 0.0) return 1; continue; }
     live_pairs++;
     for (int k = 0; k < 2; k++) {
       const int h = 2 * p + k;
       const int n = h_next(c, h);
-      if (h_prev(c, n) != h || h_src(c, n) != h_tgt(c, h)) return 2;
+      if (h_prev(c, n) != h || !same_pt(P_src(c, n), P_tgt(c, h))) return 2;
       if (h_face(c, n) != h_face(c, h)) return 3;
       const int nh = h_nhf(c, h);
-      if (nh >= 0 && (h_phf(c, nh) != h || h_src(c, nh) != h_tgt(c, h) || h_seg(c, nh) != h_seg(c, h))) return 4;
+      if (nh >= 0 && (h_phf(c, nh) != h || !same_pt(P_src(c, nh), P_tgt(c, h)) || h_seg(c, nh) != h_seg(c, h))) return 4;
       if (h_seg(c, h) != h_seg(c, h ^ 1) || h_dir(c, h) == h_dir(c, h ^ 1)) return 5;
     }
     const double l = dist(P_src(c, 2 * p), P_tgt(c, 2 * p));
