@@ -42,6 +42,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints
+# its version banner on stdout), so file descriptor 1 is pointed at stderr for the whole
+# run and the result line goes to a private duplicate of the original stdout.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
 import numpy as np  # noqa: E402
 
 ACS = ["edge_length", "face_area_2", "face_sum_of_angles", "is_segment_internal"]
@@ -260,7 +270,7 @@ def run_smf(args, rank, local_rank, world, nccl_id, dist, torch):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
 
 
@@ -286,7 +296,7 @@ def run_cpu_reference_smf(args, n_gpus, rank):
                          "sample": "2 s of one chain from the empty window per step (%d proposals, %d segments)" % (done, nseg)},
         "e2e": {"value": val, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_cpu_reference(args, n_gpus, rank):
@@ -334,7 +344,7 @@ def run_cpu_reference(args, n_gpus, rank):
         "e2e": {"value": val, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "lpl": v,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -572,7 +582,7 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
