@@ -17,6 +17,10 @@ Workloads:
                   of the same tessellation in contiguous shards).
     --workload c3 : config C3 — ~10^5-cell tessellation, 1.25*10^7 splits per GPU
                   (10^8 at N=8), the north star's multi-GPU sizing.
+    --workload c4 : config C4 — loop 3a alone: sample isotropic lines (Philox) and clip them
+                  against their faces on a ~10^5-cell tessellation, 1.25*10^8 lines per GPU per
+                  step (10^9 at N=8), checksum mode (nothing stored); the store mode
+                  (e1,e2,p1,p2,x,angle,U per line) is timed beside it.  Metric: lines/s.
     --workload c5 : config C5 — ensemble of independent SMF chains under the checkACS
                   energy (applications/checkACS.cpp, tau=6), 8192 chains per GPU (65536 at
                   N=8); a step is one checkACS batch of 250 proposals on every chain and the
@@ -129,6 +133,182 @@ class ClockSampler(threading.Thread):
 
 def soa_bytes(soa):
     return int(sum(a.nbytes for a in soa.a.values()) + 8)
+
+
+F_ALG_CLIP = 300.0     # DP flop per line (sample + clip)
+B_ALG_CLIP_STORE = 40.0  # bytes written per line in store mode (2 x i32 + 4 x f64)
+
+
+def run_lines(args, rank, local_rank, world, nccl_id, dist, torch):
+    """Workload C4: random-line sampling and face clipping throughput."""
+    import lite_b200
+    cells = args.cells or 100000
+    per_gpu = args.splits or 125_000_000
+    n_global = per_gpu * world
+    t, _tau = lite_b200.generate_crtt(cells, seed=5)
+    soa = t.export()
+    ctx = lite_b200.Context(local_rank, rank, world, nccl_id)
+    ctx.tess_upload(soa)
+    fp64_peak = ctx.measure_fp64_peak()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    def allmax(v):
+        if world > 1:
+            tt = torch.tensor([v], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        return v
+
+    for k in range(args.warmup):
+        ctx.lines_sample_clip(n_global, SEED, k * n_global, mode=0)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    ms_k = 0.0
+    ctx.timer_mark(0)
+    for k in range(args.steps):
+        cs = ctx.lines_sample_clip(n_global, SEED, (args.warmup + k) * n_global, mode=0)
+        ms_k += ctx.last_kernel_ms()[0]
+    ctx.timer_mark(1)
+    barrier()
+    ms_total = allmax(ctx.timer_elapsed(0, 1))
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    value = n_global / (ms_total / args.steps * 1e-3)
+    # end to end: tessellation from host buffers every step, checksum back to the host
+    for k in range(2):
+        ctx.tess_upload(soa)
+        ctx.lines_sample_clip(n_global, SEED, 0, mode=0)
+    barrier()
+    ctx.timer_mark(2)
+    for k in range(args.steps):
+        ctx.tess_upload(soa)
+        ctx.lines_sample_clip(n_global, SEED, k * n_global, mode=0)
+    ctx.timer_mark(3)
+    barrier()
+    ms_e2e = allmax(ctx.timer_elapsed(2, 3))
+    # store mode (64 B written per line, 40 B of them the reference's Split members)
+    n_store = min(per_gpu, 50_000_000)
+    ctx.clear_splits()
+    ctx.lines_sample_clip(n_store * world, SEED, 0, mode=1)
+    ms_store = 0.0
+    for k in range(3):
+        ctx.clear_splits()
+        ctx.lines_sample_clip(n_store * world, SEED, k * n_store * world, mode=1)
+        ms_store += ctx.last_kernel_ms()[0]
+    ms_store /= 3
+    status = ctx.fetch("STATUS")
+    k_s = ms_k / args.steps * 1e-3
+    rate = per_gpu / k_s
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    store_rate = n_store / (ms_store * 1e-3)
+    roofline = {
+        "kernel": "k_split<philox|checksum> (K1: Philox sample + clip, nothing stored)",
+        "bound": "fp64", "achieved": rate * F_ALG_CLIP / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": rate * F_ALG_CLIP / 1e12 / fp64_peak,
+        "peak_source": "DFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 figure)",
+        "alg_flop_per_line": F_ALG_CLIP, "lines_per_launch": per_gpu, "avg_launch_ms": k_s * 1e3, "traffic": None,
+        "store_mode": {"lines_per_sec": store_rate, "avg_launch_ms": ms_store, "lines_per_launch": n_store,
+                       "alg_bytes_per_line": B_ALG_CLIP_STORE, "written_bytes_per_line": 64,
+                       "hbm_achieved_gbs": store_rate * B_ALG_CLIP_STORE / 1e9,
+                       "hbm_frac": store_rate * B_ALG_CLIP_STORE / 1e9 / hbm_peak,
+                       "hbm_frac_written": store_rate * 64 / 1e9 / hbm_peak},
+    }
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_cpu as oc
+        arrays = dict(soa.a)
+        arrays["int_length"] = soa.int_length
+        T = oc.Tess(arrays)
+        cores = oc.hardware_threads()
+        sample = args.cpu_sample or max(1_000_000, 1_000_000 * cores)
+        oc.lines_clip(T, sample, SEED, 0, 0, sample // 10, cores)
+        reps, t0 = 0, time.perf_counter()
+        while True:
+            oc.lines_clip(T, n_global, SEED, args.warmup * n_global, reps * sample, sample, cores)
+            reps += 1
+            if time.perf_counter() - t0 > 10.0 or reps >= 20:
+                break
+        dt = time.perf_counter() - t0
+        cs_cpu, _bad = oc.lines_clip(T, 2_000_000, SEED, 7, 0, 2_000_000, cores)
+        cs_gpu = ctx.lines_sample_clip(2_000_000 * world, SEED, 7, mode=0) if world == 1 else None
+        cpu = {"value": sample * reps / dt, "unit": "lines/s", "cores": cores, "kind": "port",
+               "sample": "%d passes of %d lines of the step's %d, %d threads; C++ double restatement of split_sample + "
+                         "the Split constructor (oracle/oracle_cpu.cpp: oracle_lines_clip)" % (reps, sample, per_gpu, cores),
+               "checksum_2e6_lines_equal": bool(cs_gpu is not None and int(cs_cpu[0]) == int(cs_gpu[0])
+                                                and int(cs_cpu[1]) == int(cs_gpu[1]))}
+    if rank == 0:
+        line = {
+            "metric": "random_lines_sampled_and_clipped_per_sec", "value": value, "unit": "lines/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4: %d isotropic lines per GPU (%d in all) sampled (Philox, length-weighted "
+                                   "halfedge, x uniform, angle = acos(1-2U)) and clipped against the faces of a %d-cell "
+                                   "CRTT tessellation of the unit square; checksum mode" % (per_gpu, n_global, soa.n_cells()),
+                       "cells": soa.n_cells(), "lines_per_gpu": per_gpu, "lines_global": n_global,
+                       "l2": "the %0.1f MB tessellation is L2-resident by design and nothing is stored in checksum "
+                             "mode; store mode writes 64 B per line (%d MB per launch, larger than L2); no flush"
+                             % (soa_bytes(soa) / 1e6, n_store * 64 // 1_000_000),
+                       "sharding": "contiguous shards of the batch, tessellation replicated, no collective",
+                       "no_exit_lines": int(status[0])},
+            "clocks": clocks,
+            "e2e": {"value": n_global / (ms_e2e / args.steps * 1e-3), "unit": "lines/s",
+                    "h2d_bytes_per_step": soa_bytes(soa), "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps,
+                    "path": "lite_tess_upload(host SoA) + lite_lines_sample_clip -> host checksum"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "fp64_peak_tflops_measured": fp64_peak,
+            "checksum": [int(cs[0]), int(cs[1])],
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        emit(line)
+    ctx.close()
+
+
+def run_cpu_reference_lines(args, n_gpus, rank):
+    """`--impl reference --workload c4`: split_sample + Split constructor on all host threads."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_cpu as oc
+    import lite_b200
+    cells = args.cells or 100000
+    per_gpu = args.splits or 125_000_000
+    t, _tau = lite_b200.generate_crtt(cells, seed=5)
+    soa = t.export()
+    arrays = dict(soa.a)
+    arrays["int_length"] = soa.int_length
+    T = oc.Tess(arrays)
+    cores = oc.hardware_threads()
+    sample = args.cpu_sample or max(1_000_000, 1_000_000 * cores)
+    for _ in range(args.warmup):
+        oc.lines_clip(T, sample, SEED, 0, 0, sample // 10, cores)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        oc.lines_clip(T, per_gpu * n_gpus, SEED, k * per_gpu * n_gpus, 0, sample, cores)
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    emit({"impl": "reference", "metric": "random_lines_sampled_and_clipped_per_sec", "value": val, "unit": "lines/s",
+          "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+          "config": {"workload": "C4: %d-cell CRTT tessellation; CPU arm clips a bounded sample of the step's lines"
+                                 % soa.n_cells(), "cells": soa.n_cells(), "lines_per_step_sampled": int(sample)},
+          "cpu_baseline": {"value": val, "unit": "lines/s", "cores": cores, "kind": "port",
+                           "sample": "%d of the step's %d lines per GPU, per step (oracle/oracle_cpu.cpp)" % (sample, per_gpu)},
+          "e2e": {"value": val, "unit": "lines/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 SMF_TAU = 6.0                      # applications/checkACS.cpp:29
@@ -306,6 +486,8 @@ def run_cpu_reference(args, n_gpus, rank):
         return
     if args.workload == "c5":
         return run_cpu_reference_smf(args, n_gpus, rank)
+    if args.workload == "c4":
+        return run_cpu_reference_lines(args, n_gpus, rank)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_cpu as oc
     import lite_b200
@@ -353,7 +535,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--chains", type=int, default=0, help="c5: chains per GPU (default 8192)")
     ap.add_argument("--cells", type=int, default=0, help="override the tessellation size")
     ap.add_argument("--splits", type=int, default=0, help="override the dummy splits per GPU per step")
@@ -393,8 +575,8 @@ def main():
         dist.broadcast(idt, 0)
         nccl_id = bytes(idt.cpu().tolist())
 
-    if args.workload == "c5":
-        run_smf(args, rank, local_rank, world, nccl_id, dist, torch)
+    if args.workload in ("c4", "c5"):
+        (run_smf if args.workload == "c5" else run_lines)(args, rank, local_rank, world, nccl_id, dist, torch)
         if world > 1:
             dist.destroy_process_group()
         return

@@ -759,6 +759,57 @@ int oracle_sample_splits(const lite_tess_soa *s, int64_t n_batch, uint64_t seed,
   return 0;
 }
 
+/* Config "random_lines sampling and face clipping" (loop 3a alone): split_sample
+ * (lib/ttessel.cpp:1783-1795) + the Split constructor (:2090-2132) for candidates
+ * j0 .. j0+n-1 of a batch, nothing stored; checksum2 as lite_lines_sample_clip:
+ * [0] xor of hash(e1<<32|e2), [1] sum of e2.  Returns the number of lines without exit. */
+int64_t oracle_lines_clip(const lite_tess_soa *s, int64_t n_batch, uint64_t seed, uint64_t ctr0, int64_t j0,
+                          int64_t n, uint64_t *checksum2, int nthreads) {
+  View T;
+  std::string err;
+  if (!build_view(s, T, err)) { g_err = err; return -1; }
+  std::vector<double> cum;
+  std::vector<int> cum_he;
+  double cl = 0;
+  for (int f = 0; f < s->n_faces; f++) {
+    if (!s->face_inside[f]) continue;
+    for (int k = 0; k < s->face_he_count[f]; k++) {
+      int h = s->face_he_list[s->face_he_offset[f] + k];
+      cl += s->he_length[h];
+      cum.push_back(cl);
+      cum_he.push_back(h);
+    }
+  }
+  if (cum.empty()) { g_err = "no inside halfedge"; return -1; }
+  std::atomic<int64_t> bad(0);
+  std::atomic<uint64_t> cx(0), cs(0);
+  parallel_for(n, nthreads, [&](int64_t a, int64_t b, int) {
+    uint64_t lx = 0, ls = 0;
+    int64_t lbad = 0;
+    for (int64_t i = a; i < b; i++) {
+      uint64_t j = (uint64_t)(j0 + i);
+      uint32_t r[4];
+      philox4x32_10(ctr0 + j, 0u, seed, r);
+      double x = u53(r[0], r[1]);
+      uint32_t spare = ((r[0] & 31u) << 17) | ((r[1] & 63u) << 11) | ((r[2] & 31u) << 6) | (r[3] & 63u);
+      double U = u53(r[2], r[3]), jit = (double)spare * (1.0 / 4194304.0);
+      double sel = ((double)j + jit) * (cl / (double)n_batch);
+      size_t k = std::upper_bound(cum.begin(), cum.end(), sel) - cum.begin();
+      if (k >= cum.size()) k = cum.size() - 1;
+      int he = cum_he[k];
+      SplitC sp = make_split(T, he, x, acos(1.0 - 2.0 * U));
+      int e2 = sp.ok ? sp.e2 : -1;
+      if (!sp.ok) lbad++;
+      uint64_t key = ((uint64_t)(uint32_t)he << 32) | (uint32_t)e2;
+      key *= 0x9E3779B97F4A7C15ull; key ^= key >> 29;
+      lx ^= key; ls += (uint64_t)(uint32_t)e2;
+    }
+    cx ^= lx; cs += ls; bad += lbad;
+  });
+  if (checksum2) { checksum2[0] = cx.load(); checksum2[1] = cs.load(); }
+  return bad.load();
+}
+
 /* PseudoLikDiscrete::AddGivenSplit over a list (lib/ttessel.cpp:3360-3364):
  * stat[i*d+k] = -statistic_variation(Split(he[i],x[i],angle[i]))[k].
  * e2_out / pts_out (p1x,p1y,p2x,p2y per candidate) may be NULL.

@@ -121,6 +121,20 @@ def sample_splits(t, n_batch, seed, ctr0=0, j0=0, n=None, nthreads=1):
     return he, x, ang
 
 
+def lines_clip(t, n_batch, seed, ctr0=0, j0=0, n=None, nthreads=1):
+    """Sample + clip only (config C4); returns (checksum[2], lines without exit)."""
+    n = n_batch if n is None else n
+    cs = np.zeros(2, dtype=np.uint64)
+    L = lib()
+    L.oracle_lines_clip.restype = C.c_int64
+    L.oracle_lines_clip.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64,
+                                    C.c_void_p, C.c_int]
+    bad = L.oracle_lines_clip(t.ref(), n_batch, seed, ctr0, j0, n, _p(cs), nthreads)
+    if bad < 0:
+        raise RuntimeError(L.oracle_last_error().decode())
+    return cs, int(bad)
+
+
 def split_stats(t, features, he, x, angle, nthreads=1):
     fid = _ids(features)
     he = np.ascontiguousarray(he, dtype=np.int32)

@@ -254,6 +254,10 @@ def test_random_lines_sample_clip_modes_and_oracle(lite):
     np.testing.assert_array_equal(e2, r["split_e2"])
     np.testing.assert_allclose(p1, r["split_p1"], rtol=0, atol=1e-13)
     np.testing.assert_allclose(p2, r["split_p2"], rtol=0, atol=1e-12)
+    # the CPU arm of `bench.py --workload c4` computes the same checksum
+    cs_cpu, bad = oc.lines_clip(t, n, seed, off, nthreads=4)
+    assert bad == 0
+    np.testing.assert_array_equal(cs_only, cs_cpu)
     ctx.close()
 
 

@@ -88,3 +88,25 @@ def test_port_whole_pass_crtt_closed_form():
         assert v == pytest.approx(th * t.n_nb - (u / math.pi) * math.exp(th) - 2 * t.n_b, rel=1e-12)
         assert g[0] == pytest.approx(t.n_nb - (u / math.pi) * math.exp(th), rel=1e-12)
         assert H[0, 0] == pytest.approx(-(u / math.pi) * math.exp(th), rel=1e-12)
+
+
+def test_port_lines_clip_checksum_is_the_checksum_of_its_parts():
+    """oracle_lines_clip (config C4: sample + clip, nothing stored) against
+    sample_splits + the Split constructor run separately."""
+    soa, _ = load_golden("t100")
+    t = oc.Tess(soa)
+    n, seed, off = 50000, 99, 5
+    cs, bad = oc.lines_clip(t, n, seed, off, nthreads=3)
+    he, x, ang = oc.sample_splits(t, n, seed, off, nthreads=2)
+    r = oc.split_stats(t, ["face_number"], he, x, ang, nthreads=2)
+    assert bad == r["bad"] == 0
+    key = (he.astype(np.uint64) << np.uint64(32)) | r["split_e2"].astype(np.uint32).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        key = key * np.uint64(0x9E3779B97F4A7C15)
+        key ^= key >> np.uint64(29)
+    assert int(np.bitwise_xor.reduce(key)) == int(cs[0])
+    assert int(r["split_e2"].astype(np.uint32).astype(np.uint64).sum()) == int(cs[1])
+    # a shard of the batch: counters are global, so two halves combine to the whole
+    a, _ = oc.lines_clip(t, n, seed, off, 0, n // 2, 2)
+    b, _ = oc.lines_clip(t, n, seed, off, n // 2, n - n // 2, 2)
+    assert int(a[0]) ^ int(b[0]) == int(cs[0]) and (int(a[1]) + int(b[1])) % 2 ** 64 == int(cs[1])
