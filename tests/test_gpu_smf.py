@@ -163,3 +163,56 @@ def test_exported_chain_feeds_the_pseudo_likelihood_path(ctx):
     h.crtt_run(tau, 2000, 1)
     h.check()
     ctx.smf_destroy()
+
+
+def test_simulate_gibbs_model_then_recover_theta_by_pl_newton(ctx):
+    """End to end over both device paths: tessellations are simulated on the GPU under a
+    Gibbs energy with a face interaction (theta_angles * face_sum_of_angles + theta_seg *
+    is_segment_internal, the angle and segment terms of demos/sim_acs.cpp:64-76), brought
+    back, and the pseudo-likelihood path (SetEnergy + AddSplits + damped Newton on
+    value / gradient / Hessian, lib/ttessel.cpp:3454-3505) must recover the parameters
+    that generated them, on average over independent chains."""
+    tau, th_ang = 5.0, 1.0
+    names = ["face_sum_of_angles", "is_segment_internal"]
+    truth = np.array([th_ang, -math.log(tau)])
+    n_chains = 24
+    ctx.smf_create(n_chains, 1000, seed=77)
+    ctx.smf_set_model(names, truth, 0.33, 0.33)
+    rows = ctx.smf_run(2, 30000)
+    ctx.smf_stats(validate=True)
+    n_end = rows[-1, COL["n"]]
+    assert n_end.min() > 30                      # a real tessellation, not the empty window
+    # stationarity: the second half of the run does not change the mean size much
+    assert abs(rows[1, COL["n"]].mean() - rows[0, COL["n"]].mean()) < 0.15 * rows[0, COL["n"]].mean()
+    est = []
+    for k in range(n_chains):
+        h = ctx.smf_export(k)
+        soa = h.export()
+        ctx.tess_upload(soa)
+        ctx.energy_set(names)
+        ctx.merges_flips()
+        ctx.clear_splits()
+        ctx.add_splits_philox(200000, 1000 + k, 0)
+        th = np.zeros(2)
+        lpl, g, H = ctx.pl_eval(th)
+        for _ in range(50):                      # damped Newton on a concave function
+            step = np.linalg.solve(H, g)
+            lam = 1.0
+            while True:
+                cand = th - lam * step
+                l2, g2, H2 = ctx.pl_eval(cand)
+                if l2 >= lpl or lam < 1e-6:
+                    break
+                lam *= 0.5
+            th, lpl, g, H = cand, l2, g2, H2
+            if np.abs(g).max() < 1e-7 * max(1.0, abs(lpl)):
+                break
+        assert np.abs(g).max() < 1e-5 * max(1.0, abs(lpl)), "Newton did not converge on chain %d" % k
+        assert np.all(np.linalg.eigvalsh(H) < 0)
+        est.append(th)
+    est = np.array(est)
+    mean, sem = est.mean(0), est.std(0, ddof=1) / math.sqrt(n_chains)
+    # within 4 standard errors of the truth (plus a small allowance for the bias of the
+    # maximum pseudo-likelihood estimator on ~100-cell tessellations)
+    assert np.all(np.abs(mean - truth) < 4 * sem + 0.05 * np.abs(truth)), (mean, sem, truth)
+    ctx.smf_destroy()
