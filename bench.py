@@ -81,7 +81,9 @@ def workload(n_gpus, args):
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
 
-    def __init__(self, index, period=0.004):
+    def __init__(self, index, period=None):
+        if period is None:
+            period = float(os.environ.get("LITE_BENCH_CLOCK_PERIOD", "0.004"))
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.sm, self.reasons, self.max_mhz = [], set(), None

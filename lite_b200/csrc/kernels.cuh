@@ -395,6 +395,7 @@ struct SlotData {
   int off, n, k1;     // face slot range, position of the halfedge in it
   double2 P, Q;       // source and target of the halfedge
   double ang1;        // atan2 of its direction
+  double ux, uy;      // its unit direction (cos, sin of ang1) from the end points
   double half_tot;    // area of its face (shoelace, prefix summation)
   uint32_t fl1;       // SF_* of the slot
 };
@@ -405,6 +406,11 @@ __device__ __forceinline__ SlotData load_slot(const TessDev &T, int s1) {
   S.P = ldpt(T.pt, s1);
   S.Q = ldpt(T.pt, fo.x + ((S.k1 + 1 == fo.y) ? 0 : S.k1 + 1));
   S.ang1 = __ldg(T.ang + s1);
+  {
+    const double ex = S.Q.x - S.P.x, ey = S.Q.y - S.P.y;
+    const double inv = 1.0 / sqrt(ex * ex + ey * ey);
+    S.ux = ex * inv; S.uy = ey * inv;
+  }
   S.half_tot = 0.5 * __ldg(T.stot2 + s1);
   S.fl1 = __ldg(T.flg + s1);
   return S;
@@ -430,18 +436,23 @@ __device__ __noinline__ double corner_min(const uint32_t *flg, const double *ca,
   return m;
 }
 
+// The proposal angle arrives as (cos, sin) and, when a registered feature or the record
+// needs the angle itself, as `angle`.  The line's normal is a = sin(l), b = -cos(l) with
+// l = ang1 + angle (lib/ttessel.cpp:2094-2100), formed by the addition formulas from the
+// halfedge's unit direction: for a sampled candidate cos(angle) = 1 - 2U is the draw
+// itself, so neither acos nor sincos is on the path unless an angle feature asks for it
+// (they were 24 % of the kernel's instructions, profiles/r1_k_split.txt).
 template <bool WITH_STAT, class PG>
 __device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, const SlotData &S, double x,
-                                           double angle, double *__restrict__ stat_col0,
-                                           size_t cap, SplitOut &o) {
+                                           double angle, double cos_angle, double sin_angle,
+                                           double *__restrict__ stat_col0, size_t cap, SplitOut &o) {
   const int off = S.off, n = S.n, k1 = S.k1;
   const int k1n = (k1 + 1 == n) ? 0 : k1 + 1;
   const double2 P = S.P, Q = S.Q;
   // lib/ttessel.cpp:2094-2105, evaluated as the reference does (no contraction)
-  const double l = S.ang1 + angle;
-  double a, c;
-  sincos(l, &a, &c);
-  const double b = -c;
+  const double l = S.ang1 + angle;  // only read by the angle features
+  const double a = S.uy * cos_angle + S.ux * sin_angle;   // sin(l)
+  const double b = S.uy * sin_angle - S.ux * cos_angle;   // -cos(l)
   const double u = __dadd_rn(__dmul_rn(a, P.x), __dmul_rn(b, P.y));
   const double v = __dadd_rn(__dmul_rn(a, Q.x), __dmul_rn(b, Q.y));
   const double w = __dadd_rn(u, __dmul_rn(x, __dadd_rn(v, -u)));
@@ -719,7 +730,7 @@ __global__ void __launch_bounds__(LITE_SPLIT_TB, LITE_SPLIT_MINB) k_split(TessDe
     const long end = min(beg + len, A.n_local);
     m = -1;
   for (long i = beg + lane; i < end; i += 32) {
-    double x, angle, U = 0.0;
+    double x, angle, ca, sa, U = 0.0;
     if (PHILOX) {
       const long j = A.j0 + i;
       uint32_t r[4];
@@ -734,12 +745,17 @@ __global__ void __launch_bounds__(LITE_SPLIT_TB, LITE_SPLIT_MINB) k_split(TessDe
       if (m < 0) m_new = sample_slot(T, sel);
       else while (m_new < T.n_cum - 1 && sel >= cum_hi) cum_hi = __ldg(T.cum + ++m_new);
       if (m_new != m) { m = m_new; cum_hi = __ldg(T.cum + m); S = load_slot(T, m); }
-      angle = acos(1.0 - 2.0 * U);  // lib/ttessel.cpp:1792
+      // angle = acos(1 - 2U) (lib/ttessel.cpp:1792): cos(angle) is the draw, sin(angle) >= 0
+      ca = 1.0 - 2.0 * U;
+      sa = 2.0 * sqrt(U * (1.0 - U));
+      const bool need_angle = RECORD || (STAT && (PG::mask(G) & MASK_FACE_ANG));
+      angle = need_angle ? acos(ca) : 0.0;
     } else {
       S = load_slot(T, __ldg(T.he_slot + A.in_he[i])); x = A.in_x[i]; angle = A.in_angle[i];
+      sincos(angle, &sa, &ca);
     }
     SplitOut o;
-    split_eval<STAT, PG>(T, G, S, x, angle, A.stat + A.base + i, A.cap, o);
+    split_eval<STAT, PG>(T, G, S, x, angle, ca, sa, A.stat + A.base + i, A.cap, o);
     if (o.e2 < 0) bad++;
     if (RECORD || CHECK) {
       const int h = __ldg(T.slot_he + S.off + S.k1);
@@ -786,11 +802,8 @@ __device__ __forceinline__ void merge_one(const TessDev &T, const Prog &G, const
   bool bnd_e2 = fe2 & SF_BND, bnd_e1 = fe1 & SF_BND;
   // neighbours along the blocking lines: X = tgt(next), Y = src(prev_hf(next))
   double2 X2 = ldpt(T.pt, o1 + (ke1 + 1) % n1), X1 = ldpt(T.pt, o2 + (kt1 + 1) % n2);
-  int he2 = T.slot_he[o1 + ke1], he1 = T.slot_he[o2 + kt1];
-  int ph2 = T.he_prev_hf[he2], ph1 = T.he_prev_hf[he1];
   // Y2 is the vertex before p2 in face(twin e), Y1 the vertex before p1 in face(e)
   double2 Y2 = ldpt(T.pt, o2 + (kt + n2 - 1) % n2), Y1 = ldpt(T.pt, o1 + (ke + n1 - 1) % n1);
-  (void)ph2; (void)ph1;
   double elen = plen(p1, p2);
 
   double acc[LITE_MAX_D];
