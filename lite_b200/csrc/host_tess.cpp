@@ -634,6 +634,186 @@ ChainCounts crtt_chain(HostTess &t, double tau, uint64_t n_steps, uint64_t seed,
 // ---------------------------------------------------------------------------
 // text format (LineTes::write/read, lib/ttessel.cpp:1331-1441), doubles
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// simultaneous construction from maximal segments
+// ---------------------------------------------------------------------------
+bool build_from_segments(HostTess &t, const std::vector<double> &wx, const std::vector<double> &wy,
+                         const std::vector<std::vector<double>> &segs, std::string &err) {
+  const int nw = (int)wx.size();
+  if (nw < 3) { err = "no window"; return false; }
+  struct S { double x0, y0, x1, y1; std::vector<std::pair<double, int>> on; };  // (parameter, vertex)
+  std::vector<S> L;
+  for (int i = 0; i < nw; i++) L.push_back({wx[i], wy[i], wx[(i + 1) % nw], wy[(i + 1) % nw], {}});
+  for (const auto &c : segs) {
+    if (c.size() != 4) { err = "a segment needs four coordinates"; return false; }
+    L.push_back({c[0], c[1], c[2], c[3], {}});
+  }
+  const int nL = (int)L.size();
+  double xmin = wx[0], xmax = wx[0], ymin = wy[0], ymax = wy[0];
+  for (int i = 0; i < nw; i++) { xmin = fmin(xmin, wx[i]); xmax = fmax(xmax, wx[i]); ymin = fmin(ymin, wy[i]); ymax = fmax(ymax, wy[i]); }
+  const double scale = fmax(xmax - xmin, ymax - ymin);
+  const double eps = 1e-9 * scale;
+  // uniform grid over the window: every segment is listed in the cells its box meets
+  const int G = std::max(1, std::min(2048, (int)sqrt((double)nL)));
+  const double cw = (xmax - xmin) / G + 1e-300, ch = (ymax - ymin) / G + 1e-300;
+  auto cx = [&](double x) { return std::max(0, std::min(G - 1, (int)((x - xmin) / cw))); };
+  auto cy = [&](double y) { return std::max(0, std::min(G - 1, (int)((y - ymin) / ch))); };
+  std::vector<std::vector<int>> grid((size_t)G * G);
+  for (int i = 0; i < nL; i++) {
+    // walk the cells along the segment (conservative: the cells of its bounding box row by row,
+    // restricted to the columns the segment spans in that row)
+    const S &s = L[i];
+    const int r0 = cy(fmin(s.y0, s.y1) - eps), r1 = cy(fmax(s.y0, s.y1) + eps);
+    for (int r = r0; r <= r1; r++) {
+      double xa = fmin(s.x0, s.x1), xb = fmax(s.x0, s.x1);
+      if (s.y1 != s.y0) {
+        const double ylo = ymin + r * ch - eps, yhi = ymin + (r + 1) * ch + eps;
+        const double ta = (ylo - s.y0) / (s.y1 - s.y0), tb = (yhi - s.y0) / (s.y1 - s.y0);
+        const double t0 = fmax(0.0, fmin(ta, tb)), t1 = fmin(1.0, fmax(ta, tb));
+        const double x0 = s.x0 + t0 * (s.x1 - s.x0), x1 = s.x0 + t1 * (s.x1 - s.x0);
+        xa = fmin(x0, x1); xb = fmax(x0, x1);
+      }
+      for (int q = cx(xa - eps); q <= cx(xb + eps); q++) grid[(size_t)r * G + q].push_back(i);
+    }
+  }
+  // no two segments may cross in their interiors (X-vertex): distances of the ends of one
+  // to the line of the other have opposite signs, both ways
+  {
+    auto side = [&](const S &a, double px, double py) {
+      const double ex = a.x1 - a.x0, ey = a.y1 - a.y0;
+      const double d = (ex * (py - a.y0) - ey * (px - a.x0)) / sqrt(ex * ex + ey * ey);
+      return d > eps ? 1 : (d < -eps ? -1 : 0);
+    };
+    for (const auto &cell : grid)
+      for (size_t p = 0; p < cell.size(); p++)
+        for (size_t q = p + 1; q < cell.size(); q++) {
+          const S &a = L[cell[p]], &b = L[cell[q]];
+          if (side(a, b.x0, b.y0) * side(a, b.x1, b.y1) < 0 && side(b, a.x0, a.y0) * side(b, a.x1, a.y1) < 0) {
+            err = "two segments cross (X-vertex): not a T-tessellation";
+            return false;
+          }
+        }
+  }
+  // vertices: window corners first, then the two ends of every internal segment
+  t = HostTess();
+  t.win_x = wx; t.win_y = wy;
+  std::vector<double> vx, vy;
+  for (int i = 0; i < nw; i++) { vx.push_back(wx[i]); vy.push_back(wy[i]); }
+  for (int i = 0; i < nw; i++) { L[i].on.push_back({0.0, i}); L[i].on.push_back({1.0, (i + 1) % nw}); }
+  for (int i = nw; i < nL; i++) {
+    for (int e = 0; e < 2; e++) {
+      const double px = e ? L[i].x1 : L[i].x0, py = e ? L[i].y1 : L[i].y0;
+      const int v = (int)vx.size();
+      vx.push_back(px); vy.push_back(py);
+      L[i].on.push_back({(double)e, v});
+      // the segment this end point abuts on
+      int host = -1; double best = eps, host_t = 0;
+      for (int j : grid[(size_t)cy(py) * G + cx(px)]) {
+        if (j == i) continue;
+        const S &h = L[j];
+        const double ex = h.x1 - h.x0, ey = h.y1 - h.y0, l2 = ex * ex + ey * ey;
+        const double tt = ((px - h.x0) * ex + (py - h.y0) * ey) / l2;
+        if (tt < 0 || tt > 1) continue;
+        const double qx = h.x0 + tt * ex - px, qy = h.y0 + tt * ey - py;
+        const double d = sqrt(qx * qx + qy * qy);
+        if (d <= best) { best = d; host = j; host_t = tt; }
+      }
+      if (host < 0) { err = "a segment end lies on no other segment and not on the window boundary"; return false; }
+      const double hl = sqrt((L[host].x1 - L[host].x0) * (L[host].x1 - L[host].x0) + (L[host].y1 - L[host].y0) * (L[host].y1 - L[host].y0));
+      if (host_t * hl <= eps || (1 - host_t) * hl <= eps) { err = "two segments meet at their end points (L- or X-vertex): not a T-tessellation"; return false; }
+      L[host].on.push_back({host_t, v});
+    }
+  }
+  // edges along every segment
+  struct E { int v0, v1, seg, prev_hf, next_hf; bool bnd; };
+  std::vector<E> edges;
+  for (int i = 0; i < nL; i++) {
+    auto &on = L[i].on;
+    std::sort(on.begin(), on.end());
+    for (size_t k = 0; k + 1 < on.size(); k++) {
+      if (on[k + 1].first - on[k].first <= 0) { err = "two vertices coincide on a segment"; return false; }
+      E e; e.v0 = on[k].second; e.v1 = on[k + 1].second; e.seg = i; e.bnd = i < nw;
+      e.prev_hf = k ? (int)edges.size() - 1 : -1; e.next_hf = (k + 2 < on.size()) ? (int)edges.size() + 1 : -1;
+      edges.push_back(e);
+    }
+  }
+  const int nE = (int)edges.size(), nV = (int)vx.size();
+  // DCEL arrays: halfedge 2e runs v0 -> v1 (dir true), 2e+1 back
+  t.vx = vx; t.vy = vy; t.v_inc.assign(nV, -1); t.v_alive.assign(nV, 1);
+  t.h_src.assign(2 * nE, -1); t.h_next.assign(2 * nE, -1); t.h_prev.assign(2 * nE, -1); t.h_face.assign(2 * nE, -1);
+  t.h_seg.assign(2 * nE, -1); t.h_next_hf.assign(2 * nE, -1); t.h_prev_hf.assign(2 * nE, -1);
+  t.h_dir.assign(2 * nE, 0); t.h_alive.assign(2 * nE, 1); t.h_len.assign(2 * nE, 0.0);
+  std::vector<std::vector<int>> out(nV);
+  for (int e = 0; e < nE; e++) {
+    const E &ed = edges[e];
+    t.h_src[2 * e] = ed.v0; t.h_src[2 * e + 1] = ed.v1;
+    t.h_seg[2 * e] = t.h_seg[2 * e + 1] = ed.seg;
+    t.h_dir[2 * e] = 1; t.h_dir[2 * e + 1] = 0;
+    t.h_next_hf[2 * e] = ed.next_hf >= 0 ? 2 * ed.next_hf : -1;
+    t.h_prev_hf[2 * e] = ed.prev_hf >= 0 ? 2 * ed.prev_hf : -1;
+    t.h_next_hf[2 * e + 1] = ed.prev_hf >= 0 ? 2 * ed.prev_hf + 1 : -1;
+    t.h_prev_hf[2 * e + 1] = ed.next_hf >= 0 ? 2 * ed.next_hf + 1 : -1;
+    const double dx = vx[ed.v1] - vx[ed.v0], dy = vy[ed.v1] - vy[ed.v0];
+    t.h_len[2 * e] = t.h_len[2 * e + 1] = sqrt(dx * dx + dy * dy);
+    out[ed.v0].push_back(2 * e); out[ed.v1].push_back(2 * e + 1);
+    t.v_inc[ed.v1] = 2 * e; t.v_inc[ed.v0] = 2 * e + 1;
+  }
+  // next(): at the head of h, turn to the outgoing halfedge that follows twin(h) clockwise
+  for (int v = 0; v < nV; v++) {
+    auto &o = out[v];
+    if (o.size() < 2) { err = "dangling vertex"; return false; }
+    std::sort(o.begin(), o.end(), [&](int a, int b) {
+      const int ta = t.h_src[a ^ 1], tb = t.h_src[b ^ 1];
+      return atan2(vy[ta] - vy[v], vx[ta] - vx[v]) < atan2(vy[tb] - vy[v], vx[tb] - vx[v]);
+    });
+    const int k = (int)o.size();
+    for (int i = 0; i < k; i++) {
+      const int in = o[i] ^ 1;              // arrives at v
+      const int nx = o[(i + k - 1) % k];    // the next outgoing halfedge clockwise
+      t.h_next[in] = nx; t.h_prev[nx] = in;
+    }
+  }
+  // faces: one per cycle; the clockwise cycle is the outside
+  int n_outer = 0;
+  for (int h0 = 0; h0 < 2 * nE; h0++) {
+    if (t.h_face[h0] >= 0) continue;
+    double a2 = 0;
+    int h = h0, guard = 0;
+    do {
+      const int s = t.h_src[h], d = t.h_src[h ^ 1];
+      a2 += vx[s] * vy[d] - vx[d] * vy[s];
+      h = t.h_next[h];
+      if (h < 0 || ++guard > 2 * nE) { err = "broken boundary cycle"; return false; }
+    } while (h != h0);
+    const bool inside = a2 > 0;
+    if (!inside) n_outer++;
+    const int f = (int)t.f_he.size();
+    t.f_he.push_back(h0); t.f_inside.push_back(inside); t.f_alive.push_back(1);
+    h = h0;
+    do { t.h_face[h] = f; h = t.h_next[h]; } while (h != h0);
+  }
+  if (n_outer != 1) { err = "the segments do not form one connected tessellation of the window"; return false; }
+  // segments and the blocking / non-blocking lists, in input order
+  t.s_he.assign(nL, -1); t.s_nedges.assign(nL, 0); t.s_pos.assign(nL, -1); t.s_bnd.assign(nL, 0);
+  t.s_alive.assign(nL, 1); t.s_kind.assign(nL, 0);
+  t.nb_list.clear(); t.b_list.clear();
+  for (int e = 0; e < nE; e++) { const int s = edges[e].seg; if (t.s_he[s] < 0) t.s_he[s] = 2 * e; t.s_nedges[s]++; }
+  t.int_length = 0;
+  for (int h = 0; h < 2 * nE; h++) if (t.f_inside[t.h_face[h]]) t.int_length += t.h_len[h];
+  for (int s = 0; s < nL; s++) {
+    t.s_bnd[s] = s < nw;
+    if (s < nw) continue;
+    if (t.s_nedges[s] == 1) { t.s_kind[s] = 1; t.s_pos[s] = (int)t.nb_list.size(); t.nb_list.push_back(s); }
+    else { t.s_kind[s] = 2; t.s_pos[s] = (int)t.b_list.size(); t.b_list.push_back(s); }
+  }
+  // a window side must bound the outside face on its right
+  for (int i = 0; i < nw; i++) if (t.f_inside[t.h_face[t.s_he[i] ^ 1]]) { err = "window side with an inside face on both sides"; return false; }
+  t.finish_import();
+  std::string bad = t.check();
+  if (!bad.empty()) { err = "inconsistent tessellation: " + bad; return false; }
+  return true;
+}
+
 static bool parse_ratio(const std::string &tok, double &out) {
   size_t sl = tok.find('/');
   std::string num = tok.substr(0, sl), den = sl == std::string::npos ? "1" : tok.substr(sl + 1);
@@ -661,6 +841,7 @@ bool read_text(HostTess &t, const std::string &text, std::string &err) {
   std::istringstream is(text);
   std::string line;
   std::vector<std::vector<double>> segs;
+  std::vector<double> win_x_in, win_y_in;
   bool have_window = false;
   while (std::getline(is, line)) {
     std::istringstream ls(line);
@@ -680,59 +861,15 @@ bool read_text(HostTess &t, const std::string &text, std::string &err) {
       double a = 0;
       for (size_t i = 0; i < x.size(); i++) { size_t j = (i + 1) % x.size(); a += x[i] * y[j] - x[j] * y[i]; }
       if (a <= 0) { err = "Invalid orientation of a domain ccb"; return false; }
-      t.insert_window_polygon(x, y);
+      win_x_in = x; win_y_in = y;
       have_window = true;
     } else {
       if (!have_window) { err = "segment before window"; return false; }
       segs.push_back(c);
     }
   }
-  // insert the segments in dependency order: an end must lie on an existing edge
-  const double eps = 1e-9;
-  auto locate = [&](double px, double py, int &he, int &vert) {
-    he = -1; vert = -1;
-    for (size_t v = 0; v < t.vx.size(); v++)
-      if (t.v_alive[v] && fabs(t.vx[v] - px) <= eps && fabs(t.vy[v] - py) <= eps) { vert = (int)v; return true; }
-    for (size_t h = 0; h < t.h_src.size(); h += 2) {
-      if (!t.h_alive[h]) continue;
-      double ax = t.vx[t.h_src[h]], ay = t.vy[t.h_src[h]], bx = t.vx[t.tgt((int)h)], by = t.vy[t.tgt((int)h)];
-      double ex = bx - ax, ey = by - ay, L2 = ex * ex + ey * ey;
-      double s = ((px - ax) * ex + (py - ay) * ey) / L2;
-      if (s <= 0 || s >= 1) continue;
-      double qx = ax + s * ex - px, qy = ay + s * ey - py;
-      if (qx * qx + qy * qy <= eps * eps) { he = (int)h; return true; }
-    }
-    return false;
-  };
-  std::vector<bool> done(segs.size(), false);
-  size_t left = segs.size();
-  bool progress = true;
-  while (left && progress) {
-    progress = false;
-    for (size_t i = 0; i < segs.size(); i++) {
-      if (done[i]) continue;
-      int h1, v1, h2, v2;
-      if (!locate(segs[i][0], segs[i][1], h1, v1) || !locate(segs[i][2], segs[i][3], h2, v2)) continue;
-      if (v1 >= 0 || v2 >= 0) continue;  // T-tessellation: ends lie inside edges
-      // choose the halfedges bounding the face that contains the segment midpoint side
-      double mx = 0.5 * (segs[i][0] + segs[i][2]), my = 0.5 * (segs[i][1] + segs[i][3]);
-      auto left_of = [&](int h) {
-        double ax = t.vx[t.h_src[h]], ay = t.vy[t.h_src[h]], bx = t.vx[t.tgt(h)], by = t.vy[t.tgt(h)];
-        return (bx - ax) * (my - ay) - (by - ay) * (mx - ax) > 0;
-      };
-      int e1 = left_of(h1) ? h1 : (h1 ^ 1), e2 = left_of(h2) ? h2 : (h2 ^ 1);
-      if (t.h_face[e1] != t.h_face[e2] || !t.f_inside[t.h_face[e1]]) continue;
-      // the segment must not cross existing edges of that face (cyclic dependencies
-      // are resolved by later passes)
-      SplitMove m;
-      m.e1 = e1; m.e2 = e2; m.p1x = segs[i][0]; m.p1y = segs[i][1]; m.p2x = segs[i][2]; m.p2y = segs[i][3];
-      m.valid = true;
-      t.update_split(m);
-      done[i] = true; left--; progress = true;
-    }
-  }
-  if (left) { err = "segments cannot be inserted one by one as splits (cyclic T-dependencies)"; return false; }
-  return true;
+  (void)have_window;
+  return build_from_segments(t, win_x_in, win_y_in, segs, err);
 }
 
 // a double is m*2^e exactly: print it as the rational num/den the format wants

@@ -136,6 +136,15 @@ struct ChainCounts {
 ChainCounts crtt_chain(HostTess &t, double tau, uint64_t n_steps, uint64_t seed,
                        double p_split = 0.33, double p_merge = 0.33);
 
+// Build a T-tessellation from its maximal segments, all at once (the reference reads a
+// file by LineTes::insert_segment on each line, lib/ttessel.cpp:904-980, which handles any
+// order; successive splits cannot, because T-tessellations contain cycles of segments each
+// ending on the next).  window: a hole-free polygon, counter-clockwise; segs: x0 y0 x1 y1
+// per internal segment, every end point on the interior of another segment or of a window
+// side.  Anything else (crossings, L/X/I-vertices, ends in the void) is an error.
+bool build_from_segments(HostTess &t, const std::vector<double> &wx, const std::vector<double> &wy,
+                         const std::vector<std::vector<double>> &segs, std::string &err);
+
 // LineTes::read / write text format (lib/ttessel.cpp:1331-1441), double precision
 bool read_text(HostTess &t, const std::string &text, std::string &err);
 std::string write_text(const HostTess &t);

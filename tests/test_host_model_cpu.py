@@ -112,11 +112,45 @@ def test_generator_reaches_equilibrium_estimate():
 def test_text_roundtrip_and_fixture():
     here = os.path.dirname(os.path.abspath(__file__))
     text = open(os.path.join(here, "golden", "tessellation_data.txt")).read()
-    try:
-        h = lite_b200.HostTess(text=text)
-    except lite_b200.LiteError as e:
-        pytest.skip("fixture needs simultaneous insertion: %s" % e)
+    h = lite_b200.HostTess(text=text)
     assert h.counts()[0] == 11
     h.check()
     h2 = lite_b200.HostTess(text=h.write_text())
     assert h2.counts() == h.counts()
+    # the same cells as the exact oracle builds from the same file
+    window, segs = lo.parse_text(text)
+    assert _cells_from_soa(h.export().a) == _cells_from_oracle(lo.ttessel_from_segments(window, segs))
+
+
+def test_reader_builds_cyclic_t_dependencies_at_once():
+    """After flips a T-tessellation contains cycles of segments each ending on the next
+    (no order of successive splits rebuilds them); the reference reads such a file by
+    LineTes::insert_segment line by line (lib/ttessel.cpp:1377-1441, :904-980)."""
+    h = lite_b200.HostTess((0, 0, 1, 1))
+    h.crtt_run(4.0, 20000, 5)
+    text = h.write_text()
+    h2 = lite_b200.HostTess(text=text)
+    h2.check()
+    assert h2.counts() == h.counts()
+    a, b = h.export(), h2.export()
+    assert _cells_from_soa(a.a) == _cells_from_soa(b.a)
+    assert b.int_length == pytest.approx(a.int_length, rel=1e-12)
+    # the rebuilt model is a working one: the chain carries on from it
+    h2.crtt_run(4.0, 3000, 1)
+    h2.check()
+    # the exact oracle reads the same file to the same cells (t100 is such a tessellation)
+    t100 = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "t100.txt")).read()
+    window, segs = lo.parse_text(t100)
+    assert _cells_from_soa(lite_b200.HostTess(text=t100).export().a) == \
+        _cells_from_oracle(lo.ttessel_from_segments(window, segs))
+
+
+@pytest.mark.parametrize("bad,msg", [
+    ("0/1 0/1 1/1 0/1 1/1 1/1 0/1 1/1\n1/4 0/1 1/4 1/2\n", "lies on no other segment"),       # end in the void
+    ("0/1 0/1 1/1 0/1 1/1 1/1 0/1 1/1\n0/1 0/1 1/1 1/1\n", "L- or X-vertex"),                 # corner to corner
+    ("0/1 0/1 1/1 0/1 1/1 1/1 0/1 1/1\n1/4 0/1 1/4 1/1\n0/1 1/2 1/1 1/2\n", "cross"),  # a crossing
+    ("0/1 0/1 0/1 1/1 1/1 1/1 1/1 0/1\n", "orientation"),                                       # clockwise window
+])
+def test_reader_rejects_what_is_not_a_t_tessellation(bad, msg):
+    with pytest.raises(lite_b200.LiteError, match=msg):
+        lite_b200.HostTess(text=bad)
