@@ -389,3 +389,35 @@ def test_c2_scale_against_cpu_port(lite, feats_tag):
         np.testing.assert_allclose(g, wg, rtol=RTOL, atol=1e-12 * max(1.0, np.abs(wg).max()))
         np.testing.assert_allclose(H, wH, rtol=RTOL, atol=1e-12 * max(1.0, np.abs(wH).max()))
     ctx.close()
+
+
+def test_convex_polygonal_window_against_live_oracle(lite):
+    """Nothing on the path assumes a rectangle: a hexagonal window (TTessel::insert_window
+    with a polygon, lib/ttessel.cpp:1516-1540), a tessellation grown by the exact oracle's
+    SMF chain, then every merge and flip and 400 device-sampled splits for all twelve
+    features against the exact oracle."""
+    import lite_oracle as lo
+    hexagon = [lo._pt(1, 0), lo._pt(3, 0), lo._pt(4, 2), lo._pt(3, 4), lo._pt(1, 4), lo._pt(0, 2)]
+    t = lo.TTessel(lo.Rng(3))
+    t.insert_window([(hexagon, [])])
+    eng = lo.make_energy(["minus_is_segment_internal"], [math.log(1.2)], t)
+    lo.SMFChain(eng, 0.4, 0.2).step(160)
+    assert len(t.internal_faces()) > 12 and t.blocking_segments and t.non_blocking_segments
+    soa = lo.export_soa(t)
+    ctx = _ctx(lite, soa, ALL12)
+    nm, nf = ctx.merges_flips()
+    ctx.add_splits_philox(400, 11, 0)
+    he, x, ang = ctx.fetch("SPLIT_E1"), ctx.fetch("SPLIT_X"), ctx.fetch("SPLIT_ANGLE")
+    res = lo.eval_candidates(t, lo.make_energy(lo.ALL12, None, t), he, x, ang)
+    np.testing.assert_array_equal(ctx.fetch("SPLIT_E2"), res["split_e2"])
+    np.testing.assert_array_equal(ctx.fetch("MERGE_HE"), res["merge_he"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_E1"), res["flip_e1"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_E2"), res["flip_e2"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_RIGHT"), res["flip_right"])
+    _assert_stats("split", ctx.fetch("SPLIT_STAT"), res["split_stat"], ALL12)
+    _assert_stats("merge", ctx.fetch("MERGE_STAT"), res["merge_stat"], ALL12)
+    _assert_stats("flip", ctx.fetch("FLIP_STAT"), res["flip_stat"], ALL12)
+    # some candidates do start or end on the slanted window sides
+    bnd = soa["seg_on_boundary"][soa["he_seg"]]
+    assert bnd[he].any() and bnd[res["split_e2"]].any()
+    ctx.close()
