@@ -421,3 +421,39 @@ def test_convex_polygonal_window_against_live_oracle(lite):
     bnd = soa["seg_on_boundary"][soa["he_seg"]]
     assert bnd[he].any() and bnd[res["split_e2"]].any()
     ctx.close()
+
+
+def test_non_convex_window_against_live_oracle(lite):
+    """An L-shaped window (hole-free, non-convex): the cell at the reflex corner is not
+    convex, so a line may cross its boundary more than twice and ray_exit_face's nearest-hit
+    rule (lib/ttessel.cpp:4563) decides.  All twelve features, every move type, against the
+    exact oracle."""
+    import lite_oracle as lo
+    ell = [lo._pt(0, 0), lo._pt(4, 0), lo._pt(4, 2), lo._pt(2, 2), lo._pt(2, 4), lo._pt(0, 4)]
+    t = lo.TTessel(lo.Rng(3))
+    t.insert_window([(ell, [])])
+    eng = lo.make_energy(["minus_is_segment_internal"], [math.log(1.2)], t)
+    lo.SMFChain(eng, 0.4, 0.2).step(120)
+    soa = lo.export_soa(t)
+
+    def convex(f):
+        pts = [(float(p[0]), float(p[1])) for p in lo.face2poly(f)[0]]
+        n = len(pts)
+        return all((pts[(i + 1) % n][0] - pts[i][0]) * (pts[(i + 2) % n][1] - pts[(i + 1) % n][1]) -
+                   (pts[(i + 1) % n][1] - pts[i][1]) * (pts[(i + 2) % n][0] - pts[(i + 1) % n][0]) > 0 for i in range(n))
+    non_convex = [f for f in t.internal_faces() if not convex(f)]
+    assert non_convex
+    ctx = _ctx(lite, soa, ALL12)
+    ctx.merges_flips()
+    ctx.add_splits_philox(1500, 11, 0)
+    he, x, ang = ctx.fetch("SPLIT_E1"), ctx.fetch("SPLIT_X"), ctx.fetch("SPLIT_ANGLE")
+    in_non_convex = [i for i in range(len(he)) if any(t.halfedges[int(he[i])].face is f for f in non_convex)]
+    assert len(in_non_convex) > 20
+    res = lo.eval_candidates(t, lo.make_energy(lo.ALL12, None, t), he, x, ang)
+    np.testing.assert_array_equal(ctx.fetch("SPLIT_E2"), res["split_e2"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_E2"), res["flip_e2"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_RIGHT"), res["flip_right"])
+    _assert_stats("split", ctx.fetch("SPLIT_STAT"), res["split_stat"], ALL12)
+    _assert_stats("merge", ctx.fetch("MERGE_STAT"), res["merge_stat"], ALL12)
+    _assert_stats("flip", ctx.fetch("FLIP_STAT"), res["flip_stat"], ALL12)
+    ctx.close()
