@@ -74,3 +74,29 @@ def test_long_chain_stays_consistent_and_near_equilibrium(tmp_path):
     tail = trace[15000:]
     est = tail["n_nb"].mean() * math.pi / tail["int_length"].mean()
     assert abs(est - 6.0) < 0.6, est
+
+
+def test_chain_source_is_clean_under_address_and_ub_sanitizers(tmp_path):
+    """compute-sanitizer is not available on the GPU pool; the chain logic is one source for
+    host and device, so its memory safety is checked on the host build: a long chain, all
+    twelve features, and a chain that runs into its capacity limit."""
+    exe = str(tmp_path / "smf_host_asan")
+    src = os.path.join(HERE, "cpp", "smf_host.cpp")
+    cc = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                         "-o", exe, src], capture_output=True, text=True)
+    if cc.returncode != 0:
+        pytest.skip("no sanitizer runtime for g++ here: " + cc.stderr[-200:])
+    trace = str(tmp_path / "t.bin")
+    names, thetas = ENERGIES["all"]
+    feats = []
+    for n, th in zip(names, thetas):
+        feats += [str(FEATURE_IDS[n]), repr(float(th))]
+    runs = [
+        ["1024", "12000", "5", "1", "0.33", "0.33", trace, "2", "3", repr(-math.log(6.0)), "1", repr(5 / math.pi)],
+        ["300", "6000", "7", "2", "0.33", "0.33", trace, str(len(names))] + feats,
+        ["24", "4000", "5", "0", "0.33", "0.33", trace, "1", "3", repr(-math.log(6.0))],
+    ]
+    for args in runs:
+        res = subprocess.run([exe] + args, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr[-2000:]
+        assert "runtime error" not in res.stderr and "AddressSanitizer" not in res.stderr, res.stderr[-2000:]
