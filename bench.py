@@ -227,6 +227,17 @@ def run_lines(args, rank, local_rank, world, nccl_id, dist, torch):
                        "hbm_frac": store_rate * B_ALG_CLIP_STORE / 1e9 / hbm_peak,
                        "hbm_frac_written": store_rate * 64 / 1e9 / hbm_peak},
     }
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            tr = json.load(open(prof))
+            roofline["traffic"] = tr.get("k_split_clip")   # read-only: the L2-resident tessellation
+            fx = tr.get("k_split_clip_dp_flop_per_line_executed")
+            if fx:
+                roofline["executed_flop_per_line"] = fx
+                roofline["executed_frac"] = rate * fx / 1e12 / fp64_peak
+        except Exception:
+            pass
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))

@@ -103,13 +103,41 @@ def kernel(rep, name):
 
 
 launches()
-traffic = {}
+tj = os.path.join(HERE, "traffic.json")
+traffic = json.load(open(tj)) if os.path.exists(tj) else {}
 for rep, name in (("prof_split_%s.ncu-rep" % tag, "k_split"), ("prof_reduce_%s.ncu-rep" % tag, "k_reduce"),
-                  ("prof_mf_%s.ncu-rep" % tag, "k_merges_flips")):
+                  ("prof_mf_%s.ncu-rep" % tag, "k_merges_flips"), ("prof_clip_%s.ncu-rep" % tag, "k_split_clip")):
     t = kernel(rep, name)
     if t is not None:
         traffic[name] = t
-if traffic:
-    traffic["_source"] = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, capture tag %s" % tag
-    json.dump(traffic, open(os.path.join(HERE, "traffic.json"), "w"), indent=1)
+traffic["_source"] = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, capture tag %s" % tag
+
+
+def dp_flop(rep):
+    """2*DFMA + DADD + DMUL thread instructions of one launch (what the kernel executes)."""
+    p = os.path.join(OUT, rep)
+    if not os.path.exists(p):
+        return None
+    r = list(csv.reader(io.StringIO(ncu(["-i", p, "--page", "raw", "--csv"]))))
+    d = dict(zip(r[0], r[2]))
+
+    def num(k):
+        try:
+            return float(d[k].replace(",", ""))
+        except Exception:
+            return 0.0
+    per_cycle = (2 * num("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed") +
+                 num("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed") +
+                 num("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed"))
+    return per_cycle * num("smsp__cycles_elapsed.avg")
+
+
+f = dp_flop("prof_split_%s.ncu-rep" % tag)
+if f:
+    traffic["k_split_dp_flop_per_candidate_executed"] = round(f / 1e7, 1)   # one launch = 10^7 candidates (C2)
+    traffic["_dp_flop_source"] = "ncu %s: (2*dfma + dadd + dmul thread instructions per elapsed cycle) x elapsed cycles / candidates of the captured launch" % tag
+f = dp_flop("prof_clip_%s.ncu-rep" % tag)
+if f:
+    traffic["k_split_clip_dp_flop_per_line_executed"] = round(f / 1.25e8, 1)  # one launch = 1.25e8 lines (C4)
+json.dump(traffic, open(tj, "w"), indent=1)
 print("wrote", sorted(os.listdir(HERE)))
