@@ -345,57 +345,75 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   r |= up(c, c->nb_list, s->non_blocking, s->n_non_blocking);
   r |= up(c, c->b_list, s->blocking, s->n_blocking);
   if (r) return r;
-  // helper threads pack the raw arrays into the pinned block while this thread validates
-  // the links and accumulates the sampler's cumulative lengths
+  // Host side of an upload = packing into the pinned block + the export assertions (in the
+  // spirit of TTessel::is_valid, lib/ttessel.cpp:1721-1753).  Both are split over a few
+  // threads; only the sampler's cumulative lengths stay sequential (their summation order
+  // is part of the sampler's definition).
   std::vector<std::thread> packers;
+  const int nt = 4;
+  std::vector<int> bad_face(nt, -1), bad_he(nt, -1), bad_list_f(nt, -1), bad_list_k(nt, -1);
+  std::vector<int64_t> part_listed(nt, 0), part_inside(nt, 0);
+  c->h_he_inside.assign(nH, 0);
   {
-    const int nt = 3;
     for (int t = 0; t < nt; t++)
-      packers.emplace_back([c, t, nt] {
+      packers.emplace_back([=, &bad_face, &bad_he, &bad_list_f, &bad_list_k, &part_listed, &part_inside] {
         for (size_t k = t; k < c->pack_jobs.size(); k += nt) memcpy(c->pack_jobs[k].dst, c->pack_jobs[k].src, c->pack_jobs[k].bytes);
+        // faces [f0, f1): list ranges, and the list of an inside face is its ccb
+        const int f0 = (int)((int64_t)nF * t / nt), f1 = (int)((int64_t)nF * (t + 1) / nt);
+        int64_t listed = 0;
+        for (int f = f0; f < f1 && bad_face[t] < 0 && bad_list_f[t] < 0; f++) {
+          const int off = s->face_he_offset[f], cnt = s->face_he_count[f];
+          if (cnt < 0 || off < 0 || off + cnt > s->n_face_he || (s->face_inside[f] && cnt < 3)) { bad_face[t] = f; break; }
+          for (int k = 0; k < cnt; k++) {
+            const int h = s->face_he_list[off + k];
+            if (h < 0 || h >= nH ||
+                (s->face_inside[f] && (s->he_face[h] != f || s->he_next[h] != s->face_he_list[off + (k + 1 == cnt ? 0 : k + 1)]))) {
+              bad_list_f[t] = f; bad_list_k[t] = k; break;
+            }
+          }
+          if (s->face_inside[f]) listed += cnt;
+        }
+        part_listed[t] = listed;
+        // halfedges [h0, h1): links in range, twin of twin
+        const int h0 = (int)((int64_t)nH * t / nt), h1 = (int)((int64_t)nH * (t + 1) / nt);
+        int64_t inside = 0;
+        for (int h = h0; h < h1; h++) {
+          const int f = s->he_face[h], tw = s->he_twin[h];
+          if (f < 0 || f >= nF || tw < 0 || tw >= nH || s->he_twin[tw] != h || s->he_src[h] < 0 ||
+              s->he_src[h] >= nV || s->he_seg[h] < 0 || s->he_seg[h] >= nS || s->he_next[h] < 0 || s->he_next[h] >= nH) { bad_he[t] = h; break; }
+          if (!s->face_inside[f]) continue;
+          inside++;
+          c->h_he_inside[h] = 1;
+        }
+        part_inside[t] = inside;
       });
   }
   struct Joiner { std::vector<std::thread> &v; ~Joiner() { for (auto &x : v) if (x.joinable()) x.join(); } } joiner{packers};
-  // ---- export assertions (in the spirit of TTessel::is_valid, lib/ttessel.cpp:1721-1753)
-  int64_t listed = 0;
-  for (int f = 0; f < nF; f++) {
-    if (s->face_he_count[f] < 0 || s->face_he_offset[f] < 0 ||
-        s->face_he_offset[f] + s->face_he_count[f] > s->n_face_he)
-      return fail(LITE_EINVAL, "face %d: halfedge list out of range", f);
-    if (s->face_inside[f]) {
-      if (s->face_he_count[f] < 3) return fail(LITE_EINVAL, "inside face %d has %d halfedges", f, s->face_he_count[f]);
-      listed += s->face_he_count[f];
-    }
-  }
-  c->h_he_inside.assign(nH, 0);
-  int64_t inside_he = 0;
-  for (int h = 0; h < nH; h++) {
-    int f = s->he_face[h], t = s->he_twin[h];
-    if (f < 0 || f >= nF || t < 0 || t >= nH || s->he_twin[t] != h || s->he_src[h] < 0 ||
-        s->he_src[h] >= nV || s->he_seg[h] < 0 || s->he_seg[h] >= nS)
-      return fail(LITE_EINVAL, "halfedge %d: inconsistent links", h);
-    if (!s->face_inside[f]) continue;
-    inside_he++;
-    c->h_he_inside[h] = 1;
-  }
   // cumulative halfedge lengths of the sampler (cumlen += e->get_length(),
   // lib/ttessel.cpp:1980), accumulated in SLOT order: faces in index order, each
-  // face in ccb order from outer_ccb().  Entry m of `cum` is slot m.
+  // face in ccb order from outer_ccb().  Entry m of `cum` is slot m.  (Indices are
+  // clamped here; the workers report anything out of range.)
   std::vector<double> &cum = c->h_cum;
   cum.assign((size_t)s->n_face_he, 0.0);
   double cl = 0.0;
   for (int f = 0; f < nF; f++) {
     const int off = s->face_he_offset[f], cnt = s->face_he_count[f];
+    if (off < 0 || cnt < 0 || off + cnt > s->n_face_he) break;
+    if (!s->face_inside[f]) { for (int k = 0; k < cnt; k++) cum[off + k] = cl; continue; }
     for (int k = 0; k < cnt; k++) {
       const int h = s->face_he_list[off + k];
-      if (h < 0 || h >= nH) return fail(LITE_EINVAL, "face %d: halfedge id out of range", f);
-      // the list is the ccb of the face: consecutive entries are linked by next()
-      if (s->face_inside[f] &&
-          (s->he_face[h] != f || s->he_next[h] != s->face_he_list[off + (k + 1 == cnt ? 0 : k + 1)]))
-        return fail(LITE_EINVAL, "face %d: halfedge list disagrees with he_next/he_face at position %d", f, k);
-      if (s->face_inside[f]) cl += s->he_length[h];
+      if (h >= 0 && h < nH) cl += s->he_length[h];
       cum[off + k] = cl;
     }
+  }
+  for (auto &x : packers) x.join();
+  int64_t listed = 0, inside_he = 0;
+  for (int t = 0; t < nt; t++) {
+    if (bad_face[t] >= 0) return fail(LITE_EINVAL, "face %d: halfedge list out of range or fewer than 3 halfedges", bad_face[t]);
+    if (bad_list_f[t] >= 0)
+      return fail(LITE_EINVAL, "face %d: halfedge list disagrees with he_next/he_face at position %d", bad_list_f[t], bad_list_k[t]);
+    if (bad_he[t] >= 0) return fail(LITE_EINVAL, "halfedge %d: inconsistent links", bad_he[t]);
+    listed += part_listed[t]; inside_he += part_inside[t];
   }
   if (inside_he != listed)
     return fail(LITE_EINVAL,
@@ -416,7 +434,6 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
       return fail(LITE_EINVAL, "blocking segment %d must be internal with at least two edges", sg);
   }
   t1 = now_ms();
-  for (auto &x : packers) x.join();
   c->pack_jobs.clear();
   r |= up(c, c->cum, cum.data(), cum.size());
   if (c->guide.alloc((size_t)n_guide)) return LITE_ECUDA;
