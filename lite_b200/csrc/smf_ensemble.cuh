@@ -224,8 +224,11 @@ extern "C" int lite_smf_run(lite_ctx *c, int32_t n_samples, int64_t steps_per_sa
     // vs 5.3e7 chain-steps/s at 8192 chains); (3) a larger one runs at 128 registers so
     // that 512 chains per SM are resident (2.3e8 at 65536 chains; 64 registers: 2.0e8).
     static const char *env_minb = getenv("LITE_SMF_MINB"), *env_lpc = getenv("LITE_SMF_LPC");
-    int shift = 0;
-    if (env_lpc) while ((1 << (shift + 1)) <= atoi(env_lpc) && shift < 5) shift++;
+    // (4) when even two lanes per chain fit that way, 16 chains per warp beat 32 (8.5e7 vs
+    // 7.4e7 at 8192 chains); thinner than that loses again (local-memory lines are shared
+    // by the lanes of a warp, so sparse warps waste L1).
+    int shift = ((long)n * 2 <= (long)c->sm_count * 4 * LITE_SMF_TB) ? 1 : 0;
+    if (env_lpc) { shift = 0; while ((1 << (shift + 1)) <= atoi(env_lpc) && shift < 5) shift++; }
     const long threads = (long)n << shift;
     int minb = (threads <= (long)c->sm_count * 4 * LITE_SMF_TB) ? 4 : 8;
     if (env_minb) minb = atoi(env_minb);
