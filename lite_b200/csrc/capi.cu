@@ -10,6 +10,9 @@
 #include <string.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -96,11 +99,61 @@ struct Arena {
 };
 static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
+// A few persistent host threads per context: an upload's packing and export assertions run
+// on them (spawning threads per call cost about as much as the work itself).
+struct HostPool {
+  std::vector<std::thread> th;
+  std::mutex m;
+  std::condition_variable cv_go, cv_done;
+  std::function<void(int)> job;
+  unsigned long gen = 0;
+  int pending = 0;
+  bool stop = false;
+  void start(int n) {
+    for (int i = 0; i < n; i++)
+      th.emplace_back([this, i] {
+        unsigned long seen = 0;
+        for (;;) {
+          std::function<void(int)> f;
+          {
+            std::unique_lock<std::mutex> lk(m);
+            cv_go.wait(lk, [&] { return stop || gen != seen; });
+            if (stop) return;
+            seen = gen;
+            f = job;
+          }
+          f(i);
+          {
+            std::lock_guard<std::mutex> lk(m);
+            if (--pending == 0) cv_done.notify_all();
+          }
+        }
+      });
+  }
+  // run f(0..n-1) on the workers; returns at once, wait() joins
+  void run(const std::function<void(int)> &f) {
+    std::lock_guard<std::mutex> lk(m);
+    job = f; pending = (int)th.size(); gen++;
+    cv_go.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    cv_done.wait(lk, [&] { return pending == 0; });
+  }
+  void shutdown() {
+    { std::lock_guard<std::mutex> lk(m); stop = true; }
+    cv_go.notify_all();
+    for (auto &t : th) if (t.joinable()) t.join();
+    th.clear();
+  }
+};
+
 struct SmfState;  // ensemble of SMF chains, smf_ensemble.cuh
 
 struct lite_ctx {
   int device = 0, rank = 0, world = 1;
   SmfState *smf = nullptr;
+  HostPool *pool = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;   // merges+flips run here, beside the split kernel
   cudaEvent_t ev_fork = nullptr, ev_mf = nullptr;
@@ -210,6 +263,8 @@ extern "C" int lite_ctx_create(lite_ctx **out, int device, int rank, int world_s
     ncclResult_t ne = g_nccl.CommInitRank(&c->comm, world_size, id, rank);
     if (ne != 0) return fail(LITE_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(ne) : "?");
   }
+  c->pool = new HostPool();
+  c->pool->start(4);
   CU(cudaStreamSynchronize(c->stream));
   *out = c;
   return 0;
@@ -222,6 +277,7 @@ extern "C" int lite_ctx_destroy(lite_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   smf_release(c);
+  if (c->pool) { c->pool->shutdown(); delete c->pool; c->pool = nullptr; }
   if (c->stream2) cudaStreamSynchronize(c->stream2);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -349,14 +405,12 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   // spirit of TTessel::is_valid, lib/ttessel.cpp:1721-1753).  Both are split over a few
   // threads; only the sampler's cumulative lengths stay sequential (their summation order
   // is part of the sampler's definition).
-  std::vector<std::thread> packers;
   const int nt = 4;
   std::vector<int> bad_face(nt, -1), bad_he(nt, -1), bad_list_f(nt, -1), bad_list_k(nt, -1);
   std::vector<int64_t> part_listed(nt, 0), part_inside(nt, 0);
   c->h_he_inside.assign(nH, 0);
   {
-    for (int t = 0; t < nt; t++)
-      packers.emplace_back([=, &bad_face, &bad_he, &bad_list_f, &bad_list_k, &part_listed, &part_inside] {
+      c->pool->run([=, &bad_face, &bad_he, &bad_list_f, &bad_list_k, &part_listed, &part_inside](int t) {
         for (size_t k = t; k < c->pack_jobs.size(); k += nt) memcpy(c->pack_jobs[k].dst, c->pack_jobs[k].src, c->pack_jobs[k].bytes);
         // faces [f0, f1): list ranges, and the list of an inside face is its ccb
         const int f0 = (int)((int64_t)nF * t / nt), f1 = (int)((int64_t)nF * (t + 1) / nt);
@@ -388,7 +442,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
         part_inside[t] = inside;
       });
   }
-  struct Joiner { std::vector<std::thread> &v; ~Joiner() { for (auto &x : v) if (x.joinable()) x.join(); } } joiner{packers};
+  struct Joiner { HostPool *p; ~Joiner() { p->wait(); } } joiner{c->pool};  // the job reads this frame
   // cumulative halfedge lengths of the sampler (cumlen += e->get_length(),
   // lib/ttessel.cpp:1980), accumulated in SLOT order: faces in index order, each
   // face in ccb order from outer_ccb().  Entry m of `cum` is slot m.  (Indices are
@@ -406,7 +460,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
       cum[off + k] = cl;
     }
   }
-  for (auto &x : packers) x.join();
+  c->pool->wait();
   int64_t listed = 0, inside_he = 0;
   for (int t = 0; t < nt; t++) {
     if (bad_face[t] >= 0) return fail(LITE_EINVAL, "face %d: halfedge list out of range or fewer than 3 halfedges", bad_face[t]);
