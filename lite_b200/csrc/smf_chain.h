@@ -345,7 +345,7 @@ LITE_HD inline void init_window(Chain &c, int cap, double x0, double y0, double 
 // ---------------------------------------------------------------------------
 // LineTes::split_edge, lib/ttessel.cpp:606-655: e keeps its source, the new pair runs
 // from the new vertex to the old target
-LITE_HD inline int split_edge(Chain &c, int e, double px, double py) {
+SMF_FN int split_edge(Chain &c, int e, double px, double py) {
   const int e_nhf = h_nhf(c, e);
   const int s = h_seg(c, e);
   const bool e_dir = h_dir(c, e);
@@ -394,7 +394,7 @@ LITE_HD inline int merge_edge(Chain &c, int e1, int e2) {
 // LineTes::add_edge, lib/ttessel.cpp:700-740: new edge from tgt(prev1) to tgt(prev2)
 // inside their common face; ext_prev is the halfedge whose straight continuation the
 // new edge is (-1: it starts a new segment)
-LITE_HD inline int add_edge(Chain &c, int prev1, int prev2, int ext_prev) {
+SMF_FN int add_edge(Chain &c, int prev1, int prev2, int ext_prev) {
   const Pt v1 = P_tgt(c, prev1), v2 = P_tgt(c, prev2);
   const int f = h_face(c, prev1);
   const int a1 = h_next(c, prev1), a2 = h_next(c, prev2);
@@ -451,7 +451,7 @@ LITE_HD inline void remove_edge(Chain &c, int e) {
 
 // LineTes::suppress_edge, lib/ttessel.cpp:201-236: remove the edge, then dissolve its
 // end vertices where they are left with two collinear edges
-LITE_HD inline void suppress_edge(Chain &c, int e) {
+SMF_FN void suppress_edge(Chain &c, int e) {
   const int p1 = h_prev(c, e), p2 = h_prev(c, e ^ 1);  // arrive at src(e), tgt(e)
   remove_edge(c, e);
   const int ps[2] = {p1, p2};
@@ -509,11 +509,21 @@ SMF_FN int ray_exit(const Chain &c, int start_he, double a, double b, double w, 
   return res;
 }
 
-// Split::Split(e,x,angle), lib/ttessel.cpp:2090-2132
-SMF_FN SplitMove make_split(const Chain &c, int e, double x, double angle) {
-  SplitMove m;
+// What ray_exit needs: the supporting line, the ray, where to start the walk and the two
+// halfedges whose hit is the ray's own source.  Split and flip proposals build one and
+// share a single ray_exit call site in smf_step (lanes of a warp working on either kind of
+// move run the face walk together instead of one kind after the other).
+struct Ray {
+  double a, b, w, dx, dy;
+  Pt p;
+  int start, skip0, skip1;
+  bool ok;
+};
+// Split::Split(e,x,angle), lib/ttessel.cpp:2090-2132, up to the ray
+LITE_HD inline void prepare_split(const Chain &c, int e, double x, double angle, SplitMove &m, Ray &r) {
   m.e1 = e; m.e2 = -1; m.x = x; m.angle = angle; m.valid = false;
   m.p1.x = m.p1.y = m.p2.x = m.p2.y = 0;
+  r.ok = false;
   const Pt P = P_src(c, e), Q = P_tgt(c, e);
   const double e1_angle = atan2(Q.y - P.y, Q.x - P.x);
   const double l = e1_angle + angle;
@@ -521,22 +531,17 @@ SMF_FN SplitMove make_split(const Chain &c, int e, double x, double angle) {
   const double u = dadd(dmul(a, P.x), dmul(b, P.y)), v = dadd(dmul(a, Q.x), dmul(b, Q.y));
   const double w = dadd(u, dmul(x, dadd(v, -u)));
   const double sP = fma(a, P.x, fma(b, P.y, -w)), sQ = fma(a, Q.x, fma(b, Q.y, -w));
-  if (!(sP != sQ)) return m;
+  if (!(sP != sQ)) return;
   const double t1 = sP / (sP - sQ);
   m.p1.x = fma(t1, Q.x - P.x, P.x); m.p1.y = fma(t1, Q.y - P.y, P.y);
-  double dx, dy;
-  if (sQ < 0.0) { dx = b; dy = -a; } else { dx = -b; dy = a; }
-  const int skip1 = (x == 0.0) ? h_prev(c, e) : -1;
-  const int e2 = ray_exit(c, e, a, b, w, m.p1, dx, dy, e, skip1, m.p2);
-  if (e2 < 0) return m;
-  m.e2 = e2; m.valid = true;
-  return m;
+  r.a = a; r.b = b; r.w = w; r.p = m.p1;
+  if (sQ < 0.0) { r.dx = b; r.dy = -a; } else { r.dx = -b; r.dy = a; }
+  r.start = e; r.skip0 = e; r.skip1 = (x == 0.0) ? h_prev(c, e) : -1;
+  r.ok = true;
 }
-
-// Flip::Flip(e1), lib/ttessel.cpp:2432-2454: a = src(e1) is where another segment (the
-// one of e3) ends on e1's segment; the flip removes e1 and prolongs e3 beyond a
-SMF_FN FlipMove make_flip(const Chain &c, int e1) {
-  FlipMove m;
+// Flip::Flip(e1), lib/ttessel.cpp:2432-2454, up to the ray: a = src(e1) is where another
+// segment (the one of e3) ends on e1's segment; the flip removes e1 and prolongs e3 beyond a
+LITE_HD inline void prepare_flip(const Chain &c, int e1, FlipMove &m, Ray &r) {
   m.e1 = e1; m.e2 = -1; m.valid = false; m.p2.x = m.p2.y = 0;
   const int hp = h_prev(c, e1);
   const bool right = (hp != h_phf(c, e1));
@@ -546,65 +551,10 @@ SMF_FN FlipMove make_flip(const Chain &c, int e1) {
   double dx = A.x - S3.x, dy = A.y - S3.y;
   const double nrm = sqrt(dx * dx + dy * dy);
   dx /= nrm; dy /= nrm;
-  const double la = dy, lb = -dx, lw = la * A.x + lb * A.y;
-  int start, skip0, skip1;
-  if (right) { skip0 = e1 ^ 1; skip1 = h_next(c, e1 ^ 1); start = skip0; }
-  else { skip0 = e1; skip1 = h_prev(c, e1); start = e1; }
-  const int e2 = ray_exit(c, start, la, lb, lw, A, dx, dy, skip0, skip1, m.p2);
-  if (e2 < 0) return m;
-  m.e2 = e2; m.valid = true;
-  return m;
-}
-
-// TTessel::update(Split), lib/ttessel.cpp:1580-1597
-SMF_FN int update_split(Chain &c, const SplitMove &sp) {
-  const int e1n = split_edge(c, sp.e1, sp.p1.x, sp.p1.y);
-  const int e2n = split_edge(c, sp.e2, sp.p2.x, sp.p2.y);
-  const int e = add_edge(c, e1n, e2n, -1);
-  c.H->int_length += 2 * h_len(c, e);
-  list_add(c, h_seg(c, e), 1);
-  const int ends[2] = {h_seg(c, h_next(c, e)), h_seg(c, h_next(c, e ^ 1))};
-  for (int k = 0; k < 2; k++) {
-    const int s = ends[k];
-    if (!seg_bnd(s) && c.seg[s].nedges <= 2 && c.seg[s].kind == 1) { list_remove(c, s); list_add(c, s, 2); }
-  }
-  return e;
-}
-// TTessel::update(Merge), lib/ttessel.cpp:1604-1638
-SMF_FN void update_merge(Chain &c, int e) {
-  const int s = h_seg(c, e);
-  list_remove(c, s);
-  const int ends[2] = {h_seg(c, h_next(c, e)), h_seg(c, h_next(c, e ^ 1))};
-  for (int k = 0; k < 2; k++) {
-    const int sx = ends[k];
-    if (!seg_bnd(sx) && c.seg[sx].nedges <= 2 && c.seg[sx].kind == 2) { list_remove(c, sx); list_add(c, sx, 1); }
-  }
-  const double suppressed = h_len(c, e);
-  suppress_edge(c, e);
-  c.H->int_length -= 2 * suppressed;
-}
-// TTessel::update(Flip), lib/ttessel.cpp:1644-1701
-SMF_FN int update_flip(Chain &c, const FlipMove &fl) {
-  const int e1 = fl.e1;
-  const int s1 = h_seg(c, e1);
-  const int s1_i = h_seg(c, h_next(c, e1));
-  const int e3 = fl.e3;
-  const int s2 = h_seg(c, e3);
-  // split_from_vertex (:161-189): the halfedge arriving at a in the face of e2
-  const int prev_a = fl.right ? (e1 ^ 1) : h_prev(c, e1);
-  const int e2n = split_edge(c, fl.e2, fl.p2.x, fl.p2.y);
-  const int new_e = add_edge(c, prev_a, e2n, e3);
-  c.H->int_length += 2 * h_len(c, new_e);
-  c.H->int_length -= 2 * h_len(c, e1);
-  const int s2_i = h_seg(c, h_next(c, new_e));
-  suppress_edge(c, e1);
-  if (c.seg[s2].nedges <= 2 && c.seg[s2].kind == 1) { list_remove(c, s2); list_add(c, s2, 2); }
-  if (c.seg[s1].nedges <= 1 && c.seg[s1].kind == 2) { list_remove(c, s1); list_add(c, s1, 1); }
-  if (s2_i != s1_i) {
-    if (!seg_bnd(s2_i) && c.seg[s2_i].nedges <= 2 && c.seg[s2_i].kind == 1) { list_remove(c, s2_i); list_add(c, s2_i, 2); }
-    if (!seg_bnd(s1_i) && c.seg[s1_i].nedges <= 1 && c.seg[s1_i].kind == 2) { list_remove(c, s1_i); list_add(c, s1_i, 1); }
-  }
-  return new_e;
+  r.a = dy; r.b = -dx; r.w = r.a * A.x + r.b * A.y; r.p = A; r.dx = dx; r.dy = dy;
+  if (right) { r.skip0 = e1 ^ 1; r.skip1 = h_next(c, e1 ^ 1); r.start = r.skip0; }
+  else { r.skip0 = e1; r.skip1 = h_prev(c, e1); r.start = e1; }
+  r.ok = true;
 }
 
 // TTessel::length_weighted_random_halfedge (lib/ttessel.cpp:1948-1966) by two-level
@@ -995,123 +945,172 @@ struct ChainParams {
 };
 
 // Returns false if the chain cannot go on (capacity exhausted / broken state).
+//
+// The three kinds of move are laid out in common phases rather than three branches:
+// candidate -> ray (splits, flips) -> Hastings ratio -> DCEL primitives -> bookkeeping, and
+// every out-of-line step (ray_exit, split_edge, add_edge, suppress_edge) has ONE call site.
+// 32 chains share a warp; with one site per primitive the lanes that need it run it
+// together whatever their kind of move.
 LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, const StepRng &R, TraceRec *tr) {
   if (c.H->status != ST_OK) return false;
   const uint64_t t = c.H->step;
-#ifdef SMF_INCREMENTAL_BSUM
-  if ((t & (REFRESH_PERIOD - 1)) == REFRESH_PERIOD - 1) refresh_all_blocks(c);
-#endif
   uint32_t r4[4];
   draw4(R, t, 0, r4);
   const double r0 = u53(r4[0], r4[1]);  // SMFChain::propose_modif_type, :3143-3151
   const double x = u53(r4[2], r4[3]);   // acceptance uniform, :3268
-  double dv[LITE_MAX_D];
+  const int type = (r0 <= cp.p_split) ? 0 : ((r0 <= cp.p_split + cp.p_merge) ? 1 : 2);
+  c.H->counts[2 * type]++;
   if (tr) {
-    tr->status = 0; tr->r = 0; tr->e_var = 0; tr->x_accept = x;
+    tr->type = type; tr->status = 0; tr->r = 0; tr->e_var = 0; tr->x_accept = x;
     tr->e1s[0] = tr->e1s[1] = tr->e1t[0] = tr->e1t[1] = 0; tr->x = tr->angle = 0;
     tr->p1[0] = tr->p1[1] = tr->p2[0] = tr->p2[1] = 0;
     tr->e2s[0] = tr->e2s[1] = tr->e2t[0] = tr->e2t[1] = 0;
   }
-  if (r0 <= cp.p_split) {
-    c.H->counts[0]++;
-    if (tr) tr->type = 0;
+  // ---- the candidate (TTessel::propose_split / _merge / _flip, :1755-1777)
+  bool have = false;
+  int e1 = -1;
+  SplitMove sm; FlipMove fm; Ray ray;
+  sm.valid = false; sm.e2 = -1; fm.valid = false; fm.e2 = -1; fm.e3 = -1; fm.right = false; ray.ok = false;
+  if (type == 0) {
     if (c.H->n_seg + 1 > c.H->cap) { c.H->status = ST_CAPACITY; return false; }
     draw4(R, t, 1, r4);
-    const int e = sample_halfedge(c, u53(r4[0], r4[1]));
+    e1 = sample_halfedge(c, u53(r4[0], r4[1]));
     const double xs = u53(r4[2], r4[3]);
     draw4(R, t, 2, r4);
-    const double ang = acos(1.0 - 2.0 * u53(r4[0], r4[1]));  // TTessel::propose_split, :1757
-    const SplitMove s = make_split(c, e, xs, ang);
-    if (tr) {
-      const Pt A = P_src(c, e), B = P_tgt(c, e);
-      tr->e1s[0] = A.x; tr->e1s[1] = A.y; tr->e1t[0] = B.x; tr->e1t[1] = B.y;
-      tr->x = xs; tr->angle = ang; tr->status = -1;
-    }
-    if (s.valid) {
-      // SMFChain::Hasting_ratio(Split), :3158-3176
-      int delta_nb = 1;
-      const int sa = h_seg(c, s.e1), sb = h_seg(c, s.e2);
-      if (c.seg[sa].nedges == 1 && !seg_bnd(sa)) delta_nb--;
-      if (c.seg[sb].nedges == 1 && !seg_bnd(sb)) delta_nb--;
-      double r = cp.p_merge / cp.p_split;
-      r *= (1 / kPi) * c.H->int_length / (c.H->n_nb + delta_nb);
-      split_variation(c, G, s, dv);
-      const double ev = dot_theta(G, dv);
-      r *= exp(-ev);
-      const bool acc = (r > 1 || x < r);
-      if (tr) {
-        const Pt A = P_src(c, s.e2), B = P_tgt(c, s.e2);
-        tr->e2s[0] = A.x; tr->e2s[1] = A.y; tr->e2t[0] = B.x; tr->e2t[1] = B.y;
-        tr->p1[0] = s.p1.x; tr->p1[1] = s.p1.y; tr->p2[0] = s.p2.x; tr->p2[1] = s.p2.y;
-        tr->r = r; tr->e_var = ev; tr->status = acc ? 2 : 1;
-      }
-      if (acc) { c.H->counts[1]++; update_split(c, s); c.H->energy += ev; }
-    }
-  } else if (r0 <= cp.p_split + cp.p_merge) {
-    c.H->counts[2]++;
-    if (tr) tr->type = 1;
+    const double ang = acos(1.0 - 2.0 * u53(r4[0], r4[1]));
+    prepare_split(c, e1, xs, ang, sm, ray);
+    have = true;
+    if (tr) { tr->x = xs; tr->angle = ang; }
+  } else if (type == 1) {
     if (c.H->n_nb > 0) {
       draw4(R, t, 1, r4);
-      int n = (int)(u53(r4[0], r4[1]) * c.H->n_nb);  // TTessel::propose_merge, :1761
+      int n = (int)(u53(r4[0], r4[1]) * c.H->n_nb);
       if (n >= c.H->n_nb) n = c.H->n_nb - 1;
-      const int sg = c.nb_list[n];
-      const int e = c.seg[sg].he;
-      // SMFChain::Hasting_ratio(Merge), :3184-3193
-      double r = cp.p_split / cp.p_merge;
-      r *= kPi * c.H->n_nb / (c.H->int_length - 2 * h_len(c, e));
-      merge_variation(c, G, e, dv);
-      const double ev = dot_theta(G, dv);
-      r *= exp(-ev);
-      const bool acc = (r > 1 || x < r);
-      if (tr) {
-        const Pt A = P_src(c, e), B = P_tgt(c, e);
-        tr->e1s[0] = A.x; tr->e1s[1] = A.y; tr->e1t[0] = B.x; tr->e1t[1] = B.y;
-        tr->r = r; tr->e_var = ev; tr->status = acc ? 2 : 1;
-      }
-      if (acc) { c.H->counts[3]++; update_merge(c, e); c.H->energy += ev; }
+      e1 = c.seg[c.nb_list[n]].he;
+      have = true;
     }
   } else {
-    c.H->counts[4]++;
-    if (tr) tr->type = 2;
     if (c.H->n_b > 0) {
       draw4(R, t, 1, r4);
-      int n = (int)(u53(r4[0], r4[1]) * c.H->n_b);  // TTessel::propose_flip, :1766-1777
+      int n = (int)(u53(r4[0], r4[1]) * c.H->n_b);
       if (n >= c.H->n_b) n = c.H->n_b - 1;
       const int sg = c.b_list[n];
       const int side = (u53(r4[2], r4[3]) < 0.5) ? 0 : 1;
-      const int e1 = side == 0 ? (seg_start(c, sg) ^ 1) : seg_end(c, sg);
-      const FlipMove f = make_flip(c, e1);
-      if (tr) {
-        const Pt A = P_src(c, e1), B = P_tgt(c, e1);
-        tr->e1s[0] = A.x; tr->e1s[1] = A.y; tr->e1t[0] = B.x; tr->e1t[1] = B.y;
-        tr->status = -1;
+      e1 = side == 0 ? (seg_start(c, sg) ^ 1) : seg_end(c, sg);
+      prepare_flip(c, e1, fm, ray);
+      have = true;
+    }
+  }
+  if (tr && have) {
+    const Pt A = P_src(c, e1), B = P_tgt(c, e1);
+    tr->e1s[0] = A.x; tr->e1s[1] = A.y; tr->e1t[0] = B.x; tr->e1t[1] = B.y;
+    tr->status = (type == 1) ? 0 : -1;
+  }
+  // ---- the ray of a split or a flip: one call site
+  int e2 = -1;
+  Pt p2; p2.x = p2.y = 0;
+  if (ray.ok) e2 = ray_exit(c, ray.start, ray.a, ray.b, ray.w, ray.p, ray.dx, ray.dy, ray.skip0, ray.skip1, p2);
+  bool valid = have && (type == 1 || e2 >= 0);
+  if (type == 0) { sm.e2 = e2; sm.p2 = p2; sm.valid = valid; }
+  if (type == 2) { fm.e2 = e2; fm.p2 = p2; fm.valid = valid; }
+  // ---- Hastings ratio (SMFChain::Hasting_ratio x3, :3158-3252) and acceptance
+  bool acc = false;
+  double ev = 0;
+  if (valid) {
+    double dv[LITE_MAX_D];
+    double r;
+    if (type == 0) {
+      int delta_nb = 1;
+      const int sa = h_seg(c, e1), sb = h_seg(c, e2);
+      if (c.seg[sa].nedges == 1 && !seg_bnd(sa)) delta_nb--;
+      if (c.seg[sb].nedges == 1 && !seg_bnd(sb)) delta_nb--;
+      r = cp.p_merge / cp.p_split;
+      r *= (1 / kPi) * c.H->int_length / (c.H->n_nb + delta_nb);
+      split_variation(c, G, sm, dv);
+    } else if (type == 1) {
+      r = cp.p_split / cp.p_merge;
+      r *= kPi * c.H->n_nb / (c.H->int_length - 2 * h_len(c, e1));
+      merge_variation(c, G, e1, dv);
+    } else {
+      int db = 0;
+      if (c.seg[h_seg(c, e1)].nedges == 2) db--;
+      if (c.seg[h_seg(c, fm.e3)].nedges == 1) db++;
+      const int i_short = h_seg(c, h_next(c, e1)), i_ext = h_seg(c, e2);
+      if (i_short != i_ext) {
+        if (c.seg[i_short].nedges == 2 && !seg_bnd(i_short)) db--;
+        if (c.seg[i_ext].nedges == 1 && !seg_bnd(i_ext)) db++;
       }
-      if (f.valid) {
-        // SMFChain::Hasting_ratio(Flip), :3201-3252
-        int db = 0;
-        const int s_short = h_seg(c, f.e1);
-        if (c.seg[s_short].nedges == 2) db--;
-        if (c.seg[h_seg(c, f.e3)].nedges == 1) db++;
-        const int i_short = h_seg(c, h_next(c, f.e1)), i_ext = h_seg(c, f.e2);
-        if (i_short != i_ext) {
-          if (c.seg[i_short].nedges == 2 && !seg_bnd(i_short)) db--;
-          if (c.seg[i_ext].nedges == 1 && !seg_bnd(i_ext)) db++;
-        }
-        const double sb = (double)c.H->n_b;
-        double r = (c.H->n_b == -db) ? sb : sb / (sb + db);
-        flip_variation(c, G, f, dv);
-        const double ev = dot_theta(G, dv);
-        r *= exp(-ev);
-        const bool acc = (r > 1 || x < r);
-        if (tr) {
-          const Pt A = P_src(c, f.e2), B = P_tgt(c, f.e2);
-          tr->e2s[0] = A.x; tr->e2s[1] = A.y; tr->e2t[0] = B.x; tr->e2t[1] = B.y;
-          tr->p2[0] = f.p2.x; tr->p2[1] = f.p2.y;
-          tr->r = r; tr->e_var = ev; tr->status = acc ? 2 : 1;
-        }
-        if (acc) { c.H->counts[5]++; update_flip(c, f); c.H->energy += ev; }
+      const double sb = (double)c.H->n_b;
+      r = (c.H->n_b == -db) ? sb : sb / (sb + db);
+      flip_variation(c, G, fm, dv);
+    }
+    ev = dot_theta(G, dv);
+    r *= exp(-ev);
+    acc = (r > 1 || x < r);
+    if (tr) {
+      if (type != 1) {
+        const Pt A = P_src(c, e2), B = P_tgt(c, e2);
+        tr->e2s[0] = A.x; tr->e2s[1] = A.y; tr->e2t[0] = B.x; tr->e2t[1] = B.y;
+        tr->p2[0] = p2.x; tr->p2[1] = p2.y;
+        if (type == 0) { tr->p1[0] = sm.p1.x; tr->p1[1] = sm.p1.y; }
+      }
+      tr->r = r; tr->e_var = ev; tr->status = acc ? 2 : 1;
+    }
+  }
+  // ---- TTessel::update (:1580-1701) as a sequence of shared primitives
+  if (acc) {
+    c.H->counts[2 * type + 1]++;
+    // what the bookkeeping needs from the tessellation BEFORE it changes
+    int s1 = -1, s1_i = -1, s2 = -1, prev_a = -1;
+    double gone = 0;
+    if (type == 2) {
+      s1 = h_seg(c, e1); s1_i = h_seg(c, h_next(c, e1)); s2 = h_seg(c, fm.e3);
+      prev_a = fm.right ? (e1 ^ 1) : h_prev(c, e1);  // split_from_vertex, :161-189
+    }
+    if (type == 1) {  // TTessel::update(Merge), :1604-1638
+      list_remove(c, h_seg(c, e1));
+      const int ends[2] = {h_seg(c, h_next(c, e1)), h_seg(c, h_next(c, e1 ^ 1))};
+      for (int k = 0; k < 2; k++) {
+        const int sx = ends[k];
+        if (!seg_bnd(sx) && c.seg[sx].nedges <= 2 && c.seg[sx].kind == 2) { list_remove(c, sx); list_add(c, sx, 1); }
+      }
+      gone = h_len(c, e1);
+    }
+    // split_edge: at p1 on e1 (splits), then at p2 on e2 (splits and flips)
+    int en[2] = {-1, -1};
+    for (int k = (type == 0 ? 0 : 1); k < 2 && type != 1; k++) {
+      const int he = (k == 0) ? e1 : e2;
+      const Pt q = (k == 0) ? sm.p1 : p2;
+      en[k] = split_edge(c, he, q.x, q.y);
+    }
+    int ne = -1;
+    if (type != 1) ne = add_edge(c, type == 0 ? en[0] : prev_a, en[1], type == 0 ? -1 : fm.e3);
+    if (type == 0) {  // TTessel::update(Split), :1580-1597
+      c.H->int_length += 2 * h_len(c, ne);
+      list_add(c, h_seg(c, ne), 1);
+      const int ends[2] = {h_seg(c, h_next(c, ne)), h_seg(c, h_next(c, ne ^ 1))};
+      for (int k = 0; k < 2; k++) {
+        const int s = ends[k];
+        if (!seg_bnd(s) && c.seg[s].nedges <= 2 && c.seg[s].kind == 1) { list_remove(c, s); list_add(c, s, 2); }
       }
     }
+    int s2_i = -1;
+    if (type == 2) {  // TTessel::update(Flip), :1644-1701
+      c.H->int_length += 2 * h_len(c, ne);
+      c.H->int_length -= 2 * h_len(c, e1);
+      s2_i = h_seg(c, h_next(c, ne));
+    }
+    if (type != 0) suppress_edge(c, e1);
+    if (type == 1) c.H->int_length -= 2 * gone;
+    if (type == 2) {
+      if (c.seg[s2].nedges <= 2 && c.seg[s2].kind == 1) { list_remove(c, s2); list_add(c, s2, 2); }
+      if (c.seg[s1].nedges <= 1 && c.seg[s1].kind == 2) { list_remove(c, s1); list_add(c, s1, 1); }
+      if (s2_i != s1_i) {
+        if (!seg_bnd(s2_i) && c.seg[s2_i].nedges <= 2 && c.seg[s2_i].kind == 1) { list_remove(c, s2_i); list_add(c, s2_i, 2); }
+        if (!seg_bnd(s1_i) && c.seg[s1_i].nedges <= 1 && c.seg[s1_i].kind == 2) { list_remove(c, s1_i); list_add(c, s1_i, 1); }
+      }
+    }
+    c.H->energy += ev;
   }
   c.H->step = t + 1;
   if (tr) {
