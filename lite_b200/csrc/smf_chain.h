@@ -520,14 +520,20 @@ struct Ray {
   bool ok;
 };
 // Split::Split(e,x,angle), lib/ttessel.cpp:2090-2132, up to the ray
-LITE_HD inline void prepare_split(const Chain &c, int e, double x, double angle, SplitMove &m, Ray &r) {
+// The line's normal (sin l, -cos l), l = atan2(e1) + angle (:2094-2100), comes from the
+// addition formulas with e1's unit direction and (cos, sin) of the proposal angle: for a
+// drawn angle cos = 1 - 2U and sin = 2 sqrt(U(1-U)), so no atan2 / sin / cos / acos is
+// evaluated on the way (the angle itself is only needed by the trace).
+LITE_HD inline void prepare_split(const Chain &c, int e, double x, double angle, double cos_angle, double sin_angle,
+                                  SplitMove &m, Ray &r) {
   m.e1 = e; m.e2 = -1; m.x = x; m.angle = angle; m.valid = false;
   m.p1.x = m.p1.y = m.p2.x = m.p2.y = 0;
   r.ok = false;
   const Pt P = P_src(c, e), Q = P_tgt(c, e);
-  const double e1_angle = atan2(Q.y - P.y, Q.x - P.x);
-  const double l = e1_angle + angle;
-  const double a = sin(l), b = -cos(l);
+  const double ex = Q.x - P.x, ey = Q.y - P.y;
+  const double inv = 1.0 / sqrt(ex * ex + ey * ey);
+  const double ux = ex * inv, uy = ey * inv;
+  const double a = uy * cos_angle + ux * sin_angle, b = uy * sin_angle - ux * cos_angle;
   const double u = dadd(dmul(a, P.x), dmul(b, P.y)), v = dadd(dmul(a, Q.x), dmul(b, Q.y));
   const double w = dadd(u, dmul(x, dadd(v, -u)));
   const double sP = fma(a, P.x, fma(b, P.y, -w)), sQ = fma(a, Q.x, fma(b, Q.y, -w));
@@ -977,8 +983,11 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
     e1 = sample_halfedge(c, u53(r4[0], r4[1]));
     const double xs = u53(r4[2], r4[3]);
     draw4(R, t, 2, r4);
-    const double ang = acos(1.0 - 2.0 * u53(r4[0], r4[1]));
-    prepare_split(c, e1, xs, ang, sm, ray);
+    // angle = acos(1 - 2U), TTessel::propose_split :1757
+    const double U = u53(r4[0], r4[1]);
+    const double ca = 1.0 - 2.0 * U, sa = 2.0 * sqrt(U * (1.0 - U));
+    const double ang = tr ? acos(ca) : 0.0;
+    prepare_split(c, e1, xs, ang, ca, sa, sm, ray);
     have = true;
     if (tr) { tr->x = xs; tr->angle = ang; }
   } else if (type == 1) {
