@@ -77,7 +77,19 @@ if os.path.exists(rep):
     tmp = "/tmp/src_smf.csv"
     open(tmp, "w").write(src)
     hot = subprocess.run([sys.executable, os.path.join(HERE, "srclines.py"), tmp, "25"], capture_output=True, text=True).stdout
-    lines += ["", "# hottest source lines (warp-stall samples)", hot]
+    # ncu files the out-of-line chain functions under the including file's name while keeping
+    # their line numbers in smf_chain.h: show the text of that line
+    chain_src = open(os.path.join(os.path.dirname(HERE), "lite_b200", "csrc", "smf_chain.h")).read().split("\n")
+    fixed = []
+    for ln in hot.split("\n"):
+        parts = ln.split()
+        if parts and parts[0].startswith("smf_ensemble") and len(parts) > 1 and parts[1].isdigit():
+            k = int(parts[1])
+            text = chain_src[k - 1].strip()[:90] if 0 < k <= len(chain_src) else ""
+            if len(parts) >= 9:
+                ln = "%-14s %5s %7s %7s %7s %6s %6s %6s %7s  %s" % (("smf_chain.h",) + tuple(parts[1:9]) + (text,))
+        fixed.append(ln)
+    lines += ["", "# hottest source lines (warp-stall samples)", "\n".join(fixed)]
     open(os.path.join(HERE, "%s_k_smf_run.txt" % tag), "w").write("\n".join(lines))
     tj = os.path.join(HERE, "traffic.json")
     t = json.load(open(tj)) if os.path.exists(tj) else {}
