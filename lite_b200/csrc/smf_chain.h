@@ -71,12 +71,14 @@ struct alignas(16) Header {
   int32_t n_nb, n_b;                       // sizes of the non-blocking / blocking lists
   int32_t n_seg;                           // live segments, window sides included
   int32_t status;
-  int32_t pad0[3];
+  int32_t n_dirty;                         // weight blocks whose sum is stale (empty between proposals)
+  int32_t pad0[2];
   double int_length;                       // TTessel::int_length (include/ttessel.h:786)
   double perimeter;                        // of the window
   double energy;                           // Energy::value, updated on acceptance (:3284)
   uint64_t step;                           // proposals made so far = Philox counter
   int64_t counts[6];                       // ModifCounts since the last reset
+  int16_t dirty[8];                        // their ids
 };
 
 struct Energy {
@@ -175,36 +177,36 @@ LITE_HD inline double cross2(double ax, double ay, double bx, double by) { retur
 // ---------------------------------------------------------------------------
 // sampling weights
 // ---------------------------------------------------------------------------
-// A block sum is recomputed from its 32 weights whenever one of them changes: exact,
-// and measured faster on B200 than the incremental update `bsum += new - old`
-// (-DSMF_INCREMENTAL_BSUM; 2.3e8 vs 1.3e8 chain-steps/s at 65536 chains,
-// gpurun_out/smf_ab1.log).  Every REFRESH_PERIOD proposals all sums are rebuilt, which
-// only matters for the incremental variant (bounds its rounding drift).
-static const int REFRESH_PERIOD = 1024;
-LITE_HD inline void refresh_all_blocks(Chain &c) {
-  const int nb = (c.H->n_p + WBLOCK - 1) / WBLOCK;
-  for (int b = 0; b < nb; b++) {
-    const double *w = c.w + b * WBLOCK;
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    for (int k = 0; k < WBLOCK; k += 4) { s0 += w[k]; s1 += w[k + 1]; s2 += w[k + 2]; s3 += w[k + 3]; }
-    c.bsum[b] = (s0 + s1) + (s2 + s3);
-  }
+// A move changes up to five weights in as many calls.  Recomputing a block sum right away
+// costs one memory round trip per call, one after the other; instead the block is marked,
+// its two cache lines are requested (non-blocking), and all marked blocks are summed once
+// at the end of the proposal, when their lines arrive together.  In this latency-bound
+// kernel the number of DEPENDENT round trips is what counts.
+LITE_HD inline void prefetch_line(const void *p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+LITE_HD inline void sum_block(Chain &c, int b) {
+  const double *w = c.w + b * WBLOCK;
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  for (int k = 0; k < WBLOCK; k += 4) { s0 += w[k]; s1 += w[k + 1]; s2 += w[k + 2]; s3 += w[k + 3]; }
+  c.bsum[b] = (s0 + s1) + (s2 + s3);
+}
+LITE_HD inline void flush_dirty(Chain &c) {
+  for (int i = 0; i < c.H->n_dirty; i++) sum_block(c, c.H->dirty[i]);
+  c.H->n_dirty = 0;
 }
 LITE_HD inline void set_pair_weight(Chain &c, int p, double wnew) {
-  const double wold = c.w[p];
   c.w[p] = wnew;
-#ifndef SMF_INCREMENTAL_BSUM
-  (void)wold;
-  {
-    const int b = p / WBLOCK;
-    const double *w = c.w + b * WBLOCK;
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    for (int k = 0; k < WBLOCK; k += 4) { s0 += w[k]; s1 += w[k + 1]; s2 += w[k + 2]; s3 += w[k + 3]; }
-    c.bsum[b] = (s0 + s1) + (s2 + s3);
-  }
-#else
-  c.bsum[p / WBLOCK] += wnew - wold;
-#endif
+  const int b = p / WBLOCK;
+  for (int i = 0; i < c.H->n_dirty; i++) if (c.H->dirty[i] == b) return;
+  if (c.H->n_dirty == 8) flush_dirty(c);
+  c.H->dirty[c.H->n_dirty++] = (int16_t)b;
+  prefetch_line(c.w + b * WBLOCK);
+  prefetch_line(c.w + b * WBLOCK + WBLOCK / 2);
 }
 LITE_HD inline void set_weight(Chain &c, int h, double len) {
   set_pair_weight(c, h >> 1, h_bnd(c, h) ? len : 2.0 * len);
@@ -313,7 +315,8 @@ LITE_HD inline void init_window(Chain &c, int cap, double x0, double y0, double 
   H.cap = cap;
   H.n_p = H.n_f = H.n_s = 0;
   H.free_p = H.free_f = H.free_s = -1;
-  H.n_nb = H.n_b = 0; H.n_seg = 0; H.status = ST_OK; H.pad0[0] = H.pad0[1] = H.pad0[2] = 0;
+  H.n_nb = H.n_b = 0; H.n_seg = 0; H.status = ST_OK; H.n_dirty = 0; H.pad0[0] = H.pad0[1] = 0;
+  for (int k = 0; k < 8; k++) H.dirty[k] = 0;
   H.int_length = 0; H.energy = 0; H.step = 0;
   for (int k = 0; k < 6; k++) H.counts[k] = 0;
   const int nb = n_blocks_cap(cap);
@@ -335,6 +338,7 @@ LITE_HD inline void init_window(Chain &c, int cap, double x0, double y0, double 
     set_len(c, h);
   }
   c.f_he[fi] = (idx)hs[0]; c.f_he[fo] = (idx)(hs[0] ^ 1);
+  flush_dirty(c);
   H.perimeter = 0;
   for (int i = 0; i < 4; i++) H.perimeter += h_len(c, hs[i]);
   H.int_length = H.perimeter;
@@ -1120,6 +1124,7 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
       }
     }
     c.H->energy += ev;
+    flush_dirty(c);
   }
   c.H->step = t + 1;
   if (tr) {
