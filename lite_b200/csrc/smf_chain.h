@@ -58,8 +58,10 @@ struct alignas(32) HE {
   idx next, prev, face, segd /* seg | dir << 15; 0xFFFF = dead pair */, nhf, phf;
   uint32_t pad;
 };
-struct alignas(8) SegRec {
+struct alignas(16) SegRec {
   idx he, nedges, pos, kind;  // kind: 0 none (window side), 1 non-blocking, 2 blocking, NIL dead
+  idx start, end;             // first and last halfedge along the segment's direction (dir == true):
+  idx pad[2];                 // Seg::halfedges_start()/end() without walking the segment
 };
 
 enum Status { ST_OK = 0, ST_CAPACITY = 1, ST_BROKEN = 2 };
@@ -259,6 +261,7 @@ LITE_HD inline int new_seg(Chain &c, int he) {
     s = c.H->n_s++;
   }
   SegRec r; r.he = (idx)he; r.nedges = 1; r.pos = (idx)NIL; r.kind = 0;
+  r.start = r.end = (idx)he; r.pad[0] = r.pad[1] = 0;  // callers pass the dir == true halfedge
   c.seg[s] = r;
   c.H->n_seg++;
   return s;
@@ -296,16 +299,21 @@ LITE_HD inline void set_junction(Chain &c, int e1, int e2) {
 }
 // Seg::set_halfedge_handle, lib/ttessel.cpp:841-851: keep the halfedge with dir == true
 LITE_HD inline void seg_set_handle(Chain &c, int s, int h) { c.seg[s].he = (idx)(h_dir(c, h) ? h : (h ^ 1)); }
-LITE_HD inline int seg_start(const Chain &c, int s) {
+LITE_HD inline int seg_start(const Chain &c, int s) { return c.seg[s].start; }
+LITE_HD inline int seg_end(const Chain &c, int s) { return c.seg[s].end; }
+// the same by walking the along-segment links (consistency check only)
+LITE_HD inline int seg_start_walk(const Chain &c, int s) {
   int e = c.seg[s].he;
   for (int p; (p = h_phf(c, e)) >= 0;) e = p;
   return e;
 }
-LITE_HD inline int seg_end(const Chain &c, int s) {
+LITE_HD inline int seg_end_walk(const Chain &c, int s) {
   int e = c.seg[s].he;
   for (int n; (n = h_nhf(c, e)) >= 0;) e = n;
   return e;
 }
+// the halfedge of the pair of h that runs along its segment's direction
+LITE_HD inline int dir_true(const Chain &c, int h) { return h_dir(c, h) ? h : (h ^ 1); }
 
 // ---------------------------------------------------------------------------
 // window (LineTes::insert_window, lib/ttessel.cpp:60-120; rectangle)
@@ -368,6 +376,9 @@ SMF_FN int split_edge(Chain &c, int e, double px, double py) {
   set_len(c, e); set_len(c, e2);
   c.seg[s].nedges++;
   seg_set_handle(c, s, e);
+  // the new pair follows e: after it along the segment if e runs with the segment, before it otherwise
+  if (e_dir) { if (c.seg[s].end == (idx)e) c.seg[s].end = (idx)e2; }
+  else { if (c.seg[s].start == (idx)t) c.seg[s].start = (idx)t2; }
   return e;
 }
 
@@ -392,6 +403,8 @@ LITE_HD inline int merge_edge(Chain &c, int e1, int e2) {
   set_weight(c, e1, new_len);
   c.seg[s].nedges--;
   seg_set_handle(c, s, e1);
+  if (h_dir(c, e1)) { if (c.seg[s].end == (idx)e2) c.seg[s].end = (idx)e1; }
+  else { if (c.seg[s].start == (idx)t2) c.seg[s].start = (idx)t1; }
   return e1;
 }
 
@@ -416,6 +429,8 @@ SMF_FN int add_edge(Chain &c, int prev1, int prev2, int ext_prev) {
     const bool d = h_dir(c, ext_prev);
     set_segdir(c, h, s, d); set_segdir(c, t, s, !d);
     c.seg[s].nedges++;
+    if (d) { if (c.seg[s].end == (idx)ext_prev) c.seg[s].end = (idx)h; }
+    else { if (c.seg[s].start == (idx)(ext_prev ^ 1)) c.seg[s].start = (idx)t; }
   } else {
     const int s = new_seg(c, h);
     set_segdir(c, h, s, true); set_segdir(c, t, s, false);
@@ -439,6 +454,14 @@ LITE_HD inline void remove_edge(Chain &c, int e) {
   } else {
     c.seg[s].nedges--;
     seg_set_handle(c, s, phf >= 0 ? phf : nhf);
+    {
+      // e is the first or the last edge of its segment: the neighbour takes over that end
+      const int d = dir_true(c, e);
+      const int dn = h_dir(c, e) ? nhf : (phf >= 0 ? (phf ^ 1) : -1);   // after d along the segment
+      const int dp = h_dir(c, e) ? phf : (nhf >= 0 ? (nhf ^ 1) : -1);   // before d
+      if (c.seg[s].start == (idx)d && dn >= 0) c.seg[s].start = (idx)dn;
+      if (c.seg[s].end == (idx)d && dp >= 0) c.seg[s].end = (idx)dp;
+    }
   }
   c.he[p1].next = (idx)n2; c.he[n2].prev = (idx)p1; c.he[p2].next = (idx)n1; c.he[n1].prev = (idx)p2;
   del_pair(c, e);
@@ -1173,6 +1196,7 @@ LITE_HD inline int check(const Chain &c) {
   for (int i = 0; i < c.H->n_b; i++) { const int s = c.b_list[i]; if (c.seg[s].nedges < 2 || c.seg[s].kind != 2 || c.seg[s].pos != i) return 10; }
   for (int s = 0; s < c.H->n_s; s++) {
     if (c.seg[s].kind == NIL) continue;
+    if (seg_start(c, s) != seg_start_walk(c, s) || seg_end(c, s) != seg_end_walk(c, s)) return 17;
     int n = 1, e = seg_start(c, s);
     if (h_seg(c, e) != s) return 11;
     for (int nx; (nx = h_nhf(c, e)) >= 0;) { e = nx; n++; }
