@@ -526,7 +526,10 @@ SMF_FN int ray_exit(const Chain &c, int start_he, double a, double b, double w, 
         const double rx = X - p.x, ry = Y - p.y;
         if (rx * dx + ry * dy >= 0.0) {
           const double len = sqrt(rx * rx + ry * ry);
-          if (len != 0.0 && len < best) { best = len; res = h; hit.x = X; hit.y = Y; }
+          // The window of an ensemble is a rectangle, so every face is convex: the line
+          // meets its boundary once besides the ray's own edge and the first forward hit is
+          // the nearest one (:4563).  Stopping here halves the pointer chase on average.
+          if (len != 0.0 && len < best) { hit.x = X; hit.y = Y; return h; }
         }
       }
     }
