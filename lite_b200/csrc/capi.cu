@@ -191,7 +191,9 @@ struct lite_ctx {
   DBuf<double> r_x, r_angle, r_u, in_x, in_angle;
   size_t rcap = 0;
   // merges / flips
-  DBuf<double> mstat, fstat, sums;  // sums: [d merges | d flips]
+  DBuf<double> mstat, fstat, sums;  // sums: per-block column sums of mstat then fstat, [blocks][LITE_MAX_D]
+  double *h_part = nullptr; size_t h_part_cap = 0;  // pinned copy of them
+  int mf_gm = 0, mf_blocks = 0;
   DBuf<int> m_he, fl_e1, fl_e2, fl_right;
   DBuf<double2> fl_p2;
   std::vector<double> h_sum_m, h_sum_f;
@@ -283,6 +285,7 @@ extern "C" int lite_ctx_destroy(lite_ctx *c) {
   for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < LITE_TIMER_SLOTS; i++) if (c->tev[i]) cudaEventDestroy(c->tev[i]);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  if (c->h_part) cudaFreeHost(c->h_part);
   // DBuf members are released explicitly (no destructors: keep the struct POD-like)
   c->vx.release(); c->vy.release(); c->he_length.release();
   c->he_src.release(); c->he_twin.release(); c->he_next.release(); c->he_face.release();
@@ -536,6 +539,10 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   k_prep_faces<<<gb, tb, 0, c->stream>>>(T, c->ca.p, c->f_area.p, c->f_perim.p, c->f_sumang.p, c->f_minang.p,
                                          c->pre.p, c->plen.p, c->f_tot2.p, c->sfo.p, c->stot2.p);
   c->launches += 3;
+  // the merge/flip stream only depends on the tessellation being in place: it forks here,
+  // not from whatever the main stream is doing when SetEnergy is called (the split kernel,
+  // if AddSplits came first: the two then run side by side)
+  CU(cudaEventRecord(c->ev_fork, c->stream));
   t3 = now_ms();
   // no synchronisation: the link checks were done on the host above, the copy and the
   // preparation kernels run behind the caller's next calls on the same stream
@@ -593,9 +600,18 @@ extern "C" int lite_energy_set(lite_ctx *c, int d, const int32_t *fid) {
 static void finalize_mf(lite_ctx *c) {
   if (!c->mf_pending) return;
   const int d = c->G.d;
-  c->h_sum_m.assign(c->h_pinned + 512, c->h_pinned + 512 + d);
-  c->h_sum_f.assign(c->h_pinned + 512 + LITE_MAX_D, c->h_pinned + 512 + LITE_MAX_D + d);
+  // blocks [0, gm) hold merges, the others flips; summed in block order (deterministic)
+  c->h_sum_m.assign(d, 0.0); c->h_sum_f.assign(d, 0.0);
+  for (int b = 0; b < c->mf_blocks; b++) {
+    double *dst = (b < c->mf_gm) ? c->h_sum_m.data() : c->h_sum_f.data();
+    for (int k = 0; k < d; k++) dst[k] += c->h_part[(size_t)b * LITE_MAX_D + k];
+  }
   cudaEventElapsedTime(&c->ms_mf, c->ev[4], c->ev[5]);
+  if (g_trace && c->ev01) {
+    float a = 0, b = 0;
+    if (cudaEventElapsedTime(&a, c->ev[0], c->ev[4]) == cudaSuccess && cudaEventElapsedTime(&b, c->ev[1], c->ev[5]) == cudaSuccess)
+      fprintf(stderr, "[lite_b200] merge/flip kernels start %.3f ms after the split kernel starts, end %.3f ms after it ends\n", a, b);
+  }
   c->mf_pending = false;
 }
 
@@ -605,28 +621,36 @@ extern "C" int lite_candidates_merges_flips(lite_ctx *c, int32_t *n_merges, int3
   CU(cudaSetDevice(c->device));
   const int d = c->G.d, nm = c->n_nb, nf = 2 * c->n_b;
   if (c->mstat.alloc((size_t)d * (nm ? nm : 1)) || c->fstat.alloc((size_t)d * (nf ? nf : 1)) ||
-      c->sums.alloc(2 * LITE_MAX_D) || c->m_he.alloc(nm ? nm : 1) || c->fl_e1.alloc(nf ? nf : 1) ||
+      c->m_he.alloc(nm ? nm : 1) || c->fl_e1.alloc(nf ? nf : 1) ||
       c->fl_e2.alloc(nf ? nf : 1) || c->fl_right.alloc(nf ? nf : 1) || c->fl_p2.alloc(nf ? nf : 1))
     return LITE_ECUDA;
+  const int blocks = (nm + 127) / 128 + (nf + 127) / 128;
+  c->mf_gm = (nm + 127) / 128; c->mf_blocks = blocks;
+  if (c->sums.alloc((size_t)(blocks ? blocks : 1) * LITE_MAX_D)) return LITE_ECUDA;
+  if ((size_t)blocks * LITE_MAX_D > c->h_part_cap) {
+    if (c->mf_inflight) CU(cudaStreamSynchronize(c->stream2));
+    if (c->h_part) cudaFreeHost(c->h_part);
+    c->h_part = nullptr; c->h_part_cap = 0;
+    CU(cudaMallocHost((void **)&c->h_part, (size_t)blocks * LITE_MAX_D * sizeof(double)));
+    c->h_part_cap = (size_t)blocks * LITE_MAX_D;
+  }
   // fork: the merge/flip kernels are independent of the split kernel and run beside it
   if (c->mf_inflight) CU(cudaStreamSynchronize(c->stream2));
-  CU(cudaEventRecord(c->ev_fork, c->stream));
-  CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-  CU(cudaMemsetAsync(c->sums.p, 0, 2 * LITE_MAX_D * sizeof(double), c->stream2));
+  CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));  // recorded by lite_tess_upload
   CU(cudaEventRecord(c->ev[4], c->stream2));
   if (nm + nf > 0) {
     MFArgs A{};
     A.nb_seg = c->nb_list.p; A.nm = nm; A.mstat = c->mstat.p; A.m_he = c->m_he.p; A.gm = (nm + 127) / 128;
     A.b_seg = c->b_list.p; A.nb = c->n_b; A.fstat = c->fstat.p; A.f_e1 = c->fl_e1.p; A.f_e2 = c->fl_e2.p;
-    A.f_right = c->fl_right.p; A.f_p2 = c->fl_p2.p; A.status = c->status.p + 1;
-    k_merges_flips<<<A.gm + (nf + 127) / 128, 128, 0, c->stream2>>>(c->T, c->G, A);
-    k_colsum2<<<dim3(d, 2), 1024, 0, c->stream2>>>(c->mstat.p, nm, c->fstat.p, nf, c->sums.p);
-    c->launches += 2;
+    A.f_right = c->fl_right.p; A.f_p2 = c->fl_p2.p; A.status = c->status.p + 1; A.part = c->sums.p;
+    k_merges_flips<<<blocks, 128, 0, c->stream2>>>(c->T, c->G, A);
+    c->launches += 1;
   }
   CU(cudaEventRecord(c->ev[5], c->stream2));
-  // the two sums come back with the next synchronisation (lite_pl_eval / lite_pl_sums):
+  // the partial sums come back with the next synchronisation (lite_pl_eval / lite_pl_sums):
   // SetEnergy itself does not stall the stream
-  CU(cudaMemcpyAsync(c->h_pinned + 512, c->sums.p, 2 * LITE_MAX_D * sizeof(double), cudaMemcpyDeviceToHost, c->stream2));
+  if (blocks > 0)
+    CU(cudaMemcpyAsync(c->h_part, c->sums.p, (size_t)blocks * LITE_MAX_D * sizeof(double), cudaMemcpyDeviceToHost, c->stream2));
   CU(cudaEventRecord(c->ev_mf, c->stream2));
   c->mf_pending = true; c->mf_inflight = true;
   c->have_mf = true;

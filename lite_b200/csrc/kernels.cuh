@@ -1091,40 +1091,37 @@ __device__ __forceinline__ void flip_one(const TessDev &T, const Prog &G, const 
   }
 }
 
-// column sums of a (d x n) SoA block, deterministic (one block per column)
 // all merges and all flips in one launch: blocks [0, gm) take the merges, the rest the flips
 struct MFArgs {
   const int *nb_seg; int nm; double *mstat; int *m_he; int gm;
   const int *b_seg; int nb; double *fstat; int *f_e1, *f_e2, *f_right; double2 *f_p2;
   unsigned long long *status;
+  double *part;  // [gridDim.x][LITE_MAX_D]: per-block column sums of the statistics just written
 };
+// Each block also leaves the column sums of its 128 statistics rows (fixed tree): the host
+// adds the blocks' partials in block order to get sum_stat_merges / sum_stat_flips
+// (lib/ttessel.cpp:3337, :3345).  A separate 1024-thread summing kernel found no room
+// beside k_split, which fills every SM, and finished only after it (scripts/step_variants.py).
 __global__ void __launch_bounds__(128) k_merges_flips(TessDev T, Prog G, MFArgs A) {
-  if ((int)blockIdx.x < A.gm) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < A.nm) merge_one(T, G, A.nb_seg, i, A.mstat, (size_t)A.nm, A.m_he);
-  } else {
-    int i = (blockIdx.x - A.gm) * blockDim.x + threadIdx.x;
-    if (i < 2 * A.nb) flip_one(T, G, A.b_seg, A.nb, i, A.fstat, (size_t)(2 * A.nb), A.f_e1, A.f_e2, A.f_p2, A.f_right, A.status);
+  __shared__ double sh[128];
+  const bool merges = (int)blockIdx.x < A.gm;
+  const int i = (merges ? blockIdx.x : blockIdx.x - A.gm) * blockDim.x + threadIdx.x;
+  const int n = merges ? A.nm : 2 * A.nb;
+  const double *stat = merges ? A.mstat : A.fstat;
+  if (i < n) {
+    if (merges) merge_one(T, G, A.nb_seg, i, A.mstat, (size_t)A.nm, A.m_he);
+    else flip_one(T, G, A.b_seg, A.nb, i, A.fstat, (size_t)(2 * A.nb), A.f_e1, A.f_e2, A.f_p2, A.f_right, A.status);
   }
-}
-
-// column sums of the merge (blockIdx.y == 0) and flip (== 1) statistic blocks,
-// deterministic: one block per column, fixed tree
-__global__ void __launch_bounds__(1024) k_colsum2(const double *mstat, int nm, const double *fstat, int nf,
-                                                  double *out /* [2][LITE_MAX_D] */) {
-  __shared__ double sh[1024];
-  const int k = blockIdx.x;
-  const double *stat = blockIdx.y ? fstat : mstat;
-  const int n = blockIdx.y ? nf : nm;
-  double s = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s += stat[(size_t)k * n + i];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int w = blockDim.x / 2; w; w >>= 1) {
-    if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+  for (int k = 0; k < G.d; k++) {
+    sh[threadIdx.x] = (i < n) ? stat[(size_t)k * n + i] : 0.0;
+    __syncthreads();
+    for (int w = 64; w; w >>= 1) {
+      if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) A.part[(size_t)blockIdx.x * LITE_MAX_D + k] = sh[0];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[blockIdx.y * LITE_MAX_D + k] = sh[0];
 }
 
 // ---------------------------------------------------------------------------
