@@ -853,25 +853,24 @@ extern "C" int lite_candidates_count(lite_ctx *c, int64_t *nl, int64_t *ng) {
 }
 
 template <int D>
-static void launch_reduce(lite_ctx *c, const double *stat, size_t cap, long n, int rev, const Theta &th,
-                          int grid, double *out) {
-  k_reduce<D><<<grid, 256, 0, c->stream>>>(stat, cap, n, rev, th, c->partials.p, c->counter.p, out);
+static void launch_reduce(lite_ctx *c, const RedSeg &A, const RedSeg &B, const Theta &th) {
+  k_reduce<D><<<A.grid + B.grid, 256, 0, c->stream>>>(A, B, th);
 }
-static void reduce_dispatch(lite_ctx *c, int d, const double *stat, size_t cap, long n, int rev,
-                            const Theta &th, int grid, double *out) {
+static void reduce_dispatch(lite_ctx *c, int d, const RedSeg &A, const RedSeg &B, const Theta &th) {
   switch (d) {
-    case 1: launch_reduce<1>(c, stat, cap, n, rev, th, grid, out); break;
-    case 2: launch_reduce<2>(c, stat, cap, n, rev, th, grid, out); break;
-    case 3: launch_reduce<3>(c, stat, cap, n, rev, th, grid, out); break;
-    case 4: launch_reduce<4>(c, stat, cap, n, rev, th, grid, out); break;
-    case 5: launch_reduce<5>(c, stat, cap, n, rev, th, grid, out); break;
-    case 6: launch_reduce<6>(c, stat, cap, n, rev, th, grid, out); break;
-    case 7: launch_reduce<7>(c, stat, cap, n, rev, th, grid, out); break;
-    case 8: launch_reduce<8>(c, stat, cap, n, rev, th, grid, out); break;
-    case 9: launch_reduce<9>(c, stat, cap, n, rev, th, grid, out); break;
-    case 10: launch_reduce<10>(c, stat, cap, n, rev, th, grid, out); break;
-    case 11: launch_reduce<11>(c, stat, cap, n, rev, th, grid, out); break;
-    case 12: launch_reduce<12>(c, stat, cap, n, rev, th, grid, out); break;
+    case 1: launch_reduce<1>(c, A, B, th); break;
+    case 2: launch_reduce<2>(c, A, B, th); break;
+    case 3: launch_reduce<3>(c, A, B, th); break;
+    case 4: launch_reduce<4>(c, A, B, th); break;
+    case 5: launch_reduce<5>(c, A, B, th); break;
+    case 6: launch_reduce<6>(c, A, B, th); break;
+    case 7: launch_reduce<7>(c, A, B, th); break;
+    case 8: launch_reduce<8>(c, A, B, th); break;
+    case 9: launch_reduce<9>(c, A, B, th); break;
+    case 10: launch_reduce<10>(c, A, B, th); break;
+    case 11: launch_reduce<11>(c, A, B, th); break;
+    case 12: launch_reduce<12>(c, A, B, th); break;
+    default: break;
   }
   c->launches += 1;
 }
@@ -887,27 +886,23 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
   Theta th{};
   for (int i = 0; i < d; i++) th.v[i] = theta[i];
   const int maxgrid = c->sm_count * 2;
-  if (c->partials.alloc((size_t)maxgrid * NT) || c->red_out.alloc(2 * 128)) return LITE_ECUDA;
+  if (c->partials.alloc((size_t)2 * maxgrid * NT) || c->red_out.alloc(2 * 128)) return LITE_ECUDA;
   if (c->mf_inflight) CU(cudaStreamWaitEvent(c->stream, c->ev_mf, 0));  // join the merge/flip stream
   CU(cudaEventRecord(c->ev[2], c->stream));
-  // splits (this rank's shard)
-  long n = (long)c->n_local;
-  int grid = (int)((n + 2047) / 2048);
+  // one launch: this rank's shard of the splits, then the flips (replicated on every rank)
+  const long n = (long)c->n_local, nf = 2L * c->n_b;
+  int grid = (int)((n + 2047) / 2048), gf = (int)((nf + 1023) / 1024);
   if (grid > maxgrid) grid = maxgrid;
+  if (gf > maxgrid) gf = maxgrid;
   c->rev = !c->rev;  // boustrophedon: the end the previous pass (or k_split) touched last is still in L2
+  RedSeg A{c->stat.p, c->cap, n, c->rev ? 1 : 0, c->partials.p, c->counter.p, c->red_out.p, n > 0 ? (grid < 1 ? 1 : grid) : 0};
+  RedSeg B{c->fstat.p, (size_t)nf, nf, 0, c->partials.p + (size_t)maxgrid * NT, c->counter.p + 1, c->red_out.p + 128,
+           nf > 0 ? (gf < 1 ? 1 : gf) : 0};
+  if (n == 0) CU(cudaMemsetAsync(c->red_out.p, 0, 128 * sizeof(double), c->stream));
+  if (nf == 0) CU(cudaMemsetAsync(c->red_out.p + 128, 0, 128 * sizeof(double), c->stream));
   CU(cudaEventRecord(c->ev[6], c->stream));
-  if (n > 0) reduce_dispatch(c, d, c->stat.p, c->cap, n, c->rev ? 1 : 0, th, grid < 1 ? 1 : grid, c->red_out.p);
-  else CU(cudaMemsetAsync(c->red_out.p, 0, 128 * sizeof(double), c->stream));
+  if (A.grid + B.grid > 0) reduce_dispatch(c, d, A, B, th);
   CU(cudaEventRecord(c->ev[7], c->stream));
-  // flips (replicated on every rank; cheap)
-  long nf = 2L * c->n_b;
-  if (nf > 0) {
-    int gf = (int)((nf + 1023) / 1024);
-    if (gf > maxgrid) gf = maxgrid;
-    reduce_dispatch(c, d, c->fstat.p, (size_t)nf, nf, 0, th, gf < 1 ? 1 : gf, c->red_out.p + 128);
-  } else {
-    CU(cudaMemsetAsync(c->red_out.p + 128, 0, 128 * sizeof(double), c->stream));
-  }
   if (c->world > 1) {
     ncclResult_t ne = g_nccl.AllReduce(c->red_out.p, c->red_out.p, (size_t)NT, ncclFloat64, ncclSum, c->comm, c->stream);
     if (ne != 0) return fail(LITE_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(ne) : "?");

@@ -1164,16 +1164,32 @@ __device__ __forceinline__ void reduce_one(const Theta &th, const double (&p)[D]
 // the HBM latency-bandwidth product with 2 x 256 threads per SM.  `rev` walks the
 // block from its end: right after k_split, and on every other evaluation of a
 // Newton loop, the tail of the statistic block is still in the 126 MB L2.
+// One launch reduces two statistic blocks: blocks [0, A.grid) the dummy splits of this rank,
+// the next B.grid blocks the flips (a few thousand rows: as a launch of its own it only added
+// its latency to the critical path).  Each segment has its own partials, counter and output.
+struct RedSeg {
+  const double *stat; size_t cap; long n; int rev;
+  double *partials; unsigned int *counter; double *out;
+  int grid;
+};
 template <int D>
-__global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ stat, size_t cap,
-                                                long n, int rev, Theta th, double *partials,
-                                                unsigned int *counter, double *out) {
+__global__ void __launch_bounds__(256) k_reduce(RedSeg A, RedSeg B, Theta th) {
+  const bool second = (int)blockIdx.x >= A.grid;
+  const double *__restrict__ stat = second ? B.stat : A.stat;
+  const size_t cap = second ? B.cap : A.cap;
+  const long n = second ? B.n : A.n;
+  const int rev = second ? B.rev : A.rev;
+  double *partials = second ? B.partials : A.partials;
+  unsigned int *counter = second ? B.counter : A.counter;
+  double *out = second ? B.out : A.out;
+  const unsigned int nblk = (unsigned int)(second ? B.grid : A.grid);
+  const unsigned int bid = blockIdx.x - (second ? (unsigned int)A.grid : 0u);
   constexpr int NT = 1 + D + D * (D + 1) / 2;
   double acc[NT];
 #pragma unroll
   for (int t = 0; t < NT; t++) acc[t] = 0.0;
-  const long stride = (long)gridDim.x * blockDim.x;
-  const long gtid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long stride = (long)nblk * blockDim.x;
+  const long gtid = (long)bid * blockDim.x + threadIdx.x;
   const long npair = n >> 1;
   long i = gtid;
   // two loads per column in flight only while the accumulators leave room for them
@@ -1233,13 +1249,13 @@ __global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ stat,
     double v = 0;
     int nw = blockDim.x >> 5;
     for (int w2 = 0; w2 < nw; w2++) v += sh[w2][threadIdx.x];
-    partials[(size_t)blockIdx.x * NT + threadIdx.x] = v;
+    partials[(size_t)bid * NT + threadIdx.x] = v;
   }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned int prev = atomicAdd(counter, 1u);
-    last = (prev == gridDim.x - 1);
+    last = (prev == nblk - 1);
   }
   __syncthreads();
   if (last) {
@@ -1248,7 +1264,7 @@ __global__ void __launch_bounds__(256) k_reduce(const double *__restrict__ stat,
     __threadfence();
     for (int t = wid; t < NT; t += (blockDim.x >> 5)) {
       double v = 0;
-      for (unsigned int b = lane; b < gridDim.x; b += 32) v += __ldcg(partials + (size_t)b * NT + t);
+      for (unsigned int b = lane; b < nblk; b += 32) v += __ldcg(partials + (size_t)b * NT + t);
 #pragma unroll
       for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
       if (lane == 0) out[t] = v;
