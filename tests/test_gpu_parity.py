@@ -457,3 +457,42 @@ def test_non_convex_window_against_live_oracle(lite):
     _assert_stats("merge", ctx.fetch("MERGE_STAT"), res["merge_stat"], ALL12)
     _assert_stats("flip", ctx.fetch("FLIP_STAT"), res["flip_stat"], ALL12)
     ctx.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_random_tessellations_against_live_oracle(lite, seed):
+    """Six more tessellations grown by the exact oracle's chain from different seeds (with
+    different proposal probabilities, so different mixes of blocking and non-blocking
+    segments), each checked in full: every merge, every flip and 250 sampled splits, all
+    twelve features, integers bit exact."""
+    import lite_oracle as lo
+    t = lo.TTessel(lo.Rng(100 + seed))
+    t.insert_window_rect(0, 0, 1, 1)
+    eng = lo.make_energy(["minus_is_segment_internal"], [math.log(1.0 + 0.5 * seed)], t)
+    lo.SMFChain(eng, 0.25 + 0.05 * seed, 0.15).step(90)
+    soa = lo.export_soa(t)
+    ctx = _ctx(lite, soa, ALL12)
+    nm, nf = ctx.merges_flips()
+    assert nm == len(t.non_blocking_segments) and nf == 2 * len(t.blocking_segments)
+    ctx.add_splits_philox(250, 1000 + seed, 0)
+    he, x, ang = ctx.fetch("SPLIT_E1"), ctx.fetch("SPLIT_X"), ctx.fetch("SPLIT_ANGLE")
+    res = lo.eval_candidates(t, lo.make_energy(lo.ALL12, None, t), he, x, ang)
+    np.testing.assert_array_equal(ctx.fetch("SPLIT_E2"), res["split_e2"])
+    np.testing.assert_array_equal(ctx.fetch("MERGE_HE"), res["merge_he"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_E1"), res["flip_e1"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_E2"), res["flip_e2"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_RIGHT"), res["flip_right"])
+    np.testing.assert_allclose(ctx.fetch("SPLIT_P1"), res["split_p1"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(ctx.fetch("SPLIT_P2"), res["split_p2"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(ctx.fetch("FLIP_P2"), res["flip_p2"], rtol=0, atol=1e-12)
+    _assert_stats("split", ctx.fetch("SPLIT_STAT"), res["split_stat"], ALL12)
+    _assert_stats("merge", ctx.fetch("MERGE_STAT"), res["merge_stat"], ALL12)
+    _assert_stats("flip", ctx.fetch("FLIP_STAT"), res["flip_stat"], ALL12)
+    # and the pseudo-likelihood built from them
+    th = 0.1 * np.random.default_rng(seed).standard_normal(len(ALL12))
+    lpl, g, H = ctx.pl_eval(th)
+    wl, wg, wH = lo.pl_from_stats(th, res["split_stat"], res["merge_stat"], res["flip_stat"], float(soa["int_length"]))
+    assert lpl == pytest.approx(wl, rel=RTOL)
+    np.testing.assert_allclose(g, wg, rtol=RTOL, atol=1e-12 * max(1.0, np.abs(wg).max()))
+    np.testing.assert_allclose(H, wH, rtol=RTOL, atol=1e-12 * max(1.0, np.abs(wH).max()))
+    ctx.close()
