@@ -17,7 +17,15 @@
 #include <thread>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "kernels.cuh"
+
+// NVTX range over one C-ABI call (header-only NVTX 3: a no-op unless a profiler is attached)
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ---- minimal NCCL surface, resolved at run time (libnccl.so.2) --------------
 typedef struct ncclComm *ncclComm_t;
@@ -366,6 +374,7 @@ static double now_ms() {
 static const bool g_trace = getenv("LITE_B200_TRACE") != nullptr;
 
 extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
+  NvtxRange nvtx_("lite_tess_upload");
   if (!c || !s) return fail(LITE_EINVAL, "null argument");
   if (c->mf_inflight) { cudaStreamSynchronize(c->stream2); c->mf_inflight = false; }
   const double t0 = now_ms();
@@ -616,6 +625,7 @@ static void finalize_mf(lite_ctx *c) {
 }
 
 extern "C" int lite_candidates_merges_flips(lite_ctx *c, int32_t *n_merges, int32_t *n_flips) {
+  NvtxRange nvtx_("lite_candidates_merges_flips");
   if (!c) return fail(LITE_EINVAL, "null context");
   if (!c->have_tess || !c->have_prog) return fail(LITE_ESTATE, "upload a tessellation and set the energy first");
   CU(cudaSetDevice(c->device));
@@ -734,6 +744,7 @@ static void fill_split_args(lite_ctx *c, SplitArgs &A) {
 extern "C" int lite_candidates_add_splits_given(lite_ctx *c, int64_t n, const int32_t *he,
                                                 const double *x, const double *angle,
                                                 int64_t n_global_total) {
+  NvtxRange nvtx_("lite_candidates_add_splits_given");
   if (!c) return fail(LITE_EINVAL, "null context");
   if (!c->have_tess || !c->have_prog) return fail(LITE_ESTATE, "upload a tessellation and set the energy first");
   if (n < 0 || n_global_total < n) return fail(LITE_EINVAL, "bad candidate counts");
@@ -777,6 +788,7 @@ static void shard_range(int64_t n, int rank, int world, int64_t &j0, int64_t &cn
 
 extern "C" int lite_candidates_add_splits_philox(lite_ctx *c, int64_t n_global, uint64_t seed,
                                                  uint64_t offset) {
+  NvtxRange nvtx_("lite_candidates_add_splits_philox");
   if (!c) return fail(LITE_EINVAL, "null context");
   if (!c->have_tess || !c->have_prog) return fail(LITE_ESTATE, "upload a tessellation and set the energy first");
   if (n_global < 0) return fail(LITE_EINVAL, "negative count");
@@ -803,6 +815,7 @@ extern "C" int lite_candidates_add_splits_philox(lite_ctx *c, int64_t n_global, 
 
 extern "C" int lite_lines_sample_clip(lite_ctx *c, int64_t n_global, uint64_t seed, uint64_t offset,
                                       int mode, uint64_t *checksum2) {
+  NvtxRange nvtx_("lite_lines_sample_clip");
   if (!c) return fail(LITE_EINVAL, "null context");
   if (!c->have_tess) return fail(LITE_ESTATE, "upload a tessellation first");
   if (n_global < 0 || (mode != 0 && mode != 1)) return fail(LITE_EINVAL, "bad arguments");
@@ -876,6 +889,7 @@ static void reduce_dispatch(lite_ctx *c, int d, const RedSeg &A, const RedSeg &B
 }
 
 extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, double *grad, double *hess) {
+  NvtxRange nvtx_("lite_pl_eval");
   if (!c || !theta) return fail(LITE_EINVAL, "null argument");
   if (!c->have_tess || !c->have_prog) return fail(LITE_ESTATE, "upload a tessellation and set the energy first");
   if (!c->have_mf) return fail(LITE_ESTATE, "call lite_candidates_merges_flips (SetEnergy) before evaluating");

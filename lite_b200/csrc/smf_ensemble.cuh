@@ -201,6 +201,7 @@ static int smf_report_bad(lite_ctx *c) {
 }
 
 extern "C" int lite_smf_run(lite_ctx *c, int32_t n_samples, int64_t steps_per_sample, double *rows_out) {
+  NvtxRange nvtx_("lite_smf_run");
   if (!c || !c->smf) return fail(LITE_ESTATE, "lite_smf_create first");
   SmfState *S = c->smf;
   if (!S->have_model) return fail(LITE_ESTATE, "lite_smf_set_model first");
