@@ -23,7 +23,9 @@ explicitly through the SoA export instead).
 
 Pinned by: the reference's split/flip constructor known answers
 (``tests/check_lite.cpp:671-873``), its face-prediction property
-(``tests/check_lite.cpp:339-397``, ``:875-1040``), the 11-cell fixture
+(``tests/check_lite.cpp:339-397``, ``:875-1049``: the scripted flip, the square and the
+non-convex holed domain, i.e. all four cases of ``hpolygon_insert_edge`` /
+``hpolygon_remove_edge``), the 11-cell fixture
 (``wrap/R/RLiTe/inst/tessellation_data.txt``) and the closed-form CRTT
 pseudo-likelihood (``demos/pseudo_lik_inference.cpp:80-81``); see
 ``tests/test_oracle_golden.py``.
@@ -865,13 +867,62 @@ def polygon_insert_edge(e1, e2, p1, p2):
     return res
 
 
+def filter_holes(holes, poly):
+    """lib/ttessel.cpp:4996-5009: which holes have their first vertex strictly inside poly."""
+    return [bounded_side_2(poly, h[0]) > 0 for h in holes]
+
+
 def hpolygon_insert_edge(hpoly, i1, i2, e1, e2, p1, p2):
-    """lib/ttessel.cpp:4659-4795, "cas 1" only (hole-free faces)."""
-    if len(hpoly) != 1:
-        raise NotImplementedError("holed faces (cas 2-4) are outside the hot-path scope")
-    outer1 = polygon_insert_edge(e1, e2, p1, p2)
-    outer2 = polygon_insert_edge(e2, e1, p2, p1)
-    return [(outer1, []), (outer2, [])]
+    """lib/ttessel.cpp:4659-4795.  hpoly = [outer, hole, ...] as given by boundaries();
+    returns a list of (outer, holes): two faces when the inserted segment joins two points
+    of the outer boundary (cas 1) or of one hole (cas 2), one modified face when it
+    joins the outer boundary to a hole (cas 3) or two holes (cas 4)."""
+    if len(hpoly) == 1:
+        cas = 1
+    elif i1 == i2:
+        cas = 1 if i1 == 0 else 2
+    elif i1 == 0 or i2 == 0:
+        cas = 3
+    else:
+        cas = 4
+    if cas == 1:
+        outer1 = polygon_insert_edge(e1, e2, p1, p2)
+        outer2 = polygon_insert_edge(e2, e1, p2, p1)
+        holes1, holes2 = [], []
+        if len(hpoly) > 1:
+            inside = filter_holes(hpoly[1:], outer1)
+            for ii in range(1, len(hpoly)):
+                (holes1 if inside[ii - 1] else holes2).append(hpoly[ii])
+        return [(outer1, holes1), (outer2, holes2)]
+    if cas == 2:
+        # mother face (the old face minus the daughter) and daughter face (along the hole)
+        outer1 = hpoly[0]
+        c21 = polygon_insert_edge(e2, e1, p2, p1)
+        if bounded_side_2(c21, e2.target()) >= 0:   # != ON_UNBOUNDED_SIDE
+            outer2 = polygon_insert_edge(e1, e2, p1, p2)
+            enlarged_hole = c21
+        else:
+            outer2 = c21
+            enlarged_hole = polygon_insert_edge(e1, e2, p1, p2)
+        inside = filter_holes(hpoly[1:], outer2)
+        holes1, holes2 = [], []
+        for ii in range(1, len(hpoly)):
+            if ii == i1:
+                holes1.append(enlarged_hole)
+            elif inside[ii - 1]:
+                holes2.append(hpoly[ii])
+            else:
+                holes1.append(hpoly[ii])
+        return [(outer1, holes1), (outer2, holes2)]
+    if cas == 3:
+        # the outer boundary folds into the face and takes the hole in
+        outer1 = polygon_insert_edge(e1, e2, p1, p2)
+        j = i1 if i1 > 0 else i2
+        return [(outer1, [hpoly[ii] for ii in range(1, len(hpoly)) if ii != j])]
+    # cas 4: two holes become one
+    holes1 = [hpoly[ii] for ii in range(1, len(hpoly)) if ii != i1 and ii != i2]
+    holes1.append(polygon_insert_edge(e1, e2, p1, p2))
+    return [(hpoly[0], holes1)]
 
 
 def polygon_remove_edge(e1, e2):
@@ -891,10 +942,43 @@ def polygon_remove_edge(e1, e2):
 
 
 def hpolygon_remove_edge(hpoly, hpoly_twin, i, i_twin, e, e_twin, single):
-    """lib/ttessel.cpp:4816-4925, "cas 1" only."""
-    if single or len(hpoly) != 1 or len(hpoly_twin) != 1:
-        raise NotImplementedError("holed faces (cas 2-4) are outside the hot-path scope")
-    return (polygon_remove_edge(e, e_twin), [])
+    """lib/ttessel.cpp:4816-4925.  Returns (outer, holes)."""
+    if (not single) and len(hpoly) == 1 and len(hpoly_twin) == 1:
+        cas = 1
+    elif single and i == i_twin:
+        cas = 3 if i == 0 else 4
+    elif i > 0:
+        cas = 2
+    else:
+        cas = 1 if i_twin == 0 else 2
+    if cas == 1:
+        # the edge separates two faces: they merge, holes of both are kept
+        return (polygon_remove_edge(e, e_twin), list(hpoly[1:]) + list(hpoly_twin[1:]))
+    if cas == 2:
+        # the edge joins two vertices of one hole of the mother face: the daughter face
+        # on its other side dissolves into the mother
+        mother, daughter = (hpoly, hpoly_twin) if i > 0 else (hpoly_twin, hpoly)
+        j = i if i > 0 else i_twin
+        holes = list(daughter[1:])
+        for ii in range(1, len(mother)):
+            if ii != j:
+                holes.append(mother[ii])
+            else:
+                holes.append(polygon_remove_edge(e, e_twin) if i > 0 else polygon_remove_edge(e_twin, e))
+        return (mother[0], holes)
+    if cas == 3:
+        # an isthmus from the outer boundary to what becomes a hole again
+        outer_new = polygon_remove_edge(e, e_twin)
+        inner_new = polygon_remove_edge(e_twin, e)
+        if poly_area(outer_new) <= 0:
+            outer_new, inner_new = inner_new, outer_new
+        return (outer_new, list(hpoly[1:]) + [inner_new])
+    # cas 4: an isthmus between two holes: the merged hole divides again
+    holes = list(hpoly[1:])
+    del holes[i - 1]
+    holes.append(polygon_remove_edge(e, e_twin))
+    holes.append(polygon_remove_edge(e_twin, e))
+    return (hpoly[0], holes)
 
 
 # ----------------------------------------------------------------------------
@@ -1078,13 +1162,22 @@ class Merge:
         i, pe = find_edge_in_polygons(fb, (e.src.p, e.tgt.p))
         m.del_faces.append(simplify_h(f))
         if single:
-            raise NotImplementedError("merge inside one (holed) face is outside the hot-path scope")
+            # both sides of e are the same face (an isthmus), :2343-2352
+            it, pet = find_edge_in_polygons(fb, (e.tgt.p, e.src.p))
+            hp = hpolygon_remove_edge(fb, fb, i, it, pe, pet, True)
+            m.add_faces.append(simplify_h(hp))
+            return self._segments(m, e1, e2, p1, p2)
         ft = face2poly(e.twin.face, False)
         ftb = boundaries(ft)
         it, pet = find_edge_in_polygons(ftb, (e.tgt.p, e.src.p))
         m.del_faces.append(simplify_h(ft))
         hp = hpolygon_remove_edge(fb, ftb, i, it, pe, pet, single)
         m.add_faces.append(simplify_h(hp))
+        return self._segments(m, e1, e2, p1, p2)
+
+    @staticmethod
+    def _segments(m, e1, e2, p1, p2):
+        """:2366-2403: the two segments e abutted on lose a vertex, e's segment goes."""
         seg = e1.seg.list_of_points()
         m.del_segs.append(list(seg))
         seg.remove(p1)

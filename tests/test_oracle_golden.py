@@ -168,6 +168,66 @@ def test_squared_domain_random_smf(seed):
     assert kinds["M"] > 5 and kinds["F"] > 5
 
 
+def _canon_h(hp):
+    """Canonical form of a holed polygon: outer boundary and holes each rotated to their
+    smallest vertex, holes sorted."""
+    outer, holes = hp
+    return (_canon(list(outer)), tuple(sorted(_canon(list(h)) for h in holes)))
+
+
+def _faces_h(t):
+    return sorted(_canon_h(lo.simplify_h(lo.face2poly(f, False))) for f in t.internal_faces())
+
+
+def _prediction_is_right_h(t, modif):
+    """prediction_is_right<> on whole holed polygons (outer boundary and holes)."""
+    before = _faces_h(t)
+    ml = modif.modified_elements()
+    t.update(modif)
+    after = _faces_h(t)
+    removed = sorted(p for p in before if p not in after)
+    added = sorted(p for p in after if p not in before)
+    pred_del = sorted(_canon_h(lo.simplify_h(hp)) for hp in ml.del_faces)
+    pred_add = sorted(_canon_h(lo.simplify_h(hp)) for hp in ml.add_faces)
+    return removed == pred_del and added == pred_add
+
+
+def test_non_convex_holed_domain_random_smf():
+    """check_predictions_4_random_smf(5,5,m,holed_polygons()), check_lite.cpp:1042-1049:
+    five splits, then a long mixed sequence kept at a low segment count so that faces
+    with holes stay common.  Exercises cas 2-4 of hpolygon_insert_edge / _remove_edge
+    (lib/ttessel.cpp:4722-4792, :4866-4922): segments joining a hole to the outer
+    boundary, two holes, or two points of one hole, and their removal."""
+    n, m = 5, 700
+    t = lo.TTessel(lo.Rng(5))
+    t.insert_window(holed_polygons())
+    kinds = {"S": 0, "M": 0, "F": 0}
+    holed_moves = 0
+    for i in range(n + m):
+        if i < n or i % 3 == 0:
+            mod = t.propose_split()
+            k = "S"
+            holed = bool(mod.e1.face.holes)
+        elif i % 3 == 1:
+            if not t.non_blocking_segments:
+                continue
+            mod = t.propose_merge()
+            k = "M"
+            holed = bool(mod.e.face.holes) or bool(mod.e.twin.face.holes) or mod.e.face is mod.e.twin.face
+        else:
+            if not t.blocking_segments:
+                continue
+            mod = t.propose_flip()
+            k = "F"
+            holed = bool(mod.e2.face.holes) or bool(mod.e1.face.holes) or bool(mod.e1.twin.face.holes)
+        kinds[k] += 1
+        holed_moves += holed
+        assert _prediction_is_right_h(t, mod), "iteration %d (%s)" % (i, k)
+        assert t.is_valid()
+    assert min(kinds.values()) > 100
+    assert holed_moves > 150, holed_moves
+
+
 def test_fixture_text_roundtrip():
     path = os.path.join(HERE, "golden", "tessellation_data.txt")
     text = open(path).read()
