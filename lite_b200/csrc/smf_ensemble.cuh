@@ -217,17 +217,17 @@ extern "C" int lite_smf_run(lite_ctx *c, int32_t n_samples, int64_t steps_per_sa
   }
   CU(cudaEventRecord(c->ev[6], c->stream));
   if (n > 0) {
-    // Launch shape, measured on B200 (gpurun_out/smf_sweep1.log, smf_ab2.log, smf_ab3.log).
-    // The kernel is bound by the latency of dependent loads, so: (1) chains are packed 32
-    // to a warp (the diverged lanes of a warp overlap their misses: 32 chains per warp cost
-    // 1.8x one chain per warp); (2) an ensemble that fits the GPU at 255 registers per
-    // thread runs the unconstrained build in one-warp blocks spread over all SMs (6.5e7
-    // vs 5.3e7 chain-steps/s at 8192 chains); (3) a larger one runs at 128 registers so
-    // that 512 chains per SM are resident (2.3e8 at 65536 chains; 64 registers: 2.0e8).
+    // Launch shape, from sweeps on B200 (gpurun_out/smf_sweep1.log, smf_ab2.log, smf_ab3.log;
+    // LITE_SMF_MINB / LITE_SMF_LPC override it for such sweeps).  The kernel is bound by
+    // the latency of dependent loads, so what counts is how the chains share warps and SMs:
+    //  * the diverged lanes of a warp overlap their misses (32 chains per warp cost 1.8x one
+    //    chain per warp), so chains are packed, 16 per warp while the ensemble still fits
+    //    the GPU that way and 32 otherwise; thinner warps lose again (the lanes of a warp
+    //    share local-memory lines, sparse warps waste L1);
+    //  * an ensemble that fits at 255 registers per thread runs the unconstrained build in
+    //    one-warp blocks spread over all SMs; a larger one runs at 128 registers, 512 chains
+    //    resident per SM (64 registers measured slower).
     static const char *env_minb = getenv("LITE_SMF_MINB"), *env_lpc = getenv("LITE_SMF_LPC");
-    // (4) when even two lanes per chain fit that way, 16 chains per warp beat 32 (8.5e7 vs
-    // 7.4e7 at 8192 chains); thinner than that loses again (local-memory lines are shared
-    // by the lanes of a warp, so sparse warps waste L1).
     int shift = ((long)n * 2 <= (long)c->sm_count * 4 * LITE_SMF_TB) ? 1 : 0;
     if (env_lpc) { shift = 0; while ((1 << (shift + 1)) <= atoi(env_lpc) && shift < 5) shift++; }
     const long threads = (long)n << shift;
