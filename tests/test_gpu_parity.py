@@ -496,3 +496,36 @@ def test_random_tessellations_against_live_oracle(lite, seed):
     np.testing.assert_allclose(g, wg, rtol=RTOL, atol=1e-12 * max(1.0, np.abs(wg).max()))
     np.testing.assert_allclose(H, wH, rtol=RTOL, atol=1e-12 * max(1.0, np.abs(wH).max()))
     ctx.close()
+
+
+def test_host_generated_non_convex_window_against_cpu_port(lite):
+    """A 350-cell tessellation of an L-shaped window grown by the host model's chain:
+    20 000 sampled splits, every merge and flip, all twelve features against the C++ port."""
+    import oracle_cpu as oc
+    h = lite.HostTess(text="0/1 0/1 4/1 0/1 4/1 2/1 2/1 2/1 2/1 4/1 0/1 4/1\n")
+    h.crtt_run(1.5, 5000, 3)
+    soa = h.export()
+    arrays = dict(soa.a)
+    arrays["int_length"] = soa.int_length
+    T = oc.Tess(arrays)
+    ctx = lite.Context(0)
+    ctx.tess_upload(soa)
+    ctx.energy_set(ALL12)
+    ctx.record_splits(True)
+    ctx.merges_flips()
+    n = 20000
+    ctx.add_splits_philox(n, 5, 0)
+    he, x, ang = oc.sample_splits(T, n, 5, 0, nthreads=4)
+    np.testing.assert_array_equal(ctx.fetch("SPLIT_E1"), he)
+    r = oc.split_stats(T, ALL12, he, x, ctx.fetch("SPLIT_ANGLE"), nthreads=4)
+    assert r["bad"] == 0
+    np.testing.assert_array_equal(ctx.fetch("SPLIT_E2"), r["split_e2"])
+    _assert_split_stats_adjudicated(soa.a, ctx.fetch("SPLIT_STAT"), r["split_stat"], ALL12, he, x,
+                                    ctx.fetch("SPLIT_ANGLE"), max_outliers=10)
+    m, f = oc.merge_stats(T, ALL12, nthreads=4), oc.flip_stats(T, ALL12, nthreads=4)
+    np.testing.assert_array_equal(ctx.fetch("MERGE_HE"), m["merge_he"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_E2"), f["flip_e2"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_RIGHT"), f["flip_right"])
+    _assert_stats("merge", ctx.fetch("MERGE_STAT"), m["merge_stat"], ALL12, term_scale=True)
+    _assert_stats("flip", ctx.fetch("FLIP_STAT"), f["flip_stat"], ALL12, term_scale=True)
+    ctx.close()

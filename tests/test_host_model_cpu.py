@@ -154,3 +154,21 @@ def test_reader_builds_cyclic_t_dependencies_at_once():
 def test_reader_rejects_what_is_not_a_t_tessellation(bad, msg):
     with pytest.raises(lite_b200.LiteError, match=msg):
         lite_b200.HostTess(text=bad)
+
+
+def test_host_model_on_a_non_convex_window():
+    """An L-shaped window (read from the text format: one polygon line): the chain keeps a
+    valid T-tessellation inside it, and the file round-trips."""
+    ell = "0/1 0/1 4/1 0/1 4/1 2/1 2/1 2/1 2/1 4/1 0/1 4/1\n"
+    h = lite_b200.HostTess(text=ell)
+    assert h.counts() == (1, 0, 0)
+    h.crtt_run(1.5, 5000, 3)
+    h.check()
+    cells, nnb, nb = h.counts()
+    assert cells > 100 and cells == nnb + nb + 1
+    a = h.export().a
+    assert not np.any((a["vx"] > 2 + 1e-12) & (a["vy"] > 2 + 1e-12))     # nothing in the notch
+    h2 = lite_b200.HostTess(text=h.write_text())
+    h2.check()
+    assert h2.counts() == h.counts()
+    assert _cells_from_soa(h2.export().a) == _cells_from_soa(a)
