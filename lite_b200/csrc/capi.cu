@@ -543,11 +543,13 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   T.sfo = c->sfo.p; T.pre = c->pre.p; T.plen = c->plen.p; T.f_tot2 = c->f_tot2.p; T.stot2 = c->stot2.p;
   int tb = 128, gb = (nF + tb - 1) / tb;
   k_build_guide<<<(n_guide + 255) / 256, 256, 0, c->stream>>>(c->cum.p, (int)cum.size(), cl / (double)n_guide, n_guide, c->guide.p);
-  k_prep_slots<<<gb, tb, 0, c->stream>>>(A);
+  CU(cudaMemsetAsync(c->slot_face.p, 0xFF, nSl * sizeof(int), c->stream));
+  k_prep_slot_face<<<gb, tb, 0, c->stream>>>(A);
+  k_prep_slots<<<(unsigned)((nSl + 127) / 128), 128, 0, c->stream>>>(A, (int)nSl);
   // outside faces: count 0 in the device view
   k_prep_faces<<<gb, tb, 0, c->stream>>>(T, c->ca.p, c->f_area.p, c->f_perim.p, c->f_sumang.p, c->f_minang.p,
                                          c->pre.p, c->plen.p, c->f_tot2.p, c->sfo.p, c->stot2.p);
-  c->launches += 3;
+  c->launches += 4;
   // the merge/flip stream only depends on the tessellation being in place: it forks here,
   // not from whatever the main stream is doing when SetEnergy is called (the split kernel,
   // if AddSplits came first: the two then run side by side)

@@ -226,33 +226,41 @@ struct PrepArgs {
   int *err;  // consistency errors
 };
 
-__global__ void k_prep_slots(PrepArgs A) {
+// slot -> face (one thread per face, no dependent loads), then everything per slot with one
+// thread per slot: the loads of a slot chain four deep (list -> halfedge -> vertex / twin ->
+// face), and one thread per FACE walked its ~6 slots one after the other (50 us at 10^4 cells)
+__global__ void k_prep_slot_face(PrepArgs A) {
   int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= A.n_faces) return;
   int n = A.face_he_count[f];
   if (n == 0 || !A.face_inside[f]) return;
   int off = A.face_he_offset[f];
-  for (int k = 0; k < n; k++) {
-    int h = A.face_he_list[off + k];
-    int hp = A.face_he_list[off + (k == 0 ? n - 1 : k - 1)];
-    int hn = A.face_he_list[off + (k + 1 == n ? 0 : k + 1)];
-    if (A.he_next[h] != hn || A.he_face[h] != f) atomicAdd(A.err, 1);
-    int vs = A.he_src[h], vt = A.he_src[hn];
-    double sx = A.vx[vs], sy = A.vy[vs], tx = A.vx[vt], ty = A.vy[vt];
-    A.pt[off + k] = make_double2(sx, sy);
-    A.ang[off + k] = atan2(ty - sy, tx - sx);
-    A.len[off + k] = A.he_length[h];
-    uint32_t fl = 0;
-    int nhf = A.he_next_hf[hp];
-    if (nhf < 0 || nhf != A.he_next[hp]) fl |= SF_CORNER;  // face2poly, lib/ttessel.cpp:4325-4327
-    if (!A.face_inside[A.he_face[A.he_twin[h]]]) fl |= SF_BND;
-    if (A.he_dir[h]) fl |= SF_DIR;
-    A.flg[off + k] = fl;
-    A.slot_he[off + k] = h;
-    A.slot_seg[off + k] = A.he_seg[h];
-    A.slot_face[off + k] = f;
-    A.he_slot[h] = off + k;
-  }
+  for (int k = 0; k < n; k++) A.slot_face[off + k] = f;
+}
+__global__ void k_prep_slots(PrepArgs A, int n_slots) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_slots) return;
+  const int f = A.slot_face[m];
+  if (f < 0) return;  // a slot of an outside face
+  const int n = A.face_he_count[f], off = A.face_he_offset[f], k = m - off;
+  int h = A.face_he_list[off + k];
+  int hp = A.face_he_list[off + (k == 0 ? n - 1 : k - 1)];
+  int hn = A.face_he_list[off + (k + 1 == n ? 0 : k + 1)];
+  if (A.he_next[h] != hn || A.he_face[h] != f) atomicAdd(A.err, 1);
+  int vs = A.he_src[h], vt = A.he_src[hn];
+  double sx = A.vx[vs], sy = A.vy[vs], tx = A.vx[vt], ty = A.vy[vt];
+  A.pt[m] = make_double2(sx, sy);
+  A.ang[m] = atan2(ty - sy, tx - sx);
+  A.len[m] = A.he_length[h];
+  uint32_t fl = 0;
+  int nhf = A.he_next_hf[hp];
+  if (nhf < 0 || nhf != A.he_next[hp]) fl |= SF_CORNER;  // face2poly, lib/ttessel.cpp:4325-4327
+  if (!A.face_inside[A.he_face[A.he_twin[h]]]) fl |= SF_BND;
+  if (A.he_dir[h]) fl |= SF_DIR;
+  A.flg[m] = fl;
+  A.slot_he[m] = h;
+  A.slot_seg[m] = A.he_seg[h];
+  A.he_slot[h] = m;
 }
 
 __global__ void k_prep_faces(TessDev T, double *ca, double *f_area, double *f_perim,
