@@ -132,9 +132,27 @@ int lite_candidates_count(lite_ctx *ctx, int64_t *n_splits_local, int64_t *n_spl
 
 /* PseudoLikDiscrete::GetValue / GetGradient / GetHessian in one pass
  * (lib/ttessel.cpp:3387-3443).  grad: d doubles, hess: d*d row-major; any of
- * the three outputs may be NULL.  With world_size > 1 one ncclAllReduce of
- * 1+d+d*d doubles combines the shards. */
+ * the three outputs may be NULL.  With world_size > 1 the shards' 1+d+d(d+1)/2
+ * sums (S0, S1, upper triangle of S2) are added across the GPUs inside the reduce
+ * kernel, over NVLink peer memory (lite_comm_info; ncclAllReduce when the peers
+ * cannot be mapped or LITE_B200_ALLREDUCE=nccl); every rank gets the bitwise
+ * identical result.  Collective: every rank must make the call. */
 int lite_pl_eval(lite_ctx *ctx, const double *theta, double *lpl, double *grad, double *hess);
+/* The host arithmetic at the end of lite_pl_eval (lib/ttessel.cpp:3387-3443) on sums
+ * supplied by the caller: S, F = [S0, S1_k, S2_kl (k<=l)] over the dummy splits of ALL
+ * ranks / over the flips, M, Fl = sum_stat_merges, sum_stat_flips.  Needs no device. */
+int lite_pl_combine(int d, int64_t n_splits_global, double int_length, const double *theta,
+                    const double *S, const double *F, const double *M, const double *Fl,
+                    double *lpl, double *grad, double *hess);
+/* Shard [first, first+count) of a batch of n held by `rank` of `world`. */
+int lite_shard_range(int64_t n, int rank, int world, int64_t *first, int64_t *count);
+/* Candidates behind the last lite_pl_eval whose ray found no exit edge (their statistic
+ * row is all zero, which biases S0 by 1 each): counts since the last ClearSplits /
+ * SetEnergy.  0 on every tessellation the tests know; see DESIGN.md. */
+int lite_pl_failures(lite_ctx *ctx, int64_t *split_no_exit, int64_t *flip_no_exit);
+/* mode: 0 single rank, 1 ncclAllReduce, 2 peer memory (NVLink) inside the reduce kernel;
+ * exchange_ms: device time the last lite_pl_eval spent combining the ranks. */
+int lite_comm_info(lite_ctx *ctx, int32_t *mode, float *exchange_ms);
 
 /* Energy::statistic_variation sums kept by SetEnergy: sum_stat_merges,
  * sum_stat_flips (d doubles each, already negated as in the reference). */

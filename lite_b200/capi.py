@@ -36,6 +36,7 @@ SYMBOLS = [
     "lite_measure_fp64_peak", "lite_last_reduce_ms", "lite_timer_mark", "lite_timer_elapsed",
     "lite_smf_create", "lite_smf_destroy", "lite_smf_set_model", "lite_smf_run", "lite_smf_stats",
     "lite_smf_trace", "lite_smf_export", "lite_smf_count", "lite_smf_last_ms",
+    "lite_pl_combine", "lite_shard_range", "lite_pl_failures", "lite_comm_info",
 ]
 
 # columns of lite_smf_run / lite_smf_stats (applications/checkACS.cpp:136-148 + energy)
@@ -168,6 +169,10 @@ def load_library():
     L.lite_smf_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                  C.POINTER(C.c_int64)]
     L.lite_smf_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.lite_pl_combine.argtypes = [C.c_int, C.c_int64, C.c_double] + [C.c_void_p] * 8
+    L.lite_shard_range.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.lite_pl_failures.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.lite_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_float)]
     _LIB = L
     return L
 
@@ -185,11 +190,30 @@ def nccl_unique_id():
 
 
 def shard_range(n, rank, world):
-    """Contiguous shard [r*n/G, (r+1)*n/G) — the partition used by
-    lite_candidates_add_splits_philox."""
-    j0 = (n * rank) // world
-    j1 = (n * (rank + 1)) // world
-    return j0, j1 - j0
+    """Contiguous shard [r*n/G, (r+1)*n/G) of rank r: lite_shard_range, the partition
+    lite_candidates_add_splits_philox uses.  Returns (first, count)."""
+    L = load_library()
+    a, b = C.c_int64(), C.c_int64()
+    _ck(L, L.lite_shard_range(int(n), int(rank), int(world), C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def pl_combine(theta, n_splits_global, int_length, S, F, M, Fl):
+    """lite_pl_combine: log-PL, gradient, Hessian from reduced sums (host arithmetic of
+    lite_pl_eval; S, F packed [S0, S1_k, S2_kl (k<=l)])."""
+    L = load_library()
+    th = np.ascontiguousarray(theta, dtype=np.float64)
+    d = len(th)
+    arr = [np.ascontiguousarray(a, dtype=np.float64) for a in (S, F, M, Fl)]
+    nt = 1 + d + d * (d + 1) // 2
+    assert len(arr[0]) >= nt and len(arr[1]) >= nt and len(arr[2]) >= d and len(arr[3]) >= d
+    lpl = C.c_double()
+    g = np.zeros(d)
+    H = np.zeros((d, d))
+    _ck(L, L.lite_pl_combine(d, int(n_splits_global), float(int_length), th.ctypes.data_as(C.c_void_p),
+                             *[a.ctypes.data_as(C.c_void_p) for a in arr], C.cast(C.byref(lpl), C.c_void_p),
+                             g.ctypes.data_as(C.c_void_p), H.ctypes.data_as(C.c_void_p)))
+    return lpl.value, g, H
 
 
 class Context:
@@ -204,6 +228,7 @@ class Context:
         _ck(self.L, self.L.lite_ctx_create(C.byref(self.h), device, rank, world_size, idbuf))
         self.d = 0
         self.rank, self.world = rank, world_size
+        self.device = device
 
     def close(self):
         if self.h:
@@ -270,6 +295,18 @@ class Context:
         _ck(self.L, self.L.lite_pl_eval(self.h, th.ctypes.data_as(C.c_void_p), C.byref(lpl),
                                         g.ctypes.data_as(C.c_void_p), H.ctypes.data_as(C.c_void_p)))
         return lpl.value, g, H
+
+    def pl_failures(self):
+        """(split, flip) candidates behind the last pl_eval whose ray found no exit edge."""
+        a, b = C.c_int64(), C.c_int64()
+        _ck(self.L, self.L.lite_pl_failures(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def comm_info(self):
+        """(mode, exchange_ms): 0 single rank, 1 ncclAllReduce, 2 peer memory in k_reduce."""
+        m, t = C.c_int32(), C.c_float()
+        _ck(self.L, self.L.lite_comm_info(self.h, C.byref(m), C.byref(t)))
+        return m.value, t.value
 
     def pl_sums(self):
         m = np.zeros(self.d)

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <condition_variable>
@@ -31,7 +32,7 @@ struct NvtxRange {
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat64 = 8 };
+enum { ncclInt8 = 0, ncclFloat64 = 8 };
 enum { ncclSum = 0 };
 struct NcclApi {
   void *lib = nullptr;
@@ -39,10 +40,12 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
 
+static const bool g_trace = getenv("LITE_B200_TRACE") != nullptr;
 static thread_local std::string g_err;
 static int fail(int code, const char *fmt, ...) {
   char buf[1024];
@@ -73,6 +76,7 @@ static int nccl_load() {
   g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(lib, "ncclAllReduce");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(lib, "ncclAllGather");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce)
     return fail(LITE_ENCCL, "libnccl.so.2 lacks the expected symbols");
@@ -167,6 +171,15 @@ struct lite_ctx {
   cudaEvent_t ev_fork = nullptr, ev_mf = nullptr;
   bool mf_inflight = false;         // stream must wait for ev_mf before using the flip statistics
   ncclComm_t comm = nullptr;
+  // cross-GPU sum over peer memory (kernels.cuh: PeerArgs); off -> ncclAllReduce
+  bool peer_on = false;
+  double *peer_local = nullptr;                 // this rank's mailbox
+  double *peer_box[LITE_MAX_WORLD] = {};        // every rank's mailbox as mapped here
+  bool peer_ipc[LITE_MAX_WORLD] = {};           // mapped with cudaIpcOpenMemHandle (to be closed)
+  unsigned long long peer_seq = 0;
+  DBuf<unsigned long long> peer_info;           // [0] timeout marker, [1] wait ns
+  double peer_wait_us = 0;
+  float ms_exchange = 0;                        // NCCL path: device time of the allreduce
   bool have_tess = false, have_prog = false, have_mf = false;
   bool record = false;
   bool mf_pending = false;  // sums of the last merges_flips still in flight
@@ -213,6 +226,7 @@ struct lite_ctx {
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t tev[LITE_TIMER_SLOTS] = {};  // user timer marks (lite_timer_mark)
   float ms_split = 0, ms_eval = 0, ms_mf = 0, ms_reduce = 0;
+  int64_t fail_splits = 0, fail_flips = 0;  // no-exit counts behind the last evaluation
   bool ev01 = false;  // ev[0]/ev[1] have been recorded
   std::vector<uint8_t> h_he_inside;
   std::vector<double> h_cum;        // cumulative slot lengths of the last upload (host copy)
@@ -236,6 +250,116 @@ extern "C" int lite_nccl_unique_id(void *out128) {
   return 0;
 }
 
+// Map every rank's mailbox into this process.  Collective over the context's NCCL
+// communicator (used here for the plumbing only: one all-gather of the IPC handles, one
+// all-reduce so that all ranks agree on the outcome).  Any failure leaves peer_on false and
+// lite_pl_eval uses ncclAllReduce.
+struct PeerCard {
+  cudaIpcMemHandle_t handle;
+  long long pid;
+  unsigned long long ptr;
+  int device, ok;
+  char host[64];
+};
+static int peer_setup(lite_ctx *c) {
+  const char *force = getenv("LITE_B200_ALLREDUCE");
+  const bool want = c->world <= LITE_MAX_WORLD && g_nccl.AllGather && !(force && !strcmp(force, "nccl"));
+  PeerCard mine{};
+  mine.pid = (long long)getpid(); mine.device = c->device; mine.ok = 0;
+  gethostname(mine.host, sizeof mine.host - 1);
+  if (want && cudaMalloc((void **)&c->peer_local, LITE_BOX_DOUBLES * sizeof(double)) == cudaSuccess) {
+    cudaMemsetAsync(c->peer_local, 0, LITE_BOX_DOUBLES * sizeof(double), c->stream);
+    if (cudaIpcGetMemHandle(&mine.handle, c->peer_local) == cudaSuccess) mine.ok = 1;
+    mine.ptr = (unsigned long long)c->peer_local;
+  }
+  (void)cudaGetLastError();
+  DBuf<char> dsend, drecv;
+  if (dsend.alloc(sizeof(PeerCard)) || drecv.alloc(sizeof(PeerCard) * c->world)) return LITE_ECUDA;
+  std::vector<PeerCard> cards(c->world);
+  CU(cudaMemcpyAsync(dsend.p, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+  if (!g_nccl.AllGather) { dsend.release(); drecv.release(); return 0; }
+  ncclResult_t ne = g_nccl.AllGather(dsend.p, drecv.p, sizeof(PeerCard), ncclInt8, c->comm, c->stream);
+  if (ne != 0) return fail(LITE_ENCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(ne) : "?");
+  CU(cudaMemcpyAsync(cards.data(), drecv.p, sizeof(PeerCard) * c->world, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  int ok = mine.ok;
+  for (int r = 0; r < c->world && ok; r++) {
+    const PeerCard &k = cards[r];
+    if (!k.ok || strncmp(k.host, mine.host, sizeof mine.host)) { ok = 0; break; }
+    if (r == c->rank) { c->peer_box[r] = c->peer_local; continue; }
+    if (k.pid == mine.pid) {  // another context of this process: address it directly
+      int can = 0;
+      if (k.device != c->device) {
+        if (cudaDeviceCanAccessPeer(&can, c->device, k.device) != cudaSuccess || !can) { ok = 0; break; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(k.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ok = 0; break; }
+        (void)cudaGetLastError();
+      }
+      c->peer_box[r] = (double *)k.ptr;
+    } else {
+      void *q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, k.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+      c->peer_box[r] = (double *)q; c->peer_ipc[r] = true;
+    }
+  }
+  (void)cudaGetLastError();
+  // all or nothing: the ranks must take the same path
+  double votes = ok ? 1.0 : 0.0, *dv = (double *)dsend.p;
+  CU(cudaMemcpyAsync(dv, &votes, sizeof votes, cudaMemcpyHostToDevice, c->stream));
+  ne = g_nccl.AllReduce(dv, dv, 1, ncclFloat64, ncclSum, c->comm, c->stream);
+  if (ne != 0) return fail(LITE_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(ne) : "?");
+  CU(cudaMemcpyAsync(&votes, dv, sizeof votes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->peer_on = (votes == (double)c->world);
+  dsend.release(); drecv.release();
+  if (g_trace) fprintf(stderr, "[lite_b200] rank %d/%d: cross-GPU sum over %s\n", c->rank, c->world,
+                       c->peer_on ? "peer memory (NVLink)" : "ncclAllReduce");
+  return 0;
+}
+static void peer_release(lite_ctx *c) {
+  for (int r = 0; r < LITE_MAX_WORLD; r++) {
+    if (c->peer_ipc[r] && c->peer_box[r]) cudaIpcCloseMemHandle(c->peer_box[r]);
+    c->peer_box[r] = nullptr; c->peer_ipc[r] = false;
+  }
+  if (c->peer_local) cudaFree(c->peer_local);
+  c->peer_local = nullptr; c->peer_on = false;
+}
+
+static int ctx_init(lite_ctx *c, const void *nccl_unique_id) {
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_upload, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_mf, cudaEventDisableTiming));
+  for (int i = 0; i < 8; i++) CU(cudaEventCreate(&c->ev[i]));
+  for (int i = 0; i < LITE_TIMER_SLOTS; i++) CU(cudaEventCreate(&c->tev[i]));
+  CU(cudaMallocHost((void **)&c->h_pinned, 4096 * sizeof(double)));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, c->device));
+  c->sm_count = prop.multiProcessorCount;
+  if (c->status.alloc(8) || c->counter.alloc(4) || c->err.alloc(1) || c->peer_info.alloc(2)) return LITE_ECUDA;
+  CU(cudaMemsetAsync(c->status.p, 0, 8 * sizeof(unsigned long long), c->stream));
+  CU(cudaMemsetAsync(c->counter.p, 0, 4 * sizeof(unsigned int), c->stream));
+  CU(cudaMemsetAsync(c->peer_info.p, 0, 2 * sizeof(unsigned long long), c->stream));
+  if (c->world > 1) {
+    if (!nccl_unique_id) return fail(LITE_EINVAL, "world_size > 1 needs a NCCL unique id");
+    int r = nccl_load();
+    if (r) return r;
+    ncclUniqueId id;
+    memcpy(&id, nccl_unique_id, 128);
+    ncclResult_t ne = g_nccl.CommInitRank(&c->comm, c->world, id, c->rank);
+    if (ne != 0) return fail(LITE_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(ne) : "?");
+    r = peer_setup(c);
+    if (r) return r;
+  }
+  c->pool = new HostPool();
+  c->pool->start(4);
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int lite_ctx_destroy(lite_ctx *c);
+
 extern "C" int lite_ctx_create(lite_ctx **out, int device, int rank, int world_size,
                                const void *nccl_unique_id) {
   if (!out) return fail(LITE_EINVAL, "null output");
@@ -250,32 +374,13 @@ extern "C" int lite_ctx_create(lite_ctx **out, int device, int rank, int world_s
   CU(cudaSetDevice(device));
   lite_ctx *c = new lite_ctx();
   c->device = device; c->rank = rank; c->world = world_size;
-  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-  CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-  CU(cudaEventCreateWithFlags(&c->ev_upload, cudaEventDisableTiming));
-  CU(cudaEventCreateWithFlags(&c->ev_mf, cudaEventDisableTiming));
-  for (int i = 0; i < 8; i++) CU(cudaEventCreate(&c->ev[i]));
-  for (int i = 0; i < LITE_TIMER_SLOTS; i++) CU(cudaEventCreate(&c->tev[i]));
-  CU(cudaMallocHost((void **)&c->h_pinned, 4096 * sizeof(double)));
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, device));
-  c->sm_count = prop.multiProcessorCount;
-  if (c->status.alloc(8) || c->counter.alloc(4) || c->err.alloc(1)) return LITE_ECUDA;
-  CU(cudaMemsetAsync(c->status.p, 0, 8 * sizeof(unsigned long long), c->stream));
-  CU(cudaMemsetAsync(c->counter.p, 0, 4 * sizeof(unsigned int), c->stream));
-  if (world_size > 1) {
-    if (!nccl_unique_id) return fail(LITE_EINVAL, "world_size > 1 needs a NCCL unique id");
-    int r = nccl_load();
-    if (r) return r;
-    ncclUniqueId id;
-    memcpy(&id, nccl_unique_id, 128);
-    ncclResult_t ne = g_nccl.CommInitRank(&c->comm, world_size, id, rank);
-    if (ne != 0) return fail(LITE_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(ne) : "?");
+  const int r = ctx_init(c, nccl_unique_id);
+  if (r) {  // release whatever was created; the message of the failure survives
+    const std::string msg = g_err;
+    lite_ctx_destroy(c);
+    g_err = msg;
+    return r;
   }
-  c->pool = new HostPool();
-  c->pool->start(4);
-  CU(cudaStreamSynchronize(c->stream));
   *out = c;
   return 0;
 }
@@ -285,8 +390,10 @@ static void smf_release(lite_ctx *c);
 extern "C" int lite_ctx_destroy(lite_ctx *c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   smf_release(c);
+  peer_release(c);
+  c->peer_info.release();
   if (c->pool) { c->pool->shutdown(); delete c->pool; c->pool = nullptr; }
   if (c->stream2) cudaStreamSynchronize(c->stream2);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
@@ -317,7 +424,8 @@ extern "C" int lite_ctx_destroy(lite_ctx *c) {
   if (c->ev_upload) cudaEventDestroy(c->ev_upload);
   if (c->ev_mf) cudaEventDestroy(c->ev_mf);
   if (c->stream2) cudaStreamDestroy(c->stream2);
-  cudaStreamDestroy(c->stream);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  (void)cudaGetLastError();
   delete c;
   return 0;
 }
@@ -371,12 +479,16 @@ static int arena_reserve(lite_ctx *c, size_t need) {
 static double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
-static const bool g_trace = getenv("LITE_B200_TRACE") != nullptr;
 
 extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   NvtxRange nvtx_("lite_tess_upload");
   if (!c || !s) return fail(LITE_EINVAL, "null argument");
   if (c->mf_inflight) { cudaStreamSynchronize(c->stream2); c->mf_inflight = false; }
+  // From here on the context holds no tessellation until this upload has succeeded: the
+  // views into the arena are re-pointed as the arrays are staged, so after a failure the
+  // previous tessellation is gone and every call that needs one returns LITE_ESTATE.
+  c->have_tess = false; c->have_mf = false; c->mf_pending = false;
+  c->n_local = 0; c->n_global = 0;
   const double t0 = now_ms();
   double t1 = t0, t2 = t0, t3 = t0, t4 = t0;
   CU(cudaSetDevice(c->device));
@@ -519,6 +631,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
     return LITE_ECUDA;
   CU(cudaMemsetAsync(c->he_slot.p, 0xFF, nH * sizeof(int), c->stream));
   CU(cudaMemsetAsync(c->err.p, 0, sizeof(int), c->stream));
+  CU(cudaMemsetAsync(c->status.p, 0, 2 * sizeof(unsigned long long), c->stream));  // no-exit counters
   PrepArgs A{};
   A.vx = c->vx.p; A.vy = c->vy.p; A.he_src = c->he_src.p; A.he_twin = c->he_twin.p;
   A.he_next = c->he_next.p; A.he_face = c->he_face.p; A.he_seg = c->he_seg.p;
@@ -650,6 +763,7 @@ extern "C" int lite_candidates_merges_flips(lite_ctx *c, int32_t *n_merges, int3
   if (c->mf_inflight) CU(cudaStreamSynchronize(c->stream2));
   CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));  // recorded by lite_tess_upload
   CU(cudaEventRecord(c->ev[4], c->stream2));
+  CU(cudaMemsetAsync(c->status.p + 1, 0, sizeof(unsigned long long), c->stream2));
   if (nm + nf > 0) {
     MFArgs A{};
     A.nb_seg = c->nb_list.p; A.nm = nm; A.mstat = c->mstat.p; A.m_he = c->m_he.p; A.gm = (nm + 127) / 128;
@@ -829,8 +943,8 @@ extern "C" int lite_lines_sample_clip(lite_ctx *c, int64_t n_global, uint64_t se
     Prog G0{};  // no features
     bool rec_save = c->record;
     if (mode == 1) {
-      c->record = true;
       if (c->n_local != 0) return fail(LITE_ESTATE, "store mode needs an empty split list");
+      c->record = true;
       int r = grow_splits(c, n);
       c->record = rec_save;
       if (r) return r;
@@ -857,6 +971,8 @@ extern "C" int lite_lines_sample_clip(lite_ctx *c, int64_t n_global, uint64_t se
 extern "C" int lite_candidates_clear_splits(lite_ctx *c) {
   if (!c) return fail(LITE_EINVAL, "null context");
   c->n_local = 0; c->n_global = 0;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemsetAsync(c->status.p, 0, sizeof(unsigned long long), c->stream));
   return 0;
 }
 
@@ -868,26 +984,67 @@ extern "C" int lite_candidates_count(lite_ctx *c, int64_t *nl, int64_t *ng) {
 }
 
 template <int D>
-static void launch_reduce(lite_ctx *c, const RedSeg &A, const RedSeg &B, const Theta &th) {
-  k_reduce<D><<<A.grid + B.grid, 256, 0, c->stream>>>(A, B, th);
+static void launch_reduce(lite_ctx *c, const RedSeg &A, const RedSeg &B, const Theta &th, const PeerArgs &P) {
+  k_reduce<D><<<A.grid + B.grid, 256, 0, c->stream>>>(A, B, th, P);
 }
-static void reduce_dispatch(lite_ctx *c, int d, const RedSeg &A, const RedSeg &B, const Theta &th) {
+static void reduce_dispatch(lite_ctx *c, int d, const RedSeg &A, const RedSeg &B, const Theta &th, const PeerArgs &P) {
   switch (d) {
-    case 1: launch_reduce<1>(c, A, B, th); break;
-    case 2: launch_reduce<2>(c, A, B, th); break;
-    case 3: launch_reduce<3>(c, A, B, th); break;
-    case 4: launch_reduce<4>(c, A, B, th); break;
-    case 5: launch_reduce<5>(c, A, B, th); break;
-    case 6: launch_reduce<6>(c, A, B, th); break;
-    case 7: launch_reduce<7>(c, A, B, th); break;
-    case 8: launch_reduce<8>(c, A, B, th); break;
-    case 9: launch_reduce<9>(c, A, B, th); break;
-    case 10: launch_reduce<10>(c, A, B, th); break;
-    case 11: launch_reduce<11>(c, A, B, th); break;
-    case 12: launch_reduce<12>(c, A, B, th); break;
+    case 1: launch_reduce<1>(c, A, B, th, P); break;
+    case 2: launch_reduce<2>(c, A, B, th, P); break;
+    case 3: launch_reduce<3>(c, A, B, th, P); break;
+    case 4: launch_reduce<4>(c, A, B, th, P); break;
+    case 5: launch_reduce<5>(c, A, B, th, P); break;
+    case 6: launch_reduce<6>(c, A, B, th, P); break;
+    case 7: launch_reduce<7>(c, A, B, th, P); break;
+    case 8: launch_reduce<8>(c, A, B, th, P); break;
+    case 9: launch_reduce<9>(c, A, B, th, P); break;
+    case 10: launch_reduce<10>(c, A, B, th, P); break;
+    case 11: launch_reduce<11>(c, A, B, th, P); break;
+    case 12: launch_reduce<12>(c, A, B, th, P); break;
     default: break;
   }
   c->launches += 1;
+}
+
+// GetValue / GetGradient / GetHessian from the reduced sums (lib/ttessel.cpp:3387-3443).
+// S: split sums over ALL ranks [S0, S1_k, S2_kl (k<=l)], F: the same over the flips,
+// M / Fl: sum_stat_merges / sum_stat_flips.  The normaliser uses the GLOBAL number of
+// dummy splits (:3396).  Host arithmetic only: exported so that the CPU tests can drive it.
+extern "C" int lite_pl_combine(int d, int64_t n_splits_global, double int_length, const double *theta,
+                               const double *S, const double *F, const double *M, const double *Fl,
+                               double *lpl, double *grad, double *hess) {
+  if (d < 1 || d > LITE_MAX_D || !theta || !S || !F || !M || !Fl) return fail(LITE_EINVAL, "bad argument");
+  if (n_splits_global <= 0) return fail(LITE_ENOSPLIT, "no dummy splits: the reference divides by stat_splits.size()");
+  // lib/ttessel.cpp:3396: int_length/(pi*|S|)
+  const double cn = int_length / (LITE_PI * (double)n_splits_global);
+  if (lpl) {
+    double tm = 0, tf = 0;
+    for (int i = 0; i < d; i++) { tm += theta[i] * M[i]; tf += theta[i] * Fl[i]; }
+    double v = -tm;
+    v -= cn * S[0];
+    v -= tf;
+    v -= F[0];
+    *lpl = v;
+  }
+  if (grad)
+    for (int i = 0; i < d; i++) grad[i] = -M[i] - cn * S[1 + i] - Fl[i] - F[1 + i];
+  if (hess) {
+    int t = 1 + d;
+    for (int k = 0; k < d; k++)
+      for (int l = k; l < d; l++, t++) {
+        double v = -cn * S[t] - F[t];
+        hess[k * d + l] = v;
+        hess[l * d + k] = v;
+      }
+  }
+  return 0;
+}
+
+// the contiguous shard of rank r; exported for the CPU tests
+extern "C" int lite_shard_range(int64_t n, int rank, int world, int64_t *first, int64_t *count) {
+  if (n < 0 || world < 1 || rank < 0 || rank >= world || !first || !count) return fail(LITE_EINVAL, "bad argument");
+  shard_range(n, rank, world, *first, *count);
+  return 0;
 }
 
 extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, double *grad, double *hess) {
@@ -911,51 +1068,75 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
   if (grid > maxgrid) grid = maxgrid;
   if (gf > maxgrid) gf = maxgrid;
   c->rev = !c->rev;  // boustrophedon: the end the previous pass (or k_split) touched last is still in L2
-  RedSeg A{c->stat.p, c->cap, n, c->rev ? 1 : 0, c->partials.p, c->counter.p, c->red_out.p, n > 0 ? (grid < 1 ? 1 : grid) : 0};
+  // with peers the split segment always runs (at least one block): its last block does the exchange
+  const bool exch = c->world > 1 && c->peer_on;
+  RedSeg A{c->stat.p, c->cap, n, c->rev ? 1 : 0, c->partials.p, c->counter.p, c->red_out.p,
+           (n > 0 || exch) ? (grid < 1 ? 1 : grid) : 0};
   RedSeg B{c->fstat.p, (size_t)nf, nf, 0, c->partials.p + (size_t)maxgrid * NT, c->counter.p + 1, c->red_out.p + 128,
            nf > 0 ? (gf < 1 ? 1 : gf) : 0};
-  if (n == 0) CU(cudaMemsetAsync(c->red_out.p, 0, 128 * sizeof(double), c->stream));
+  PeerArgs P{};
+  P.world = exch ? c->world : 1; P.rank = c->rank; P.info = c->peer_info.p;
+  if (exch) {
+    P.seq = ++c->peer_seq;
+    for (int r = 0; r < c->world; r++) P.box[r] = c->peer_box[r];
+  }
+  if (A.grid == 0) CU(cudaMemsetAsync(c->red_out.p, 0, 128 * sizeof(double), c->stream));
   if (nf == 0) CU(cudaMemsetAsync(c->red_out.p + 128, 0, 128 * sizeof(double), c->stream));
   CU(cudaEventRecord(c->ev[6], c->stream));
-  if (A.grid + B.grid > 0) reduce_dispatch(c, d, A, B, th);
+  if (A.grid + B.grid > 0) reduce_dispatch(c, d, A, B, th, P);
   CU(cudaEventRecord(c->ev[7], c->stream));
-  if (c->world > 1) {
+  if (c->world > 1 && !exch) {
     ncclResult_t ne = g_nccl.AllReduce(c->red_out.p, c->red_out.p, (size_t)NT, ncclFloat64, ncclSum, c->comm, c->stream);
     if (ne != 0) return fail(LITE_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(ne) : "?");
   }
   CU(cudaEventRecord(c->ev[3], c->stream));
   CU(cudaMemcpyAsync(c->h_pinned, c->red_out.p, 256 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  // geometric failures of the candidates behind these sums (no exit edge found): they ride
+  // back with the results, see lite_pl_failures
+  CU(cudaMemcpyAsync(c->h_pinned + 256, c->status.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  if (exch) CU(cudaMemcpyAsync(c->h_pinned + 260, c->peer_info.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
   c->mf_inflight = false;
   finalize_mf(c);
   cudaEventElapsedTime(&c->ms_eval, c->ev[2], c->ev[3]);
   cudaEventElapsedTime(&c->ms_reduce, c->ev[6], c->ev[7]);
+  c->ms_exchange = 0; c->peer_wait_us = 0;
+  if (c->world > 1 && !exch) cudaEventElapsedTime(&c->ms_exchange, c->ev[7], c->ev[3]);
   if (c->ev01) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->ms_split = ms; }
-  const double *S = c->h_pinned, *F = c->h_pinned + 128;
-  // lib/ttessel.cpp:3396: int_length/(pi*|S|)
-  const double cn = c->int_length / (LITE_PI * (double)c->n_global);
-  const double *M = c->h_sum_m.data(), *Fl = c->h_sum_f.data();
-  if (lpl) {
-    double tm = 0, tf = 0;
-    for (int i = 0; i < d; i++) { tm += theta[i] * M[i]; tf += theta[i] * Fl[i]; }
-    double v = -tm;
-    v -= cn * S[0];
-    v -= tf;
-    v -= F[0];
-    *lpl = v;
+  {
+    const unsigned long long *st = (const unsigned long long *)(c->h_pinned + 256);
+    c->fail_splits = (int64_t)st[0]; c->fail_flips = (int64_t)st[1];
   }
-  if (grad)
-    for (int i = 0; i < d; i++) grad[i] = -M[i] - cn * S[1 + i] - Fl[i] - F[1 + i];
-  if (hess) {
-    int t = 1 + d;
-    for (int k = 0; k < d; k++)
-      for (int l = k; l < d; l++, t++) {
-        double v = -cn * S[t] - F[t];
-        hess[k * d + l] = v;
-        hess[l * d + k] = v;
-      }
+  if (exch) {
+    const unsigned long long *pi = (const unsigned long long *)(c->h_pinned + 260);
+    if (pi[0] == P.seq)
+      return fail(LITE_ENCCL, "rank %d: the peers' sums of evaluation %llu did not arrive within %.1f s "
+                  "(did every rank call lite_pl_eval?)", c->rank, P.seq, LITE_PEER_TIMEOUT_NS * 1e-9);
+    c->peer_wait_us = (double)pi[1] * 1e-3;
+    c->ms_exchange = (float)(c->peer_wait_us * 1e-3);
   }
+  return lite_pl_combine(d, c->n_global, c->int_length, theta, c->h_pinned, c->h_pinned + 128, c->h_sum_m.data(),
+                         c->h_sum_f.data(), lpl, grad, hess);
+}
+
+// No-exit candidates among those the last lite_pl_eval summed: a split or flip whose ray found
+// no edge to land on contributes an all-zero statistic row (e^0 = 1 to S0), a bias the caller
+// should know about.  Counted since the last lite_candidates_clear_splits / SetEnergy.
+extern "C" int lite_pl_failures(lite_ctx *c, int64_t *split_no_exit, int64_t *flip_no_exit) {
+  if (!c) return fail(LITE_EINVAL, "null context");
+  if (split_no_exit) *split_no_exit = c->fail_splits;
+  if (flip_no_exit) *flip_no_exit = c->fail_flips;
+  return 0;
+}
+
+// How lite_pl_eval combines the ranks: 0 single rank, 1 ncclAllReduce, 2 peer memory inside
+// k_reduce; exchange_ms = device time the last evaluation spent in that exchange (NCCL: the
+// allreduce; peer memory: push + wait for the slowest rank + sum, measured by the kernel).
+extern "C" int lite_comm_info(lite_ctx *c, int32_t *mode, float *exchange_ms) {
+  if (!c) return fail(LITE_EINVAL, "null context");
+  if (mode) *mode = c->world <= 1 ? 0 : (c->peer_on ? 2 : 1);
+  if (exchange_ms) *exchange_ms = c->ms_exchange;
   return 0;
 }
 

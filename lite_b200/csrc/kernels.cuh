@@ -1180,8 +1180,49 @@ struct RedSeg {
   double *partials; unsigned int *counter; double *out;
   int grid;
 };
+
+// Cross-GPU sum of the split sums, fused into the last block of k_reduce (the
+// one exchange step of the path, 1+d+d(d+1)/2 doubles).  Every rank owns a *mailbox* in its
+// HBM and maps its peers' mailboxes over NVLink (CUDA IPC, capi.cu: peer_setup).  Slot
+// (parity, source rank) of a mailbox holds LITE_BOX_SLOT doubles: the NT sums, and in the
+// last word the sequence number of the evaluation they belong to.  The finishing block
+// stores its sums into its slot of EVERY mailbox (its own included), fences, publishes the
+// sequence number, waits until all world slots of its own mailbox carry that number and
+// adds them in rank order — so every rank gets the bitwise identical total, with no kernel
+// launch and no host rendezvous on the critical path (an ncclAllReduce of 120 bytes there
+// cost a launch plus its small-message latency on every evaluation).  Two parities: rank A
+// can only reach evaluation s+2 after B has published s+1, i.e. after B has read s.
+#define LITE_MAX_WORLD 16
+#define LITE_BOX_SLOT 128
+#define LITE_BOX_DOUBLES (2 * LITE_MAX_WORLD * LITE_BOX_SLOT)
+struct PeerArgs {
+  int world, rank;
+  unsigned long long seq;          // this evaluation (>= 1, the same on every rank)
+  double *box[LITE_MAX_WORLD];     // mailbox of rank r as this GPU addresses it; box[rank] is local
+  unsigned long long *info;        // [0] set to seq when a wait timed out, [1] ns spent waiting for the peers
+};
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ size_t box_slot(int parity, int src_rank) {
+  return ((size_t)parity * LITE_MAX_WORLD + src_rank) * LITE_BOX_SLOT;
+}
+#ifndef LITE_PEER_TIMEOUT_NS
+#define LITE_PEER_TIMEOUT_NS 4000000000ull
+#endif
+
 template <int D>
-__global__ void __launch_bounds__(256) k_reduce(RedSeg A, RedSeg B, Theta th) {
+__global__ void __launch_bounds__(256) k_reduce(RedSeg A, RedSeg B, Theta th, PeerArgs P) {
   const bool second = (int)blockIdx.x >= A.grid;
   const double *__restrict__ stat = second ? B.stat : A.stat;
   const size_t cap = second ? B.cap : A.cap;
@@ -1270,14 +1311,46 @@ __global__ void __launch_bounds__(256) k_reduce(RedSeg A, RedSeg B, Theta th) {
     // fixed-order finish: warp w sums output t = w, w+8, ..; its lanes stride over the
     // blocks' partials and a shuffle tree combines them (same order every run)
     __threadfence();
+    __shared__ double fin[NT];
     for (int t = wid; t < NT; t += (blockDim.x >> 5)) {
       double v = 0;
       for (unsigned int b = lane; b < nblk; b += 32) v += __ldcg(partials + (size_t)b * NT + t);
 #pragma unroll
       for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-      if (lane == 0) out[t] = v;
+      if (lane == 0) fin[t] = v;
     }
     if (threadIdx.x == 0) *counter = 0;
+    __syncthreads();
+    if (second || P.world <= 1) {  // flips are replicated on every rank: nothing to exchange
+      if (threadIdx.x < NT) out[threadIdx.x] = fin[threadIdx.x];
+      return;
+    }
+    const int par = (int)(P.seq & 1ull);
+    unsigned long long t0 = 0;
+    if (threadIdx.x == 0) t0 = gtimer_ns();
+    for (int idx = threadIdx.x; idx < P.world * NT; idx += blockDim.x) {
+      const int r = idx / NT, t = idx - r * NT;
+      *(volatile double *)(P.box[r] + box_slot(par, P.rank) + t) = fin[t];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < P.world) {
+      const int r = threadIdx.x;
+      st_release_sys((unsigned long long *)(P.box[r] + box_slot(par, P.rank) + (LITE_BOX_SLOT - 1)), P.seq);
+      const unsigned long long *mine =
+          (const unsigned long long *)(P.box[P.rank] + box_slot(par, r) + (LITE_BOX_SLOT - 1));
+      const unsigned long long w0 = gtimer_ns();
+      while (ld_acquire_sys(mine) < P.seq) {
+        if (gtimer_ns() - w0 > LITE_PEER_TIMEOUT_NS) { atomicExch(P.info, P.seq); break; }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < NT) {
+      double v = 0;
+      for (int r = 0; r < P.world; r++) v += __ldcg(P.box[P.rank] + box_slot(par, r) + threadIdx.x);
+      out[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) P.info[1] = gtimer_ns() - t0;
   }
 }
 

@@ -529,3 +529,61 @@ def test_host_generated_non_convex_window_against_cpu_port(lite):
     _assert_stats("merge", ctx.fetch("MERGE_STAT"), m["merge_stat"], ALL12, term_scale=True)
     _assert_stats("flip", ctx.fetch("FLIP_STAT"), f["flip_stat"], ALL12, term_scale=True)
     ctx.close()
+
+
+def test_benched_kernel_instantiation_is_value_checked(lite):
+    """bench.py times k_split<philox|stat, ProgACS> with NO record.  (i) With the record
+    on (the instantiation every integer parity test reads) the evaluation is bit-identical,
+    for the compile-time ACS program and for a run-time program; (ii) the record-off
+    evaluation agrees with the CPU port's pl_pass on the same seed / offset / batch."""
+    import oracle_cpu as oc
+    t, _tau = lite.generate_crtt(10000, seed=5)
+    soa = t.export()
+    n, seed, off = 1_000_001, 0x5EED, 12345
+    th = np.array([11 / np.pi, 12.0 ** 4 * 0.05, 1.0, -np.log(12.0)])
+    res = {}
+    for feats, theta in ((ACS, th), (ACS[1:], th[1:])):
+        for rec in (False, True):
+            ctx = _ctx(lite, soa.a | {"int_length": soa.int_length}, feats, record=rec)
+            ctx.merges_flips()
+            ctx.add_splits_philox(n, seed, off)
+            res[(len(feats), rec)] = ctx.pl_eval(theta)
+            assert ctx.pl_failures() == (0, 0)
+            ctx.close()
+        a, b = res[(len(feats), False)], res[(len(feats), True)]
+        assert a[0] == b[0]
+        np.testing.assert_array_equal(a[1], b[1])
+        np.testing.assert_array_equal(a[2], b[2])
+    arrays = dict(soa.a)
+    arrays["int_length"] = soa.int_length
+    v, g, H = oc.pl_pass(oc.Tess(arrays), ACS, th, n, seed, off, oc.hardware_threads())
+    lpl, gg, HH = res[(4, False)]
+    assert lpl == pytest.approx(v, rel=RTOL)
+    np.testing.assert_allclose(gg, g, rtol=RTOL, atol=RTOL * np.abs(g).max())
+    np.testing.assert_allclose(HH, H, rtol=RTOL, atol=RTOL * np.abs(H).max())
+
+
+def test_failed_upload_leaves_no_tessellation(lite):
+    """A rejected lite_tess_upload must not leave the previous tessellation half replaced:
+    every later call that needs one fails with a state error instead of reading stale views."""
+    soa, gold = load_golden("t100")
+    ctx = _ctx(lite, soa, ACS, record=False)
+    ctx.merges_flips()
+    ctx.add_splits_given(gold["cand_he"][:100], gold["cand_x"][:100], gold["cand_angle"][:100])
+    ctx.pl_eval(gold["pl_acs_1_theta"])
+    small, _ = load_golden("t11")
+    bad = dict(small)
+    bad["int_length"] = float(small["int_length"]) + 1.0
+    with pytest.raises(lite.LiteError):
+        ctx.tess_upload(lite.TessSoA(bad))
+    for call in (ctx.merges_flips, lambda: ctx.add_splits_given(gold["cand_he"][:4], gold["cand_x"][:4], gold["cand_angle"][:4]),
+                 lambda: ctx.add_splits_philox(10, 1, 0), lambda: ctx.pl_eval(gold["pl_acs_1_theta"])):
+        with pytest.raises(lite.LiteError, match="upload a tessellation"):
+            call()
+    assert ctx.count() == (0, 0)
+    # and the context recovers with a good upload
+    ctx.tess_upload(lite.TessSoA(soa))
+    ctx.merges_flips()
+    ctx.add_splits_given(gold["cand_he"], gold["cand_x"], gold["cand_angle"])
+    assert ctx.pl_eval(gold["pl_acs_1_theta"])[0] == pytest.approx(float(gold["pl_acs_1_lpl"]), rel=RTOL)
+    ctx.close()

@@ -172,3 +172,15 @@ def test_host_model_on_a_non_convex_window():
     h2.check()
     assert h2.counts() == h.counts()
     assert _cells_from_soa(h2.export().a) == _cells_from_soa(a)
+
+
+def test_bench_fixture_is_the_generated_c2_tessellation():
+    """bench.py's CPU arm loads tests/golden/c2_soa.npz (numpy only, no product library); the GPU
+    arm generates its input with generate_crtt(10000, seed=5).  They must be the same tessellation."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c2_soa.npz"))
+    t, _tau = lite_b200.generate_crtt(10000, seed=5)
+    soa = t.export()
+    assert float(z["int_length"]) == soa.int_length
+    for k, v in soa.a.items():
+        np.testing.assert_array_equal(z[k], v, err_msg=k)

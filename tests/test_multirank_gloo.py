@@ -1,23 +1,37 @@
-"""World-size-2 test of the N > 1 path on CPU (gloo): the candidate batch is cut
-into the contiguous shards `lite_b200.shard_range` gives (the partition
-lite_candidates_add_splits_philox uses on each rank), every rank evaluates its
-shard with the CPU port of the oracle, one all_reduce(SUM) combines the packed
-[lpl, grad, hess] buffer — the role ncclAllReduce plays inside lite_pl_eval — and
-the result must equal the single-rank evaluation of the whole batch, with the
-GLOBAL number of splits in the normaliser (reference lib/ttessel.cpp:3396)."""
+"""World-size-2 test of the host logic of the N > 1 path, on CPU (gloo).
+
+What it covers: the product's own shard arithmetic (`lite_shard_range`, the partition
+`lite_candidates_add_splits_philox` applies on each rank) and the product's own final
+arithmetic (`lite_pl_combine`, the tail of `lite_pl_eval`: global |S| in the normaliser,
+reference lib/ttessel.cpp:3396; merges and flips replicated on every rank and NOT summed
+across ranks), with the per-candidate statistics supplied by the CPU port of the oracle and
+gloo's all_reduce standing in for the cross-GPU sum of the 1+d+d(d+1)/2 split sums.
+
+What it does not cover: the kernels, the NCCL communicator and the peer-memory exchange in
+k_reduce — those need GPUs; tests/test_gpu_multirank.py is the gate for them (two ranks equal
+one rank, an empty shard, both exchange paths) wherever two devices exist."""
 import os
 import sys
 
 import numpy as np
-import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 ACS = ["edge_length", "face_area_2", "face_sum_of_angles", "is_segment_internal"]
-N, SEED, OFF = 4001, 0x5EED, 17   # odd on purpose: uneven shards
+SEED, OFF = 0x5EED, 17
 
 
-def _worker(rank, world, port, out_path):
+def packed_sums(theta, stat):
+    """[S0, S1_k, S2_kl (k<=l)] of a statistic block, the layout k_reduce produces."""
+    d = len(theta)
+    e = np.exp(stat @ theta) if len(stat) else np.zeros(0)
+    out = [e.sum()]
+    out += [(e * stat[:, k]).sum() for k in range(d)]
+    out += [(e * stat[:, k] * stat[:, l]).sum() for k in range(d) for l in range(k, d)]
+    return np.array(out)
+
+
+def _worker(rank, world, port, out_dir, n_total):
     for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -31,52 +45,71 @@ def _worker(rank, world, port, out_path):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     soa, gold = load_golden("t100")
     t = oc.Tess(soa)
-    th = gold["pl_acs_1_theta"]
+    th = np.asarray(gold["pl_acs_1_theta"], dtype=np.float64)
     d = len(ACS)
-    j0, cnt = lite_b200.shard_range(N, rank, world)
-    he, x, ang = oc.sample_splits(t, N, SEED, OFF, j0=j0, n=cnt)
-    ss = oc.split_stats(t, ACS, he, x, ang)["split_stat"]
-    if rank == 0:  # merges and flips are not sharded: one rank contributes them
-        ms = oc.merge_stats(t, ACS)["merge_stat"]
-        fs = oc.flip_stats(t, ACS)["flip_stat"]
+    j0, cnt = lite_b200.shard_range(n_total, rank, world)          # the product's partition
+    if cnt:
+        he, x, ang = oc.sample_splits(t, n_total, SEED, OFF, j0=j0, n=cnt)
+        ss = oc.split_stats(t, ACS, he, x, ang)["split_stat"]
     else:
-        ms, fs = np.zeros((0, d)), np.zeros((0, d))
-    v, g, H = oc.pl(th, ss, fs, ms.sum(0) if len(ms) else np.zeros(d), fs.sum(0) if len(fs) else np.zeros(d),
-                    float(soa["int_length"]), n_global=N)
-    buf = torch.tensor(np.concatenate([[v], g, H.ravel()]), dtype=torch.float64)
-    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
-    if rank == 0:
-        np.save(out_path, np.concatenate([[float(cnt)], buf.numpy()]))
+        ss = np.zeros((0, d))
+    # merges and flips: evaluated on EVERY rank, as lite_candidates_merges_flips does
+    ms = oc.merge_stats(t, ACS)["merge_stat"]
+    fs = oc.flip_stats(t, ACS)["flip_stat"]
+    S = torch.tensor(packed_sums(th, ss), dtype=torch.float64)
+    dist.all_reduce(S, op=dist.ReduceOp.SUM)                         # the only exchange of the path
+    lpl, g, H = lite_b200.pl_combine(th, n_total, float(soa["int_length"]), S.numpy(), packed_sums(th, fs),
+                                     ms.sum(0), fs.sum(0))
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), cnt=cnt, lpl=lpl, g=g, H=H)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_shards_allreduce_equals_single_rank(tmp_path):
-    import torch.multiprocessing as mp
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import lite_b200
+def _single(n_total):
     import oracle_cpu as oc
     from util import load_golden
-    # shards tile the batch exactly
-    for n in (0, 1, 7, N):
+    soa, gold = load_golden("t100")
+    t = oc.Tess(soa)
+    th = gold["pl_acs_1_theta"]
+    he, x, ang = oc.sample_splits(t, n_total, SEED, OFF)
+    ss = oc.split_stats(t, ACS, he, x, ang)["split_stat"]
+    ms = oc.merge_stats(t, ACS)["merge_stat"]
+    fs = oc.flip_stats(t, ACS)["flip_stat"]
+    return oc.pl(th, ss, fs, ms.sum(0), fs.sum(0), float(soa["int_length"]))
+
+
+def _run(tmp_path, n_total, salt):
+    import torch.multiprocessing as mp
+    port = 29500 + ((os.getpid() + salt) % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), n_total), nprocs=2, join=True)
+    return [np.load(str(tmp_path / ("r%d.npz" % r))) for r in (0, 1)]
+
+
+def test_shards_tile_the_batch():
+    import lite_b200
+    for n in (0, 1, 7, 4001, 10 ** 8 + 1):
         for w in (1, 2, 3, 8):
             parts = [lite_b200.shard_range(n, r, w) for r in range(w)]
             assert parts[0][0] == 0 and sum(c for _, c in parts) == n
             assert all(parts[r][0] + parts[r][1] == parts[r + 1][0] for r in range(w - 1))
-    out = str(tmp_path / "r0.npy")
-    port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
-    got = np.load(out)
-    assert got[0] == N // 2  # rank 0 holds [0, N/2)
-    soa, gold = load_golden("t100")
-    t = oc.Tess(soa)
-    th = gold["pl_acs_1_theta"]
-    he, x, ang = oc.sample_splits(t, N, SEED, OFF)
-    ss = oc.split_stats(t, ACS, he, x, ang)["split_stat"]
-    ms = oc.merge_stats(t, ACS)["merge_stat"]
-    fs = oc.flip_stats(t, ACS)["flip_stat"]
-    v, g, H = oc.pl(th, ss, fs, ms.sum(0), fs.sum(0), float(soa["int_length"]))
-    d = len(ACS)
-    want = np.concatenate([[v], g, H.ravel()])
-    scale = np.maximum(1.0, np.abs(want).max())
-    np.testing.assert_allclose(got[1:], want, rtol=1e-9, atol=1e-12 * scale)
+            assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def test_two_rank_shards_equal_single_rank(tmp_path):
+    n_total = 4001                                # odd on purpose: uneven shards
+    r0, r1 = _run(tmp_path, n_total, 0)
+    assert int(r0["cnt"]) == n_total // 2 and int(r0["cnt"]) + int(r1["cnt"]) == n_total
+    v, g, H = _single(n_total)
+    for r in (r0, r1):                            # every rank holds the combined result
+        assert abs(float(r["lpl"]) - v) <= 1e-9 * abs(v)
+        np.testing.assert_allclose(r["g"], g, rtol=1e-9, atol=1e-12 * max(1.0, np.abs(g).max()))
+        np.testing.assert_allclose(r["H"], H, rtol=1e-9, atol=1e-12 * max(1.0, np.abs(H).max()))
+    assert float(r0["lpl"]) == float(r1["lpl"])
+
+
+def test_empty_shard_on_one_rank(tmp_path):
+    r0, r1 = _run(tmp_path, 1, 1)                 # one split in all: rank 0 holds none
+    assert int(r0["cnt"]) == 0 and int(r1["cnt"]) == 1
+    v, g, H = _single(1)
+    assert abs(float(r0["lpl"]) - v) <= 1e-9 * abs(v)
+    np.testing.assert_allclose(r0["H"], H, rtol=1e-9, atol=1e-12 * max(1.0, np.abs(H).max()))
