@@ -666,6 +666,7 @@ def run_secondary(ctx, lite_b200, soa_c2, fp64_peak, hbm_peak):
         pass
     # ---- config 2 as BASELINE.json words it: the Newton fit ----------------------------
     try:
+        ctx.clear_splits()
         ctx.energy_set(ACS3)
         n_fit = 10_000_000
         newton_fit(ctx, 200_000, [0.0, 0.0, 0.0], 1)             # warm-up: allocations, module load
@@ -688,6 +689,7 @@ def run_secondary(ctx, lite_b200, soa_c2, fp64_peak, hbm_peak):
                          "note": "passes alternate direction, so the end of the 240 MB block the previous pass "
                                  "touched last is still in the 126 MB L2: above 1 means L2 hits, not faster HBM"},
         }
+        ctx.clear_splits()
         ctx.energy_set(ACS)
     except Exception as e:  # a secondary entry must never take the headline down
         out["c2_newton_fit"] = {"error": repr(e)}
@@ -864,13 +866,16 @@ def run_pl(args, rank, local_rank, world, nccl_id, dist, torch):
     # ---- device-resident arm -------------------------------------------------
     for k in range(args.warmup):
         step(k)
-    barrier()
-    # clocks: one sampling thread in the whole job (rank 0's GPU stands for the box; every
-    # rank polling NVML every few ms was one suspect for the host jitter each step's exchange pays)
+    # Clocks: one sampling thread in the whole job, on rank 0 (its GPU stands for the box), created
+    # and started BEFORE the barrier.  nvmlInit takes milliseconds; in round 1 every rank ran it
+    # between the barrier and its first timed step, so the ranks entered the loop up to ~7 ms apart
+    # at N=8 and the first step's exchange absorbed that skew (0.37 ms per step over 20 steps: the
+    # whole of the 0.54 weak-scaling efficiency the driver measured).
     which = os.environ.get("LITE_BENCH_SAMPLER", "rank0")
     sampler = ClockSampler(local_rank) if (which == "all" or (which == "rank0" and rank == 0)) else None
     if sampler:
         sampler.start()
+    barrier()
     l0 = ctx.launch_count()
     ms_split = ms_reduce = ms_mf = ms_exch = 0.0
     host_ms = []
