@@ -2256,8 +2256,8 @@ def export_soa(t):
         inside.append(1 if f.data else 0)
         off.append(len(lst))
         if f.data:
-            if f.holes:
-                raise ValueError("export_soa: face with holes (outside the hot-path scope)")
+            # only outer_ccb() is listed (the layout of lite_tess_soa): the inner boundaries of
+            # a face with holes are the other halfedges whose face it is
             c = ccb(f.outer)
             lst.extend(hid[id(h)] for h in c)
             cnt.append(len(c))
