@@ -21,6 +21,7 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include "kernels.cuh"
+#include "gen_kernels.cuh"
 
 // NVTX range over one C-ABI call (header-only NVTX 3: a no-op unless a profiler is attached)
 struct NvtxRange {
@@ -196,6 +197,16 @@ struct lite_ctx {
   DBuf<int2> sfo;
   DBuf<uint32_t> flg;
   DBuf<int> slot_he, slot_seg, slot_face, he_slot, guide, err;
+  // faces that are not simple polygons (windows with holes): gen_face.h / gen_kernels.cuh
+  int n_general = 0;                 // how many the uploaded tessellation has
+  gen::Cycles cyc;                   // their boundary cycles (host)
+  std::vector<int> x_off, x_cnt, x_list;   // per-face halfedge lists extended by the inner boundaries
+  std::vector<uint8_t> x_gen;
+  DBuf<int> g_outer, g_hole_off, g_hole_cnt, g_hole_he;
+  DBuf<uint8_t> g_fgen;
+  gen::Tess GT{};
+  gen::Pt *gen_scratch = nullptr;    // LITE_GEN_PTS points per thread of the general kernels
+  int gen_blocks = 0;
   Arena arena;
   struct PackJob { char *dst; const void *src; size_t bytes; };
   std::vector<PackJob> pack_jobs;  // host->pinned copies of one upload, run on a few threads
@@ -394,6 +405,8 @@ extern "C" int lite_ctx_destroy(lite_ctx *c) {
   smf_release(c);
   peer_release(c);
   c->peer_info.release();
+  if (c->gen_scratch) cudaFree(c->gen_scratch);
+  c->g_outer.release(); c->g_hole_off.release(); c->g_hole_cnt.release(); c->g_hole_he.release(); c->g_fgen.release();
   if (c->pool) { c->pool->shutdown(); delete c->pool; c->pool = nullptr; }
   if (c->stream2) cudaStreamSynchronize(c->stream2);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
@@ -496,8 +509,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   if (nH <= 0 || nF <= 0 || nS <= 0 || nV <= 0 || s->n_face_he <= 0 || s->n_non_blocking < 0 || s->n_blocking < 0)
     return fail(LITE_EINVAL, "empty tessellation or negative counts");
   // ---- copies: everything is packed into one pinned block and sent in one transfer
-  int n_guide = 1;
-  while (n_guide < 2 * s->n_face_he) n_guide <<= 1;
+  int n_guide = 1;  // sized once the number of slots is known
   {
     size_t need = 0;
     need += 2 * align256((size_t)nV * 8);
@@ -506,6 +518,8 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
     need += 3 * align256((size_t)nS * 4) + align256((size_t)nS);
     need += align256((size_t)(s->n_non_blocking + 1) * 4) + align256((size_t)(s->n_blocking + 1) * 4);
     need += align256((size_t)s->n_face_he * 8) + 64 * 256;
+    // room for the extended lists of a tessellation with holes (staged only if it has any)
+    need += 2 * align256((size_t)nH * 4) + align256((size_t)nH * 8) + 5 * align256((size_t)nF * 4) + align256((size_t)nF);
     int ra = arena_reserve(c, need);
     if (ra) return ra;
   }
@@ -531,10 +545,10 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   // is part of the sampler's definition).
   const int nt = 4;
   std::vector<int> bad_face(nt, -1), bad_he(nt, -1), bad_list_f(nt, -1), bad_list_k(nt, -1);
-  std::vector<int64_t> part_listed(nt, 0), part_inside(nt, 0);
+  std::vector<int64_t> part_listed(nt, 0), part_inside(nt, 0), part_twice(nt, 0);
   c->h_he_inside.assign(nH, 0);
   {
-      c->pool->run([=, &bad_face, &bad_he, &bad_list_f, &bad_list_k, &part_listed, &part_inside](int t) {
+      c->pool->run([=, &bad_face, &bad_he, &bad_list_f, &bad_list_k, &part_listed, &part_inside, &part_twice](int t) {
         for (size_t k = t; k < c->pack_jobs.size(); k += nt) memcpy(c->pack_jobs[k].dst, c->pack_jobs[k].src, c->pack_jobs[k].bytes);
         // faces [f0, f1): list ranges, and the list of an inside face is its ccb
         const int f0 = (int)((int64_t)nF * t / nt), f1 = (int)((int64_t)nF * (t + 1) / nt);
@@ -554,7 +568,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
         part_listed[t] = listed;
         // halfedges [h0, h1): links in range, twin of twin
         const int h0 = (int)((int64_t)nH * t / nt), h1 = (int)((int64_t)nH * (t + 1) / nt);
-        int64_t inside = 0;
+        int64_t inside = 0, twice = 0;
         for (int h = h0; h < h1; h++) {
           const int f = s->he_face[h], tw = s->he_twin[h];
           if (f < 0 || f >= nF || tw < 0 || tw >= nH || s->he_twin[tw] != h || s->he_src[h] < 0 ||
@@ -562,8 +576,10 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
           if (!s->face_inside[f]) continue;
           inside++;
           c->h_he_inside[h] = 1;
+          if (s->he_face[tw] == f) twice++;   // the face runs along both sides of this edge
         }
         part_inside[t] = inside;
+        part_twice[t] = twice;
       });
   }
   struct Joiner { HostPool *p; ~Joiner() { p->wait(); } } joiner{c->pool};  // the job reads this frame
@@ -585,19 +601,61 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
     }
   }
   c->pool->wait();
-  int64_t listed = 0, inside_he = 0;
+  int64_t listed = 0, inside_he = 0, twice = 0;
   for (int t = 0; t < nt; t++) {
     if (bad_face[t] >= 0) return fail(LITE_EINVAL, "face %d: halfedge list out of range or fewer than 3 halfedges", bad_face[t]);
     if (bad_list_f[t] >= 0)
       return fail(LITE_EINVAL, "face %d: halfedge list disagrees with he_next/he_face at position %d", bad_list_f[t], bad_list_k[t]);
     if (bad_he[t] >= 0) return fail(LITE_EINVAL, "halfedge %d: inconsistent links", bad_he[t]);
-    listed += part_listed[t]; inside_he += part_inside[t];
+    listed += part_listed[t]; inside_he += part_inside[t]; twice += part_twice[t];
   }
-  if (inside_he != listed)
-    return fail(LITE_EINVAL,
-                "%lld halfedges bound inside faces but %lld are listed on outer boundaries: faces with "
-                "holes are outside the scope of this library",
+  if (inside_he < listed)
+    return fail(LITE_EINVAL, "%lld halfedges bound inside faces but %lld are listed on outer boundaries",
                 (long long)inside_he, (long long)listed);
+  // Faces that are not simple polygons: more halfedges bound inside faces than the outer
+  // boundaries list (inner boundaries: holes), or a face lies on both sides of an edge.  Their
+  // slots are the outer boundary followed by the inner ones, their candidates go through
+  // gen_face.h.  A rectangular window never has any and skips all of this.
+  const bool general = inside_he != listed || twice != 0;
+  c->n_general = 0;
+  const int32_t *l_off = s->face_he_offset, *l_cnt = s->face_he_count, *l_list = s->face_he_list;
+  size_t n_slots = (size_t)s->n_face_he;
+  if (general) {
+    gen::derive_cycles(nH, nF, s->he_next, s->he_face, s->he_twin, s->face_inside, s->face_he_offset,
+                       s->face_he_count, s->face_he_list, c->cyc);
+    c->n_general = c->cyc.n_general;
+    c->x_off.assign(nF, 0); c->x_cnt.assign(nF, 0); c->x_gen.assign(nF, 0);
+    c->x_list.clear();
+    c->x_list.reserve((size_t)inside_he);
+    for (int f = 0; f < nF; f++) {
+      c->x_off[f] = (int)c->x_list.size();
+      if (!s->face_inside[f]) continue;
+      bool tw = false;
+      for (int k = 0; k < s->face_he_count[f]; k++) {
+        const int h = s->face_he_list[s->face_he_offset[f] + k];
+        c->x_list.push_back(h);
+        tw |= s->he_face[s->he_twin[h]] == f;
+      }
+      for (int q = 0; q < c->cyc.f_hole_cnt[f]; q++) {
+        const int h0 = c->cyc.hole_he[c->cyc.f_hole_off[f] + q];
+        int h = h0, guard = 0;
+        do { c->x_list.push_back(h); h = s->he_next[h]; } while (h != h0 && ++guard < nH);
+      }
+      c->x_cnt[f] = (int)c->x_list.size() - c->x_off[f];
+      c->x_gen[f] = (c->cyc.f_hole_cnt[f] > 0 || tw) ? 1 : 0;
+    }
+    if ((int64_t)c->x_list.size() != inside_he)
+      return fail(LITE_EINVAL, "boundary cycles of the inside faces hold %zu halfedges, %lld bound inside faces",
+                  c->x_list.size(), (long long)inside_he);
+    l_off = c->x_off.data(); l_cnt = c->x_cnt.data(); l_list = c->x_list.data();
+    n_slots = c->x_list.size();
+    // the sampler's cumulative lengths over the extended slots
+    cum.assign(n_slots, 0.0);
+    cl = 0.0;
+    for (int f = 0; f < nF; f++)
+      for (int k = 0; k < l_cnt[f]; k++) { cl += s->he_length[l_list[l_off[f] + k]]; cum[(size_t)l_off[f] + k] = cl; }
+  }
+  while (n_guide < 2 * (int)n_slots) n_guide <<= 1;
   if (!(fabs(cl - s->int_length) <= 1e-9 * fmax(1.0, fabs(cl))))
     return fail(LITE_EINVAL, "int_length %.17g differs from the sum of inside halfedge lengths %.17g",
                 s->int_length, cl);
@@ -614,6 +672,15 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   t1 = now_ms();
   c->pack_jobs.clear();
   r |= up(c, c->cum, cum.data(), cum.size());
+  if (general) {  // the extended lists replace the caller's, the cycles go along
+    r |= up(c, c->f_off, l_off, (size_t)nF); r |= up(c, c->f_cnt, l_cnt, (size_t)nF);
+    r |= up(c, c->f_list, l_list, n_slots);
+    r |= up(c, c->g_outer, c->cyc.f_outer.data(), (size_t)nF);
+    r |= up(c, c->g_hole_off, c->cyc.f_hole_off.data(), (size_t)nF);
+    r |= up(c, c->g_hole_cnt, c->cyc.f_hole_cnt.data(), (size_t)nF);
+    r |= up(c, c->g_hole_he, c->cyc.hole_he.data(), c->cyc.hole_he.size());
+    r |= up(c, c->g_fgen, c->x_gen.data(), (size_t)nF);
+  }
   if (c->guide.alloc((size_t)n_guide)) return LITE_ECUDA;
   if (r) return r;
   for (size_t k = 0; k < c->pack_jobs.size(); k++) memcpy(c->pack_jobs[k].dst, c->pack_jobs[k].src, c->pack_jobs[k].bytes);
@@ -622,7 +689,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   CU(cudaMemcpyAsync(c->arena.d, c->arena.h, c->arena.used, cudaMemcpyHostToDevice, c->stream));
   CU(cudaEventRecord(c->ev_upload, c->stream));
   c->upload_inflight = true;
-  const size_t nSl = (size_t)s->n_face_he;
+  const size_t nSl = n_slots;
   if (c->pt.alloc(nSl) || c->ang.alloc(nSl) || c->len.alloc(nSl) || c->ca.alloc(nSl) ||
       c->flg.alloc(nSl) || c->slot_he.alloc(nSl) || c->slot_seg.alloc(nSl) ||
       c->slot_face.alloc(nSl) || c->he_slot.alloc(nH) || c->f_area.alloc(nF) ||
@@ -632,10 +699,12 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   CU(cudaMemsetAsync(c->he_slot.p, 0xFF, nH * sizeof(int), c->stream));
   CU(cudaMemsetAsync(c->err.p, 0, sizeof(int), c->stream));
   CU(cudaMemsetAsync(c->status.p, 0, 2 * sizeof(unsigned long long), c->stream));  // no-exit counters
+  CU(cudaMemsetAsync(c->status.p + 6, 0, sizeof(unsigned long long), c->stream));  // general-face scratch overflows
   PrepArgs A{};
   A.vx = c->vx.p; A.vy = c->vy.p; A.he_src = c->he_src.p; A.he_twin = c->he_twin.p;
   A.he_next = c->he_next.p; A.he_face = c->he_face.p; A.he_seg = c->he_seg.p;
   A.he_next_hf = c->he_next_hf.p; A.he_dir = c->he_dir.p; A.face_inside = c->face_inside.p;
+  A.f_gen = general ? c->g_fgen.p : nullptr;
   A.he_length = c->he_length.p; A.face_he_offset = c->f_off.p; A.face_he_count = c->f_cnt.p;
   A.face_he_list = c->f_list.p; A.n_faces = nF;
   A.pt = c->pt.p; A.ang = c->ang.p; A.len = c->len.p; A.ca = c->ca.p; A.flg = c->flg.p;
@@ -647,13 +716,26 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   T.slot_he = c->slot_he.p; T.slot_seg = c->slot_seg.p; T.slot_face = c->slot_face.p;
   T.he_slot = c->he_slot.p; T.he_twin = c->he_twin.p; T.he_src = c->he_src.p;
   T.he_next_hf = c->he_next_hf.p; T.he_prev_hf = c->he_prev_hf.p;
-  T.f_off = c->f_off.p; T.f_cnt = c->f_cnt.p;
+  T.f_off = c->f_off.p; T.f_cnt = c->f_cnt.p; T.f_gen = general ? c->g_fgen.p : nullptr;
   T.f_area = c->f_area.p; T.f_perim = c->f_perim.p; T.f_sumang = c->f_sumang.p; T.f_minang = c->f_minang.p;
   T.seg_n_edges = c->seg_n_edges.p; T.seg_he_start = c->seg_he_start.p; T.seg_he_end = c->seg_he_end.p;
   T.seg_bnd = c->seg_bnd.p;
   T.cum = c->cum.p; T.guide = c->guide.p; T.n_cum = (int)cum.size(); T.n_guide = n_guide;
   T.total_len = cl; T.guide_scale = (double)n_guide / cl;
   T.sfo = c->sfo.p; T.pre = c->pre.p; T.plen = c->plen.p; T.f_tot2 = c->f_tot2.p; T.stot2 = c->stot2.p;
+  if (general) {
+    gen::Tess &GT = c->GT;
+    GT.n_he = nH; GT.n_faces = nF; GT.vx = c->vx.p; GT.vy = c->vy.p;
+    GT.he_src = c->he_src.p; GT.he_twin = c->he_twin.p; GT.he_next = c->he_next.p; GT.he_face = c->he_face.p;
+    GT.he_seg = c->he_seg.p; GT.he_next_hf = c->he_next_hf.p; GT.he_prev_hf = c->he_prev_hf.p;
+    GT.he_dir = c->he_dir.p; GT.face_inside = c->face_inside.p; GT.seg_bnd = c->seg_bnd.p;
+    GT.seg_n_edges = c->seg_n_edges.p; GT.f_outer = c->g_outer.p; GT.f_hole_off = c->g_hole_off.p;
+    GT.f_hole_cnt = c->g_hole_cnt.p; GT.hole_he = c->g_hole_he.p;
+    if (!c->gen_scratch) {
+      c->gen_blocks = c->sm_count;
+      CU(cudaMalloc((void **)&c->gen_scratch, (size_t)c->gen_blocks * LITE_GEN_TB * LITE_GEN_PTS * sizeof(gen::Pt)));
+    }
+  }
   int tb = 128, gb = (nF + tb - 1) / tb;
   k_build_guide<<<(n_guide + 255) / 256, 256, 0, c->stream>>>(c->cum.p, (int)cum.size(), cl / (double)n_guide, n_guide, c->guide.p);
   CU(cudaMemsetAsync(c->slot_face.p, 0xFF, nSl * sizeof(int), c->stream));
@@ -769,6 +851,10 @@ extern "C" int lite_candidates_merges_flips(lite_ctx *c, int32_t *n_merges, int3
     A.nb_seg = c->nb_list.p; A.nm = nm; A.mstat = c->mstat.p; A.m_he = c->m_he.p; A.gm = (nm + 127) / 128;
     A.b_seg = c->b_list.p; A.nb = c->n_b; A.fstat = c->fstat.p; A.f_e1 = c->fl_e1.p; A.f_e2 = c->fl_e2.p;
     A.f_right = c->fl_right.p; A.f_p2 = c->fl_p2.p; A.status = c->status.p + 1; A.part = c->sums.p;
+    if (c->n_general > 0) {  // rows of the merges / flips next to a face with holes, first
+      k_gen_mf<<<c->gen_blocks, LITE_GEN_TB, 0, c->stream2>>>(c->T, c->GT, c->G, A, c->gen_scratch, c->status.p + 6);
+      c->launches += 1;
+    }
     k_merges_flips<<<blocks, 128, 0, c->stream2>>>(c->T, c->G, A);
     c->launches += 1;
   }
@@ -848,6 +934,13 @@ static void launch_split(lite_ctx *c, const Prog &G, const SplitArgs &A, int gri
   if ((MODE & 4) && prog_is_acs(G)) k_split<MODE, ProgACS><<<grid, LITE_SPLIT_TB, 0, c->stream>>>(c->T, G, A);
   else k_split<MODE, ProgDyn><<<grid, LITE_SPLIT_TB, 0, c->stream>>>(c->T, G, A);
   c->launches += 1;
+  if (c->n_general > 0) {  // the candidates on faces with holes, which k_split left out
+    GenSplitArgs X{};
+    X.A = A; X.philox = MODE & 1; X.record = (MODE & 2) ? 1 : 0; X.stat = (MODE & 4) ? 1 : 0; X.check = (MODE & 8) ? 1 : 0;
+    X.scratch = c->gen_scratch; X.overflow = c->status.p + 6;
+    k_gen_splits<<<c->gen_blocks, LITE_GEN_TB, 0, c->stream>>>(c->T, c->GT, G, X);
+    c->launches += 1;
+  }
 }
 
 static void fill_split_args(lite_ctx *c, SplitArgs &A) {
@@ -1094,6 +1187,7 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
   // geometric failures of the candidates behind these sums (no exit edge found): they ride
   // back with the results, see lite_pl_failures
   CU(cudaMemcpyAsync(c->h_pinned + 256, c->status.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->h_pinned + 258, c->status.p + 6, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   if (exch) CU(cudaMemcpyAsync(c->h_pinned + 260, c->peer_info.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
@@ -1107,6 +1201,9 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
   {
     const unsigned long long *st = (const unsigned long long *)(c->h_pinned + 256);
     c->fail_splits = (int64_t)st[0]; c->fail_flips = (int64_t)st[1];
+    if (st[2] != 0)
+      return fail(LITE_ECAPACITY, "%llu candidates on faces with holes needed polygons of more than %d vertices",
+                  st[2], LITE_GEN_PTS);
   }
   if (exch) {
     const unsigned long long *pi = (const unsigned long long *)(c->h_pinned + 260);

@@ -784,8 +784,8 @@ GEN_HD inline void flip_general(const Tess &T, const Prog &G, Scratch &S, int e1
 }
 
 
-#if !defined(__CUDA_ARCH__)
 }  // namespace gen
+#include <utility>
 #include <vector>
 namespace gen {
 // Boundary cycles of the inside faces from the uploaded arrays (host, once per upload): the
@@ -829,6 +829,5 @@ inline void derive_cycles(int n_he, int n_faces, const int *he_next, const int *
   for (int f = 0; f < n_faces; f++)
     if (face_inside[f] && (C.f_hole_cnt[f] > 0 || twice[f])) C.n_general++;
 }
-#endif
 
 }  // namespace gen

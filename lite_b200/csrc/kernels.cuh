@@ -29,6 +29,7 @@
 #define SF_CORNER 1u  // the source vertex of the slot is a polygon corner of its face
 #define SF_BND 2u     // the halfedge lies on the window boundary
 #define SF_DIR 4u     // LineTes_halfedge::get_dir()
+#define SF_GENERAL 8u // the face has holes or bounds an edge on both sides: gen_face.h evaluates it
 
 struct TessDev {
   int n_slots, n_faces, n_he, n_seg;
@@ -46,6 +47,7 @@ struct TessDev {
   const int *he_slot, *he_twin, *he_src, *he_next_hf, *he_prev_hf;
   // per face
   const int *f_off, *f_cnt;
+  const uint8_t *f_gen;  // 1 = not a simple polygon (holes, doubly-bounded edges); null if the tessellation has none
   const double *f_area, *f_perim, *f_sumang, *f_minang;
   const double *f_tot2;  // whole-face shoelace sum (twice the area) by the same prefix summation
   const double *stot2;   // the same, copied to every slot of the face
@@ -216,6 +218,7 @@ struct PrepArgs {
   const double *vx, *vy;
   const int *he_src, *he_twin, *he_next, *he_face, *he_seg, *he_next_hf;
   const uint8_t *he_dir, *face_inside;
+  const uint8_t *f_gen;  // null when every face is a simple polygon
   const double *he_length;
   const int *face_he_offset, *face_he_count, *face_he_list;
   int n_faces;
@@ -244,9 +247,24 @@ __global__ void k_prep_slots(PrepArgs A, int n_slots) {
   if (f < 0) return;  // a slot of an outside face
   const int n = A.face_he_count[f], off = A.face_he_offset[f], k = m - off;
   int h = A.face_he_list[off + k];
-  int hp = A.face_he_list[off + (k == 0 ? n - 1 : k - 1)];
-  int hn = A.face_he_list[off + (k + 1 == n ? 0 : k + 1)];
-  if (A.he_next[h] != hn || A.he_face[h] != f) atomicAdd(A.err, 1);
+  int hp, hn;
+  const bool general = A.f_gen && A.f_gen[f];
+  if (general) {
+    // the slots of such a face list several boundary cycles one after the other: neighbours
+    // come from the DCEL (previous halfedge: rotate around the source vertex)
+    hn = A.he_next[h];
+    hp = h;
+    for (int o = h, guard = 0; guard < 64; guard++) {
+      const int i = A.he_twin[o];
+      if (A.he_next[i] == h) { hp = i; break; }
+      o = A.he_next[i];
+    }
+    if (A.he_face[h] != f) atomicAdd(A.err, 1);
+  } else {
+    hp = A.face_he_list[off + (k == 0 ? n - 1 : k - 1)];
+    hn = A.face_he_list[off + (k + 1 == n ? 0 : k + 1)];
+    if (A.he_next[h] != hn || A.he_face[h] != f) atomicAdd(A.err, 1);
+  }
   int vs = A.he_src[h], vt = A.he_src[hn];
   double sx = A.vx[vs], sy = A.vy[vs], tx = A.vx[vt], ty = A.vy[vt];
   A.pt[m] = make_double2(sx, sy);
@@ -257,6 +275,7 @@ __global__ void k_prep_slots(PrepArgs A, int n_slots) {
   if (nhf < 0 || nhf != A.he_next[hp]) fl |= SF_CORNER;  // face2poly, lib/ttessel.cpp:4325-4327
   if (!A.face_inside[A.he_face[A.he_twin[h]]]) fl |= SF_BND;
   if (A.he_dir[h]) fl |= SF_DIR;
+  if (general) fl |= SF_GENERAL;
   A.flg[m] = fl;
   A.slot_he[m] = h;
   A.slot_seg[m] = A.he_seg[h];
@@ -762,6 +781,7 @@ __global__ void __launch_bounds__(LITE_SPLIT_TB, LITE_SPLIT_MINB) k_split(TessDe
       S = load_slot(T, __ldg(T.he_slot + A.in_he[i])); x = A.in_x[i]; angle = A.in_angle[i];
       sincos(angle, &sa, &ca);
     }
+    if (S.fl1 & SF_GENERAL) continue;  // k_gen_splits evaluates it (gen_face.h)
     SplitOut o;
     split_eval<STAT, PG>(T, G, S, x, angle, ca, sa, A.stat + A.base + i, A.cap, o);
     if (o.e2 < 0) bad++;
@@ -802,6 +822,7 @@ __device__ __forceinline__ void merge_one(const TessDev &T, const Prog &G, const
   out_he[i] = e;
   int se = T.he_slot[e], st_ = T.he_slot[t];
   int f1 = T.slot_face[se], f2 = T.slot_face[st_];
+  if (T.f_gen && (T.f_gen[f1] | T.f_gen[f2])) return;  // k_gen_mf has written this row (gen_face.h)
   int o1 = T.f_off[f1], n1 = T.f_cnt[f1], o2 = T.f_off[f2], n2 = T.f_cnt[f2];
   int ke = se - o1, kt = st_ - o2;
   int ke1 = (ke + 1) % n1, kt1 = (kt + 1) % n2;  // e2() = next(e), e1() = next(twin e)
@@ -895,6 +916,7 @@ __device__ __forceinline__ void flip_one(const TessDev &T, const Prog &G, const 
   int t1 = T.he_twin[e1];
   int s1 = T.he_slot[e1], st1 = T.he_slot[t1];
   int fL = T.slot_face[s1], fT = T.slot_face[st1];  // face(e1), face(twin e1)
+  if (T.f_gen && (T.f_gen[fL] | T.f_gen[fT])) return;  // k_gen_mf has written this row and its outputs
   int oL = T.f_off[fL], nL = T.f_cnt[fL], oT = T.f_off[fT], nT = T.f_cnt[fT];
   int k1 = s1 - oL, kt = st1 - oT;
   // e3: incoming halfedge at a = src(e1) that is not on e1's segment (:2435-2438)

@@ -587,3 +587,72 @@ def test_failed_upload_leaves_no_tessellation(lite):
     ctx.add_splits_given(gold["cand_he"], gold["cand_x"], gold["cand_angle"])
     assert ctx.pl_eval(gold["pl_acs_1_theta"])[0] == pytest.approx(float(gold["pl_acs_1_lpl"]), rel=RTOL)
     ctx.close()
+
+
+@pytest.mark.parametrize("which,seed,n_moves", [("holed", 5, 0), ("holed", 5, 12), ("holed", 11, 60), ("holed", 13, 90),
+                                                 ("flips", 4, 25), ("hole_to_hole", 23, 0)])
+def test_windows_with_holes_against_live_oracle(lite, which, seed, n_moves):
+    """The reference's holed domains (tests/check_lite.cpp:129-229): faces with inner
+    boundaries and isthmus edges, i.e. cas 2-4 of hpolygon_insert_edge / hpolygon_remove_edge and
+    the twin tie-break of ray_exit_face (lib/ttessel.cpp:4554-4562, :4722-4792, :4866-4922),
+    on the device (gen_kernels.cuh beside the fast kernels).  Device-sampled splits (they land on
+    inner boundaries too), every merge and every flip, all twelve features, integers bit exact,
+    and the pseudo-likelihood built from them."""
+    import lite_oracle as lo
+    from test_gen_face_cpu import _split_of_kind, grow
+    from test_oracle_golden import holed_polygons, holed_polygons_for_flips
+    if which == "hole_to_hole":
+        t = lo.TTessel(lo.Rng(seed))
+        t.insert_window(holed_polygons())
+        for k in ("two_holes", "same_hole"):
+            t.update(_split_of_kind(t, k))
+    else:
+        t = grow(holed_polygons() if which == "holed" else holed_polygons_for_flips(), seed, 5, n_moves)
+    soa = lo.export_soa(t)
+    holed_faces = [f for f in t.internal_faces() if f.holes]
+    assert holed_faces
+    ctx = _ctx(lite, soa, ALL12)
+    nm, nf = ctx.merges_flips()
+    assert nm == len(t.non_blocking_segments) and nf == 2 * len(t.blocking_segments)
+    ctx.add_splits_philox(400, 77 + seed, 0)
+    he, x, ang = ctx.fetch("SPLIT_E1"), ctx.fetch("SPLIT_X"), ctx.fetch("SPLIT_ANGLE")
+    on_holed = sum(1 for h in he if t.halfedges[int(h)].face.holes)
+    on_inner = sum(1 for h in he if t.halfedges[int(h)].face.holes and
+                   not any(e is t.halfedges[int(h)] for e in lo.ccb(t.halfedges[int(h)].face.outer)))
+    assert on_holed > 20 and on_inner > 5
+    res = lo.eval_candidates(t, lo.make_energy(lo.ALL12, None, t), he, x, ang)
+    np.testing.assert_array_equal(ctx.fetch("SPLIT_E2"), res["split_e2"])
+    np.testing.assert_array_equal(ctx.fetch("MERGE_HE"), res["merge_he"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_E1"), res["flip_e1"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_E2"), res["flip_e2"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_RIGHT"), res["flip_right"])
+    np.testing.assert_allclose(ctx.fetch("SPLIT_P1"), res["split_p1"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(ctx.fetch("SPLIT_P2"), res["split_p2"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(ctx.fetch("FLIP_P2"), res["flip_p2"], rtol=0, atol=1e-11)
+    # face_area_2 of a move is a difference of squared face areas of order `scale` (the domain
+    # spans 21 x 15 units): a few ulp of that is the floor, for the oracle's own double sum too
+    scale = max(lo.face_area_2(lo.face2poly(f), t) for f in t.internal_faces())
+    k_a2 = ALL12.index("face_area_2")
+    for name, got, want in (("split", ctx.fetch("SPLIT_STAT"), res["split_stat"]),
+                            ("merge", ctx.fetch("MERGE_STAT"), res["merge_stat"]),
+                            ("flip", ctx.fetch("FLIP_STAT"), res["flip_stat"])):
+        assert np.all(np.abs(got[:, k_a2] - want[:, k_a2]) <= ATOL_STAT + RTOL * np.abs(want[:, k_a2]) + 16 * 2.3e-16 * scale), name
+        keep = [k for k in range(len(ALL12)) if k != k_a2]
+        _assert_stats(name, got[:, keep], want[:, keep], [ALL12[k] for k in keep])
+    th = 0.01 * np.random.default_rng(seed).standard_normal(len(ALL12))
+    th[k_a2] *= 1e-4
+    lpl, g, H = ctx.pl_eval(th)
+    assert ctx.pl_failures() == (0, 0)
+    wl, wg, wH = lo.pl_from_stats(th, res["split_stat"], res["merge_stat"], res["flip_stat"], float(soa["int_length"]))
+    assert lpl == pytest.approx(wl, rel=RTOL)
+    np.testing.assert_allclose(g, wg, rtol=RTOL, atol=1e-9 * max(1.0, np.abs(wg).max()))
+    np.testing.assert_allclose(H, wH, rtol=RTOL, atol=1e-9 * max(1.0, np.abs(wH).max()))
+    # the fed list takes the same route
+    ctx.clear_splits()
+    ctx.add_splits_given(he, x, ang)
+    np.testing.assert_array_equal(ctx.fetch("SPLIT_E2"), res["split_e2"])
+    assert ctx.pl_eval(th)[0] == pytest.approx(wl, rel=RTOL)
+    # and the clip-only mode counts them in its checksum
+    cs = ctx.lines_sample_clip(400, 77 + seed, 0, mode=0)
+    assert int(cs[1]) == int(res["split_e2"].astype(np.int64).sum())
+    ctx.close()
