@@ -733,7 +733,8 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
     GT.f_hole_cnt = c->g_hole_cnt.p; GT.hole_he = c->g_hole_he.p;
     if (!c->gen_scratch) {
       c->gen_blocks = c->sm_count;
-      CU(cudaMalloc((void **)&c->gen_scratch, (size_t)c->gen_blocks * LITE_GEN_TB * LITE_GEN_PTS * sizeof(gen::Pt)));
+      // two blocks of scratch: the merge/flip kernel runs on the second stream, beside the split kernel
+      CU(cudaMalloc((void **)&c->gen_scratch, 2 * (size_t)c->gen_blocks * LITE_GEN_TB * LITE_GEN_PTS * sizeof(gen::Pt)));
     }
   }
   int tb = 128, gb = (nF + tb - 1) / tb;
@@ -852,7 +853,8 @@ extern "C" int lite_candidates_merges_flips(lite_ctx *c, int32_t *n_merges, int3
     A.b_seg = c->b_list.p; A.nb = c->n_b; A.fstat = c->fstat.p; A.f_e1 = c->fl_e1.p; A.f_e2 = c->fl_e2.p;
     A.f_right = c->fl_right.p; A.f_p2 = c->fl_p2.p; A.status = c->status.p + 1; A.part = c->sums.p;
     if (c->n_general > 0) {  // rows of the merges / flips next to a face with holes, first
-      k_gen_mf<<<c->gen_blocks, LITE_GEN_TB, 0, c->stream2>>>(c->T, c->GT, c->G, A, c->gen_scratch, c->status.p + 6);
+      k_gen_mf<<<c->gen_blocks, LITE_GEN_TB, 0, c->stream2>>>(c->T, c->GT, c->G, A,
+                                                               c->gen_scratch + (size_t)c->gen_blocks * LITE_GEN_TB * LITE_GEN_PTS, c->status.p + 6);
       c->launches += 1;
     }
     k_merges_flips<<<blocks, 128, 0, c->stream2>>>(c->T, c->G, A);

@@ -270,7 +270,13 @@ GEN_HD inline int hpolygon_insert_edge(Scratch &S, const HPoly &hp, int i1, int 
     // mother face (the old face minus the daughter) and daughter face (along the hole)
     Poly c21 = polygon_insert_edge(S, e2, e1, p2, p1), outer2, enlarged;
     const Pt &t2 = pe_tgt(e2);
-    if (bounded_side(c21, t2.x, t2.y) >= 0) { outer2 = polygon_insert_edge(S, e1, e2, p1, p2); enlarged = c21; }
+    // bounded_side_2(c21, target of e2) != ON_UNBOUNDED_SIDE (:4737).  The target can lie ON c21: a
+    // hole made of two holes joined by an isthmus visits the isthmus' end vertices twice.  A DCEL
+    // vertex is on the boundary of c21 iff it is one of its vertices.
+    bool not_outside = false;
+    for (int k = 0; k < c21.n && !not_outside; k++) not_outside = c21.p[k].vid == t2.vid;
+    if (!not_outside) not_outside = bounded_side(c21, t2.x, t2.y) > 0;
+    if (not_outside) { outer2 = polygon_insert_edge(S, e1, e2, p1, p2); enlarged = c21; }
     else { outer2 = c21; enlarged = polygon_insert_edge(S, e1, e2, p1, p2); }
     res[0].nb = res[1].nb = 0;
     res[0].b[res[0].nb++] = hp.b[0];

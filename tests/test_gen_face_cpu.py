@@ -154,7 +154,7 @@ def test_removal_of_hole_to_hole_segments(tmp_path, kinds):
     t.insert_window(holed_polygons())
     for k in kinds:
         t.update(_split_of_kind(t, k))
-    got = check_against_oracle(tmp_path, t, 120, 31)
+    got = check_against_oracle(tmp_path, t, 300, 31)
     CASES["insert"] += got["insert_cases"]
     CASES["remove"] += got["remove_cases"]
 
