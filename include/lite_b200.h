@@ -98,6 +98,17 @@ int lite_ctx_destroy(lite_ctx *ctx);
 int lite_ctx_sync(lite_ctx *ctx);
 /* option ids */
 #define LITE_OPT_RECORD_SPLITS 1 /* keep per-split e1,e2,p1,p2,x,angle for lite_debug_fetch */
+/* Which joint law lite_candidates_add_splits_philox / lite_lines_sample_clip give the positions
+ * of a batch along the cumulative halfedge length (the marginal law of every candidate is the
+ * reference's in both: halfedge with probability proportional to its length, then x, angle):
+ *   LITE_SAMPLER_STRATIFIED (default): one position per stratum of width L/n, jittered inside it.
+ *     Unbiased for the pseudo-likelihood sums, lower variance, no sort; NOT the joint law of the
+ *     reference (its n positions are independent).
+ *   LITE_SAMPLER_IID: n independent uniform positions, sorted, exactly as TTessel::split_sample /
+ *     alt_length_weighted_random_halfedge(n) draw and sort them (lib/ttessel.cpp:1968-1991). */
+#define LITE_OPT_SAMPLER 2
+#define LITE_SAMPLER_STRATIFIED 0
+#define LITE_SAMPLER_IID 1
 int lite_ctx_set_option(lite_ctx *ctx, int option, int64_t value);
 
 /* Energy::set_ttessel (lib/ttessel.cpp:2862): replicate the tessellation on the GPU. */

@@ -247,6 +247,11 @@ class Context:
     def record_splits(self, on=True):
         _ck(self.L, self.L.lite_ctx_set_option(self.h, 1, 1 if on else 0))
 
+    def sampler(self, iid):
+        """LITE_OPT_SAMPLER: i.i.d. sorted positions (the reference's split_sample law) or the
+        default stratified sampler."""
+        _ck(self.L, self.L.lite_ctx_set_option(self.h, 2, 1 if iid else 0))
+
     def tess_upload(self, soa: TessSoA):
         s = soa.as_struct()
         _ck(self.L, self.L.lite_tess_upload(self.h, C.byref(s)))

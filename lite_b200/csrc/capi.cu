@@ -18,6 +18,7 @@
 #include <thread>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <nvtx3/nvToolsExt.h>
 
 #include "kernels.cuh"
@@ -183,6 +184,10 @@ struct lite_ctx {
   float ms_exchange = 0;                        // NCCL path: device time of the allreduce
   bool have_tess = false, have_prog = false, have_mf = false;
   bool record = false;
+  bool iid = false;         // LITE_OPT_SAMPLER: i.i.d. positions + sort instead of the stratified sampler
+  DBuf<double> sel_a, sel_b;   // positions of the current batch shard, unsorted / sorted
+  DBuf<long long> id_a, id_b;  // their batch indices
+  DBuf<char> sort_tmp;
   bool mf_pending = false;  // sums of the last merges_flips still in flight
   bool rev = false;  // direction of the next theta-reduce pass over the split statistics
   int64_t launches = 0;
@@ -192,7 +197,7 @@ struct lite_ctx {
   DBuf<uint8_t> he_dir, face_inside, seg_bnd;
   DBuf<int> f_off, f_cnt, f_list, seg_he_start, seg_he_end, seg_n_edges, nb_list, b_list;
   // derived
-  DBuf<double2> pt;
+  DBuf<double2> pt, udir;
   DBuf<double> ang, len, ca, f_area, f_perim, f_sumang, f_minang, cum, pre, plen, f_tot2, stot2;
   DBuf<int2> sfo;
   DBuf<uint32_t> flg;
@@ -421,7 +426,8 @@ extern "C" int lite_ctx_destroy(lite_ctx *c) {
   c->he_dir.release(); c->face_inside.release(); c->seg_bnd.release();
   c->f_off.release(); c->f_cnt.release(); c->f_list.release(); c->seg_he_start.release();
   c->seg_he_end.release(); c->seg_n_edges.release(); c->nb_list.release(); c->b_list.release();
-  c->pt.release(); c->ang.release(); c->len.release(); c->ca.release(); c->f_area.release();
+  c->sel_a.release(); c->sel_b.release(); c->id_a.release(); c->id_b.release(); c->sort_tmp.release();
+  c->pt.release(); c->udir.release(); c->ang.release(); c->len.release(); c->ca.release(); c->f_area.release();
   c->f_perim.release(); c->f_sumang.release(); c->f_minang.release(); c->cum.release(); c->pre.release(); c->plen.release(); c->f_tot2.release(); c->stot2.release(); c->sfo.release();
   c->flg.release(); c->slot_he.release(); c->slot_seg.release(); c->slot_face.release();
   c->he_slot.release(); c->guide.release(); c->err.release();
@@ -456,6 +462,11 @@ extern "C" int lite_ctx_set_option(lite_ctx *c, int option, int64_t value) {
   if (option == LITE_OPT_RECORD_SPLITS) {
     if (c->n_local != 0) return fail(LITE_ESTATE, "clear the splits before changing the record option");
     c->record = value != 0;
+    return 0;
+  }
+  if (option == LITE_OPT_SAMPLER) {
+    if (value != LITE_SAMPLER_STRATIFIED && value != LITE_SAMPLER_IID) return fail(LITE_EINVAL, "unknown sampler %lld", (long long)value);
+    c->iid = value == LITE_SAMPLER_IID;
     return 0;
   }
   return fail(LITE_EINVAL, "unknown option %d", option);
@@ -690,7 +701,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   CU(cudaEventRecord(c->ev_upload, c->stream));
   c->upload_inflight = true;
   const size_t nSl = n_slots;
-  if (c->pt.alloc(nSl) || c->ang.alloc(nSl) || c->len.alloc(nSl) || c->ca.alloc(nSl) ||
+  if (c->pt.alloc(nSl) || c->udir.alloc(nSl) || c->ang.alloc(nSl) || c->len.alloc(nSl) || c->ca.alloc(nSl) ||
       c->flg.alloc(nSl) || c->slot_he.alloc(nSl) || c->slot_seg.alloc(nSl) ||
       c->slot_face.alloc(nSl) || c->he_slot.alloc(nH) || c->f_area.alloc(nF) ||
       c->f_perim.alloc(nF) || c->f_sumang.alloc(nF) || c->f_minang.alloc(nF) || c->pre.alloc(nSl) ||
@@ -707,12 +718,12 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   A.f_gen = general ? c->g_fgen.p : nullptr;
   A.he_length = c->he_length.p; A.face_he_offset = c->f_off.p; A.face_he_count = c->f_cnt.p;
   A.face_he_list = c->f_list.p; A.n_faces = nF;
-  A.pt = c->pt.p; A.ang = c->ang.p; A.len = c->len.p; A.ca = c->ca.p; A.flg = c->flg.p;
+  A.pt = c->pt.p; A.udir = c->udir.p; A.ang = c->ang.p; A.len = c->len.p; A.ca = c->ca.p; A.flg = c->flg.p;
   A.slot_he = c->slot_he.p; A.slot_seg = c->slot_seg.p; A.slot_face = c->slot_face.p;
   A.he_slot = c->he_slot.p; A.err = c->err.p;
   TessDev &T = c->T;
   T.n_slots = (int)nSl; T.n_faces = nF; T.n_he = nH; T.n_seg = nS;
-  T.pt = c->pt.p; T.ang = c->ang.p; T.len = c->len.p; T.ca = c->ca.p; T.flg = c->flg.p;
+  T.pt = c->pt.p; T.udir = c->udir.p; T.ang = c->ang.p; T.len = c->len.p; T.ca = c->ca.p; T.flg = c->flg.p;
   T.slot_he = c->slot_he.p; T.slot_seg = c->slot_seg.p; T.slot_face = c->slot_face.p;
   T.he_slot = c->he_slot.p; T.he_twin = c->he_twin.p; T.he_src = c->he_src.p;
   T.he_next_hf = c->he_next_hf.p; T.he_prev_hf = c->he_prev_hf.p;
@@ -997,6 +1008,23 @@ static void shard_range(int64_t n, int rank, int world, int64_t &j0, int64_t &cn
   cnt = j1 - j0;
 }
 
+// LITE_SAMPLER_IID: draw this shard's positions independently, sort them with their batch
+// indices (split_sample sorts its draws so that the candidates come out in halfedge order,
+// lib/ttessel.cpp:1974; here the order also keeps the lanes of a warp on one face)
+static int iid_prepare(lite_ctx *c, SplitArgs &A, int64_t n, int64_t j0, uint64_t seed, uint64_t offset) {
+  if (c->sel_a.alloc((size_t)n) || c->sel_b.alloc((size_t)n) || c->id_a.alloc((size_t)n) || c->id_b.alloc((size_t)n))
+    return LITE_ECUDA;
+  k_iid_draw<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((long)n, (long)j0, seed, offset, c->T.total_len,
+                                                                 c->sel_a.p, c->id_a.p);
+  size_t tmp = 0;
+  CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->sel_a.p, c->sel_b.p, c->id_a.p, c->id_b.p, (int)n, 0, 64, c->stream));
+  if (c->sort_tmp.alloc(tmp + 256)) return LITE_ECUDA;
+  CU(cub::DeviceRadixSort::SortPairs(c->sort_tmp.p, tmp, c->sel_a.p, c->sel_b.p, c->id_a.p, c->id_b.p, (int)n, 0, 64, c->stream));
+  c->launches += 2;
+  A.sel_sorted = c->sel_b.p; A.sel_id = c->id_b.p;
+  return 0;
+}
+
 extern "C" int lite_candidates_add_splits_philox(lite_ctx *c, int64_t n_global, uint64_t seed,
                                                  uint64_t offset) {
   NvtxRange nvtx_("lite_candidates_add_splits_philox");
@@ -1014,6 +1042,11 @@ extern "C" int lite_candidates_add_splits_philox(lite_ctx *c, int64_t n_global, 
     A.n_local = n; A.j0 = j0; A.sel_step = c->T.total_len / (double)n_global; A.seed = seed; A.ctr0 = offset;
     int g = split_grid(c, n);
     CU(cudaEventRecord(c->ev[0], c->stream));
+    if (c->iid) {
+      if (n > 0x7fffffff) return fail(LITE_EINVAL, "the i.i.d. sampler sorts at most 2^31-1 positions per rank and batch");
+      r = iid_prepare(c, A, n, j0, seed, offset);
+      if (r) return r;
+    }
     if (c->record) launch_split<4 | 2 | 1>(c, c->G, A, g);
     else launch_split<4 | 1>(c, c->G, A, g);
     CU(cudaEventRecord(c->ev[1], c->stream));
@@ -1050,6 +1083,11 @@ extern "C" int lite_lines_sample_clip(lite_ctx *c, int64_t n_global, uint64_t se
     A.n_local = n; A.j0 = j0; A.sel_step = c->T.total_len / (double)n_global; A.seed = seed; A.ctr0 = offset;
     int g = split_grid(c, n);
     CU(cudaEventRecord(c->ev[0], c->stream));
+    if (c->iid) {
+      if (n > 0x7fffffff) return fail(LITE_EINVAL, "the i.i.d. sampler sorts at most 2^31-1 positions per rank and batch");
+      int r = iid_prepare(c, A, n, j0, seed, offset);
+      if (r) return r;
+    }
     if (mode == 1) launch_split<8 | 2 | 1>(c, G0, A, g);
     else launch_split<8 | 1>(c, G0, A, g);
     CU(cudaEventRecord(c->ev[1], c->stream));

@@ -36,11 +36,12 @@ __global__ void __launch_bounds__(LITE_GEN_TB) k_gen_splits(TessDev T, gen::Tess
     int m;
     double x, angle, U = 0.0;
     if (X.philox) {
-      const long j = A.j0 + i;
+      const bool iid = A.sel_sorted != nullptr;
+      const long j = iid ? (long)A.sel_id[i] : A.j0 + i;
       uint32_t r[4];
       philox4x32_10(A.ctr0 + (uint64_t)j, 0u, A.seed, r);
       const uint32_t spare = ((r[0] & 31u) << 17) | ((r[1] & 63u) << 11) | ((r[2] & 31u) << 6) | (r[3] & 63u);
-      const double sel = ((double)j + (double)spare * (1.0 / 4194304.0)) * A.sel_step;
+      const double sel = iid ? A.sel_sorted[i] : ((double)j + (double)spare * (1.0 / 4194304.0)) * A.sel_step;
       m = sample_slot(T, sel);
       if (!(__ldg(T.flg + m) & SF_GENERAL)) continue;
       x = u53(r[0], r[1]);

@@ -36,6 +36,7 @@ struct TessDev {
   // per slot
   const double2 *pt;   // source point
   const double *ang;   // atan2(dy,dx) of the halfedge (lib/ttessel.cpp:2095)
+  const double2 *udir; // its unit direction from the end points
   const double *len;   // LineTes_halfedge length
   const double *ca;    // interior angle at the source vertex (corners only)
   const uint32_t *flg; // SF_*
@@ -89,6 +90,43 @@ __device__ __forceinline__ double wrap_pi(double d) {
   // to (-pi, pi]
   return d - (2 * LITE_PI) * rint(d * (1.0 / (2 * LITE_PI)));
 }
+// acos(c) for the cosine c of an angle in [0, pi] whose sine s = sqrt(1 - c^2) >= 0 is already
+// known (a sampled proposal: c = 1 - 2U, s = 2 sqrt(U (1 - U))).  The smaller of |c| and s is at
+// most sin(pi/4), so one odd polynomial asin(z) = z + z^3 Q(z^2) on z^2 <= 1/2 serves every case
+// without the square root and the two divergent branches of the library acos (15.8 % of the
+// kernel's instructions, profiles/r1_k_split.txt); |error| <= 1 ulp of the result.  Q: degree-18
+// interpolant at the Chebyshev nodes of [0, 0.5], fitted in 60-digit arithmetic.
+__device__ __forceinline__ double acos_cs(double c, double s) {
+  const double ac = fabs(c);
+  const bool small_c = ac <= s;
+  const double z = small_c ? ac : s;
+  const double w = z * z;
+  double q = 0.8387686144806944;
+  q = fma(q, w, -3.0948600063047733);
+  q = fma(q, w, 5.436394922152539);
+  q = fma(q, w, -5.883246068449167);
+  q = fma(q, w, 4.384722306509683);
+  q = fma(q, w, -2.353535874499935);
+  q = fma(q, w, 0.9522680642152734);
+  q = fma(q, w, -0.28099565631446904);
+  q = fma(q, w, 0.07377365207108956);
+  q = fma(q, w, -0.003294232668448929);
+  q = fma(q, w, 0.011310930442084787);
+  q = fma(q, w, 0.01139924543091176);
+  q = fma(q, w, 0.013975730224099243);
+  q = fma(q, w, 0.017352221536902322);
+  q = fma(q, w, 0.022372177006627192);
+  q = fma(q, w, 0.030381944084992746);
+  q = fma(q, w, 0.044642857146655654);
+  q = fma(q, w, 0.07499999999998412);
+  q = fma(q, w, 0.16666666666666669);
+  const double r = fma(z * w, q, z);  // asin(z)
+  // |c| <= s: acos(c) = pi/2 - asin(c);  otherwise the angle is r (c > 0) or pi - r (c < 0)
+  const double base = small_c ? LITE_HALF_PI : (c > 0.0 ? 0.0 : LITE_PI);
+  const double sgn = (small_c == (c > 0.0)) ? -1.0 : 1.0;
+  return fma(sgn, r, base);
+}
+
 // angle_between_vectors, lib/ttessel.cpp:4255-4268
 __device__ __forceinline__ double angle_between(double ax, double ay, double bx, double by) {
   double n1 = ax * ax + ay * ay, n2 = bx * bx + by * by;
@@ -223,7 +261,7 @@ struct PrepArgs {
   const int *face_he_offset, *face_he_count, *face_he_list;
   int n_faces;
   // outputs
-  double2 *pt; double *ang, *len, *ca; uint32_t *flg;
+  double2 *pt; double2 *udir; double *ang, *len, *ca; uint32_t *flg;
   int *slot_he, *slot_seg, *slot_face, *he_slot;
   double *f_area, *f_perim, *f_sumang, *f_minang;
   int *err;  // consistency errors
@@ -269,6 +307,11 @@ __global__ void k_prep_slots(PrepArgs A, int n_slots) {
   double sx = A.vx[vs], sy = A.vy[vs], tx = A.vx[vt], ty = A.vy[vt];
   A.pt[m] = make_double2(sx, sy);
   A.ang[m] = atan2(ty - sy, tx - sx);
+  {
+    const double ex = tx - sx, ey = ty - sy;
+    const double inv = 1.0 / sqrt(ex * ex + ey * ey);
+    A.udir[m] = make_double2(ex * inv, ey * inv);
+  }
   A.len[m] = A.he_length[h];
   uint32_t fl = 0;
   int nhf = A.he_next_hf[hp];
@@ -434,9 +477,8 @@ __device__ __forceinline__ SlotData load_slot(const TessDev &T, int s1) {
   S.Q = ldpt(T.pt, fo.x + ((S.k1 + 1 == fo.y) ? 0 : S.k1 + 1));
   S.ang1 = __ldg(T.ang + s1);
   {
-    const double ex = S.Q.x - S.P.x, ey = S.Q.y - S.P.y;
-    const double inv = 1.0 / sqrt(ex * ex + ey * ey);
-    S.ux = ex * inv; S.uy = ey * inv;
+    const double2 u = __ldg(T.udir + s1);
+    S.ux = u.x; S.uy = u.y;
   }
   S.half_tot = 0.5 * __ldg(T.stot2 + s1);
   S.fl1 = __ldg(T.flg + s1);
@@ -498,7 +540,38 @@ __device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, cons
   // zero (s_k * s_{k+1} <= 0, not both zero).  In a convex face exactly one
   // halfedge other than e1 does, unless the line passes through a vertex.
   int cnt = 0, k2 = -1;
+#ifndef LITE_SCAN_LOOP
+  if (n <= 32) {
+    // sign bit of every vertex residual, vertex k at bit 32-n+k; `nz` stays set while no
+    // residual is exactly zero (then a halfedge crosses iff the signs of its ends differ)
+    uint32_t neg = 0;
+    bool nz = true;
+#pragma unroll 4
+    for (int k = 0; k < n; k++) {
+      const double2 V = ldpt(T.pt, off + k);
+      const double sv = fma(a, V.x, fma(b, V.y, -w));
+      const uint32_t hi = (uint32_t)__double2hiint(sv), lo = (uint32_t)__double2loint(sv);
+      neg = (neg >> 1) | (hi & 0x80000000u);
+      nz = nz && (((hi & 0x7fffffffu) | lo) != 0u);
+    }
+    if (nz) {
+      neg >>= (32 - n);                                        // vertex k at bit k
+      const uint32_t full = (n == 32) ? 0xffffffffu : ((1u << n) - 1u);
+      const uint32_t nxt = ((neg >> 1) | (neg << (n - 1))) & full;   // sign of vertex k+1 at bit k
+      uint32_t cross = (neg ^ nxt) & full & ~(1u << k1);
+      if (skip1 >= 0) cross &= ~(1u << skip1);
+      cnt = __popc(cross);
+      k2 = __ffs(cross) - 1;
+    } else {
+      cnt = -1;  // a vertex lies exactly on the line: the general loop below decides
+    }
+  } else {
+    cnt = -1;
+  }
+  if (cnt < 0)
+#endif
   {
+    cnt = 0; k2 = -1;
     const double2 V0 = ldpt(T.pt, off);
     const double s0 = fma(a, V0.x, fma(b, V0.y, -w));
     double sk = s0;
@@ -512,9 +585,19 @@ __device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, cons
     if (sk * s0 <= 0.0 && sk != s0 && (n - 1) != k1 && (n - 1) != skip1) { if (cnt == 0) k2 = n - 1; cnt++; }
   }
   double2 p2 = make_double2(0.0, 0.0);
-  if (cnt >= 1) {
-    // nearest forward hit among the crossing halfedges, first wins ties (:4563); cnt is 1
-    // unless the line passes through a vertex, so this loop runs once
+  if (cnt == 1) {
+    // the usual case (a convex face, the line through no vertex): one candidate halfedge, so the
+    // nearest-hit comparison needs no distance: forward and not at the source
+    const int kn = (k2 + 1 == n) ? 0 : k2 + 1;
+    const double2 Vk = ldpt(T.pt, off + k2), Vn = ldpt(T.pt, off + kn);
+    const double sk = fma(a, Vk.x, fma(b, Vk.y, -w)), sn = fma(a, Vn.x, fma(b, Vn.y, -w));
+    const double sg = sk / (sk - sn);
+    const double X = fma(sg, Vn.x - Vk.x, Vk.x), Y = fma(sg, Vn.y - Vk.y, Vk.y);
+    const double rx = X - p1.x, ry = Y - p1.y;
+    if (rx * dx + ry * dy >= 0.0 && (rx != 0.0 || ry != 0.0)) p2 = make_double2(X, Y);
+    else k2 = -1;
+  } else if (cnt > 1) {
+    // nearest forward hit among the crossing halfedges, first wins ties (:4563)
     double best = 1.7976931348623157e308;
     int kb = -1;
     for (int k = k2, left = cnt;;) {
@@ -706,6 +789,10 @@ struct SplitArgs {
   unsigned long long *status;  // [0] no-exit count
   unsigned long long *checksum;  // [0] xor hash, [1] sum of e2
   unsigned long long *ticket;  // run scheduler of this launch (zeroed before it)
+  // i.i.d. sampler (LITE_SAMPLER_IID): positions along the cumulative halfedge length drawn
+  // independently and sorted (split_sample, lib/ttessel.cpp:1968-1975), with the batch index of
+  // each draw; null = the stratified sampler
+  const double *sel_sorted; const long long *sel_id;
 };
 
 // Stratified length-weighted halfedge of candidate j (the device form of
@@ -719,6 +806,19 @@ __device__ __forceinline__ int sample_slot(const TessDev &T, double sel) {
   while (m > 0 && __ldg(T.cum + m - 1) > sel) m--;
   while (m < T.n_cum - 1 && __ldg(T.cum + m) <= sel) m++;
   return m;
+}
+
+// i.i.d. positions of a batch shard: sel_j = U_j * total_len with U_j the 53-bit uniform of
+// Philox stream 1 at counter ctr0 + j (the candidate's x and angle come from stream 0)
+#define LITE_IID_STREAM 1u
+__global__ void k_iid_draw(long n_local, long j0, uint64_t seed, uint64_t ctr0, double total_len, double *sel,
+                           long long *id) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_local) return;
+  uint32_t r[4];
+  philox4x32_10(ctr0 + (uint64_t)(j0 + i), LITE_IID_STREAM, seed, r);
+  sel[i] = u53(r[0], r[1]) * total_len;
+  id[i] = j0 + i;
 }
 
 #ifndef LITE_SPLIT_TB
@@ -759,15 +859,17 @@ __global__ void __launch_bounds__(LITE_SPLIT_TB, LITE_SPLIT_MINB) k_split(TessDe
   for (long i = beg + lane; i < end; i += 32) {
     double x, angle, ca, sa, U = 0.0;
     if (PHILOX) {
-      const long j = A.j0 + i;
+      const bool iid = A.sel_sorted != nullptr;
+      const long j = iid ? (long)A.sel_id[i] : A.j0 + i;
       uint32_t r[4];
       philox4x32_10(A.ctr0 + (uint64_t)j, 0u, A.seed, r);
       x = u53(r[0], r[1]);
       U = u53(r[2], r[3]);
       // the 22 bits u53 leaves unused place the candidate inside its stratum
       const uint32_t spare = ((r[0] & 31u) << 17) | ((r[1] & 63u) << 11) | ((r[2] & 31u) << 6) | (r[3] & 63u);
-      const double sel = ((double)j + (double)spare * (1.0 / 4194304.0)) * A.sel_step;
-      // sel grows along the lane's run, so the slot only moves forward
+      const double sel = iid ? A.sel_sorted[i] : ((double)j + (double)spare * (1.0 / 4194304.0)) * A.sel_step;
+      // sel grows along the lane's run (stratified by construction, i.i.d. after the sort), so
+      // the slot only moves forward
       int m_new = m;
       if (m < 0) m_new = sample_slot(T, sel);
       else while (m_new < T.n_cum - 1 && sel >= cum_hi) cum_hi = __ldg(T.cum + ++m_new);
@@ -776,7 +878,11 @@ __global__ void __launch_bounds__(LITE_SPLIT_TB, LITE_SPLIT_MINB) k_split(TessDe
       ca = 1.0 - 2.0 * U;
       sa = 2.0 * sqrt(U * (1.0 - U));
       const bool need_angle = RECORD || (STAT && (PG::mask(G) & MASK_FACE_ANG));
+#ifdef LITE_LIBM_ACOS
       angle = need_angle ? acos(ca) : 0.0;
+#else
+      angle = need_angle ? acos_cs(ca, sa) : 0.0;
+#endif
     } else {
       S = load_slot(T, __ldg(T.he_slot + A.in_he[i])); x = A.in_x[i]; angle = A.in_angle[i];
       sincos(angle, &sa, &ca);

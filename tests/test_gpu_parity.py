@@ -656,3 +656,98 @@ def test_windows_with_holes_against_live_oracle(lite, which, seed, n_moves):
     cs = ctx.lines_sample_clip(400, 77 + seed, 0, mode=0)
     assert int(cs[1]) == int(res["split_e2"].astype(np.int64).sum())
     ctx.close()
+
+
+def test_iid_sampler_is_the_split_sample_law(lite):
+    """LITE_SAMPLER_IID against TTessel::split_sample (lib/ttessel.cpp:1783-1795, :1968-1991):
+    n independent uniform positions along the cumulative halfedge length, sorted.
+    (i) bit-exact against the numpy restatement of the draw + sort; (ii) the halfedge histogram
+    against the exact multinomial law and against the oracle's own split_sample (two-sample
+    chi-square); (iii) the spread of the split sum S0 = sum exp(theta.p) over repeated batches
+    equals the spread over batches drawn by the oracle's split_sample, and the default stratified
+    sampler has the same mean and a smaller spread (stated in DESIGN.md)."""
+    import os
+    import lite_oracle as lo
+    import oracle_cpu as oc
+    import philox_ref
+    from util import GOLD
+    soa_g, gold = load_golden("t100")
+    window, segs = lo.parse_text(open(os.path.join(GOLD, "t100.txt")).read())
+    t = lo.ttessel_from_segments(window, segs, lo.Rng(99))
+    soa = lo.export_soa(t)
+    cum, cum_he = inside_cum(soa)
+    L = float(cum[-1])
+    ctx = _ctx(lite, soa, ACS)
+    ctx.sampler(True)
+    n, seed, off = 20000, 0xC0FFEE, 4321
+    ctx.add_splits_philox(n, seed, off)
+    # (i) the draw and the sort, restated
+    j = np.arange(n, dtype=np.uint64) + np.uint64(off)
+    z = np.zeros(n, dtype=np.uint32)
+    lo32, hi32 = (j & philox_ref.MASK).astype(np.uint32), (j >> np.uint64(32)).astype(np.uint32)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    r1 = philox_ref.philox4x32_10(lo32, hi32, z + np.uint32(1), z, k0, k1)       # stream 1: the position
+    sel = philox_ref.u53(r1[0], r1[1]) * L
+    order = np.argsort(sel, kind="stable")
+    r0 = philox_ref.philox4x32_10(lo32, hi32, z, z, k0, k1)                        # stream 0: x and U
+    xs, us = philox_ref.u53(r0[0], r0[1]), philox_ref.u53(r0[2], r0[3])
+    idx = np.minimum(np.searchsorted(cum, sel[order], side="right"), len(cum) - 1)
+    he = ctx.fetch("SPLIT_E1")
+    np.testing.assert_array_equal(he, cum_he[idx])
+    np.testing.assert_array_equal(ctx.fetch("SPLIT_X"), xs[order])
+    np.testing.assert_array_equal(ctx.fetch("SPLIT_U"), us[order])
+    # (ii) histogram: multinomial(n, length / L) ...
+    lens = soa["he_length"][cum_he]
+    pos = {int(h): k for k, h in enumerate(cum_he)}
+    counts = np.bincount([pos[int(h)] for h in he], minlength=len(cum_he))
+    expect = n * lens / L
+    chi2 = float(((counts - expect) ** 2 / expect).sum())
+    df = len(cum_he) - 1
+    assert abs(chi2 - df) < 5 * math.sqrt(2 * df), (chi2, df)
+    # ... and the oracle's own split_sample on the same tessellation
+    hid = {id(h): i for i, h in enumerate(t.halfedges)}
+    n_o = 6000
+    o_he = np.array([hid[id(e)] for e in t.alt_length_weighted_random_halfedges(n_o)])
+    o_counts = np.bincount([pos[int(h)] for h in o_he], minlength=len(cum_he))
+    # pooled two-sample chi-square over halfedges with enough expected mass
+    keep = expect * n_o / n > 3
+    a, b = counts[keep].astype(float), o_counts[keep].astype(float)
+    k1_, k2_ = math.sqrt(b.sum() / a.sum()), math.sqrt(a.sum() / b.sum())
+    chi2_2 = float((((k1_ * a - k2_ * b) ** 2) / (a + b)).sum())
+    df2 = int(keep.sum()) - 1
+    assert abs(chi2_2 - df2) < 5 * math.sqrt(2 * df2), (chi2_2, df2)
+    ctx.close()
+    # (iii) spread of the split sum over repeated batches
+    th = np.asarray(gold["pl_acs_1_theta"], dtype=np.float64)
+    T = oc.Tess(soa)
+    m, reps = 1500, 60
+
+    def gpu_s0(iid):
+        c2 = _ctx(lite, soa, ACS, record=False)
+        c2.sampler(iid)
+        c2.merges_flips()
+        out = []
+        for k in range(reps):
+            c2.clear_splits()
+            c2.add_splits_philox(m, 1234, k * m)
+            lpl, _, _ = c2.pl_eval(th)
+            out.append(lpl)
+        c2.close()
+        return np.array(out)
+    lpl_iid, lpl_str = gpu_s0(True), gpu_s0(False)
+    t.rnd = lo.Rng(2024)
+    ms, fs = oc.merge_stats(T, ACS)["merge_stat"], oc.flip_stats(T, ACS)["flip_stat"]
+    lpl_orc = []
+    for k in range(reps):
+        o_he, o_x, o_a = lo.draw_split_candidates(t, m)          # split_sample's draws, exact oracle
+        ss = oc.split_stats(T, ACS, o_he, o_x, o_a)["split_stat"]
+        lpl_orc.append(oc.pl(th, ss, fs, ms.sum(0), fs.sum(0), float(soa["int_length"]))[0])
+    lpl_orc = np.array(lpl_orc)
+    v_iid, v_str, v_orc = lpl_iid.var(ddof=1), lpl_str.var(ddof=1), lpl_orc.var(ddof=1)
+    # same law: equal means (within 5 standard errors) and equal variances (F ratio, 60 vs 60 batches)
+    se = math.sqrt(v_iid / reps + v_orc / reps)
+    assert abs(lpl_iid.mean() - lpl_orc.mean()) < 5 * se
+    assert 0.4 < v_iid / v_orc < 2.5, (v_iid, v_orc)
+    # the stratified sampler: same mean, smaller spread
+    assert abs(lpl_str.mean() - lpl_orc.mean()) < 5 * math.sqrt(v_str / reps + v_orc / reps)
+    assert v_str < v_iid, (v_str, v_iid)
