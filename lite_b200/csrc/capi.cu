@@ -22,7 +22,7 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include "kernels.cuh"
-#include "gen_kernels.cuh"
+#include "gen_launch.cuh"
 
 // NVTX range over one C-ABI call (header-only NVTX 3: a no-op unless a profiler is attached)
 struct NvtxRange {
@@ -202,7 +202,7 @@ struct lite_ctx {
   DBuf<int2> sfo;
   DBuf<uint32_t> flg;
   DBuf<int> slot_he, slot_seg, slot_face, he_slot, guide, err;
-  // faces that are not simple polygons (windows with holes): gen_face.h / gen_kernels.cuh
+  // faces that are not simple polygons (windows with holes): gen_face.h / gen_launch.cuh
   int n_general = 0;                 // how many the uploaded tessellation has
   gen::Cycles cyc;                   // their boundary cycles (host)
   std::vector<int> x_off, x_cnt, x_list;   // per-face halfedge lists extended by the inner boundaries

@@ -1,4 +1,4 @@
-// gen_kernels.cuh — kernels for the candidates that touch a face which is not a simple polygon
+// gen_launch.cuh — kernels for the candidates that touch a face which is not a simple polygon
 // (gen_face.h).  Launched only when the uploaded tessellation has such faces (a window with
 // holes); a rectangular window never gets here, so the fast kernels pay one flag test.
 //

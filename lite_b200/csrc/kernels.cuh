@@ -96,35 +96,37 @@ __device__ __forceinline__ double wrap_pi(double d) {
 // without the square root and the two divergent branches of the library acos (15.8 % of the
 // kernel's instructions, profiles/r1_k_split.txt); |error| <= 1 ulp of the result.  Q: degree-18
 // interpolant at the Chebyshev nodes of [0, 0.5], fitted in 60-digit arithmetic.
+__constant__ double c_asin_q[19] = {   // Q, ascending powers of z^2 (constant bank: the DFMAs read them as operands)
+    0.16666666666666669,   0.07499999999998412,  0.044642857146655654, 0.030381944084992746, 0.022372177006627192,
+    0.017352221536902322,  0.013975730224099243, 0.01139924543091176,  0.011310930442084787, -0.003294232668448929,
+    0.07377365207108956,   -0.28099565631446904, 0.9522680642152734,   -2.353535874499935,   4.384722306509683,
+    -5.883246068449167,    5.436394922152539,    -3.0948600063047733,  0.8387686144806944};
 __device__ __forceinline__ double acos_cs(double c, double s) {
   const double ac = fabs(c);
   const bool small_c = ac <= s;
   const double z = small_c ? ac : s;
   const double w = z * z;
-  double q = 0.8387686144806944;
-  q = fma(q, w, -3.0948600063047733);
-  q = fma(q, w, 5.436394922152539);
-  q = fma(q, w, -5.883246068449167);
-  q = fma(q, w, 4.384722306509683);
-  q = fma(q, w, -2.353535874499935);
-  q = fma(q, w, 0.9522680642152734);
-  q = fma(q, w, -0.28099565631446904);
-  q = fma(q, w, 0.07377365207108956);
-  q = fma(q, w, -0.003294232668448929);
-  q = fma(q, w, 0.011310930442084787);
-  q = fma(q, w, 0.01139924543091176);
-  q = fma(q, w, 0.013975730224099243);
-  q = fma(q, w, 0.017352221536902322);
-  q = fma(q, w, 0.022372177006627192);
-  q = fma(q, w, 0.030381944084992746);
-  q = fma(q, w, 0.044642857146655654);
-  q = fma(q, w, 0.07499999999998412);
-  q = fma(q, w, 0.16666666666666669);
+  double q = c_asin_q[18];
+#pragma unroll
+  for (int k = 17; k >= 0; k--) q = fma(q, w, c_asin_q[k]);
   const double r = fma(z * w, q, z);  // asin(z)
   // |c| <= s: acos(c) = pi/2 - asin(c);  otherwise the angle is r (c > 0) or pi - r (c < 0)
   const double base = small_c ? LITE_HALF_PI : (c > 0.0 ? 0.0 : LITE_PI);
   const double sgn = (small_c == (c > 0.0)) ? -1.0 : 1.0;
   return fma(sgn, r, base);
+}
+
+// n / d for operands in the normal range, without the library's special-case branch: 20-bit
+// reciprocal seed, two Newton steps, one correction of the quotient (error <= 1 ulp)
+__device__ __forceinline__ double div_fast(double n, double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  const double q = n * r;
+  return fma(fma(-d, q, n), r, q);
 }
 
 // angle_between_vectors, lib/ttessel.cpp:4255-4268
@@ -527,7 +529,7 @@ __device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, cons
   const double w = __dadd_rn(u, __dmul_rn(x, __dadd_rn(v, -u)));
   // p1 = e1 ∩ line(a,b,-w)   (:2110)
   const double sP = fma(a, P.x, fma(b, P.y, -w)), sQ = fma(a, Q.x, fma(b, Q.y, -w));
-  const double t1 = sP / (sP - sQ);
+  const double t1 = div_fast(sP, sP - sQ);
   const double2 p1 = make_double2(fma(t1, Q.x - P.x, P.x), fma(t1, Q.y - P.y, P.y));
   // ray direction (:2121-2127): Line_2(a,b,c) has direction (b,-a)
   double dx, dy;
@@ -591,7 +593,7 @@ __device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, cons
     const int kn = (k2 + 1 == n) ? 0 : k2 + 1;
     const double2 Vk = ldpt(T.pt, off + k2), Vn = ldpt(T.pt, off + kn);
     const double sk = fma(a, Vk.x, fma(b, Vk.y, -w)), sn = fma(a, Vn.x, fma(b, Vn.y, -w));
-    const double sg = sk / (sk - sn);
+    const double sg = div_fast(sk, sk - sn);
     const double X = fma(sg, Vn.x - Vk.x, Vk.x), Y = fma(sg, Vn.y - Vk.y, Vk.y);
     const double rx = X - p1.x, ry = Y - p1.y;
     if (rx * dx + ry * dy >= 0.0 && (rx != 0.0 || ry != 0.0)) p2 = make_double2(X, Y);

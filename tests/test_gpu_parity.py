@@ -595,7 +595,7 @@ def test_windows_with_holes_against_live_oracle(lite, which, seed, n_moves):
     """The reference's holed domains (tests/check_lite.cpp:129-229): faces with inner
     boundaries and isthmus edges, i.e. cas 2-4 of hpolygon_insert_edge / hpolygon_remove_edge and
     the twin tie-break of ray_exit_face (lib/ttessel.cpp:4554-4562, :4722-4792, :4866-4922),
-    on the device (gen_kernels.cuh beside the fast kernels).  Device-sampled splits (they land on
+    on the device (gen_launch.cuh beside the fast kernels).  Device-sampled splits (they land on
     inner boundaries too), every merge and every flip, all twelve features, integers bit exact,
     and the pseudo-likelihood built from them."""
     import lite_oracle as lo
