@@ -106,6 +106,15 @@ int lite_ctx_sync(lite_ctx *ctx);
  *     reference (its n positions are independent).
  *   LITE_SAMPLER_IID: n independent uniform positions, sorted, exactly as TTessel::split_sample /
  *     alt_length_weighted_random_halfedge(n) draw and sort them (lib/ttessel.cpp:1968-1991). */
+/* lite_tess_upload checks the consistency of what it is given (index ranges, twin links, face
+ * lists against he_next / he_face, segment lists: the export assertions, in the spirit of
+ * TTessel::is_valid).  By default the checks run on the DEVICE behind the copy: the upload returns
+ * at once, nothing dereferences an unchecked index, every kernel does nothing on a tessellation
+ * that failed, and the failure is reported (LITE_EINVAL) by the next call that synchronises
+ * (lite_pl_eval, lite_pl_sums, lite_debug_fetch, lite_ctx_sync, ...).  With this option set they run
+ * on the host inside lite_tess_upload, which then reports them itself (tessellations with holes
+ * always take this route). */
+#define LITE_OPT_VALIDATE_HOST 3
 #define LITE_OPT_SAMPLER 2
 #define LITE_SAMPLER_STRATIFIED 0
 #define LITE_SAMPLER_IID 1

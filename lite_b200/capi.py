@@ -100,6 +100,10 @@ class TessSoA:
         return int(self.a["face_inside"].sum())
 
     def as_struct(self):
+        """The lite_tess_soa view of the arrays (built once: the arrays are not to be modified
+        afterwards)."""
+        if getattr(self, "_struct", None) is not None:
+            return self._struct
         s = _SoA()
         a = self.a
         s.n_vertices = len(a["vx"])
@@ -112,6 +116,7 @@ class TessSoA:
         s.int_length = self.int_length
         for k in _DT:
             setattr(s, k, a[k].ctypes.data_as(C.c_void_p))
+        self._struct = s
         return s
 
 
@@ -246,6 +251,11 @@ class Context:
 
     def record_splits(self, on=True):
         _ck(self.L, self.L.lite_ctx_set_option(self.h, 1, 1 if on else 0))
+
+    def validate_on_host(self, on=True):
+        """LITE_OPT_VALIDATE_HOST: run the export assertions inside tess_upload (default: on the
+        device behind the copy, reported by the next synchronising call)."""
+        _ck(self.L, self.L.lite_ctx_set_option(self.h, 3, 1 if on else 0))
 
     def sampler(self, iid):
         """LITE_OPT_SAMPLER: i.i.d. sorted positions (the reference's split_sample law) or the

@@ -10,6 +10,7 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <functional>
@@ -19,6 +20,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <emmintrin.h>
 #include <nvtx3/nvToolsExt.h>
 
 #include "kernels.cuh"
@@ -184,6 +186,7 @@ struct lite_ctx {
   float ms_exchange = 0;                        // NCCL path: device time of the allreduce
   bool have_tess = false, have_prog = false, have_mf = false;
   bool record = false;
+  bool validate_host = false;  // LITE_OPT_VALIDATE_HOST: export assertions on the host, errors returned by lite_tess_upload itself
   bool iid = false;         // LITE_OPT_SAMPLER: i.i.d. positions + sort instead of the stratified sampler
   DBuf<double> sel_a, sel_b;   // positions of the current batch shard, unsorted / sorted
   DBuf<long long> id_a, id_b;  // their batch indices
@@ -247,6 +250,7 @@ struct lite_ctx {
   std::vector<uint8_t> h_he_inside;
   std::vector<double> h_cum;        // cumulative slot lengths of the last upload (host copy)
   cudaEvent_t ev_upload = nullptr;  // the H2D copy of the last upload has left the pinned block
+  cudaEvent_t ev_tr[3] = {nullptr, nullptr, nullptr};  // LITE_B200_TRACE: start of the copy, end of the copy, end of the preparation
   bool upload_inflight = false;
   int sm_count = 148;
 };
@@ -449,12 +453,14 @@ extern "C" int lite_ctx_destroy(lite_ctx *c) {
   return 0;
 }
 
+static int tess_err_sync(lite_ctx *c);
+
 extern "C" int lite_ctx_sync(lite_ctx *c) {
   if (!c) return fail(LITE_EINVAL, "null context");
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaStreamSynchronize(c->stream2));
-  return 0;
+  return tess_err_sync(c);
 }
 
 extern "C" int lite_ctx_set_option(lite_ctx *c, int option, int64_t value) {
@@ -464,6 +470,7 @@ extern "C" int lite_ctx_set_option(lite_ctx *c, int option, int64_t value) {
     c->record = value != 0;
     return 0;
   }
+  if (option == LITE_OPT_VALIDATE_HOST) { c->validate_host = value != 0; return 0; }
   if (option == LITE_OPT_SAMPLER) {
     if (value != LITE_SAMPLER_STRATIFIED && value != LITE_SAMPLER_IID) return fail(LITE_EINVAL, "unknown sampler %lld", (long long)value);
     c->iid = value == LITE_SAMPLER_IID;
@@ -500,8 +507,67 @@ static int arena_reserve(lite_ctx *c, size_t need) {
   return 0;
 }
 
+// copy into the pinned upload block with non-temporal stores (dst 16-byte aligned): the lines do
+// not stay dirty in the writing core's cache, where the copy engine would have to snoop them out
+static void memcpy_stream(char *dst, const char *src, size_t n) {
+  size_t i = 0;
+  for (; i + 16 <= n; i += 16) _mm_stream_si128((__m128i *)(dst + i), _mm_loadu_si128((const __m128i *)(src + i)));
+  for (; i < n; i++) dst[i] = src[i];
+}
+
 static double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// The export assertions on the host (faces, lists, links), over `nt` threads of the pool: the
+// path of tessellations with holes (their boundary cycles are derived on the host, which must
+// not walk unchecked links) and of LITE_OPT_VALIDATE_HOST.  Every other upload is checked on
+// the device (k_validate).  Returns 0 or fails with the first inconsistency.
+static int host_validate(lite_ctx *c, const lite_tess_soa *s) {
+  const int nH = s->n_halfedges, nF = s->n_faces, nS = s->n_segments, nV = s->n_vertices;
+  const int nt = 4;
+  std::vector<int> bad_face(nt, -1), bad_he(nt, -1), bad_list_f(nt, -1), bad_list_k(nt, -1);
+  c->pool->run([=, &bad_face, &bad_he, &bad_list_f, &bad_list_k](int t) {
+    const int f0 = (int)((int64_t)nF * t / nt), f1 = (int)((int64_t)nF * (t + 1) / nt);
+    for (int f = f0; f < f1 && bad_face[t] < 0 && bad_list_f[t] < 0; f++) {
+      const int off = s->face_he_offset[f], cnt = s->face_he_count[f];
+      if (cnt < 0 || off < 0 || off + cnt > s->n_face_he || (s->face_inside[f] && cnt < 3)) { bad_face[t] = f; break; }
+      for (int k = 0; k < cnt; k++) {
+        const int h = s->face_he_list[off + k];
+        if (h < 0 || h >= nH ||
+            (s->face_inside[f] && (s->he_face[h] != f || s->he_next[h] != s->face_he_list[off + (k + 1 == cnt ? 0 : k + 1)]))) {
+          bad_list_f[t] = f; bad_list_k[t] = k; break;
+        }
+      }
+    }
+    const int h0 = (int)((int64_t)nH * t / nt), h1 = (int)((int64_t)nH * (t + 1) / nt);
+    for (int h = h0; h < h1; h++) {
+      const int f = s->he_face[h], tw = s->he_twin[h];
+      if (f < 0 || f >= nF || tw < 0 || tw >= nH || s->he_twin[tw] != h || s->he_src[h] < 0 ||
+          s->he_src[h] >= nV || s->he_seg[h] < 0 || s->he_seg[h] >= nS || s->he_next[h] < 0 || s->he_next[h] >= nH) { bad_he[t] = h; break; }
+    }
+  });
+  c->pool->wait();
+  for (int t = 0; t < nt; t++) {
+    if (bad_face[t] >= 0) return fail(LITE_EINVAL, "face %d: halfedge list out of range or fewer than 3 halfedges", bad_face[t]);
+    if (bad_list_f[t] >= 0)
+      return fail(LITE_EINVAL, "face %d: halfedge list disagrees with he_next/he_face at position %d", bad_list_f[t], bad_list_k[t]);
+    if (bad_he[t] >= 0) return fail(LITE_EINVAL, "halfedge %d: inconsistent links", bad_he[t]);
+  }
+  for (int i = 0; i < nS; i++)
+    if (s->seg_he_start[i] < 0 || s->seg_he_start[i] >= nH || s->seg_he_end[i] < 0 || s->seg_he_end[i] >= nH)
+      return fail(LITE_EINVAL, "segment %d: halfedge out of range", i);
+  for (int i = 0; i < s->n_non_blocking; i++) {
+    int sg = s->non_blocking[i];
+    if (sg < 0 || sg >= nS || s->seg_n_edges[sg] != 1 || s->seg_on_boundary[sg])
+      return fail(LITE_EINVAL, "non-blocking segment %d must be internal with exactly one edge", sg);
+  }
+  for (int i = 0; i < s->n_blocking; i++) {
+    int sg = s->blocking[i];
+    if (sg < 0 || sg >= nS || s->seg_n_edges[sg] < 2 || s->seg_on_boundary[sg])
+      return fail(LITE_EINVAL, "blocking segment %d must be internal with at least two edges", sg);
+  }
+  return 0;
 }
 
 extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
@@ -550,76 +616,103 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   r |= up(c, c->nb_list, s->non_blocking, s->n_non_blocking);
   r |= up(c, c->b_list, s->blocking, s->n_blocking);
   if (r) return r;
-  // Host side of an upload = packing into the pinned block + the export assertions (in the
-  // spirit of TTessel::is_valid, lib/ttessel.cpp:1721-1753).  Both are split over a few
-  // threads; only the sampler's cumulative lengths stay sequential (their summation order
-  // is part of the sampler's definition).
+  // Host side of an upload, on a few threads: packing into the pinned block, ONE light pass
+  // that counts the halfedges bounding inside faces (does the tessellation have faces with
+  // holes?) and the gather of the halfedge lengths in slot order.  The export assertions proper
+  // run on the device behind the copy (k_validate); only a tessellation with holes, whose
+  // boundary cycles have to be walked here, is checked on the host first.
+  //
+  // Packing uses non-temporal stores.  With ordinary stores the lines written by several
+  // threads stay dirty in their cores' private caches and the copy engine has to snoop them out:
+  // the 3.8 MB copy of a 10^4-cell tessellation then takes 0.5 ms instead of the link's 0.08 ms
+  // (scripts/h2d_probe4.py; the whole end-to-end step went from 1.43 to 0.80 ms with this alone).
   const int nt = 4;
-  std::vector<int> bad_face(nt, -1), bad_he(nt, -1), bad_list_f(nt, -1), bad_list_k(nt, -1);
-  std::vector<int64_t> part_listed(nt, 0), part_inside(nt, 0), part_twice(nt, 0);
+  std::vector<int> bad_he(nt, -1);
+  std::vector<int64_t> part_inside(nt, 0), part_twice(nt, 0);
   c->h_he_inside.assign(nH, 0);
+  // the face lists must tile [0, n_face_he) in face order: slot order == face order
+  int64_t listed = 0;
   {
-      c->pool->run([=, &bad_face, &bad_he, &bad_list_f, &bad_list_k, &part_listed, &part_inside, &part_twice](int t) {
-        for (size_t k = t; k < c->pack_jobs.size(); k += nt) memcpy(c->pack_jobs[k].dst, c->pack_jobs[k].src, c->pack_jobs[k].bytes);
-        // faces [f0, f1): list ranges, and the list of an inside face is its ccb
-        const int f0 = (int)((int64_t)nF * t / nt), f1 = (int)((int64_t)nF * (t + 1) / nt);
-        int64_t listed = 0;
-        for (int f = f0; f < f1 && bad_face[t] < 0 && bad_list_f[t] < 0; f++) {
-          const int off = s->face_he_offset[f], cnt = s->face_he_count[f];
-          if (cnt < 0 || off < 0 || off + cnt > s->n_face_he || (s->face_inside[f] && cnt < 3)) { bad_face[t] = f; break; }
-          for (int k = 0; k < cnt; k++) {
-            const int h = s->face_he_list[off + k];
-            if (h < 0 || h >= nH ||
-                (s->face_inside[f] && (s->he_face[h] != f || s->he_next[h] != s->face_he_list[off + (k + 1 == cnt ? 0 : k + 1)]))) {
-              bad_list_f[t] = f; bad_list_k[t] = k; break;
-            }
-          }
-          if (s->face_inside[f]) listed += cnt;
-        }
-        part_listed[t] = listed;
-        // halfedges [h0, h1): links in range, twin of twin
-        const int h0 = (int)((int64_t)nH * t / nt), h1 = (int)((int64_t)nH * (t + 1) / nt);
-        int64_t inside = 0, twice = 0;
-        for (int h = h0; h < h1; h++) {
-          const int f = s->he_face[h], tw = s->he_twin[h];
-          if (f < 0 || f >= nF || tw < 0 || tw >= nH || s->he_twin[tw] != h || s->he_src[h] < 0 ||
-              s->he_src[h] >= nV || s->he_seg[h] < 0 || s->he_seg[h] >= nS || s->he_next[h] < 0 || s->he_next[h] >= nH) { bad_he[t] = h; break; }
-          if (!s->face_inside[f]) continue;
-          inside++;
-          c->h_he_inside[h] = 1;
-          if (s->he_face[tw] == f) twice++;   // the face runs along both sides of this edge
-        }
-        part_inside[t] = inside;
-        part_twice[t] = twice;
-      });
+    int64_t run = 0;
+    for (int f = 0; f < nF; f++) {
+      const int off = s->face_he_offset[f], cnt = s->face_he_count[f];
+      if (off != run || cnt < 0 || cnt > s->n_face_he - off || (s->face_inside[f] && cnt < 3))
+        return fail(LITE_EINVAL, "face %d: its halfedge list must follow the previous face's (offset %d, expected %lld) and hold "
+                    "at least 3 halfedges when the face is inside", f, off, (long long)run);
+      run += cnt;
+      if (s->face_inside[f]) listed += cnt;
+    }
+    if (run != s->n_face_he) return fail(LITE_EINVAL, "the face lists hold %lld halfedges, n_face_he is %d", (long long)run, s->n_face_he);
   }
-  struct Joiner { HostPool *p; ~Joiner() { p->wait(); } } joiner{c->pool};  // the job reads this frame
-  // cumulative halfedge lengths of the sampler (cumlen += e->get_length(),
-  // lib/ttessel.cpp:1980), accumulated in SLOT order: faces in index order, each
-  // face in ccb order from outer_ccb().  Entry m of `cum` is slot m.  (Indices are
-  // clamped here; the workers report anything out of range.)
   std::vector<double> &cum = c->h_cum;
-  cum.assign((size_t)s->n_face_he, 0.0);
+  cum.resize((size_t)s->n_face_he);
+  // The worker that finishes last starts the copy of everything packed so far (all but the
+  // cumulative lengths, which this thread is still summing): the 0.08 ms on the link overlap the
+  // rest of the host work.  Not for a tessellation with holes: its extended lists are built below.
+  const size_t bulk_bytes = c->arena.used;
+  std::atomic<int> arrived{0};
+  bool early_copy = false;
+  if (g_trace) {
+    if (!c->ev_tr[0]) for (int k = 0; k < 3; k++) cudaEventCreate(&c->ev_tr[k]);
+    else {
+      float h2d = 0, prep = 0;
+      if (cudaEventSynchronize(c->ev_tr[2]) == cudaSuccess && cudaEventElapsedTime(&h2d, c->ev_tr[0], c->ev_tr[1]) == cudaSuccess &&
+          cudaEventElapsedTime(&prep, c->ev_tr[1], c->ev_tr[2]) == cudaSuccess)
+        fprintf(stderr, "[lite_b200] previous upload on the device: copy %.3f ms, rest of the copy + checks + preparation %.3f ms\n", h2d, prep);
+    }
+  }
+  c->pool->run([=, &bad_he, &part_inside, &part_twice, &arrived, &early_copy](int t) {
+    for (size_t k = t; k < c->pack_jobs.size(); k += nt) memcpy_stream(c->pack_jobs[k].dst, (const char *)c->pack_jobs[k].src, c->pack_jobs[k].bytes);
+    _mm_sfence();
+    const int h0 = (int)((int64_t)nH * t / nt), h1 = (int)((int64_t)nH * (t + 1) / nt);
+    int64_t inside = 0, twice = 0;
+    for (int h = h0; h < h1; h++) {
+      const int f = s->he_face[h], tw = s->he_twin[h];
+      if ((unsigned)f >= (unsigned)nF || (unsigned)tw >= (unsigned)nH) { bad_he[t] = h; break; }
+      if (!s->face_inside[f]) continue;
+      inside++;
+      c->h_he_inside[h] = 1;
+      if (s->he_face[tw] == f) twice++;   // the face runs along both sides of this edge
+    }
+    part_inside[t] = inside;
+    part_twice[t] = twice;
+    if (arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == nt) {
+      int64_t ti = 0, tt = 0;
+      bool bad = false;
+      for (int q = 0; q < nt; q++) { ti += part_inside[q]; tt += part_twice[q]; bad |= bad_he[q] >= 0; }
+      if (!bad && ti == listed && tt == 0 && !c->validate_host && cudaSetDevice(c->device) == cudaSuccess) {
+        if (g_trace) cudaEventRecord(c->ev_tr[0], c->stream);
+        early_copy = cudaMemcpyAsync(c->arena.d, c->arena.h, bulk_bytes, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+        if (g_trace) cudaEventRecord(c->ev_tr[1], c->stream);
+      }
+    }
+  });
+  struct Joiner { HostPool *p; ~Joiner() { p->wait(); } } joiner{c->pool};  // the job reads this frame
+  const double t_stage = now_ms();
+  // cumulative halfedge lengths of the sampler (cumlen += e->get_length(), lib/ttessel.cpp:1980),
+  // accumulated sequentially in SLOT order (faces in index order, each in ccb order from
+  // outer_ccb()): the summation order is part of the sampler's definition.  Entry m is slot m.
   double cl = 0.0;
-  for (int f = 0; f < nF; f++) {
+  int bad_list = -1;
+  for (int f = 0; f < nF && bad_list < 0; f++) {
     const int off = s->face_he_offset[f], cnt = s->face_he_count[f];
-    if (off < 0 || cnt < 0 || off + cnt > s->n_face_he) break;
     if (!s->face_inside[f]) { for (int k = 0; k < cnt; k++) cum[off + k] = cl; continue; }
     for (int k = 0; k < cnt; k++) {
       const int h = s->face_he_list[off + k];
-      if (h >= 0 && h < nH) cl += s->he_length[h];
+      if ((unsigned)h >= (unsigned)nH) { bad_list = f; break; }
+      cl += s->he_length[h];
       cum[off + k] = cl;
     }
   }
+  const double t_cum = now_ms();
   c->pool->wait();
-  int64_t listed = 0, inside_he = 0, twice = 0;
-  for (int t = 0; t < nt; t++) {
-    if (bad_face[t] >= 0) return fail(LITE_EINVAL, "face %d: halfedge list out of range or fewer than 3 halfedges", bad_face[t]);
-    if (bad_list_f[t] >= 0)
-      return fail(LITE_EINVAL, "face %d: halfedge list disagrees with he_next/he_face at position %d", bad_list_f[t], bad_list_k[t]);
+  if (g_trace) fprintf(stderr, "[lite_b200] tess_upload host: staging %.3f ms, cumulative lengths %.3f ms, wait for the workers (pack, count) %.3f ms\n",
+                       t_stage - t0, t_cum - t_stage, now_ms() - t_cum);
+  if (bad_list >= 0) return fail(LITE_EINVAL, "face %d: halfedge list out of range", bad_list);
+  for (int t = 0; t < nt; t++)
     if (bad_he[t] >= 0) return fail(LITE_EINVAL, "halfedge %d: inconsistent links", bad_he[t]);
-    listed += part_listed[t]; inside_he += part_inside[t]; twice += part_twice[t];
-  }
+  int64_t inside_he = 0, twice = 0;
+  for (int t = 0; t < nt; t++) { inside_he += part_inside[t]; twice += part_twice[t]; }
   if (inside_he < listed)
     return fail(LITE_EINVAL, "%lld halfedges bound inside faces but %lld are listed on outer boundaries",
                 (long long)inside_he, (long long)listed);
@@ -629,6 +722,10 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   // gen_face.h.  A rectangular window never has any and skips all of this.
   const bool general = inside_he != listed || twice != 0;
   c->n_general = 0;
+  if (general || c->validate_host) {
+    const int hv = host_validate(c, s);
+    if (hv) return hv;
+  }
   const int32_t *l_off = s->face_he_offset, *l_cnt = s->face_he_count, *l_list = s->face_he_list;
   size_t n_slots = (size_t)s->n_face_he;
   if (general) {
@@ -670,16 +767,6 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   if (!(fabs(cl - s->int_length) <= 1e-9 * fmax(1.0, fabs(cl))))
     return fail(LITE_EINVAL, "int_length %.17g differs from the sum of inside halfedge lengths %.17g",
                 s->int_length, cl);
-  for (int i = 0; i < s->n_non_blocking; i++) {
-    int sg = s->non_blocking[i];
-    if (sg < 0 || sg >= nS || s->seg_n_edges[sg] != 1 || s->seg_on_boundary[sg])
-      return fail(LITE_EINVAL, "non-blocking segment %d must be internal with exactly one edge", sg);
-  }
-  for (int i = 0; i < s->n_blocking; i++) {
-    int sg = s->blocking[i];
-    if (sg < 0 || sg >= nS || s->seg_n_edges[sg] < 2 || s->seg_on_boundary[sg])
-      return fail(LITE_EINVAL, "blocking segment %d must be internal with at least two edges", sg);
-  }
   t1 = now_ms();
   c->pack_jobs.clear();
   r |= up(c, c->cum, cum.data(), cum.size());
@@ -694,10 +781,17 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   }
   if (c->guide.alloc((size_t)n_guide)) return LITE_ECUDA;
   if (r) return r;
-  for (size_t k = 0; k < c->pack_jobs.size(); k++) memcpy(c->pack_jobs[k].dst, c->pack_jobs[k].src, c->pack_jobs[k].bytes);
+  for (size_t k = 0; k < c->pack_jobs.size(); k++) memcpy_stream(c->pack_jobs[k].dst, (const char *)c->pack_jobs[k].src, c->pack_jobs[k].bytes);
+  _mm_sfence();
   c->pack_jobs.clear();
   t2 = now_ms();
-  CU(cudaMemcpyAsync(c->arena.d, c->arena.h, c->arena.used, cudaMemcpyHostToDevice, c->stream));
+  if (early_copy) {  // the bulk is on its way: only what was staged since (the cumulative lengths)
+    CU(cudaMemcpyAsync(c->arena.d + bulk_bytes, c->arena.h + bulk_bytes, c->arena.used - bulk_bytes, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    if (g_trace) cudaEventRecord(c->ev_tr[0], c->stream);
+    CU(cudaMemcpyAsync(c->arena.d, c->arena.h, c->arena.used, cudaMemcpyHostToDevice, c->stream));
+    if (g_trace) cudaEventRecord(c->ev_tr[1], c->stream);
+  }
   CU(cudaEventRecord(c->ev_upload, c->stream));
   c->upload_inflight = true;
   const size_t nSl = n_slots;
@@ -722,7 +816,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   A.slot_he = c->slot_he.p; A.slot_seg = c->slot_seg.p; A.slot_face = c->slot_face.p;
   A.he_slot = c->he_slot.p; A.err = c->err.p;
   TessDev &T = c->T;
-  T.n_slots = (int)nSl; T.n_faces = nF; T.n_he = nH; T.n_seg = nS;
+  T.n_slots = (int)nSl; T.n_faces = nF; T.n_he = nH; T.n_seg = nS; T.err = c->err.p;
   T.pt = c->pt.p; T.udir = c->udir.p; T.ang = c->ang.p; T.len = c->len.p; T.ca = c->ca.p; T.flg = c->flg.p;
   T.slot_he = c->slot_he.p; T.slot_seg = c->slot_seg.p; T.slot_face = c->slot_face.p;
   T.he_slot = c->he_slot.p; T.he_twin = c->he_twin.p; T.he_src = c->he_src.p;
@@ -748,22 +842,37 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
       CU(cudaMalloc((void **)&c->gen_scratch, 2 * (size_t)c->gen_blocks * LITE_GEN_TB * LITE_GEN_PTS * sizeof(gen::Pt)));
     }
   }
+  {
+    ValidateArgs V{};
+    V.nV = nV; V.nH = nH; V.nF = nF; V.nS = nS; V.nFH = (int)nSl; V.nNB = s->n_non_blocking; V.nB = s->n_blocking;
+    V.he_src = c->he_src.p; V.he_twin = c->he_twin.p; V.he_next = c->he_next.p; V.he_face = c->he_face.p;
+    V.he_seg = c->he_seg.p; V.he_next_hf = c->he_next_hf.p; V.he_prev_hf = c->he_prev_hf.p;
+    V.face_inside = c->face_inside.p; V.seg_bnd = c->seg_bnd.p; V.f_gen = general ? c->g_fgen.p : nullptr;
+    V.f_off = c->f_off.p; V.f_cnt = c->f_cnt.p; V.f_list = c->f_list.p; V.seg_he_start = c->seg_he_start.p;
+    V.seg_he_end = c->seg_he_end.p; V.seg_n_edges = c->seg_n_edges.p; V.nb_list = c->nb_list.p; V.b_list = c->b_list.p;
+    V.err = c->err.p;
+    int most = nH;
+    if (nF > most) most = nF;
+    if (nS > most) most = nS;
+    if ((int)nSl > most) most = (int)nSl;
+    k_validate<<<(most + 255) / 256, 256, 0, c->stream>>>(V);
+    c->launches += 1;
+  }
   int tb = 128, gb = (nF + tb - 1) / tb;
   k_build_guide<<<(n_guide + 255) / 256, 256, 0, c->stream>>>(c->cum.p, (int)cum.size(), cl / (double)n_guide, n_guide, c->guide.p);
-  CU(cudaMemsetAsync(c->slot_face.p, 0xFF, nSl * sizeof(int), c->stream));
-  k_prep_slot_face<<<gb, tb, 0, c->stream>>>(A);
   k_prep_slots<<<(unsigned)((nSl + 127) / 128), 128, 0, c->stream>>>(A, (int)nSl);
   // outside faces: count 0 in the device view
   k_prep_faces<<<gb, tb, 0, c->stream>>>(T, c->ca.p, c->f_area.p, c->f_perim.p, c->f_sumang.p, c->f_minang.p,
                                          c->pre.p, c->plen.p, c->f_tot2.p, c->sfo.p, c->stot2.p);
-  c->launches += 4;
+  c->launches += 3;
   // the merge/flip stream only depends on the tessellation being in place: it forks here,
   // not from whatever the main stream is doing when SetEnergy is called (the split kernel,
   // if AddSplits came first: the two then run side by side)
   CU(cudaEventRecord(c->ev_fork, c->stream));
+  if (g_trace) cudaEventRecord(c->ev_tr[2], c->stream);
   t3 = now_ms();
-  // no synchronisation: the link checks were done on the host above, the copy and the
-  // preparation kernels run behind the caller's next calls on the same stream
+  // no synchronisation: the copy, the checks and the preparation kernels run behind the
+  // caller's next calls on the same stream
   CU(cudaGetLastError());
   t4 = now_ms();
   if (g_trace)
@@ -773,6 +882,26 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   c->have_tess = true; c->have_mf = false; c->mf_pending = false;
   c->n_local = 0; c->n_global = 0;
   return 0;
+}
+
+// after a synchronisation of c->stream: did the uploaded tessellation pass k_validate?
+static int tess_err_report(lite_ctx *c, int code) {
+  if (!code) return 0;
+  static const char *what[] = {"?", "halfedge with links out of range or twin(twin) != itself", "face with a halfedge list out of range",
+                               "face list entry that is not a halfedge of the face followed by its next", "segment with halfedges out of range",
+                               "non-blocking segment that is not internal with exactly one edge",
+                               "blocking segment that is not internal with at least two edges"};
+  const int k = (code >> 24) & 0xff;
+  c->have_tess = false; c->have_mf = false;
+  return fail(LITE_EINVAL, "the uploaded tessellation is inconsistent: %s (element %d); upload a valid one",
+              what[(k >= 1 && k <= 6) ? k : 0], code & 0xffffff);
+}
+static int tess_err_sync(lite_ctx *c) {
+  if (!c->have_tess) return 0;
+  int code = 0;
+  CU(cudaMemcpyAsync(&code, c->err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return tess_err_report(c, code);
 }
 
 static int category_of(int fid) {
@@ -1096,6 +1225,7 @@ extern "C" int lite_lines_sample_clip(lite_ctx *c, int64_t n_global, uint64_t se
   CU(cudaMemcpyAsync(c->h_pinned, c->status.p + 2, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
+  { const int tr = tess_err_sync(c); if (tr) return tr; }
   if (n > 0) cudaEventElapsedTime(&c->ms_split, c->ev[0], c->ev[1]);
   if (checksum2) memcpy(checksum2, c->h_pinned, 2 * sizeof(uint64_t));
   return 0;
@@ -1229,8 +1359,13 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
   CU(cudaMemcpyAsync(c->h_pinned + 256, c->status.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(c->h_pinned + 258, c->status.p + 6, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   if (exch) CU(cudaMemcpyAsync(c->h_pinned + 260, c->peer_info.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->h_pinned + 264, c->err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
+  {
+    const int tr = tess_err_report(c, *(const int *)(c->h_pinned + 264));
+    if (tr) return tr;
+  }
   c->mf_inflight = false;
   finalize_mf(c);
   cudaEventElapsedTime(&c->ms_eval, c->ev[2], c->ev[3]);
@@ -1285,6 +1420,7 @@ extern "C" int lite_pl_sums(lite_ctx *c, double *sm, double *sf) {
   CU(cudaStreamSynchronize(c->stream2));
   c->mf_inflight = false;
   finalize_mf(c);
+  { const int tr = tess_err_sync(c); if (tr) return tr; }
   for (int i = 0; i < c->G.d; i++) {
     if (sm) sm[i] = c->h_sum_m[i];
     if (sf) sf[i] = c->h_sum_f[i];
@@ -1320,6 +1456,7 @@ extern "C" int lite_debug_fetch(lite_ctx *c, int which, int64_t first, int64_t c
   CU(cudaStreamSynchronize(c->stream2));
   c->mf_inflight = false;
   finalize_mf(c);
+  { const int tr = tess_err_sync(c); if (tr) return tr; }
   const size_t ns = (size_t)c->n_local, nm = (size_t)c->n_nb, nf = (size_t)2 * c->n_b;
   const bool rec = c->rcap > 0;
   switch (which) {

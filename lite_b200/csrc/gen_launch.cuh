@@ -23,6 +23,7 @@ struct GenSplitArgs {
 
 __global__ void __launch_bounds__(LITE_GEN_TB) k_gen_splits(TessDev T, gen::Tess GT, Prog G, GenSplitArgs X) {
   const SplitArgs &A = X.A;
+  if (*T.err) return;
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long)gridDim.x * blockDim.x;
   gen::Scratch S;
   S.base = X.scratch + (size_t)tid * LITE_GEN_PTS; S.cap = LITE_GEN_PTS; S.used = 0; S.overflow = 0;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(LITE_GEN_TB) k_gen_splits(TessDev T, gen::Tess
 
 __global__ void __launch_bounds__(LITE_GEN_TB) k_gen_mf(TessDev T, gen::Tess GT, Prog G, MFArgs A, gen::Pt *scratch,
                                                         unsigned long long *overflow) {
+  if (*T.err) return;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
   gen::Scratch S;
   S.base = scratch + (size_t)tid * LITE_GEN_PTS; S.cap = LITE_GEN_PTS; S.used = 0; S.overflow = 0;

@@ -33,6 +33,7 @@
 
 struct TessDev {
   int n_slots, n_faces, n_he, n_seg;
+  const int *err;      // != 0: the uploaded tessellation failed the device checks (k_validate); kernels then do nothing
   // per slot
   const double2 *pt;   // source point
   const double *ang;   // atan2(dy,dx) of the halfedge (lib/ttessel.cpp:2095)
@@ -269,22 +270,77 @@ struct PrepArgs {
   int *err;  // consistency errors
 };
 
-// slot -> face (one thread per face, no dependent loads), then everything per slot with one
-// thread per slot: the loads of a slot chain four deep (list -> halfedge -> vertex / twin ->
-// face), and one thread per FACE walked its ~6 slots one after the other (50 us at 10^4 cells)
-__global__ void k_prep_slot_face(PrepArgs A) {
-  int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= A.n_faces) return;
-  int n = A.face_he_count[f];
-  if (n == 0 || !A.face_inside[f]) return;
-  int off = A.face_he_offset[f];
-  for (int k = 0; k < n; k++) A.slot_face[off + k] = f;
+// ---------------------------------------------------------------------------
+// Export assertions on the device (in the spirit of TTessel::is_valid, lib/ttessel.cpp:1721-1753).
+// lite_tess_upload used to run them on four host threads in front of the copy (0.2-0.27 ms of
+// a 1.2 ms end-to-end step); here they run at L2 speed behind it.  Every index that a later
+// kernel dereferences is range-checked before anything follows it; the first violation leaves
+// code*2^24 + element in *err, every kernel that reads the tessellation returns at once when
+// *err != 0, and the host reports it at its next synchronisation (or right away with
+// LITE_OPT_VALIDATE_SYNC).
+// ---------------------------------------------------------------------------
+struct ValidateArgs {
+  int nV, nH, nF, nS, nFH, nNB, nB;
+  const int *he_src, *he_twin, *he_next, *he_face, *he_seg, *he_next_hf, *he_prev_hf;
+  const uint8_t *face_inside, *seg_bnd, *f_gen;
+  const int *f_off, *f_cnt, *f_list, *seg_he_start, *seg_he_end, *seg_n_edges, *nb_list, *b_list;
+  int *err;
+};
+enum { LITE_BAD_HALFEDGE = 1, LITE_BAD_FACE = 2, LITE_BAD_FACE_LIST = 3, LITE_BAD_SEGMENT = 4, LITE_BAD_NON_BLOCKING = 5,
+       LITE_BAD_BLOCKING = 6 };
+__device__ __forceinline__ void flag_bad(int *err, int code, int elem) {
+  atomicCAS(err, 0, (code << 24) | (elem & 0xffffff));
 }
+__global__ void k_validate(ValidateArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < A.nH) {  // links in range, twin of twin
+    const int f = A.he_face[i], tw = A.he_twin[i], v = A.he_src[i], sg = A.he_seg[i], nx = A.he_next[i];
+    const int nhf = A.he_next_hf[i], phf = A.he_prev_hf[i];
+    bool ok = (unsigned)f < (unsigned)A.nF && (unsigned)tw < (unsigned)A.nH && (unsigned)v < (unsigned)A.nV &&
+              (unsigned)sg < (unsigned)A.nS && (unsigned)nx < (unsigned)A.nH && nhf >= -1 && nhf < A.nH && phf >= -1 &&
+              phf < A.nH;
+    if (ok) ok = A.he_twin[tw] == i;
+    if (!ok) flag_bad(A.err, LITE_BAD_HALFEDGE, i);
+  }
+  if (i < A.nF) {  // list range; an inside face lists at least three halfedges
+    const int off = A.f_off[i], cnt = A.f_cnt[i];
+    if (cnt < 0 || off < 0 || off > A.nFH || cnt > A.nFH - off || (A.face_inside[i] && cnt < 3)) flag_bad(A.err, LITE_BAD_FACE, i);
+  }
+  if (i < A.nS) {
+    const int a = A.seg_he_start[i], b = A.seg_he_end[i];
+    if ((unsigned)a >= (unsigned)A.nH || (unsigned)b >= (unsigned)A.nH || A.seg_n_edges[i] < 1) flag_bad(A.err, LITE_BAD_SEGMENT, i);
+  }
+  if (i < A.nNB) {
+    const int sg = A.nb_list[i];
+    if ((unsigned)sg >= (unsigned)A.nS || A.seg_n_edges[sg] != 1 || A.seg_bnd[sg]) flag_bad(A.err, LITE_BAD_NON_BLOCKING, i);
+  }
+  if (i < A.nB) {
+    const int sg = A.b_list[i];
+    if ((unsigned)sg >= (unsigned)A.nS || A.seg_n_edges[sg] < 2 || A.seg_bnd[sg]) flag_bad(A.err, LITE_BAD_BLOCKING, i);
+  }
+  if (i < A.nFH) {  // a list entry is a halfedge (that it bounds the face and chains to the next entry: k_prep_all)
+    if ((unsigned)A.f_list[i] >= (unsigned)A.nH) flag_bad(A.err, LITE_BAD_FACE_LIST, i);
+  }
+}
+
+// Everything per slot with one thread per slot: the loads of a slot chain four deep (list ->
+// halfedge -> vertex / twin -> face), and one thread per FACE walking its ~6 slots one after
+// the other took 50 us at 10^4 cells.  The face of slot m is the last one whose list starts at
+// or before m (lite_tess_upload has checked that the lists tile the slots in face order).
 __global__ void k_prep_slots(PrepArgs A, int n_slots) {
   int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= n_slots) return;
-  const int f = A.slot_face[m];
-  if (f < 0) return;  // a slot of an outside face
+  if (m >= n_slots || *A.err) return;
+  int f;
+  {
+    int lo = 0, hi = A.n_faces - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(A.face_he_offset + mid) <= m) lo = mid; else hi = mid - 1;
+    }
+    f = lo;
+  }
+  if (!A.face_inside[f] || m >= A.face_he_offset[f] + A.face_he_count[f]) { A.slot_face[m] = -1; return; }  // a slot of an outside face
+  A.slot_face[m] = f;
   const int n = A.face_he_count[f], off = A.face_he_offset[f], k = m - off;
   int h = A.face_he_list[off + k];
   int hp, hn;
@@ -299,11 +355,11 @@ __global__ void k_prep_slots(PrepArgs A, int n_slots) {
       if (A.he_next[i] == h) { hp = i; break; }
       o = A.he_next[i];
     }
-    if (A.he_face[h] != f) atomicAdd(A.err, 1);
+    if (A.he_face[h] != f) flag_bad(A.err, LITE_BAD_FACE_LIST, m);
   } else {
     hp = A.face_he_list[off + (k == 0 ? n - 1 : k - 1)];
     hn = A.face_he_list[off + (k + 1 == n ? 0 : k + 1)];
-    if (A.he_next[h] != hn || A.he_face[h] != f) atomicAdd(A.err, 1);
+    if (A.he_next[h] != hn || A.he_face[h] != f) flag_bad(A.err, LITE_BAD_FACE_LIST, m);
   }
   int vs = A.he_src[h], vt = A.he_src[hn];
   double sx = A.vx[vs], sy = A.vy[vs], tx = A.vx[vt], ty = A.vy[vt];
@@ -331,7 +387,7 @@ __global__ void k_prep_faces(TessDev T, double *ca, double *f_area, double *f_pe
                              double *f_sumang, double *f_minang, double *pre, double *plen,
                              double *f_tot2, int2 *sfo, double *stot2) {
   int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= T.n_faces) return;
+  if (f >= T.n_faces || *T.err) return;
   int n = T.f_cnt[f];
   if (n == 0) return;
   int off = T.f_off[f];
@@ -371,7 +427,7 @@ __global__ void k_prep_faces(TessDev T, double *ca, double *f_area, double *f_pe
 // guide table of the sampler: guide[b] = first slot m with cum[m] > b * step, clamped
 __global__ void k_build_guide(const double *cum, int n_cum, double step, int n_guide, int *guide) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= n_guide) return;
+  if (b >= n_guide) return;  // reads cum only (host-built), no guard needed
   const double lo = (double)b * step;
   int l = 0, h = n_cum - 1;
   while (l < h) {
@@ -833,6 +889,7 @@ __global__ void k_iid_draw(long n_local, long j0, uint64_t seed, uint64_t ctr0, 
 template <int MODE, class PG>
 __global__ void __launch_bounds__(LITE_SPLIT_TB, LITE_SPLIT_MINB) k_split(TessDev T, Prog G, SplitArgs A) {
   constexpr bool PHILOX = MODE & 1, RECORD = MODE & 2, STAT = MODE & 4, CHECK = MODE & 8;
+  if (*T.err) return;  // the tessellation failed k_validate
   // Guided self-scheduling: a warp takes contiguous runs of candidates (32 per
   // iteration) from a ticket counter; run lengths halve from n/(2*warps) down to 128,
   // so the slot cache pays off on the long early runs and the short late ones even
@@ -929,6 +986,10 @@ __device__ __forceinline__ void merge_one(const TessDev &T, const Prog &G, const
   int t = T.he_twin[e];
   out_he[i] = e;
   int se = T.he_slot[e], st_ = T.he_slot[t];
+  if ((se | st_) < 0) {  // not an internal segment: both sides must bound inside faces
+    for (int k = 0; k < G.d; k++) stat[(size_t)k * cap + i] = 0.0;
+    return;
+  }
   int f1 = T.slot_face[se], f2 = T.slot_face[st_];
   if (T.f_gen && (T.f_gen[f1] | T.f_gen[f2])) return;  // k_gen_mf has written this row (gen_face.h)
   int o1 = T.f_off[f1], n1 = T.f_cnt[f1], o2 = T.f_off[f2], n2 = T.f_cnt[f2];
@@ -1023,6 +1084,12 @@ __device__ __forceinline__ void flip_one(const TessDev &T, const Prog &G, const 
   int e1 = (i < nb) ? T.he_twin[T.seg_he_start[sg]] : T.seg_he_end[sg];
   int t1 = T.he_twin[e1];
   int s1 = T.he_slot[e1], st1 = T.he_slot[t1];
+  if ((s1 | st1) < 0) {  // not an internal segment
+    out_e1[i] = e1; out_e2[i] = -1; out_right[i] = 0; out_p2[i] = make_double2(0, 0);
+    atomicAdd(status, 1ull);
+    for (int k = 0; k < G.d; k++) stat[(size_t)k * cap + i] = 0.0;
+    return;
+  }
   int fL = T.slot_face[s1], fT = T.slot_face[st1];  // face(e1), face(twin e1)
   if (T.f_gen && (T.f_gen[fL] | T.f_gen[fT])) return;  // k_gen_mf has written this row and its outputs
   int oL = T.f_off[fL], nL = T.f_cnt[fL], oT = T.f_off[fT], nT = T.f_cnt[fT];
@@ -1242,6 +1309,7 @@ struct MFArgs {
 // beside k_split, which fills every SM, and finished only after it (scripts/step_variants.py).
 __global__ void __launch_bounds__(128) k_merges_flips(TessDev T, Prog G, MFArgs A) {
   __shared__ double sh[128];
+  if (*T.err) return;  // the tessellation failed k_validate (block-uniform)
   const bool merges = (int)blockIdx.x < A.gm;
   const int i = (merges ? blockIdx.x : blockIdx.x - A.gm) * blockDim.x + threadIdx.x;
   const int n = merges ? A.nm : 2 * A.nb;

@@ -751,3 +751,43 @@ def test_iid_sampler_is_the_split_sample_law(lite):
     # the stratified sampler: same mean, smaller spread
     assert abs(lpl_str.mean() - lpl_orc.mean()) < 5 * math.sqrt(v_str / reps + v_orc / reps)
     assert v_str < v_iid, (v_str, v_iid)
+
+
+@pytest.mark.parametrize("what", ["twin", "list", "segment", "blocking", "range"])
+def test_inconsistent_tessellation_is_caught_on_the_device(lite, what):
+    """The export assertions run on the device behind the copy (k_validate): lite_tess_upload
+    returns, no kernel dereferences an unchecked index, and the next synchronising call reports
+    the inconsistency.  With LITE_OPT_VALIDATE_HOST the upload itself reports it.  The context
+    stays usable."""
+    soa, gold = load_golden("t100")
+    bad = {k: np.array(v, copy=True) for k, v in soa.items()}
+    if what == "twin":
+        bad["he_twin"][5] = bad["he_twin"][9]
+    elif what == "list":
+        f = int(np.nonzero(bad["face_inside"])[0][3])
+        o = int(bad["face_he_offset"][f])
+        bad["face_he_list"][o], bad["face_he_list"][o + 1] = bad["face_he_list"][o + 1], bad["face_he_list"][o]
+    elif what == "segment":
+        bad["seg_he_start"][2] = len(bad["he_src"]) + 1000
+    elif what == "blocking":
+        bad["blocking"][0] = bad["non_blocking"][0]
+    else:
+        bad["he_src"][11] = 10 ** 9
+    th = gold["pl_acs_1_theta"]
+    ctx = lite.Context(0)
+    ctx.energy_set(ACS)
+    ctx.tess_upload(lite.TessSoA(bad))          # returns: the checks are queued behind the copy
+    ctx.merges_flips()
+    ctx.add_splits_philox(5000, 1, 0)
+    with pytest.raises(lite.LiteError, match="inconsistent"):
+        ctx.pl_eval(th)
+    with pytest.raises(lite.LiteError, match="upload a tessellation"):
+        ctx.merges_flips()
+    ctx.validate_on_host(True)
+    with pytest.raises(lite.LiteError):
+        ctx.tess_upload(lite.TessSoA(bad))
+    ctx.tess_upload(lite.TessSoA(soa))
+    ctx.merges_flips()
+    ctx.add_splits_given(gold["cand_he"], gold["cand_x"], gold["cand_angle"])
+    assert ctx.pl_eval(th)[0] == pytest.approx(float(gold["pl_acs_1_lpl"]), rel=RTOL)
+    ctx.close()
