@@ -669,15 +669,22 @@ def run_secondary(ctx, lite_b200, soa_c2, fp64_peak, hbm_peak):
         ctx.clear_splits()
         ctx.energy_set(ACS3)
         n_fit = 10_000_000
-        newton_fit(ctx, 200_000, [0.0, 0.0, 0.0], 1)             # warm-up: allocations, module load
-        fit = newton_fit(ctx, n_fit, [0.0, 0.0, 0.0], 4)
+        # start: the closed-form CRTT estimate for the segment parameter (the tessellation IS a CRTT
+        # sample), zero for the two face parameters.  From theta = 0 the first plain
+        # Newton step overshoots by six orders of magnitude in the face_area_2 direction (areas^2 ~ 1e-8).
+        nm_c2 = ctx.merges_flips()[0]
+        theta0 = [0.0, 0.0, -math.log(nm_c2 * math.pi / soa_c2.int_length)]
+        newton_fit(ctx, 200_000, theta0, 1)             # warm-up: allocations, module load
+        fit = newton_fit(ctx, n_fit, theta0, 4)
         per_eval_ms = fit["k_reduce_ms_total"] / (fit["evaluations"] - 1)
         gbs = n_fit * 8 * len(ACS3) / (per_eval_ms * 1e-3) / 1e9
         out["c2_newton_fit"] = {
             "what": "PLInferenceNOIS-equivalent fit of the ACS energy restricted to its identifiable sub-vector "
                     "(face_area_2, face_sum_of_angles, is_segment_internal; the as-written edge_length row of the "
                     "Hessian is singular, SURVEY.md App. C 3) on the C2 tessellation: 10^7 Philox dummy splits, then 4 "
-                    "Newton iterations from theta = 0, each = gradient+Hessian pass, update, AddSplits(n_merges), value pass",
+                    "Newton iterations from (0, 0, closed-form CRTT estimate), each = gradient+Hessian pass, update, "
+                    "AddSplits(n_merges), value pass",
+            "theta_start": theta0,
             "time_to_fit_ms": fit["device_ms"], "host_ms": fit["host_ms"], "iterations": 4,
             "evaluations_over_all_splits": fit["evaluations"], "splits": fit["splits_final"],
             "theta_hat": fit["theta_path"][-1], "theta_path": fit["theta_path"], "lpl_path": fit["lpl_path"],

@@ -59,6 +59,24 @@ int main(int argc, char **argv) {
       for (int k = 1; k < 11; k++) printf(" %.0f", r[(size_t)k * chains]);
       printf("\n");
     }
+  // the reference's intersection file for the final state (:100-103, :151-172): the four window
+  // edges and the two mid-lines against every internal edge of every chain
+  {
+    const double w = width;
+    const double probes[6 * 4] = {0, 0, w, 0,  w, 0, w, w,  w, w, 0, w,  0, w, 0, 0,  0, w / 2, w, w / 2,  w / 2, 0, w / 2, w};
+    int64_t n_found = 0;
+    CK(lite_smf_intersections(ctx, 6, probes, 0, NULL, NULL, NULL, &n_found));
+    std::vector<int32_t> ch((size_t)n_found + 1), seg((size_t)n_found + 1);
+    std::vector<double> xy(2 * (size_t)n_found + 2);
+    CK(lite_smf_intersections(ctx, 6, probes, n_found, ch.data(), seg.data(), xy.data(), &n_found));
+    FILE *fi = fopen("inter_final.txt", "w");
+    if (fi) {
+      fprintf(fi, "chain seg x y\n");
+      for (int64_t k = 0; k < n_found; k++) fprintf(fi, "%d %d %.*g %.*g\n", ch[k], seg[k], prec, xy[2 * k], prec, xy[2 * k + 1]);
+      fclose(fi);
+    }
+    fprintf(stderr, "%lld intersections of internal edges with the 6 probe segments\n", (long long)n_found);
+  }
   // the final tessellation of the first chain in the reference's text format (:175)
   lite_host_tess *t;
   CK(lite_smf_export(ctx, 0, &t));

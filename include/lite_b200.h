@@ -268,6 +268,15 @@ int lite_smf_trace(lite_ctx *ctx, int64_t chain_local, int64_t n_steps, void *tr
 int lite_smf_export(lite_ctx *ctx, int64_t chain_local, struct lite_host_tess **out);
 int lite_smf_count(lite_ctx *ctx, int64_t *n_local, int64_t *n_global, int64_t *first_global,
                    int64_t *bytes_per_chain);
+/* The intersection output of applications/checkACS.cpp:151-172 for the current state of every
+ * local chain: one record (local chain index, probe index, x, y) for each internal edge (both
+ * faces bounded) that meets probe segment k = (probes[4k..4k+1]) -> (probes[4k+2..4k+3]) in a single
+ * point (crossing or touching; collinear overlaps are not points).  checkACS probes with the four
+ * window edges and the two mid-lines.  Records come in no particular order.  n_found receives the
+ * number of intersections; if it exceeds cap the first cap are returned with LITE_ECAPACITY
+ * (call with cap = 0 and NULL outputs to count). */
+int lite_smf_intersections(lite_ctx *ctx, int32_t n_probes, const double *probes, int64_t cap,
+                           int32_t *chain_out, int32_t *probe_out, double *xy_out, int64_t *n_found);
 /* Device time (ms) of the last lite_smf_run kernel. */
 int lite_smf_last_ms(lite_ctx *ctx, float *ms);
 

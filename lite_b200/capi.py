@@ -36,7 +36,7 @@ SYMBOLS = [
     "lite_measure_fp64_peak", "lite_last_reduce_ms", "lite_timer_mark", "lite_timer_elapsed",
     "lite_smf_create", "lite_smf_destroy", "lite_smf_set_model", "lite_smf_run", "lite_smf_stats",
     "lite_smf_trace", "lite_smf_export", "lite_smf_count", "lite_smf_last_ms",
-    "lite_pl_combine", "lite_shard_range", "lite_pl_failures", "lite_comm_info",
+    "lite_pl_combine", "lite_shard_range", "lite_pl_failures", "lite_comm_info", "lite_smf_intersections",
 ]
 
 # columns of lite_smf_run / lite_smf_stats (applications/checkACS.cpp:136-148 + energy)
@@ -174,6 +174,8 @@ def load_library():
     L.lite_smf_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                  C.POINTER(C.c_int64)]
     L.lite_smf_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.lite_smf_intersections.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.POINTER(C.c_int64)]
     L.lite_pl_combine.argtypes = [C.c_int, C.c_int64, C.c_double] + [C.c_void_p] * 8
     L.lite_shard_range.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.lite_pl_failures.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -435,6 +437,20 @@ class Context:
         h = C.c_void_p()
         _ck(self.L, self.L.lite_smf_export(self.h, int(chain_local), C.byref(h)))
         return HostTess(handle=h)
+
+    def smf_intersections(self, probes):
+        """checkACS's intersection output for the current state of every local chain: arrays
+        (chain, probe, xy) sorted by (chain, probe, x, y).  probes: [n, 4] segments x0 y0 x1 y1."""
+        pr = np.ascontiguousarray(probes, dtype=np.float64).reshape(-1, 4)
+        n = C.c_int64()
+        _ck(self.L, self.L.lite_smf_intersections(self.h, len(pr), pr.ctypes.data_as(C.c_void_p), 0, None, None, None, C.byref(n)))
+        cap = max(1, n.value)
+        ch, kk, xy = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32), np.zeros((cap, 2))
+        _ck(self.L, self.L.lite_smf_intersections(self.h, len(pr), pr.ctypes.data_as(C.c_void_p), cap, ch.ctypes.data_as(C.c_void_p),
+                                                  kk.ctypes.data_as(C.c_void_p), xy.ctypes.data_as(C.c_void_p), C.byref(n)))
+        m = n.value
+        order = np.lexsort((xy[:m, 1], xy[:m, 0], kk[:m], ch[:m]))
+        return ch[:m][order], kk[:m][order], xy[:m][order]
 
     def smf_last_ms(self):
         t = C.c_float()

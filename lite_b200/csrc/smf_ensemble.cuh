@@ -310,6 +310,82 @@ extern "C" int lite_smf_trace(lite_ctx *c, int64_t chain_local, int64_t n_steps,
   return 0;
 }
 
+// Intersections of the internal edges of every chain with a few probe segments: the
+// `inter_*.txt` output of applications/checkACS.cpp:151-172 (there the probes are the four window
+// edges and the two mid-lines, and a row is written when CGAL::intersection(probe, edge) is a single
+// point: crossings and touching end points, not collinear overlaps).
+__global__ void __launch_bounds__(LITE_SMF_TB) k_smf_intersect(char *blob, size_t stride, int cap, int n, int n_probes,
+                                                               const double *probes, long long out_cap, int *o_chain,
+                                                               int *o_probe, double2 *o_xy, unsigned long long *count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  smf::Header h_loc;
+  smf::Chain c;
+  c.H = &h_loc;
+  smf::bind(c, blob + (size_t)i * stride, cap);
+  smf::load(c);
+  for (int p = 0; p < c.H->n_p; p++) {
+    if (!smf::pair_alive(c, p) || smf::h_bnd(c, 2 * p)) continue;   // both faces bounded: an internal edge
+    const smf::Pt a = smf::P_src(c, 2 * p), b = smf::P_src(c, 2 * p + 1);
+    for (int k = 0; k < n_probes; k++) {
+      const double cx = probes[4 * k], cy = probes[4 * k + 1], dx = probes[4 * k + 2], dy = probes[4 * k + 3];
+      const double o1 = (b.x - a.x) * (cy - a.y) - (b.y - a.y) * (cx - a.x);   // probe ends against the edge's line
+      const double o2 = (b.x - a.x) * (dy - a.y) - (b.y - a.y) * (dx - a.x);
+      const double o3 = (dx - cx) * (a.y - cy) - (dy - cy) * (a.x - cx);       // edge ends against the probe's line
+      const double o4 = (dx - cx) * (b.y - cy) - (dy - cy) * (b.x - cx);
+      if (o1 == 0.0 && o2 == 0.0) continue;                                     // collinear: not a point
+      const bool s12 = (o1 <= 0.0 && o2 >= 0.0) || (o1 >= 0.0 && o2 <= 0.0);
+      const bool s34 = (o3 <= 0.0 && o4 >= 0.0) || (o3 >= 0.0 && o4 <= 0.0);
+      if (!s12 || !s34) continue;
+      const double t = o3 / (o3 - o4);                                          // along the edge a -> b
+      const unsigned long long at = atomicAdd(count, 1ull);
+      if ((long long)at < out_cap) {
+        o_chain[at] = i; o_probe[at] = k;
+        o_xy[at] = make_double2(fma(t, b.x - a.x, a.x), fma(t, b.y - a.y, a.y));
+      }
+    }
+  }
+}
+
+extern "C" int lite_smf_intersections(lite_ctx *c, int32_t n_probes, const double *probes, int64_t cap,
+                                      int32_t *chain_out, int32_t *probe_out, double *xy_out, int64_t *n_found) {
+  if (!c || !c->smf || !probes || !n_found) return fail(LITE_ESTATE, "lite_smf_create first");
+  if (n_probes < 1 || n_probes > 64 || cap < 0) return fail(LITE_EINVAL, "bad probe count or capacity");
+  SmfState *S = c->smf;
+  CU(cudaSetDevice(c->device));
+  const int n = (int)S->n_local;
+  *n_found = 0;
+  if (n == 0) return 0;
+  double *d_probes = nullptr; int *d_chain = nullptr, *d_probe = nullptr; double2 *d_xy = nullptr;
+  unsigned long long *d_count = nullptr, found = 0;
+  const size_t m = cap > 0 ? (size_t)cap : 1;
+  int rc = 0;
+  if (cudaMalloc((void **)&d_probes, 4 * n_probes * sizeof(double)) != cudaSuccess || cudaMalloc((void **)&d_chain, m * sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void **)&d_probe, m * sizeof(int)) != cudaSuccess || cudaMalloc((void **)&d_xy, m * sizeof(double2)) != cudaSuccess ||
+      cudaMalloc((void **)&d_count, sizeof(unsigned long long)) != cudaSuccess)
+    rc = fail(LITE_ECUDA, "cudaMalloc for %lld intersection records failed", (long long)cap);
+  if (!rc) {
+    cudaMemcpyAsync(d_probes, probes, 4 * n_probes * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), c->stream);
+    k_smf_intersect<<<(n + LITE_SMF_TB - 1) / LITE_SMF_TB, LITE_SMF_TB, 0, c->stream>>>(S->blob, S->stride, S->cap, n, n_probes, d_probes,
+                                                                                  (long long)cap, d_chain, d_probe, d_xy, d_count);
+    c->launches++;
+    cudaMemcpyAsync(&found, d_count, sizeof found, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(LITE_ECUDA, "k_smf_intersect: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  if (!rc) {
+    *n_found = (int64_t)found;
+    const size_t k = (size_t)((int64_t)found < cap ? (int64_t)found : cap);
+    if (k && chain_out) cudaMemcpy(chain_out, d_chain, k * sizeof(int), cudaMemcpyDeviceToHost);
+    if (k && probe_out) cudaMemcpy(probe_out, d_probe, k * sizeof(int), cudaMemcpyDeviceToHost);
+    if (k && xy_out) cudaMemcpy(xy_out, d_xy, k * sizeof(double2), cudaMemcpyDeviceToHost);
+    if ((int64_t)found > cap && (chain_out || probe_out || xy_out))
+      rc = fail(LITE_ECAPACITY, "%lld intersections found, room for %lld: call again with that capacity", (long long)found, (long long)cap);
+  }
+  cudaFree(d_probes); cudaFree(d_chain); cudaFree(d_probe); cudaFree(d_xy); cudaFree(d_count);
+  return rc;
+}
+
 struct lite_host_tess;
 extern "C" int lite_smf_blob_to_host_(char *blob, int cap, lite_host_tess **out);  // host_capi.cpp
 

@@ -216,3 +216,40 @@ def test_simulate_gibbs_model_then_recover_theta_by_pl_newton(ctx):
     # maximum pseudo-likelihood estimator on ~100-cell tessellations)
     assert np.all(np.abs(mean - truth) < 4 * sem + 0.05 * np.abs(truth)), (mean, sem, truth)
     ctx.smf_destroy()
+
+
+def test_intersection_output_of_checkacs(ctx):
+    """lite_smf_intersections = the inter file of applications/checkACS.cpp:151-172: every
+    internal edge against the four window edges and the two mid-lines.  Checked against a plain
+    numpy computation on the exported chains: a mid-line is crossed by the edges that straddle
+    it, a window edge is touched by the internal edges that end on it."""
+    ctx.smf_create(40, 300, seed=9)
+    ctx.smf_set_model(["is_segment_internal", "edge_length"], [-math.log(4.0), 3.0 / math.pi])
+    ctx.smf_run(1, 1500, rows=False)
+    probes = np.array([[0, 0, 1, 0], [1, 0, 1, 1], [1, 1, 0, 1], [0, 1, 0, 0], [0, .5, 1, .5], [.5, 0, .5, 1]], dtype=np.float64)
+    ch, kk, xy = ctx.smf_intersections(probes)
+    assert len(ch) > 40 * 10
+    for chain in (0, 7, 39):
+        a = ctx.smf_export(chain).export().a
+        inside = a["face_inside"][a["he_face"]].astype(bool)
+        internal = inside & inside[a["he_twin"]] & (np.arange(len(inside)) < a["he_twin"])      # one halfedge per internal edge
+        src, dst = a["he_src"][internal], a["he_src"][a["he_twin"][internal]]
+        ax, ay, bx, by = a["vx"][src], a["vy"][src], a["vx"][dst], a["vy"][dst]
+        want = []
+        for k, (x0, y0, x1, y1) in enumerate(probes):
+            if k < 4:       # window edge: touched by an end point lying on it
+                for px, py in ((ax, ay), (bx, by)):
+                    on = (px == x0) if x0 == x1 else (py == y0)
+                    want += [(k, float(u), float(v)) for u, v in zip(px[on], py[on])]
+            elif k == 4:    # y = 1/2
+                cr = (ay - .5) * (by - .5) < 0
+                t = (ay[cr] - .5) / (ay[cr] - by[cr])
+                want += [(k, float(u), .5) for u in ax[cr] + t * (bx[cr] - ax[cr])]
+            else:           # x = 1/2
+                cr = (ax - .5) * (bx - .5) < 0
+                t = (ax[cr] - .5) / (ax[cr] - bx[cr])
+                want += [(k, .5, float(v)) for v in ay[cr] + t * (by[cr] - ay[cr])]
+        got = [(int(k), float(x), float(y)) for k, x, y in zip(kk[ch == chain], xy[ch == chain, 0], xy[ch == chain, 1])]
+        assert len(got) == len(want), (chain, len(got), len(want))
+        for g, w in zip(sorted(got), sorted(want)):
+            assert g[0] == w[0] and abs(g[1] - w[1]) < 1e-12 and abs(g[2] - w[2]) < 1e-12
