@@ -624,6 +624,7 @@ def newton_fit(ctx, n_splits, theta0, iters, stepsize=1.0, seed=SEED):
     n_nb (:3458).  Returns the path and device / host times."""
     nm, _nf = ctx.merges_flips()
     ctx.clear_splits()
+    ctx.reserve_splits(n_splits + (iters + 1) * max(nm, 1))   # the growth of the set never reallocates inside the fit
     theta = np.array(theta0, dtype=np.float64)
     path, values, gnorm = [theta.copy()], [], []
     h0 = time.perf_counter()

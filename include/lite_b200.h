@@ -146,6 +146,9 @@ int lite_candidates_add_splits_given(lite_ctx *ctx, int64_t n, const int32_t *he
 int lite_candidates_add_splits_philox(lite_ctx *ctx, int64_t n_global, uint64_t seed,
                                       uint64_t offset);
 
+/* Room for n_more_local further dummy splits on this rank, so that the AddSplits(n_nb) of every
+ * PLInferenceNOIS iteration (lib/ttessel.cpp:3500) appends without reallocating. */
+int lite_candidates_reserve(lite_ctx *ctx, int64_t n_more_local);
 /* PseudoLikDiscrete::ClearSplits (lib/ttessel.cpp:3378-3380). */
 int lite_candidates_clear_splits(lite_ctx *ctx);
 int lite_candidates_count(lite_ctx *ctx, int64_t *n_splits_local, int64_t *n_splits_global);

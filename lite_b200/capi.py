@@ -36,7 +36,7 @@ SYMBOLS = [
     "lite_measure_fp64_peak", "lite_last_reduce_ms", "lite_timer_mark", "lite_timer_elapsed",
     "lite_smf_create", "lite_smf_destroy", "lite_smf_set_model", "lite_smf_run", "lite_smf_stats",
     "lite_smf_trace", "lite_smf_export", "lite_smf_count", "lite_smf_last_ms",
-    "lite_pl_combine", "lite_shard_range", "lite_pl_failures", "lite_comm_info", "lite_smf_intersections",
+    "lite_pl_combine", "lite_shard_range", "lite_pl_failures", "lite_comm_info", "lite_smf_intersections", "lite_candidates_reserve",
 ]
 
 # columns of lite_smf_run / lite_smf_stats (applications/checkACS.cpp:136-148 + energy)
@@ -152,6 +152,7 @@ def load_library():
                                                    C.c_void_p, C.c_int64]
     L.lite_candidates_add_splits_philox.argtypes = [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint64]
     L.lite_candidates_clear_splits.argtypes = [C.c_void_p]
+    L.lite_candidates_reserve.argtypes = [C.c_void_p, C.c_int64]
     L.lite_candidates_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.lite_pl_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lite_pl_sums.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -293,6 +294,9 @@ class Context:
 
     def add_splits_philox(self, n_global, seed, offset=0):
         _ck(self.L, self.L.lite_candidates_add_splits_philox(self.h, n_global, seed, offset))
+
+    def reserve_splits(self, n_more_local):
+        _ck(self.L, self.L.lite_candidates_reserve(self.h, int(n_more_local)))
 
     def clear_splits(self):
         _ck(self.L, self.L.lite_candidates_clear_splits(self.h))

@@ -1056,6 +1056,30 @@ static int grow_splits(lite_ctx *c, int64_t add) {
   return 0;
 }
 
+// Room for n more dummy splits on this rank without reallocating (PLInferenceNOIS grows the
+// set by n_nb per iteration, lib/ttessel.cpp:3500: a caller that knows how many iterations it will
+// run reserves once instead of paying a doubling of a multi-hundred-MB block inside the loop).
+extern "C" int lite_candidates_reserve(lite_ctx *c, int64_t n_more_local) {
+  if (!c) return fail(LITE_EINVAL, "null context");
+  if (!c->have_prog) return fail(LITE_ESTATE, "set the energy first");
+  if (n_more_local < 0) return fail(LITE_EINVAL, "negative count");
+  CU(cudaSetDevice(c->device));
+  const size_t need = (size_t)(c->n_local + n_more_local);
+  if (need <= c->cap) return 0;
+  const int d = c->G.d;
+  const size_t ncap = (need + 255) & ~(size_t)255;
+  DBuf<double> nb;
+  if (nb.alloc(ncap * d)) return LITE_ECUDA;
+  if (c->n_local)
+    CU(cudaMemcpy2DAsync(nb.p, ncap * sizeof(double), c->stat.p, c->cap * sizeof(double),
+                         (size_t)c->n_local * sizeof(double), d, cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->stat.release();
+  c->stat = nb;
+  c->cap = ncap;
+  return 0;
+}
+
 static int split_grid(lite_ctx *c, int64_t n) {
   // one resident wave: every warp then owns one contiguous run of candidates
   int64_t blocks = (n + LITE_SPLIT_TB - 1) / LITE_SPLIT_TB;
