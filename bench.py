@@ -885,20 +885,16 @@ def run_pl(args, rank, local_rank, world, nccl_id, dist, torch):
         sampler.start()
     barrier()
     l0 = ctx.launch_count()
-    ms_split = ms_reduce = ms_mf = ms_exch = 0.0
     host_ms = []
+    ctx.timers_accumulated(reset=True)   # the library sums its kernel times: nothing is queried inside the loop
     ctx.timer_mark(0)
     for k in range(args.steps):
         h0 = time.perf_counter()
         lpl, g, H = step(args.warmup + k)
         host_ms.append((time.perf_counter() - h0) * 1e3)   # pl_eval returns after the stream has drained
-        a, _b, m = ctx.last_kernel_ms()
-        ms_split += a
-        ms_mf += m
-        ms_reduce += ctx.last_reduce_ms()
-        ms_exch += ctx.comm_info()[1]
     ctx.timer_mark(1)
     barrier()
+    ms_split, ms_reduce, ms_mf, ms_exch, _n_eval = ctx.timers_accumulated()
     ms_total = ctx.timer_elapsed(0, 1)
     launches = ctx.launch_count() - l0
     clocks = sampler.stop() if sampler else None

@@ -217,6 +217,9 @@ int lite_debug_fetch(lite_ctx *ctx, int which, int64_t first, int64_t count, voi
 int lite_last_kernel_ms(lite_ctx *ctx, float *add_splits_ms, float *pl_eval_ms,
                         float *merges_flips_ms);
 int64_t lite_kernel_launch_count(lite_ctx *ctx);
+/* The same times summed over the lite_pl_eval calls since the last reset: out5 = split kernel,
+ * theta-reduce kernel, merges+flips kernel, cross-GPU exchange (ms), number of evaluations. */
+int lite_timers_accumulated(lite_ctx *ctx, double out5[5], int reset);
 /* Device time (ms) of the split-statistics theta-reduce kernel of the last lite_pl_eval. */
 int lite_last_reduce_ms(lite_ctx *ctx, float *ms);
 /* CUDA-event marks on the context's stream (the stream every kernel of the

@@ -36,7 +36,7 @@ SYMBOLS = [
     "lite_measure_fp64_peak", "lite_last_reduce_ms", "lite_timer_mark", "lite_timer_elapsed",
     "lite_smf_create", "lite_smf_destroy", "lite_smf_set_model", "lite_smf_run", "lite_smf_stats",
     "lite_smf_trace", "lite_smf_export", "lite_smf_count", "lite_smf_last_ms",
-    "lite_pl_combine", "lite_shard_range", "lite_pl_failures", "lite_comm_info", "lite_smf_intersections", "lite_candidates_reserve",
+    "lite_pl_combine", "lite_shard_range", "lite_pl_failures", "lite_comm_info", "lite_smf_intersections", "lite_candidates_reserve", "lite_timers_accumulated",
 ]
 
 # columns of lite_smf_run / lite_smf_stats (applications/checkACS.cpp:136-148 + energy)
@@ -161,6 +161,7 @@ def load_library():
     L.lite_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.lite_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.lite_nccl_unique_id.argtypes = [C.c_void_p]
+    L.lite_timers_accumulated.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.lite_last_reduce_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.lite_timer_mark.argtypes = [C.c_void_p, C.c_int]
     L.lite_timer_elapsed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
@@ -371,6 +372,12 @@ class Context:
         a, b, m = C.c_float(), C.c_float(), C.c_float()
         _ck(self.L, self.L.lite_last_kernel_ms(self.h, C.byref(a), C.byref(b), C.byref(m)))
         return a.value, b.value, m.value
+
+    def timers_accumulated(self, reset=False):
+        """(k_split ms, k_reduce ms, merges+flips ms, exchange ms, evaluations) summed since the last reset."""
+        out = np.zeros(5)
+        _ck(self.L, self.L.lite_timers_accumulated(self.h, out.ctypes.data_as(C.c_void_p), 1 if reset else 0))
+        return out
 
     def last_reduce_ms(self):
         t = C.c_float()

@@ -185,6 +185,7 @@ struct lite_ctx {
   double peer_wait_us = 0;
   float ms_exchange = 0;                        // NCCL path: device time of the allreduce
   bool have_tess = false, have_prog = false, have_mf = false;
+  bool mf_deferred = false;  // lite_candidates_merges_flips was called, its kernel is not enqueued yet
   bool record = false;
   bool validate_host = false;  // LITE_OPT_VALIDATE_HOST: export assertions on the host, errors returned by lite_tess_upload itself
   bool iid = false;         // LITE_OPT_SAMPLER: i.i.d. positions + sort instead of the stratified sampler
@@ -245,6 +246,7 @@ struct lite_ctx {
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t tev[LITE_TIMER_SLOTS] = {};  // user timer marks (lite_timer_mark)
   float ms_split = 0, ms_eval = 0, ms_mf = 0, ms_reduce = 0;
+  double acc_ms[5] = {0, 0, 0, 0, 0};  // sums over evaluations: split kernel, reduce kernel, merges+flips, exchange, count
   int64_t fail_splits = 0, fail_flips = 0;  // no-exit counts behind the last evaluation
   bool ev01 = false;  // ev[0]/ev[1] have been recorded
   std::vector<uint8_t> h_he_inside;
@@ -454,10 +456,12 @@ extern "C" int lite_ctx_destroy(lite_ctx *c) {
 }
 
 static int tess_err_sync(lite_ctx *c);
+static int mf_flush(lite_ctx *c);
 
 extern "C" int lite_ctx_sync(lite_ctx *c) {
   if (!c) return fail(LITE_EINVAL, "null context");
   CU(cudaSetDevice(c->device));
+  { const int fr = mf_flush(c); if (fr) return fr; }
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaStreamSynchronize(c->stream2));
   return tess_err_sync(c);
@@ -577,7 +581,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   // From here on the context holds no tessellation until this upload has succeeded: the
   // views into the arena are re-pointed as the arrays are staged, so after a failure the
   // previous tessellation is gone and every call that needs one returns LITE_ESTATE.
-  c->have_tess = false; c->have_mf = false; c->mf_pending = false;
+  c->have_tess = false; c->have_mf = false; c->mf_pending = false; c->mf_deferred = false;
   c->n_local = 0; c->n_global = 0;
   const double t0 = now_ms();
   double t1 = t0, t2 = t0, t3 = t0, t4 = t0;
@@ -939,7 +943,7 @@ extern "C" int lite_energy_set(lite_ctx *c, int d, const int32_t *fid) {
     c->cap = 0;
   }
   c->G = G;
-  c->have_prog = true; c->have_mf = false; c->mf_pending = false;
+  c->have_prog = true; c->have_mf = false; c->mf_pending = false; c->mf_deferred = false;
   return 0;
 }
 
@@ -962,10 +966,28 @@ static void finalize_mf(lite_ctx *c) {
   c->mf_pending = false;
 }
 
+// The merge/flip kernel is enqueued at once, on the second stream, BEFORE the split kernel of the
+// same step: k_split fills every SM with blocks that stay until the batch is done (6 x 128 threads
+// at 80 registers take the whole register file), so anything launched behind it only starts when
+// it drains.  Deferring this launch until after the split kernel (to get k_split onto the GPU ~15 us
+// earlier) was measured: the merge/flip kernel then ends 0.27 ms late and the step loses 20 us.
+static int mf_flush(lite_ctx *c);
+
 extern "C" int lite_candidates_merges_flips(lite_ctx *c, int32_t *n_merges, int32_t *n_flips) {
   NvtxRange nvtx_("lite_candidates_merges_flips");
   if (!c) return fail(LITE_EINVAL, "null context");
   if (!c->have_tess || !c->have_prog) return fail(LITE_ESTATE, "upload a tessellation and set the energy first");
+  c->mf_deferred = true;
+  c->have_mf = true;
+  if (n_merges) *n_merges = c->n_nb;
+  if (n_flips) *n_flips = 2 * c->n_b;
+  return mf_flush(c);
+}
+
+static int mf_flush(lite_ctx *c) {
+  if (!c->mf_deferred) return 0;
+  c->mf_deferred = false;
+  int32_t *n_merges = nullptr, *n_flips = nullptr;
   CU(cudaSetDevice(c->device));
   const int d = c->G.d, nm = c->n_nb, nf = 2 * c->n_b;
   if (c->mstat.alloc((size_t)d * (nm ? nm : 1)) || c->fstat.alloc((size_t)d * (nf ? nf : 1)) ||
@@ -1147,6 +1169,7 @@ extern "C" int lite_candidates_add_splits_given(lite_ctx *c, int64_t n, const in
   else launch_split<4>(c, c->G, A, g);
   CU(cudaEventRecord(c->ev[1], c->stream));
   c->ev01 = true;
+  { const int fr = mf_flush(c); if (fr) return fr; }
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
   cudaEventElapsedTime(&c->ms_split, c->ev[0], c->ev[1]);
@@ -1207,7 +1230,7 @@ extern "C" int lite_candidates_add_splits_philox(lite_ctx *c, int64_t n_global, 
   }
   c->n_local += n; c->n_global += n_global;
   c->rev = false;  // k_split wrote the tail last: the next reduce starts from it
-  return 0;
+  return mf_flush(c);  // the merge/flip kernel, if SetEnergy asked for it, goes out behind the split kernel
 }
 
 extern "C" int lite_lines_sample_clip(lite_ctx *c, int64_t n_global, uint64_t seed, uint64_t offset,
@@ -1341,6 +1364,7 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
   if (!c->have_mf) return fail(LITE_ESTATE, "call lite_candidates_merges_flips (SetEnergy) before evaluating");
   if (c->n_global == 0) return fail(LITE_ENOSPLIT, "no dummy splits: the reference divides by stat_splits.size()");
   CU(cudaSetDevice(c->device));
+  { const int fr = mf_flush(c); if (fr) return fr; }
   const int d = c->G.d;
   const int NT = 1 + d + d * (d + 1) / 2;
   Theta th{};
@@ -1412,6 +1436,7 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
     c->peer_wait_us = (double)pi[1] * 1e-3;
     c->ms_exchange = (float)(c->peer_wait_us * 1e-3);
   }
+  c->acc_ms[0] += c->ms_split; c->acc_ms[1] += c->ms_reduce; c->acc_ms[2] += c->ms_mf; c->acc_ms[3] += c->ms_exchange; c->acc_ms[4] += 1;
   return lite_pl_combine(d, c->n_global, c->int_length, theta, c->h_pinned, c->h_pinned + 128, c->h_sum_m.data(),
                          c->h_sum_f.data(), lpl, grad, hess);
 }
@@ -1440,6 +1465,7 @@ extern "C" int lite_pl_sums(lite_ctx *c, double *sm, double *sf) {
   if (!c) return fail(LITE_EINVAL, "null context");
   if (!c->have_mf) return fail(LITE_ESTATE, "call lite_candidates_merges_flips first");
   CU(cudaSetDevice(c->device));
+  { const int fr = mf_flush(c); if (fr) return fr; }
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaStreamSynchronize(c->stream2));
   c->mf_inflight = false;
@@ -1476,6 +1502,7 @@ static int fetch_stat(lite_ctx *c, const double *stat, size_t cap, size_t have, 
 extern "C" int lite_debug_fetch(lite_ctx *c, int which, int64_t first, int64_t count, void *out) {
   if (!c || !out) return fail(LITE_EINVAL, "null argument");
   CU(cudaSetDevice(c->device));
+  { const int fr = mf_flush(c); if (fr) return fr; }
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaStreamSynchronize(c->stream2));
   c->mf_inflight = false;
@@ -1524,6 +1551,7 @@ extern "C" int lite_debug_fetch(lite_ctx *c, int which, int64_t first, int64_t c
 extern "C" int lite_last_kernel_ms(lite_ctx *c, float *a, float *b, float *m) {
   if (!c) return fail(LITE_EINVAL, "null context");
   CU(cudaSetDevice(c->device));
+  { const int fr = mf_flush(c); if (fr) return fr; }
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaStreamSynchronize(c->stream2));
   c->mf_inflight = false;
@@ -1533,6 +1561,16 @@ extern "C" int lite_last_kernel_ms(lite_ctx *c, float *a, float *b, float *m) {
   if (a) *a = c->ms_split;
   if (b) *b = c->ms_eval;
   if (m) *m = c->ms_mf;
+  return 0;
+}
+
+// Device times summed over the lite_pl_eval calls since the last reset (so that a timed loop
+// need not query after every step): [0] split kernel, [1] theta-reduce kernel, [2] merges+flips
+// kernel, [3] cross-GPU exchange, [4] number of evaluations.
+extern "C" int lite_timers_accumulated(lite_ctx *c, double out5[5], int reset) {
+  if (!c || !out5) return fail(LITE_EINVAL, "null argument");
+  for (int k = 0; k < 5; k++) out5[k] = c->acc_ms[k];
+  if (reset) for (int k = 0; k < 5; k++) c->acc_ms[k] = 0;
   return 0;
 }
 

@@ -107,9 +107,21 @@ __device__ __forceinline__ double acos_cs(double c, double s) {
   const bool small_c = ac <= s;
   const double z = small_c ? ac : s;
   const double w = z * z;
+#ifdef LITE_ACOS_HORNER
   double q = c_asin_q[18];
 #pragma unroll
   for (int k = 17; k >= 0; k--) q = fma(q, w, c_asin_q[k]);
+#else
+  // even and odd coefficients as two Horner chains in w^2: the same 19 multiply-adds (+2), half
+  // the dependent latency (the kernel waits on such chains: issue slots are 70 % busy)
+  const double w2 = w * w;
+  double qe = c_asin_q[18], qo = c_asin_q[17];
+#pragma unroll
+  for (int k = 16; k >= 0; k -= 2) qe = fma(qe, w2, c_asin_q[k]);
+#pragma unroll
+  for (int k = 15; k >= 1; k -= 2) qo = fma(qo, w2, c_asin_q[k]);
+  const double q = fma(qo, w, qe);
+#endif
   const double r = fma(z * w, q, z);  // asin(z)
   // |c| <= s: acos(c) = pi/2 - asin(c);  otherwise the angle is r (c > 0) or pi - r (c < 0)
   const double base = small_c ? LITE_HALF_PI : (c > 0.0 ? 0.0 : LITE_PI);
