@@ -927,6 +927,8 @@ __global__ void __launch_bounds__(LITE_SPLIT_TB, LITE_SPLIT_MINB) k_split(TessDe
     if (beg >= A.n_local) break;
     const long end = min(beg + len, A.n_local);
     m = -1;
+  // (a contiguous piece of the run per lane instead of this interleaving keeps a lane on its slot
+  // longer but scatters the statistic stores: measured 2x slower at 10^4 and at 10^5 cells)
   for (long i = beg + lane; i < end; i += 32) {
     double x, angle, ca, sa, U = 0.0;
     if (PHILOX) {
