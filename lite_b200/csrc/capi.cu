@@ -254,6 +254,7 @@ struct lite_ctx {
   cudaEvent_t ev_upload = nullptr;  // the H2D copy of the last upload has left the pinned block
   cudaEvent_t ev_tr[3] = {nullptr, nullptr, nullptr};  // LITE_B200_TRACE: start of the copy, end of the copy, end of the preparation
   bool upload_inflight = false;
+  bool early_unfenced = false;  // an upload that failed after its bulk copy had been started: no ev_upload covers that copy
   int sm_count = 148;
 };
 
@@ -605,6 +606,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
     if (ra) return ra;
   }
   if (c->upload_inflight) { CU(cudaEventSynchronize(c->ev_upload)); c->upload_inflight = false; }
+  if (c->early_unfenced) { CU(cudaStreamSynchronize(c->stream)); c->early_unfenced = false; }
   c->pack_jobs.clear();
   int r = 0;
   r |= up(c, c->vx, s->vx, nV); r |= up(c, c->vy, s->vy, nV);
@@ -710,6 +712,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   }
   const double t_cum = now_ms();
   c->pool->wait();
+  c->early_unfenced = early_copy;
   if (g_trace) fprintf(stderr, "[lite_b200] tess_upload host: staging %.3f ms, cumulative lengths %.3f ms, wait for the workers (pack, count) %.3f ms\n",
                        t_stage - t0, t_cum - t_stage, now_ms() - t_cum);
   if (bad_list >= 0) return fail(LITE_EINVAL, "face %d: halfedge list out of range", bad_list);
@@ -790,14 +793,13 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   c->pack_jobs.clear();
   t2 = now_ms();
   if (early_copy) {  // the bulk is on its way: only what was staged since (the cumulative lengths)
+    // (this copy and the guide table on the second stream, beside the checks: measured, no gain)
     CU(cudaMemcpyAsync(c->arena.d + bulk_bytes, c->arena.h + bulk_bytes, c->arena.used - bulk_bytes, cudaMemcpyHostToDevice, c->stream));
   } else {
     if (g_trace) cudaEventRecord(c->ev_tr[0], c->stream);
     CU(cudaMemcpyAsync(c->arena.d, c->arena.h, c->arena.used, cudaMemcpyHostToDevice, c->stream));
     if (g_trace) cudaEventRecord(c->ev_tr[1], c->stream);
   }
-  CU(cudaEventRecord(c->ev_upload, c->stream));
-  c->upload_inflight = true;
   const size_t nSl = n_slots;
   if (c->pt.alloc(nSl) || c->udir.alloc(nSl) || c->ang.alloc(nSl) || c->len.alloc(nSl) || c->ca.alloc(nSl) ||
       c->flg.alloc(nSl) || c->slot_he.alloc(nSl) || c->slot_seg.alloc(nSl) ||
@@ -869,6 +871,8 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   k_prep_faces<<<gb, tb, 0, c->stream>>>(T, c->ca.p, c->f_area.p, c->f_perim.p, c->f_sumang.p, c->f_minang.p,
                                          c->pre.p, c->plen.p, c->f_tot2.p, c->sfo.p, c->stot2.p);
   c->launches += 3;
+  CU(cudaEventRecord(c->ev_upload, c->stream));                     // both copies have left the pinned block
+  c->upload_inflight = true; c->early_unfenced = false;
   // the merge/flip stream only depends on the tessellation being in place: it forks here,
   // not from whatever the main stream is doing when SetEnergy is called (the split kernel,
   // if AddSplits came first: the two then run side by side)
