@@ -993,7 +993,7 @@ def run_pl(args, rank, local_rank, world, nccl_id, dist, torch):
             roofline["traffic"] = tr.get("k_split")
             roofline_reduce["traffic"] = tr.get("k_reduce")
             fx = tr.get("k_split_dp_flop_per_candidate_executed")
-            roofline["executed_flop_source"] = tr.get("k_split_source")
+            roofline["executed_flop_source"] = tr.get("_dp_flop_source")
         except Exception:
             pass
     # `frac` is the HARDWARE fraction: DP flop the kernel executes per candidate (counted by ncu on
