@@ -376,7 +376,15 @@ static int ctx_init(lite_ctx *c, const void *nccl_unique_id) {
     if (r) return r;
   }
   c->pool = new HostPool();
-  c->pool->start(4);
+  {
+    // packing threads: four, fewer when the ranks of one box have to share its cores (eight ranks
+    // with five busy threads each on 16-32 cores stretched the end-to-end step by a quarter)
+    int hc = (int)std::thread::hardware_concurrency();
+    int nt = hc > 0 ? hc / c->world - 1 : 4;
+    if (nt > 4) nt = 4;
+    if (nt < 1) nt = 1;
+    c->pool->start(nt);
+  }
   CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -530,7 +538,7 @@ static double now_ms() {
 // the device (k_validate).  Returns 0 or fails with the first inconsistency.
 static int host_validate(lite_ctx *c, const lite_tess_soa *s) {
   const int nH = s->n_halfedges, nF = s->n_faces, nS = s->n_segments, nV = s->n_vertices;
-  const int nt = 4;
+  const int nt = (int)c->pool->th.size();
   std::vector<int> bad_face(nt, -1), bad_he(nt, -1), bad_list_f(nt, -1), bad_list_k(nt, -1);
   c->pool->run([=, &bad_face, &bad_he, &bad_list_f, &bad_list_k](int t) {
     const int f0 = (int)((int64_t)nF * t / nt), f1 = (int)((int64_t)nF * (t + 1) / nt);
@@ -632,7 +640,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   // threads stay dirty in their cores' private caches and the copy engine has to snoop them out:
   // the 3.8 MB copy of a 10^4-cell tessellation then takes 0.5 ms instead of the link's 0.08 ms
   // (scripts/h2d_probe4.py; the whole end-to-end step went from 1.43 to 0.80 ms with this alone).
-  const int nt = 4;
+  const int nt = (int)c->pool->th.size();
   std::vector<int> bad_he(nt, -1);
   std::vector<int64_t> part_inside(nt, 0), part_twice(nt, 0);
   c->h_he_inside.assign(nH, 0);

@@ -5,6 +5,7 @@
 // fallback of the hot path.  Reference citations are relative to /root/reference.
 #include "../../include/ttessel.h"
 
+#include <iostream>
 #include <math.h>
 #include <string.h>
 
@@ -1030,6 +1031,12 @@ void PseudoLikDiscrete::GetValueGradientHessian(CatVector theta, double *v, CatV
   std::vector<double> gg(d), hh((size_t)d * d);
   double lpl = 0;
   ck(lite_pl_eval(ctx_, th.data(), &lpl, g ? gg.data() : 0, H ? hh.data() : 0), "lite_pl_eval");
+  {  // as the reference, which reports on std::cerr and goes on (lib/ttessel.cpp:4571-4574)
+    int64_t fs = 0, ff = 0;
+    if (lite_pl_failures(ctx_, &fs, &ff) == 0 && (fs || ff))
+      std::cerr << "ray_exit_face: intersection of ray with face boundaries not found for " << fs << " split(s) and "
+                << ff << " flip(s): their statistics count as zero" << std::endl;
+  }
   if (v) *v = lpl;
   if (g) shape_like(theta, gg.data(), g);
   if (H) {
@@ -1117,6 +1124,8 @@ void PLInferenceNOIS::Step(unsigned int n) {  // :3470-3505
 CatVector PLInferenceNOIS::GetEstimate() { return GetEnergy()->get_theta(); }
 unsigned int PLInferenceNOIS::Run(double tol, unsigned int nmax) {  // :3526-3540
   if (nmax == 0) return 0;
+  if (context())  // every iteration appends n_nb dummy splits (:3500): make room once
+    lite_candidates_reserve(context(), (int64_t)nmax * (int64_t)GetEnergy()->get_ttessel()->number_of_non_blocking_segments());
   unsigned int i = 0;
   double current_lpl;
   do {
