@@ -418,22 +418,35 @@ __global__ void k_prep_faces(TessDev T, double *ca, double *f_area, double *f_pe
     f_tot2[f] = acc;
     for (int k = 0; k < n; k++) stot2[off + k] = acc;
   }
-  // corner angles at slot sources
-  for (int k = 0; k < n; k++) {
-    double a = LITE_PI;
-    if (T.flg[off + k] & SF_CORNER) {
-      double2 c = ldpt(T.pt, off + k);
-      double2 p = ldpt(T.pt, off + (k == 0 ? n - 1 : k - 1));
-      double2 q = ldpt(T.pt, off + (k + 1 == n ? 0 : k + 1));
-      a = angle_between(p.x - c.x, p.y - c.y, q.x - c.x, q.y - c.y);
+  // Corner angles at the slot sources and the features of the unmodified face, in one walk in
+  // face2poly order (first vertex = target of the outer_ccb halfedge = source of slot 1), with
+  // the arithmetic of vp_features (lib/ttessel.cpp:4215-4239, :4285-4305, :4348-4367): shoelace
+  // from the first vertex, edge lengths from the end points, angle_between at the corners, the
+  // minimum seeded with the turning angle at the first corner.
+  {
+    const double2 V0 = ldpt(T.pt, off + (1 == n ? 0 : 1));
+    double2 P = ldpt(T.pt, off), C = V0;   // previous and current vertex
+    double area2 = 0, perim = 0, sumang = 0, minang = CUDART_INF, seed = -1.0;
+    for (int i = 0; i < n; i++) {
+      const int sc = off + ((1 + i) % n);                 // slot whose source is the current vertex
+      const double2 Nx = (i + 1 < n) ? ldpt(T.pt, off + ((2 + i) % n)) : V0;
+      area2 += cross2(C.x - V0.x, C.y - V0.y, Nx.x - V0.x, Nx.y - V0.y);
+      const double ex = Nx.x - C.x, ey = Nx.y - C.y;
+      perim += sqrt(ex * ex + ey * ey);
+      double a = LITE_PI;
+      if (T.flg[sc] & SF_CORNER) {
+        a = angle_between(P.x - C.x, P.y - C.y, ex, ey);
+        if (seed < 0) seed = LITE_PI - a;
+        const double q = LITE_HALF_PI - a;
+        if (q >= 0) sumang += q;
+        minang = fmin(minang, a);
+      }
+      ca[sc] = a;
+      P = C; C = Nx;
     }
-    ca[off + k] = a;
+    f_area[f] = 0.5 * area2; f_perim[f] = perim; f_sumang[f] = sumang;
+    f_minang[f] = (seed >= 0) ? fmin(seed, minang) : 0.0;
   }
-  // face2poly order: first vertex is the target of the outer_ccb halfedge = source of slot 1
-  VPoly P; vp_init(P);
-  vp_range(P, off, n, 1, n);
-  FaceFeat F = vp_features(T, P, true);
-  f_area[f] = F.area; f_perim[f] = F.perim; f_sumang[f] = F.sumang; f_minang[f] = F.minang;
 }
 
 // guide table of the sampler: guide[b] = first slot m with cum[m] > b * step, clamped
