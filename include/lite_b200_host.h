@@ -16,7 +16,10 @@ typedef struct lite_host_tess lite_host_tess;
 
 /* TTessel::insert_window(Rectangle), lib/ttessel.cpp:1544-1550 */
 int lite_host_create_rect(lite_host_tess **out, double x0, double y0, double x1, double y1);
-/* LineTes::read, lib/ttessel.cpp:1377-1441 (hole-free single-polygon windows) */
+/* LineTes::read, lib/ttessel.cpp:1377-1441: the window (one or several polygons, outer boundaries
+ * counter-clockwise, holes clockwise) then one maximal segment per line.  A window with holes or
+ * several polygons can be checked, exported (lite_host_export -> lite_tess_upload) and written;
+ * the moves and the chain below need a single hole-free polygon. */
 int lite_host_create_from_text(lite_host_tess **out, const char *text);
 int lite_host_destroy(lite_host_tess *t);
 /* SMFChain(&mod,p_split,p_merge).step(n) under the CRTT energy

@@ -49,6 +49,7 @@ extern "C" int lite_host_destroy(lite_host_tess *t) {
 
 extern "C" int lite_host_crtt_run(lite_host_tess *h, double tau, uint64_t n_steps, uint64_t seed,
                                   int64_t counts6[6]) {
+  if (h && h->t.has_holes) return lite_set_error_(LITE_ESTATE, "the host model reads, checks, exports and writes tessellations of windows with holes but does not move them");
   if (!h || !(tau > 0)) return lite_set_error_(LITE_EINVAL, "bad argument");
   lite::ChainCounts c = lite::crtt_chain(h->t, tau, n_steps, seed);
   if (counts6) memcpy(counts6, c.c, sizeof c.c);
@@ -57,6 +58,7 @@ extern "C" int lite_host_crtt_run(lite_host_tess *h, double tau, uint64_t n_step
 }
 
 extern "C" int lite_host_update_split(lite_host_tess *h, int32_t he, double x, double angle) {
+  if (h && h->t.has_holes) return lite_set_error_(LITE_ESTATE, "the host model reads, checks, exports and writes tessellations of windows with holes but does not move them");
   if (!h || he < 0 || he >= (int)h->he_ids.size()) return lite_set_error_(LITE_EINVAL, "bad halfedge id");
   int e = h->he_ids[he];
   if (!h->t.f_inside[h->t.h_face[e]]) return lite_set_error_(LITE_EINVAL, "halfedge bounds the outer face");
@@ -68,6 +70,7 @@ extern "C" int lite_host_update_split(lite_host_tess *h, int32_t he, double x, d
 }
 
 extern "C" int lite_host_update_merge(lite_host_tess *h, int32_t i) {
+  if (h && h->t.has_holes) return lite_set_error_(LITE_ESTATE, "the host model reads, checks, exports and writes tessellations of windows with holes but does not move them");
   if (!h || i < 0 || i >= (int)h->t.nb_list.size()) return lite_set_error_(LITE_EINVAL, "bad non-blocking index");
   h->t.update_merge(h->t.s_he[h->t.nb_list[i]]);
   remember_ids(h);
@@ -75,6 +78,7 @@ extern "C" int lite_host_update_merge(lite_host_tess *h, int32_t i) {
 }
 
 extern "C" int lite_host_update_flip(lite_host_tess *h, int32_t i, int side) {
+  if (h && h->t.has_holes) return lite_set_error_(LITE_ESTATE, "the host model reads, checks, exports and writes tessellations of windows with holes but does not move them");
   if (!h || i < 0 || i >= (int)h->t.b_list.size()) return lite_set_error_(LITE_EINVAL, "bad blocking index");
   lite::FlipMove f = h->t.make_flip(h->t.flip_halfedge(h->t.b_list[i], side));
   if (!f.valid) return lite_set_error_(LITE_EINVAL, "ray_exit_face: intersection of ray with face boundaries not found");

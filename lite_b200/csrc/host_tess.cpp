@@ -639,11 +639,25 @@ ChainCounts crtt_chain(HostTess &t, double tau, uint64_t n_steps, uint64_t seed,
 // ---------------------------------------------------------------------------
 bool build_from_segments(HostTess &t, const std::vector<double> &wx, const std::vector<double> &wy,
                          const std::vector<std::vector<double>> &segs, std::string &err) {
+  return build_from_boundaries(t, {wx}, {wy}, segs, err);
+}
+
+bool build_from_boundaries(HostTess &t, const std::vector<std::vector<double>> &bx,
+                           const std::vector<std::vector<double>> &by,
+                           const std::vector<std::vector<double>> &segs, std::string &err) {
+  if (bx.empty() || bx.size() != by.size()) { err = "no window"; return false; }
+  // all boundary vertices in one list; boundary side i runs wfrom[i] -> wto[i] (vertex ids)
+  std::vector<double> wx, wy;
+  std::vector<int> wto;
+  for (size_t b = 0; b < bx.size(); b++) {
+    const int n = (int)bx[b].size(), base = (int)wx.size();
+    if (n < 3 || by[b].size() != bx[b].size()) { err = "a window boundary needs at least three vertices"; return false; }
+    for (int i = 0; i < n; i++) { wx.push_back(bx[b][i]); wy.push_back(by[b][i]); wto.push_back(base + (i + 1) % n); }
+  }
   const int nw = (int)wx.size();
-  if (nw < 3) { err = "no window"; return false; }
   struct S { double x0, y0, x1, y1; std::vector<std::pair<double, int>> on; };  // (parameter, vertex)
   std::vector<S> L;
-  for (int i = 0; i < nw; i++) L.push_back({wx[i], wy[i], wx[(i + 1) % nw], wy[(i + 1) % nw], {}});
+  for (int i = 0; i < nw; i++) L.push_back({wx[i], wy[i], wx[wto[i]], wy[wto[i]], {}});
   for (const auto &c : segs) {
     if (c.size() != 4) { err = "a segment needs four coordinates"; return false; }
     L.push_back({c[0], c[1], c[2], c[3], {}});
@@ -696,10 +710,12 @@ bool build_from_segments(HostTess &t, const std::vector<double> &wx, const std::
   }
   // vertices: window corners first, then the two ends of every internal segment
   t = HostTess();
-  t.win_x = wx; t.win_y = wy;
+  t.win_x = bx[0]; t.win_y = by[0];
+  t.win_bx = bx; t.win_by = by;
+  t.has_holes = bx.size() > 1;
   std::vector<double> vx, vy;
   for (int i = 0; i < nw; i++) { vx.push_back(wx[i]); vy.push_back(wy[i]); }
-  for (int i = 0; i < nw; i++) { L[i].on.push_back({0.0, i}); L[i].on.push_back({1.0, (i + 1) % nw}); }
+  for (int i = 0; i < nw; i++) { L[i].on.push_back({0.0, i}); L[i].on.push_back({1.0, wto[i]}); }
   for (int i = nw; i < nL; i++) {
     for (int e = 0; e < 2; e++) {
       const double px = e ? L[i].x1 : L[i].x0, py = e ? L[i].y1 : L[i].y0;
@@ -773,26 +789,65 @@ bool build_from_segments(HostTess &t, const std::vector<double> &wx, const std::
       t.h_next[in] = nx; t.h_prev[nx] = in;
     }
   }
-  // faces: one per cycle; the clockwise cycle is the outside
+  // Faces.  The window is on the LEFT of every boundary side as given, so halfedge 2e of a
+  // boundary edge (it runs along the side) bounds an inside face and its twin an outside one
+  // (the unbounded face or the inside of a hole).  A counter-clockwise cycle is the outer boundary
+  // of a face: inside unless it holds the twin of a boundary halfedge.  A clockwise cycle is an
+  // inner boundary: of the unbounded face if it holds such twins (one per window polygon),
+  // otherwise of the inside face that surrounds it (a hole that no segment touches).
+  std::vector<int> cw_cycles;   // one halfedge of each clockwise cycle of inside-facing halfedges
   int n_outer = 0;
   for (int h0 = 0; h0 < 2 * nE; h0++) {
-    if (t.h_face[h0] >= 0) continue;
+    if (t.h_face[h0] >= 0 || t.h_face[h0] == -2) continue;
     double a2 = 0;
+    bool outside_side = false;
     int h = h0, guard = 0;
     do {
       const int s = t.h_src[h], d = t.h_src[h ^ 1];
       a2 += vx[s] * vy[d] - vx[d] * vy[s];
+      if (edges[h >> 1].bnd && (h & 1)) outside_side = true;
       h = t.h_next[h];
       if (h < 0 || ++guard > 2 * nE) { err = "broken boundary cycle"; return false; }
     } while (h != h0);
-    const bool inside = a2 > 0;
-    if (!inside) n_outer++;
+    if (a2 < 0 && !outside_side) {   // inner boundary of an inside face: assigned below
+      cw_cycles.push_back(h0);
+      h = h0;
+      do { t.h_face[h] = -2; h = t.h_next[h]; } while (h != h0);
+      continue;
+    }
+    const bool inside = a2 > 0 && !outside_side;
+    if (a2 < 0) n_outer++;
     const int f = (int)t.f_he.size();
     t.f_he.push_back(h0); t.f_inside.push_back(inside); t.f_alive.push_back(1);
     h = h0;
     do { t.h_face[h] = f; h = t.h_next[h]; } while (h != h0);
   }
-  if (n_outer != 1) { err = "the segments do not form one connected tessellation of the window"; return false; }
+  if (n_outer < 1 || n_outer > (int)bx.size()) { err = "the segments do not form a tessellation of the window"; return false; }
+  for (int h0 : cw_cycles) {
+    // the smallest inside face whose outer boundary surrounds a vertex of the cycle
+    const double px = vx[t.h_src[h0]], py = vy[t.h_src[h0]];
+    int best = -1; double best_a = 0;
+    for (size_t f = 0; f < t.f_he.size(); f++) {
+      if (!t.f_inside[f]) continue;
+      bool in = false; double a2 = 0;
+      int h = t.f_he[f];
+      const int hs = h;
+      do {
+        const int s = t.h_src[h], d = t.h_src[h ^ 1];
+        a2 += vx[s] * vy[d] - vx[d] * vy[s];
+        if ((vy[s] > py) != (vy[d] > py)) {
+          const double xc = vx[s] + (py - vy[s]) * (vx[d] - vx[s]) / (vy[d] - vy[s]);
+          if (px < xc) in = !in;
+        }
+        h = t.h_next[h];
+      } while (h != hs);
+      if (in && (best < 0 || a2 < best_a)) { best = (int)f; best_a = a2; }
+    }
+    if (best < 0) { err = "a boundary cycle lies in no face of the window"; return false; }
+    int h = h0;
+    do { t.h_face[h] = best; h = t.h_next[h]; } while (h != h0);
+    t.has_holes = true;
+  }
   // segments and the blocking / non-blocking lists, in input order
   t.s_he.assign(nL, -1); t.s_nedges.assign(nL, 0); t.s_pos.assign(nL, -1); t.s_bnd.assign(nL, 0);
   t.s_alive.assign(nL, 1); t.s_kind.assign(nL, 0);
@@ -806,8 +861,9 @@ bool build_from_segments(HostTess &t, const std::vector<double> &wx, const std::
     if (t.s_nedges[s] == 1) { t.s_kind[s] = 1; t.s_pos[s] = (int)t.nb_list.size(); t.nb_list.push_back(s); }
     else { t.s_kind[s] = 2; t.s_pos[s] = (int)t.b_list.size(); t.b_list.push_back(s); }
   }
-  // a window side must bound the outside face on its right
-  for (int i = 0; i < nw; i++) if (t.f_inside[t.h_face[t.s_he[i] ^ 1]]) { err = "window side with an inside face on both sides"; return false; }
+  // a window side must bound an outside face on its right and an inside one on its left
+  for (int i = 0; i < nw; i++)
+    if (t.f_inside[t.h_face[t.s_he[i] ^ 1]] || !t.f_inside[t.h_face[t.s_he[i]]]) { err = "window side with the window on the wrong side (outer boundaries counter-clockwise, holes clockwise)"; return false; }
   t.finish_import();
   std::string bad = t.check();
   if (!bad.empty()) { err = "inconsistent tessellation: " + bad; return false; }
@@ -840,9 +896,7 @@ static bool parse_ratio(const std::string &tok, double &out) {
 bool read_text(HostTess &t, const std::string &text, std::string &err) {
   std::istringstream is(text);
   std::string line;
-  std::vector<std::vector<double>> segs;
-  std::vector<double> win_x_in, win_y_in;
-  bool have_window = false;
+  std::vector<std::vector<double>> segs, bx, by;
   while (std::getline(is, line)) {
     std::istringstream ls(line);
     std::string tok;
@@ -855,21 +909,21 @@ bool read_text(HostTess &t, const std::string &text, std::string &err) {
     if (c.empty()) continue;
     if (c.size() % 2) { err = "Uneven number of coordinates on the current line"; return false; }
     if (c.size() > 4) {
-      if (have_window) { err = "windows made of several polygons or holes are outside the scope"; return false; }
+      // a boundary of the window (lib/ttessel.cpp:1395-1415): counter-clockwise = the outer boundary
+      // of a new polygon, clockwise = a hole of the current one
       std::vector<double> x, y;
       for (size_t i = 0; i < c.size(); i += 2) { x.push_back(c[i]); y.push_back(c[i + 1]); }
       double a = 0;
       for (size_t i = 0; i < x.size(); i++) { size_t j = (i + 1) % x.size(); a += x[i] * y[j] - x[j] * y[i]; }
-      if (a <= 0) { err = "Invalid orientation of a domain ccb"; return false; }
-      win_x_in = x; win_y_in = y;
-      have_window = true;
+      if (a == 0) { err = "Invalid orientation of a domain ccb"; return false; }
+      if (a < 0 && bx.empty()) { err = "Invalid orientation of a domain ccb: a hole (clockwise) before any outer boundary"; return false; }
+      bx.push_back(x); by.push_back(y);
     } else {
-      if (!have_window) { err = "segment before window"; return false; }
+      if (bx.empty()) { err = "segment before window"; return false; }
       segs.push_back(c);
     }
   }
-  (void)have_window;
-  return build_from_segments(t, win_x_in, win_y_in, segs, err);
+  return build_from_boundaries(t, bx, by, segs, err);
 }
 
 // a double is m*2^e exactly: print it as the rational num/den the format wants
@@ -888,9 +942,16 @@ static std::string exact_ratio(double v) {
 
 std::string write_text(const HostTess &t) {
   std::ostringstream os;
-  for (size_t i = 0; i < t.win_x.size(); i++)
-    os << (i ? " " : "") << exact_ratio(t.win_x[i]) << " " << exact_ratio(t.win_y[i]);
-  os << "\n";
+  if (t.win_bx.empty()) {
+    for (size_t i = 0; i < t.win_x.size(); i++)
+      os << (i ? " " : "") << exact_ratio(t.win_x[i]) << " " << exact_ratio(t.win_y[i]);
+    os << "\n";
+  }
+  for (size_t b = 0; b < t.win_bx.size(); b++) {
+    for (size_t i = 0; i < t.win_bx[b].size(); i++)
+      os << (i ? " " : "") << exact_ratio(t.win_bx[b][i]) << " " << exact_ratio(t.win_by[b][i]);
+    os << "\n";
+  }
   for (size_t s = 0; s < t.s_he.size(); s++) {
     if (!t.s_alive[s] || t.s_bnd[s]) continue;
     int a = t.seg_start((int)s), b = t.seg_end((int)s);

@@ -59,7 +59,10 @@ class HostTess {
   std::vector<int> nb_list, b_list;
   double int_length = 0;
   bool ordered_lists = true;  // erase keeps order (reference Seg_sublist::suppress)
-  std::vector<double> win_x, win_y;
+  std::vector<double> win_x, win_y;   // the (first) outer boundary of the window, counter-clockwise
+  // every boundary of the window: outer boundaries counter-clockwise, holes clockwise, in file order
+  std::vector<std::vector<double>> win_bx, win_by;
+  bool has_holes = false;  // window with holes or several polygons: read / check / export / write only (no moves)
 
   HostTess();
   void insert_window_polygon(const std::vector<double> &x, const std::vector<double> &y);
@@ -144,6 +147,16 @@ ChainCounts crtt_chain(HostTess &t, double tau, uint64_t n_steps, uint64_t seed,
 // side.  Anything else (crossings, L/X/I-vertices, ends in the void) is an error.
 bool build_from_segments(HostTess &t, const std::vector<double> &wx, const std::vector<double> &wy,
                          const std::vector<std::vector<double>> &segs, std::string &err);
+// The same for a window given by all its boundaries (outer boundaries counter-clockwise, holes
+// clockwise: the window is on the left of every boundary edge, as LineTes::read requires,
+// lib/ttessel.cpp:1395-1415).  Faces that surround a hole no segment touches keep the hole's
+// boundary as an inner boundary: its halfedges carry the face's id and are not listed on its outer
+// boundary, which is how lite_tess_soa describes a face with holes.  Such a tessellation can be
+// checked, exported (hence evaluated on the GPU) and written; the moves of the host model do not
+// handle inner boundaries and refuse it.
+bool build_from_boundaries(HostTess &t, const std::vector<std::vector<double>> &bx,
+                           const std::vector<std::vector<double>> &by,
+                           const std::vector<std::vector<double>> &segs, std::string &err);
 
 // LineTes::read / write text format (lib/ttessel.cpp:1331-1441), double precision
 bool read_text(HostTess &t, const std::string &text, std::string &err);

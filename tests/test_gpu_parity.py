@@ -791,3 +791,58 @@ def test_inconsistent_tessellation_is_caught_on_the_device(lite, what):
     ctx.add_splits_given(gold["cand_he"], gold["cand_x"], gold["cand_angle"])
     assert ctx.pl_eval(th)[0] == pytest.approx(float(gold["pl_acs_1_lpl"]), rel=RTOL)
     ctx.close()
+
+
+def test_holed_window_from_the_text_format_through_the_host_reader(lite):
+    """The whole route a user of the reference takes with a tessellation of a window with holes:
+    the text file (LineTes::write, lib/ttessel.cpp:1348-1370) -> lite_host_create_from_text ->
+    lite_host_export -> lite_tess_upload -> pseudo-likelihood on the device, against the exact
+    oracle on the tessellation that wrote the file (halfedges matched by their end points, the
+    numbering of the two exports differs)."""
+    import lite_oracle as lo
+    from test_gen_face_cpu import grow
+    from test_oracle_golden import holed_polygons
+    t = grow(holed_polygons(), 13, 5, 90)
+    h = lite.HostTess(text=lo.write_text(t))
+    soa = h.export()
+    a = soa.a
+    ctx = lite.Context(0)
+    ctx.tess_upload(soa)
+    ctx.energy_set(ALL12)
+    ctx.record_splits(True)
+    nm, nf = ctx.merges_flips()
+    assert nm == len(t.non_blocking_segments) and nf == 2 * len(t.blocking_segments)
+    ctx.add_splits_philox(300, 19, 0)
+    he, x, ang = ctx.fetch("SPLIT_E1"), ctx.fetch("SPLIT_X"), ctx.fetch("SPLIT_ANGLE")
+    # the oracle's halfedge with the same end points
+    okey = {}
+    for k, hh in enumerate(t.halfedges):
+        okey[(float(hh.src.p[0]), float(hh.src.p[1]), float(hh.tgt.p[0]), float(hh.tgt.p[1]))] = k
+
+    def to_oracle(ids):
+        src, dst = a["he_src"][ids], a["he_src"][a["he_twin"][ids]]
+        return np.array([okey[(float(a["vx"][p]), float(a["vy"][p]), float(a["vx"][q]), float(a["vy"][q]))]
+                         for p, q in zip(src, dst)], dtype=np.int32)
+    res = lo.eval_candidates(t, lo.make_energy(lo.ALL12, None, t), to_oracle(he), x, ang)
+    np.testing.assert_array_equal(to_oracle(ctx.fetch("SPLIT_E2")), res["split_e2"])
+    scale = max(lo.face_area_2(lo.face2poly(f), t) for f in t.internal_faces())
+    k_a2 = ALL12.index("face_area_2")
+    keep = [k for k in range(len(ALL12)) if k != k_a2]
+    got = ctx.fetch("SPLIT_STAT")
+    _assert_stats("split", got[:, keep], res["split_stat"][:, keep], [ALL12[k] for k in keep])
+    assert np.all(np.abs(got[:, k_a2] - res["split_stat"][:, k_a2]) <= ATOL_STAT + RTOL * np.abs(res["split_stat"][:, k_a2]) + 16 * 2.3e-16 * scale)
+    # merges and flips come in the order of the two lists, which the file does not fix: compare as sets of rows
+    for name, want in (("MERGE_STAT", res["merge_stat"]), ("FLIP_STAT", res["flip_stat"])):
+        g = ctx.fetch(name)
+        assert g.shape == want.shape
+        gs, ws = g[np.lexsort(np.round(g, 6).T[::-1])], want[np.lexsort(np.round(want, 6).T[::-1])]
+        assert np.all(np.abs(gs[:, keep] - ws[:, keep]) <= 1e-9 + RTOL * np.abs(ws[:, keep]))
+        assert np.all(np.abs(gs[:, k_a2] - ws[:, k_a2]) <= 1e-9 + RTOL * np.abs(ws[:, k_a2]) + 16 * 2.3e-16 * scale)
+    th = 0.01 * np.random.default_rng(3).standard_normal(len(ALL12))
+    th[k_a2] *= 1e-4
+    lpl, g, H = ctx.pl_eval(th)
+    wl, wg, wH = lo.pl_from_stats(th, res["split_stat"], res["merge_stat"], res["flip_stat"], float(soa.int_length))
+    assert lpl == pytest.approx(wl, rel=RTOL)
+    np.testing.assert_allclose(g, wg, rtol=RTOL, atol=1e-9 * max(1.0, np.abs(wg).max()))
+    np.testing.assert_allclose(H, wH, rtol=RTOL, atol=1e-9 * max(1.0, np.abs(wH).max()))
+    ctx.close()

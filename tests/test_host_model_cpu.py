@@ -184,3 +184,43 @@ def test_bench_fixture_is_the_generated_c2_tessellation():
     assert float(z["int_length"]) == soa.int_length
     for k, v in soa.a.items():
         np.testing.assert_array_equal(z[k], v, err_msg=k)
+
+
+@pytest.mark.parametrize("which,seed,n_moves", [("holed", 11, 60), ("holed", 5, 0), ("flips", 4, 25)])
+def test_reader_takes_windows_with_holes(which, seed, n_moves):
+    """LineTes::read's format with several polygons and holes (lib/ttessel.cpp:1395-1415): the
+    host reader rebuilds the tessellation the exact oracle wrote, faces that surround a hole keep
+    its boundary as an inner boundary (halfedges carrying the face's id, not listed on its outer
+    boundary), the export matches the oracle's edge for edge, the text round-trips; the host
+    model's moves refuse such a tessellation."""
+    from test_gen_face_cpu import grow
+    from test_oracle_golden import holed_polygons, holed_polygons_for_flips
+    t = grow(holed_polygons() if which == "holed" else holed_polygons_for_flips(), seed, 5, n_moves)
+    text = lo.write_text(t)
+    h = lite_b200.HostTess(text=text)
+    h.check()
+    a, o = h.export().a, lo.export_soa(t)
+    assert h.export().int_length == pytest.approx(o["int_length"], rel=1e-14)
+    assert h.counts() == (int(np.sum(o["face_inside"])), len(o["non_blocking"]), len(o["blocking"]))
+
+    def edges(s):
+        """directed edge (end points) -> (bounds an inside face, listed on an outer boundary, edges of its segment)"""
+        listed = np.zeros(len(s["he_src"]), dtype=bool)
+        listed[s["face_he_list"]] = True
+        out = {}
+        for k in range(len(s["he_src"])):
+            p, q = s["he_src"][k], s["he_src"][s["he_twin"][k]]
+            key = (float(s["vx"][p]), float(s["vy"][p]), float(s["vx"][q]), float(s["vy"][q]))
+            out[key] = (bool(s["face_inside"][s["he_face"][k]]), bool(listed[k]), int(s["seg_n_edges"][s["he_seg"][k]]),
+                        bool(s["seg_on_boundary"][s["he_seg"][k]]))
+        return out
+    assert edges(a) == edges(o)
+    inside = a["face_inside"][a["he_face"]].astype(bool)
+    assert inside.sum() > len(a["face_he_list"])          # some halfedges lie on inner boundaries
+    # text round trip
+    h2 = lite_b200.HostTess(text=h.write_text())
+    assert edges(h2.export().a) == edges(a)
+    with pytest.raises(lite_b200.LiteError, match="holes"):
+        h.update_merge(0)
+    with pytest.raises(lite_b200.LiteError, match="holes"):
+        h.crtt_run(3.0, 10, 1)
