@@ -509,6 +509,10 @@ class PseudoLikDiscrete {
   void GetValueGradientHessian(CatVector, double *, CatVector *, CatMatrix *);
   void SetDevice(int device, int rank = 0, int world_size = 1, const void *nccl_unique_id = 0);
   void SetSeed(std::uint64_t seed) { seed_ = seed; }
+  /* AddSplits draws its positions as TTessel::split_sample does (n independent uniforms, sorted,
+   * lib/ttessel.cpp:1968-1991) instead of the default stratified sampler, which keeps each split's
+   * law but not the independence between splits (lower variance): see lite_b200.h, LITE_OPT_SAMPLER */
+  void SetIndependentSampling(bool on);
   Size NumberOfSplits() const { return (Size)n_splits_; }
   lite_ctx *context() { return ctx_; }
 
@@ -521,6 +525,7 @@ class PseudoLikDiscrete {
   std::vector<char> nccl_id_;
   std::uint64_t seed_, offset_;
   std::int64_t n_splits_;
+  bool iid_ = false;
   std::vector<int> he_export_;  /* internal halfedge id -> id in the uploaded SoA */
   void ensure_ctx();
   void shape(const CatVector &like, const double *flat, CatVector *out) const;

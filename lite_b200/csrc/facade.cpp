@@ -986,7 +986,14 @@ void PseudoLikDiscrete::SetDevice(int device, int rank, int world_size, const vo
   if (engy) SetEnergy(engy);
 }
 void PseudoLikDiscrete::ensure_ctx() {
-  if (!ctx_) ck(lite_ctx_create(&ctx_, device_, rank_, world_, nccl_id_.empty() ? 0 : nccl_id_.data()), "lite_ctx_create");
+  if (!ctx_) {
+    ck(lite_ctx_create(&ctx_, device_, rank_, world_, nccl_id_.empty() ? 0 : nccl_id_.data()), "lite_ctx_create");
+    ck(lite_ctx_set_option(ctx_, LITE_OPT_SAMPLER, iid_ ? LITE_SAMPLER_IID : LITE_SAMPLER_STRATIFIED), "lite_ctx_set_option");
+  }
+}
+void PseudoLikDiscrete::SetIndependentSampling(bool on) {
+  iid_ = on;
+  if (ctx_) ck(lite_ctx_set_option(ctx_, LITE_OPT_SAMPLER, on ? LITE_SAMPLER_IID : LITE_SAMPLER_STRATIFIED), "lite_ctx_set_option");
 }
 void PseudoLikDiscrete::SetEnergy(Energy *e) {  // :3327-3348: all merges, all flips, their sums
   engy = e;

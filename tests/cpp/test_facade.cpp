@@ -320,6 +320,18 @@ static void test_crtt_newton_fit() {
   CatVector th = pl.GetEstimate();
   CHECK(fabs(pl.GetGradient(th).segs[0]) < 1e-6);
   CHECK_CLOSE(pl.GetHessian(th).segs[0].segs[0], -(t.get_total_internal_length() / CGAL_PI) * exp(th.segs[0]), 1e-10);
+  // the same fit with the reference's sampling law (independent, sorted positions): the closed form
+  // does not depend on the dummy sample, so the estimate is the same
+  Energy fit2;
+  fit2.add_theta_segs(0.0);
+  fit2.add_features_segs(minus_is_segment_internal);
+  fit2.set_ttessel(&t);
+  PLInferenceNOIS pl2(&fit2, false, 1.0);
+  pl2.SetIndependentSampling(true);
+  pl2.ClearSplits();
+  pl2.AddSplits(t.number_of_non_blocking_segments());
+  pl2.Run(1e-10, 50);
+  CHECK_CLOSE(pl2.GetEstimate().segs[0], exact, 1e-8);
   delete rnd; rnd = 0;
 }
 
