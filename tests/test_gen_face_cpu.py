@@ -184,3 +184,16 @@ def test_general_code_on_ordinary_faces(tmp_path, name):
     assert_stats("split", got["split_stat"], gold["split_stat"][:n], lo.ALL12)
     assert_stats("merge", got["merge_stat"], gold["merge_stat"], lo.ALL12)
     assert_stats("flip", got["flip_stat"], gold["flip_stat"], lo.ALL12)
+
+
+def test_general_code_on_the_committed_holed_golden(tmp_path):
+    """tests/golden/holed.npz (the reference's holed domain, exact oracle) through the host build."""
+    soa, gold = load_golden("holed")
+    got = run_general(tmp_path, soa, lo.ALL12, gold["cand_he"], gold["cand_x"], gold["cand_angle"])
+    assert got["overflow"] == 0 and got["n_general"] >= 2
+    np.testing.assert_array_equal(got["split_e2"], gold["split_e2"])
+    np.testing.assert_array_equal(got["flip_e2"], gold["flip_e2"])
+    scale = float(gold["area2_scale"])
+    assert_stats("split", got["split_stat"], gold["split_stat"], lo.ALL12, scale)
+    assert_stats("merge", got["merge_stat"], gold["merge_stat"], lo.ALL12, scale)
+    assert_stats("flip", got["flip_stat"], gold["flip_stat"], lo.ALL12, scale)

@@ -846,3 +846,29 @@ def test_holed_window_from_the_text_format_through_the_host_reader(lite):
     np.testing.assert_allclose(g, wg, rtol=RTOL, atol=1e-9 * max(1.0, np.abs(wg).max()))
     np.testing.assert_allclose(H, wH, rtol=RTOL, atol=1e-9 * max(1.0, np.abs(wH).max()))
     ctx.close()
+
+
+def test_golden_window_with_holes(lite):
+    """Committed golden vectors for the reference's holed domain (tests/golden/holed.npz, made by
+    the exact oracle, make_golden_holed.py): fed split list, every merge and flip, all twelve
+    features, PL value / gradient / Hessian — no oracle at run time."""
+    soa, gold = load_golden("holed")
+    ctx = _ctx(lite, soa, ALL12)
+    ctx.merges_flips()
+    ctx.add_splits_given(gold["cand_he"], gold["cand_x"], gold["cand_angle"])
+    np.testing.assert_array_equal(ctx.fetch("SPLIT_E2"), gold["split_e2"])
+    np.testing.assert_array_equal(ctx.fetch("MERGE_HE"), gold["merge_he"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_E2"), gold["flip_e2"])
+    np.testing.assert_array_equal(ctx.fetch("FLIP_RIGHT"), gold["flip_right"])
+    k_a2, scale = ALL12.index("face_area_2"), float(gold["area2_scale"])
+    keep = [k for k in range(len(ALL12)) if k != k_a2]
+    for name, key in (("SPLIT_STAT", "split_stat"), ("MERGE_STAT", "merge_stat"), ("FLIP_STAT", "flip_stat")):
+        got, want = ctx.fetch(name), gold[key]
+        _assert_stats(name, got[:, keep], want[:, keep], [ALL12[k] for k in keep])
+        assert np.all(np.abs(got[:, k_a2] - want[:, k_a2]) <= ATOL_STAT + RTOL * np.abs(want[:, k_a2]) + 16 * 2.3e-16 * scale)
+    lpl, g, H = ctx.pl_eval(gold["pl_theta"])
+    assert lpl == pytest.approx(float(gold["pl_lpl"]), rel=RTOL)
+    np.testing.assert_allclose(g, gold["pl_grad"], rtol=RTOL, atol=1e-9 * max(1.0, np.abs(gold["pl_grad"]).max()))
+    np.testing.assert_allclose(H, gold["pl_hess"], rtol=RTOL, atol=1e-9 * max(1.0, np.abs(gold["pl_hess"]).max()))
+    assert ctx.pl_failures() == (0, 0)
+    ctx.close()
