@@ -88,6 +88,12 @@ static int nccl_load() {
   return 0;
 }
 
+// layout of the result block (doubles): two 128-word sums, 8 status words, 2 exchange words, the validation word
+#define LITE_RES_STATUS 256
+#define LITE_RES_PEER 264
+#define LITE_RES_ERR 266
+#define LITE_RES_WORDS 268
+
 template <typename T>
 struct DBuf {
   T *p = nullptr;
@@ -240,6 +246,7 @@ struct lite_ctx {
   std::vector<double> h_sum_m, h_sum_f;
   // reduce
   DBuf<double> partials, red_out;
+  DBuf<double> res;  // one block behind red_out | status | peer_info | err: a single copy brings an evaluation back
   DBuf<unsigned int> counter;
   DBuf<unsigned long long> status;  // [0] split no-exit, [1] flip no-exit, [2..3] checksum
   double *h_pinned = nullptr;       // pinned staging for results
@@ -360,7 +367,12 @@ static int ctx_init(lite_ctx *c, const void *nccl_unique_id) {
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, c->device));
   c->sm_count = prop.multiProcessorCount;
-  if (c->status.alloc(8) || c->counter.alloc(4) || c->err.alloc(1) || c->peer_info.alloc(2)) return LITE_ECUDA;
+  if (c->res.alloc(LITE_RES_WORDS) || c->counter.alloc(4)) return LITE_ECUDA;
+  c->red_out.p = c->res.p; c->red_out.n = 256; c->red_out.view = true;
+  c->status.p = (unsigned long long *)(c->res.p + LITE_RES_STATUS); c->status.n = 8; c->status.view = true;
+  c->peer_info.p = (unsigned long long *)(c->res.p + LITE_RES_PEER); c->peer_info.n = 2; c->peer_info.view = true;
+  c->err.p = (int *)(c->res.p + LITE_RES_ERR); c->err.n = 2; c->err.view = true;
+  CU(cudaMemsetAsync(c->res.p, 0, LITE_RES_WORDS * sizeof(double), c->stream));
   CU(cudaMemsetAsync(c->status.p, 0, 8 * sizeof(unsigned long long), c->stream));
   CU(cudaMemsetAsync(c->counter.p, 0, 4 * sizeof(unsigned int), c->stream));
   CU(cudaMemsetAsync(c->peer_info.p, 0, 2 * sizeof(unsigned long long), c->stream));
@@ -451,7 +463,7 @@ extern "C" int lite_ctx_destroy(lite_ctx *c) {
   c->in_x.release(); c->in_angle.release();
   c->mstat.release(); c->fstat.release(); c->sums.release(); c->m_he.release();
   c->fl_e1.release(); c->fl_e2.release(); c->fl_right.release(); c->fl_p2.release();
-  c->partials.release(); c->red_out.release(); c->counter.release(); c->status.release();
+  c->partials.release(); c->red_out.release(); c->counter.release(); c->status.release(); c->res.release();
   if (c->arena.d) cudaFree(c->arena.d);
   if (c->arena.h) cudaFreeHost(c->arena.h);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -1382,7 +1394,7 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
   Theta th{};
   for (int i = 0; i < d; i++) th.v[i] = theta[i];
   const int maxgrid = c->sm_count * 2;
-  if (c->partials.alloc((size_t)2 * maxgrid * NT) || c->red_out.alloc(2 * 128)) return LITE_ECUDA;
+  if (c->partials.alloc((size_t)2 * maxgrid * NT)) return LITE_ECUDA;
   if (c->mf_inflight) CU(cudaStreamWaitEvent(c->stream, c->ev_mf, 0));  // join the merge/flip stream
   CU(cudaEventRecord(c->ev[2], c->stream));
   // one launch: this rank's shard of the splits, then the flips (replicated on every rank)
@@ -1413,17 +1425,13 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
     if (ne != 0) return fail(LITE_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(ne) : "?");
   }
   CU(cudaEventRecord(c->ev[3], c->stream));
-  CU(cudaMemcpyAsync(c->h_pinned, c->red_out.p, 256 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  // geometric failures of the candidates behind these sums (no exit edge found): they ride
-  // back with the results, see lite_pl_failures
-  CU(cudaMemcpyAsync(c->h_pinned + 256, c->status.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(c->h_pinned + 258, c->status.p + 6, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-  if (exch) CU(cudaMemcpyAsync(c->h_pinned + 260, c->peer_info.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(c->h_pinned + 264, c->err.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  // the sums, the geometric failures of the candidates behind them (no exit edge found, see
+  // lite_pl_failures), the exchange's report and the validation word come back in one copy
+  CU(cudaMemcpyAsync(c->h_pinned, c->res.p, LITE_RES_WORDS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaGetLastError());
   {
-    const int tr = tess_err_report(c, *(const int *)(c->h_pinned + 264));
+    const int tr = tess_err_report(c, *(const int *)(c->h_pinned + LITE_RES_ERR));
     if (tr) return tr;
   }
   c->mf_inflight = false;
@@ -1434,14 +1442,14 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
   if (c->world > 1 && !exch) cudaEventElapsedTime(&c->ms_exchange, c->ev[7], c->ev[3]);
   if (c->ev01) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->ms_split = ms; }
   {
-    const unsigned long long *st = (const unsigned long long *)(c->h_pinned + 256);
+    const unsigned long long *st = (const unsigned long long *)(c->h_pinned + LITE_RES_STATUS);
     c->fail_splits = (int64_t)st[0]; c->fail_flips = (int64_t)st[1];
-    if (st[2] != 0)
+    if (st[6] != 0)
       return fail(LITE_ECAPACITY, "%llu candidates on faces with holes needed polygons of more than %d vertices",
-                  st[2], LITE_GEN_PTS);
+                  st[6], LITE_GEN_PTS);
   }
   if (exch) {
-    const unsigned long long *pi = (const unsigned long long *)(c->h_pinned + 260);
+    const unsigned long long *pi = (const unsigned long long *)(c->h_pinned + LITE_RES_PEER);
     if (pi[0] == P.seq)
       return fail(LITE_ENCCL, "rank %d: the peers' sums of evaluation %llu did not arrive within %.1f s "
                   "(did every rank call lite_pl_eval?)", c->rank, P.seq, LITE_PEER_TIMEOUT_NS * 1e-9);
