@@ -123,44 +123,64 @@ static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 // A few persistent host threads per context: an upload's packing and export assertions run
 // on them (spawning threads per call cost about as much as the work itself).
+static double now_ms();
 struct HostPool {
   std::vector<std::thread> th;
   std::mutex m;
   std::condition_variable cv_go, cv_done;
   std::function<void(int)> job;
-  unsigned long gen = 0;
-  int pending = 0;
+  std::atomic<unsigned long> gen{0};
+  std::atomic<int> pending{0};
   bool stop = false;
+  // A worker that has just finished a job polls for the next one for this long before it goes
+  // to sleep on the condition variable: in a loop of uploads (one every few hundred
+  // microseconds) the workers then start within a microsecond instead of after a futex wake-up
+  // each (tens of microseconds, one after the other).  LITE_B200_SPIN_US overrides it, 0 = never poll.
+  double spin_ms = 1.0;
   void start(int n) {
+    if (const char *e = getenv("LITE_B200_SPIN_US")) spin_ms = atof(e) * 1e-3;
     for (int i = 0; i < n; i++)
       th.emplace_back([this, i] {
         unsigned long seen = 0;
+        bool hot = false;
         for (;;) {
+          if (hot && spin_ms > 0) {
+            const double t_end = now_ms() + spin_ms;
+            for (int k = 0; gen.load(std::memory_order_acquire) == seen; k++) {
+              _mm_pause();
+              if ((k & 63) == 63 && now_ms() > t_end) break;
+            }
+          }
           std::function<void(int)> f;
           {
             std::unique_lock<std::mutex> lk(m);
-            cv_go.wait(lk, [&] { return stop || gen != seen; });
+            cv_go.wait(lk, [&] { return stop || gen.load(std::memory_order_relaxed) != seen; });
             if (stop) return;
-            seen = gen;
+            seen = gen.load(std::memory_order_relaxed);
             f = job;
           }
           f(i);
-          {
+          hot = true;
+          if (pending.fetch_sub(1, std::memory_order_acq_rel) == 1) {
             std::lock_guard<std::mutex> lk(m);
-            if (--pending == 0) cv_done.notify_all();
+            cv_done.notify_all();
           }
         }
       });
   }
   // run f(0..n-1) on the workers; returns at once, wait() joins
   void run(const std::function<void(int)> &f) {
-    std::lock_guard<std::mutex> lk(m);
-    job = f; pending = (int)th.size(); gen++;
+    {
+      std::lock_guard<std::mutex> lk(m);
+      job = f; pending.store((int)th.size(), std::memory_order_relaxed);
+      gen.fetch_add(1, std::memory_order_release);
+    }
     cv_go.notify_all();
   }
   void wait() {
+    for (int k = 0; k < 20000 && pending.load(std::memory_order_acquire) != 0; k++) _mm_pause();
     std::unique_lock<std::mutex> lk(m);
-    cv_done.wait(lk, [&] { return pending == 0; });
+    cv_done.wait(lk, [&] { return pending.load(std::memory_order_acquire) == 0; });
   }
   void shutdown() {
     { std::lock_guard<std::mutex> lk(m); stop = true; }
@@ -179,6 +199,7 @@ struct lite_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;   // merges+flips run here, beside the split kernel
   cudaEvent_t ev_fork = nullptr, ev_mf = nullptr;
+  cudaEvent_t ev_up0 = nullptr, ev_guide = nullptr;  // upload: the sampler's tables go over the second stream
   bool mf_inflight = false;         // stream must wait for ev_mf before using the flip statistics
   ncclComm_t comm = nullptr;
   // cross-GPU sum over peer memory (kernels.cuh: PeerArgs); off -> ncclAllReduce
@@ -208,7 +229,7 @@ struct lite_ctx {
   DBuf<int> f_off, f_cnt, f_list, seg_he_start, seg_he_end, seg_n_edges, nb_list, b_list;
   // derived
   DBuf<double2> pt, udir;
-  DBuf<double> ang, len, ca, f_area, f_perim, f_sumang, f_minang, cum, pre, plen, f_tot2, stot2;
+  DBuf<double> ang, len, ca, el, f_area, f_perim, f_sumang, f_minang, cum, pre, plen, f_tot2, stot2;
   DBuf<int2> sfo;
   DBuf<uint32_t> flg;
   DBuf<int> slot_he, slot_seg, slot_face, he_slot, guide, err;
@@ -359,6 +380,8 @@ static int ctx_init(lite_ctx *c, const void *nccl_unique_id) {
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_up0, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_guide, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_upload, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_mf, cudaEventDisableTiming));
   for (int i = 0; i < 8; i++) CU(cudaEventCreate(&c->ev[i]));
@@ -394,7 +417,9 @@ static int ctx_init(lite_ctx *c, const void *nccl_unique_id) {
     int hc = (int)std::thread::hardware_concurrency();
     int nt = hc > 0 ? hc / c->world - 1 : 4;
     if (nt > 4) nt = 4;
+    if (const char *e = getenv("LITE_B200_PACK_THREADS")) nt = atoi(e);
     if (nt < 1) nt = 1;
+    if (nt > 16) nt = 16;
     c->pool->start(nt);
   }
   CU(cudaStreamSynchronize(c->stream));
@@ -454,7 +479,7 @@ extern "C" int lite_ctx_destroy(lite_ctx *c) {
   c->f_off.release(); c->f_cnt.release(); c->f_list.release(); c->seg_he_start.release();
   c->seg_he_end.release(); c->seg_n_edges.release(); c->nb_list.release(); c->b_list.release();
   c->sel_a.release(); c->sel_b.release(); c->id_a.release(); c->id_b.release(); c->sort_tmp.release();
-  c->pt.release(); c->udir.release(); c->ang.release(); c->len.release(); c->ca.release(); c->f_area.release();
+  c->pt.release(); c->udir.release(); c->ang.release(); c->len.release(); c->ca.release(); c->el.release(); c->f_area.release();
   c->f_perim.release(); c->f_sumang.release(); c->f_minang.release(); c->cum.release(); c->pre.release(); c->plen.release(); c->f_tot2.release(); c->stot2.release(); c->sfo.release();
   c->flg.release(); c->slot_he.release(); c->slot_seg.release(); c->slot_face.release();
   c->he_slot.release(); c->guide.release(); c->err.release();
@@ -467,6 +492,8 @@ extern "C" int lite_ctx_destroy(lite_ctx *c) {
   if (c->arena.d) cudaFree(c->arena.d);
   if (c->arena.h) cudaFreeHost(c->arena.h);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_up0) cudaEventDestroy(c->ev_up0);
+  if (c->ev_guide) cudaEventDestroy(c->ev_guide);
   if (c->ev_upload) cudaEventDestroy(c->ev_upload);
   if (c->ev_mf) cudaEventDestroy(c->ev_mf);
   if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -626,7 +653,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
     if (ra) return ra;
   }
   if (c->upload_inflight) { CU(cudaEventSynchronize(c->ev_upload)); c->upload_inflight = false; }
-  if (c->early_unfenced) { CU(cudaStreamSynchronize(c->stream)); c->early_unfenced = false; }
+  if (c->early_unfenced) { CU(cudaStreamSynchronize(c->stream)); CU(cudaStreamSynchronize(c->stream2)); c->early_unfenced = false; }
   c->pack_jobs.clear();
   int r = 0;
   r |= up(c, c->vx, s->vx, nV); r |= up(c, c->vy, s->vy, nV);
@@ -655,28 +682,17 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   const int nt = (int)c->pool->th.size();
   std::vector<int> bad_he(nt, -1);
   std::vector<int64_t> part_inside(nt, 0), part_twice(nt, 0);
-  c->h_he_inside.assign(nH, 0);
-  // the face lists must tile [0, n_face_he) in face order: slot order == face order
-  int64_t listed = 0;
-  {
-    int64_t run = 0;
-    for (int f = 0; f < nF; f++) {
-      const int off = s->face_he_offset[f], cnt = s->face_he_count[f];
-      if (off != run || cnt < 0 || cnt > s->n_face_he - off || (s->face_inside[f] && cnt < 3))
-        return fail(LITE_EINVAL, "face %d: its halfedge list must follow the previous face's (offset %d, expected %lld) and hold "
-                    "at least 3 halfedges when the face is inside", f, off, (long long)run);
-      run += cnt;
-      if (s->face_inside[f]) listed += cnt;
-    }
-    if (run != s->n_face_he) return fail(LITE_EINVAL, "the face lists hold %lld halfedges, n_face_he is %d", (long long)run, s->n_face_he);
-  }
-  std::vector<double> &cum = c->h_cum;
-  cum.resize((size_t)s->n_face_he);
+  c->h_he_inside.resize(nH);  // every entry is written by the count below
+  std::vector<double> &cum = c->h_cum;  // only a tessellation with holes uses it (extended slots)
   // The worker that finishes last starts the copy of everything packed so far (all but the
   // cumulative lengths, which this thread is still summing): the 0.08 ms on the link overlap the
   // rest of the host work.  Not for a tessellation with holes: its extended lists are built below.
   const size_t bulk_bytes = c->arena.used;
-  std::atomic<int> arrived{0};
+  // the cumulative lengths are written straight into the pinned block, behind the bulk
+  const size_t cum_off = c->arena.used;
+  if (cum_off + align256((size_t)s->n_face_he * sizeof(double)) > c->arena.cap) return fail(LITE_ESTATE, "upload arena overflow");
+  c->arena.used += align256((size_t)s->n_face_he * sizeof(double));
+  double *const cum_pin = (double *)(c->arena.h + cum_off);
   bool early_copy = false;
   if (g_trace) {
     if (!c->ev_tr[0]) for (int k = 0; k < 3; k++) cudaEventCreate(&c->ev_tr[k]);
@@ -687,55 +703,259 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
         fprintf(stderr, "[lite_b200] previous upload on the device: copy %.3f ms, rest of the copy + checks + preparation %.3f ms\n", h2d, prep);
     }
   }
-  c->pool->run([=, &bad_he, &part_inside, &part_twice, &arrived, &early_copy](int t) {
-    for (size_t k = t; k < c->pack_jobs.size(); k += nt) memcpy_stream(c->pack_jobs[k].dst, (const char *)c->pack_jobs[k].src, c->pack_jobs[k].bytes);
-    _mm_sfence();
-    const int h0 = (int)((int64_t)nH * t / nt), h1 = (int)((int64_t)nH * (t + 1) / nt);
+  // Everything the device does with an upload except the sampler's tables needs only the bulk:
+  // the memsets, the checks and the slot / face preparation.  They are enqueued by whoever
+  // enqueues the bulk copy -- the last packing worker, while this thread is still summing the
+  // cumulative lengths, or this thread further down.
+  auto alloc_slots = [c, nH, nF](size_t nSl) -> int {
+    return c->pt.alloc(nSl) || c->udir.alloc(nSl) || c->ang.alloc(nSl) || c->len.alloc(nSl) || c->ca.alloc(nSl) || c->el.alloc(nSl) ||
+           c->flg.alloc(nSl) || c->slot_he.alloc(nSl) || c->slot_seg.alloc(nSl) ||
+           c->slot_face.alloc(nSl) || c->he_slot.alloc(nH) || c->f_area.alloc(nF) ||
+           c->f_perim.alloc(nF) || c->f_sumang.alloc(nF) || c->f_minang.alloc(nF) || c->pre.alloc(nSl) ||
+           c->plen.alloc(nSl) || c->f_tot2.alloc(nF) || c->sfo.alloc(nSl) || c->stot2.alloc(nSl);
+  };
+  auto enqueue_prep = [c, s, nH, nF, nS, nV](size_t nSl, bool general) -> cudaError_t {
+    // one memset: the no-exit counters, the general-face overflow count, the exchange's report and
+    // the validation word are the tail of the result block (the other status words are zeroed
+    // where they are used); he_slot is initialised by k_validate
+    cudaError_t e = cudaMemsetAsync(c->status.p, 0, (LITE_RES_WORDS - LITE_RES_STATUS) * sizeof(double), c->stream);
+    if (e != cudaSuccess) return e;
+    PrepArgs A{};
+    A.vx = c->vx.p; A.vy = c->vy.p; A.he_src = c->he_src.p; A.he_twin = c->he_twin.p;
+    A.he_next = c->he_next.p; A.he_face = c->he_face.p; A.he_seg = c->he_seg.p;
+    A.he_next_hf = c->he_next_hf.p; A.he_dir = c->he_dir.p; A.face_inside = c->face_inside.p;
+    A.f_gen = general ? c->g_fgen.p : nullptr;
+    A.he_length = c->he_length.p; A.face_he_offset = c->f_off.p; A.face_he_count = c->f_cnt.p;
+    A.face_he_list = c->f_list.p; A.n_faces = nF;
+    A.pt = c->pt.p; A.udir = c->udir.p; A.ang = c->ang.p; A.len = c->len.p; A.ca = c->ca.p; A.el = c->el.p; A.flg = c->flg.p;
+    A.slot_he = c->slot_he.p; A.slot_seg = c->slot_seg.p; A.slot_face = c->slot_face.p;
+    A.he_slot = c->he_slot.p; A.err = c->err.p;
+    TessDev &T = c->T;
+    T.n_slots = (int)nSl; T.n_faces = nF; T.n_he = nH; T.n_seg = nS; T.err = c->err.p;
+    T.pt = c->pt.p; T.udir = c->udir.p; T.ang = c->ang.p; T.len = c->len.p; T.ca = c->ca.p; T.flg = c->flg.p;
+    T.slot_he = c->slot_he.p; T.slot_seg = c->slot_seg.p; T.slot_face = c->slot_face.p;
+    T.he_slot = c->he_slot.p; T.he_twin = c->he_twin.p; T.he_src = c->he_src.p;
+    T.he_next_hf = c->he_next_hf.p; T.he_prev_hf = c->he_prev_hf.p;
+    T.f_off = c->f_off.p; T.f_cnt = c->f_cnt.p; T.f_gen = general ? c->g_fgen.p : nullptr;
+    T.f_area = c->f_area.p; T.f_perim = c->f_perim.p; T.f_sumang = c->f_sumang.p; T.f_minang = c->f_minang.p;
+    T.seg_n_edges = c->seg_n_edges.p; T.seg_he_start = c->seg_he_start.p; T.seg_he_end = c->seg_he_end.p;
+    T.seg_bnd = c->seg_bnd.p;
+    T.sfo = c->sfo.p; T.pre = c->pre.p; T.plen = c->plen.p; T.f_tot2 = c->f_tot2.p; T.stot2 = c->stot2.p;
+    if (general) {
+      gen::Tess &GT = c->GT;
+      GT.n_he = nH; GT.n_faces = nF; GT.vx = c->vx.p; GT.vy = c->vy.p;
+      GT.he_src = c->he_src.p; GT.he_twin = c->he_twin.p; GT.he_next = c->he_next.p; GT.he_face = c->he_face.p;
+      GT.he_seg = c->he_seg.p; GT.he_next_hf = c->he_next_hf.p; GT.he_prev_hf = c->he_prev_hf.p;
+      GT.he_dir = c->he_dir.p; GT.face_inside = c->face_inside.p; GT.seg_bnd = c->seg_bnd.p;
+      GT.seg_n_edges = c->seg_n_edges.p; GT.f_outer = c->g_outer.p; GT.f_hole_off = c->g_hole_off.p;
+      GT.f_hole_cnt = c->g_hole_cnt.p; GT.hole_he = c->g_hole_he.p;
+      if (!c->gen_scratch) {
+        c->gen_blocks = c->sm_count;
+        // two blocks of scratch: the merge/flip kernel runs on the second stream, beside the split kernel
+        e = cudaMalloc((void **)&c->gen_scratch, 2 * (size_t)c->gen_blocks * LITE_GEN_TB * LITE_GEN_PTS * sizeof(gen::Pt));
+        if (e != cudaSuccess) { c->gen_scratch = nullptr; return e; }
+      }
+    }
+    ValidateArgs V{};
+    V.nV = nV; V.nH = nH; V.nF = nF; V.nS = nS; V.nFH = (int)nSl; V.nNB = s->n_non_blocking; V.nB = s->n_blocking;
+    V.he_src = c->he_src.p; V.he_twin = c->he_twin.p; V.he_next = c->he_next.p; V.he_face = c->he_face.p;
+    V.he_seg = c->he_seg.p; V.he_next_hf = c->he_next_hf.p; V.he_prev_hf = c->he_prev_hf.p;
+    V.face_inside = c->face_inside.p; V.seg_bnd = c->seg_bnd.p; V.f_gen = general ? c->g_fgen.p : nullptr;
+    V.f_off = c->f_off.p; V.f_cnt = c->f_cnt.p; V.f_list = c->f_list.p; V.seg_he_start = c->seg_he_start.p;
+    V.seg_he_end = c->seg_he_end.p; V.seg_n_edges = c->seg_n_edges.p; V.nb_list = c->nb_list.p; V.b_list = c->b_list.p;
+    V.err = c->err.p; V.he_slot = c->he_slot.p;
+    int most = nH;
+    if (nF > most) most = nF;
+    if (nS > most) most = nS;
+    if ((int)nSl > most) most = (int)nSl;
+    k_validate<<<(most + 255) / 256, 256, 0, c->stream>>>(V);
+    k_prep_slots<<<(unsigned)((nSl + 127) / 128), 128, 0, c->stream>>>(A, (int)nSl);
+    // outside faces: count 0 in the device view
+    const int tb = 128, gb = (nF + tb - 1) / tb;
+    k_prep_faces<<<gb, tb, 0, c->stream>>>(T, c->ca.p, c->el.p, c->f_area.p, c->f_perim.p, c->f_sumang.p, c->f_minang.p,
+                                           c->pre.p, c->plen.p, c->f_tot2.p, c->sfo.p, c->stot2.p);
+    c->launches += 3;
+    return cudaGetLastError();
+  };
+  bool early_prep = false;
+  // The bulk leaves in a few groups of 64 KB pieces: a group is sent as soon as its last piece is
+  // packed, so the link works while the rest is still being packed.
+  std::vector<lite_ctx::PackJob> pieces;
+  for (const auto &j : c->pack_jobs)
+    for (size_t o = 0; o < j.bytes; o += (64u << 10))
+      pieces.push_back({j.dst + o, (const char *)j.src + o, j.bytes - o < (64u << 10) ? j.bytes - o : (size_t)(64u << 10)});
+  enum { MAX_GROUPS = 8 };
+  int n_groups = 4;
+  if (const char *e = getenv("LITE_B200_UPLOAD_GROUPS")) n_groups = atoi(e);
+  if (n_groups > MAX_GROUPS) n_groups = MAX_GROUPS;
+  if (n_groups > (int)pieces.size()) n_groups = (int)pieces.size();
+  if (n_groups < 1) n_groups = 1;
+  std::vector<uint8_t> piece_group(pieces.size(), 0);
+  size_t g_b0[MAX_GROUPS + 1];
+  std::atomic<int> g_left[MAX_GROUPS];
+  {
+    size_t total = 0, acc = 0;
+    for (const auto &q : pieces) total += q.bytes;
+    int g = 0, cnt = 0;
+    g_b0[0] = 0;
+    for (size_t k = 0; k < pieces.size(); k++) {
+      if (g + 1 < n_groups && cnt > 0 && acc >= total * (size_t)(g + 1) / (size_t)n_groups) {
+        g_left[g].store(cnt, std::memory_order_relaxed);
+        g++; cnt = 0;
+        g_b0[g] = (size_t)(pieces[k].dst - c->arena.h);
+      }
+      piece_group[k] = (uint8_t)g;
+      cnt++; acc += pieces[k].bytes;
+    }
+    g_left[g].store(cnt, std::memory_order_relaxed);
+    n_groups = g + 1;
+    g_b0[n_groups] = bulk_bytes;
+  }
+  std::atomic<size_t> next_piece{0};
+  std::atomic<int> next_count{0};
+  const int n_count_chunks = 4 * nt;
+  std::atomic<int> arrived_pack{0};
+  std::atomic<bool> copy_failed{false}, copies_started{false};
+  double wk_start[16] = {0};
+  double wk_t[3] = {0, 0, 0};  // trace: the workers' clock when the first group left, when all had, after the preparation
+  if (!c->validate_host && alloc_slots((size_t)s->n_face_he)) return LITE_ECUDA;
+  if (g_trace) cudaEventRecord(c->ev_tr[0], c->stream);
+  CU(cudaEventRecord(c->ev_up0, c->stream));  // whatever still reads the previous tessellation is in front of this
+  c->pool->run([=, &bad_he, &part_inside, &part_twice, &wk_t, &wk_start, &pieces,
+                &next_piece, &next_count, &arrived_pack, &piece_group, &g_b0, &g_left, &copy_failed, &copies_started](int t) {
+    if (g_trace) wk_start[t & 15] = now_ms();
+    // pieces handed out one at a time: the arrays differ in size by a factor of 100
+    for (;;) {
+      const size_t k = next_piece.fetch_add(1, std::memory_order_relaxed);
+      if (k >= pieces.size()) break;
+      memcpy_stream(pieces[k].dst, (const char *)pieces[k].src, pieces[k].bytes);
+      _mm_sfence();
+      const int g = piece_group[k];
+      if (g_left[g].fetch_sub(1, std::memory_order_acq_rel) == 1 && !c->validate_host) {
+        copies_started.store(true, std::memory_order_relaxed);
+        if (cudaSetDevice(c->device) != cudaSuccess ||
+            cudaMemcpyAsync(c->arena.d + g_b0[g], c->arena.h + g_b0[g], g_b0[g + 1] - g_b0[g], cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+          copy_failed.store(true, std::memory_order_relaxed);
+        if (g_trace && wk_t[0] == 0) wk_t[0] = now_ms();
+      }
+    }
+    arrived_pack.fetch_add(1, std::memory_order_acq_rel);   // every group this worker completed has been sent
+    if (g_trace) wk_t[1] = now_ms();
+    // Does a halfedge bound an inside face, and does a face lie on both sides of an edge (with
+    // the listed halfedges, this tells a tessellation with holes)?  In chunks, so that a worker
+    // that was busy sending a group takes fewer.
     int64_t inside = 0, twice = 0;
-    for (int h = h0; h < h1; h++) {
-      const int f = s->he_face[h], tw = s->he_twin[h];
-      if ((unsigned)f >= (unsigned)nF || (unsigned)tw >= (unsigned)nH) { bad_he[t] = h; break; }
-      if (!s->face_inside[f]) continue;
-      inside++;
-      c->h_he_inside[h] = 1;
-      if (s->he_face[tw] == f) twice++;   // the face runs along both sides of this edge
+    for (;;) {
+      const int q = next_count.fetch_add(1, std::memory_order_relaxed);
+      if (q >= n_count_chunks || bad_he[t] >= 0) break;
+      const int h0 = (int)((int64_t)nH * q / n_count_chunks), h1 = (int)((int64_t)nH * (q + 1) / n_count_chunks);
+      for (int h = h0; h < h1; h++) {
+        const int f = s->he_face[h], tw = s->he_twin[h];
+        if ((unsigned)f >= (unsigned)nF || (unsigned)tw >= (unsigned)nH) { bad_he[t] = h; break; }
+        const bool in = s->face_inside[f] != 0;
+        c->h_he_inside[h] = in;
+        if (!in) continue;
+        inside++;
+        if (s->he_face[tw] == f) twice++;   // the face runs along both sides of this edge
+      }
     }
     part_inside[t] = inside;
     part_twice[t] = twice;
-    if (arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == nt) {
-      int64_t ti = 0, tt = 0;
-      bool bad = false;
-      for (int q = 0; q < nt; q++) { ti += part_inside[q]; tt += part_twice[q]; bad |= bad_he[q] >= 0; }
-      if (!bad && ti == listed && tt == 0 && !c->validate_host && cudaSetDevice(c->device) == cudaSuccess) {
-        if (g_trace) cudaEventRecord(c->ev_tr[0], c->stream);
-        early_copy = cudaMemcpyAsync(c->arena.d, c->arena.h, bulk_bytes, cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
-        if (g_trace) cudaEventRecord(c->ev_tr[1], c->stream);
+  });
+  // the job reads this frame; a copy that has started must be fenced before the block is reused
+  struct Joiner {
+    lite_ctx *c; std::atomic<bool> *started;
+    ~Joiner() { c->pool->wait(); if (started->load()) c->early_unfenced = true; }
+  } joiner{c, &copies_started};
+  // the face lists must tile [0, n_face_he) in face order: slot order == face order
+  int64_t listed = 0;
+  // maximal runs of slots whose faces are all inside (or all outside): the cumulative lengths
+  // below are summed run by run, in one flat loop each
+  struct SlotRun { int begin, end; bool inside; };
+  std::vector<SlotRun> runs;
+  {
+    int64_t run = 0;
+    for (int f = 0; f < nF; f++) {
+      const int off = s->face_he_offset[f], cnt = s->face_he_count[f];
+      if (off != run || cnt < 0 || cnt > s->n_face_he - off || (s->face_inside[f] && cnt < 3))
+        return fail(LITE_EINVAL, "face %d: its halfedge list must follow the previous face's (offset %d, expected %lld) and hold "
+                    "at least 3 halfedges when the face is inside", f, off, (long long)run);
+      run += cnt;
+      const bool in = s->face_inside[f] != 0;
+      if (in) listed += cnt;
+      if (cnt > 0) {
+        if (!runs.empty() && runs.back().inside == in) runs.back().end = off + cnt;
+        else runs.push_back({off, off + cnt, in});
       }
     }
-  });
-  struct Joiner { HostPool *p; ~Joiner() { p->wait(); } } joiner{c->pool};  // the job reads this frame
+    if (run != s->n_face_he) return fail(LITE_EINVAL, "the face lists hold %lld halfedges, n_face_he is %d", (long long)run, s->n_face_he);
+  }
   const double t_stage = now_ms();
   // cumulative halfedge lengths of the sampler (cumlen += e->get_length(), lib/ttessel.cpp:1980),
   // accumulated sequentially in SLOT order (faces in index order, each in ccb order from
   // outer_ccb()): the summation order is part of the sampler's definition.  Entry m is slot m.
+  // One flat loop per run: the chain of additions is the only dependency left (the loop over
+  // faces mispredicted its exit once per face and took twice as long).  Non-temporal stores, as
+  // for the rest of the block.
   double cl = 0.0;
   int bad_list = -1;
-  for (int f = 0; f < nF && bad_list < 0; f++) {
-    const int off = s->face_he_offset[f], cnt = s->face_he_count[f];
-    if (!s->face_inside[f]) { for (int k = 0; k < cnt; k++) cum[off + k] = cl; continue; }
-    for (int k = 0; k < cnt; k++) {
-      const int h = s->face_he_list[off + k];
-      if ((unsigned)h >= (unsigned)nH) { bad_list = f; break; }
-      cl += s->he_length[h];
-      cum[off + k] = cl;
+  for (const SlotRun &R : runs) {
+    if (!R.inside) {
+      for (int k = R.begin; k < R.end; k++) _mm_stream_si64((long long *)(cum_pin + k), (long long)__builtin_bit_cast(int64_t, cl));
+      continue;
+    }
+    const int32_t *lst = s->face_he_list;
+    const double *hl = s->he_length;
+    for (int k = R.begin; k < R.end; k++) {
+      const int h = lst[k];
+      if ((unsigned)h >= (unsigned)nH) { bad_list = k; break; }
+      cl += hl[h];
+      _mm_stream_si64((long long *)(cum_pin + k), (long long)__builtin_bit_cast(int64_t, cl));
+    }
+    if (bad_list >= 0) break;
+  }
+  _mm_sfence();
+  const double t_cum = now_ms();
+  // As soon as every group of the bulk has been sent, this thread queues -- for a tessellation
+  // without holes, which the count in progress has yet to confirm -- the checks and the
+  // preparation behind the bulk, and the cumulative lengths with the guide table on the second
+  // stream, beside them (the preparation does not read them).  If the count finds holes,
+  // everything is prepared again below with the extended lists.
+  bool side_done = false;
+  int n_guide_simple = 1;
+  while (n_guide_simple < 2 * s->n_face_he) n_guide_simple <<= 1;
+  if (!c->validate_host && bad_list < 0 && cl > 0.0) {
+    while (arrived_pack.load(std::memory_order_acquire) < nt) _mm_pause();
+    if (!copy_failed.load(std::memory_order_relaxed) && c->guide.alloc((size_t)n_guide_simple) == 0) {
+      early_copy = true;
+      if (g_trace) cudaEventRecord(c->ev_tr[1], c->stream);
+      early_prep = enqueue_prep((size_t)s->n_face_he, false) == cudaSuccess;
+      if (early_prep) {
+        const size_t cum_bytes = align256((size_t)s->n_face_he * sizeof(double));
+        bool ok = cudaStreamWaitEvent(c->stream2, c->ev_up0, 0) == cudaSuccess &&
+                  cudaMemcpyAsync(c->arena.d + cum_off, c->arena.h + cum_off, cum_bytes, cudaMemcpyHostToDevice, c->stream2) == cudaSuccess;
+        if (ok) {
+          k_build_guide<<<(n_guide_simple + 255) / 256, 256, 0, c->stream2>>>((const double *)(c->arena.d + cum_off), s->n_face_he,
+                                                                             cl / (double)n_guide_simple, n_guide_simple, c->guide.p);
+          c->launches += 1;
+          ok = cudaEventRecord(c->ev_guide, c->stream2) == cudaSuccess;
+        }
+        side_done = ok;
+      }
+      if (g_trace) wk_t[2] = now_ms();
     }
   }
-  const double t_cum = now_ms();
   c->pool->wait();
-  c->early_unfenced = early_copy;
-  if (g_trace) fprintf(stderr, "[lite_b200] tess_upload host: staging %.3f ms, cumulative lengths %.3f ms, wait for the workers (pack, count) %.3f ms\n",
-                       t_stage - t0, t_cum - t_stage, now_ms() - t_cum);
-  if (bad_list >= 0) return fail(LITE_EINVAL, "face %d: halfedge list out of range", bad_list);
+  c->early_unfenced = copies_started.load();
+  if (g_trace) fprintf(stderr, "[lite_b200] tess_upload host: staging %.3f ms, cumulative lengths %.3f ms, wait for the workers (pack, count) %.3f ms; "
+                       "workers: first group sent at %.3f ms, last one packed at %.3f; preparation and tables queued at %.3f\n",
+                       t_stage - t0, t_cum - t_stage, now_ms() - t_cum, wk_t[0] - t0, wk_t[1] - t0, wk_t[2] - t0);
+  if (g_trace) {
+    fprintf(stderr, "[lite_b200] workers started at");
+    for (int t = 0; t < nt && t < 16; t++) fprintf(stderr, " %.3f", wk_start[t] - t0);
+    fprintf(stderr, " ms\n");
+  }
+  if (bad_list >= 0) return fail(LITE_EINVAL, "face list entry %d: not a halfedge", bad_list);
   for (int t = 0; t < nt; t++)
     if (bad_he[t] >= 0) return fail(LITE_EINVAL, "halfedge %d: inconsistent links", bad_he[t]);
   int64_t inside_he = 0, twice = 0;
@@ -748,6 +968,8 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   // slots are the outer boundary followed by the inner ones, their candidates go through
   // gen_face.h.  A rectangular window never has any and skips all of this.
   const bool general = inside_he != listed || twice != 0;
+  if (side_done) CU(cudaStreamWaitEvent(c->stream, c->ev_guide, 0));
+  if (general) { early_prep = false; side_done = false; }  // what was queued assumed simple faces: prepared again below
   c->n_general = 0;
   if (general || c->validate_host) {
     const int hv = host_validate(c, s);
@@ -796,7 +1018,14 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
                 s->int_length, cl);
   t1 = now_ms();
   c->pack_jobs.clear();
-  r |= up(c, c->cum, cum.data(), cum.size());
+  size_t n_cum = (size_t)s->n_face_he;
+  if (general) {
+    r |= up(c, c->cum, cum.data(), cum.size());
+    n_cum = cum.size();
+  } else {
+    if (!c->cum.view) c->cum.release();
+    c->cum.p = (double *)(c->arena.d + cum_off); c->cum.n = n_cum; c->cum.view = true;
+  }
   if (general) {  // the extended lists replace the caller's, the cycles go along
     r |= up(c, c->f_off, l_off, (size_t)nF); r |= up(c, c->f_cnt, l_cnt, (size_t)nF);
     r |= up(c, c->f_list, l_list, n_slots);
@@ -812,8 +1041,10 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   _mm_sfence();
   c->pack_jobs.clear();
   t2 = now_ms();
-  if (early_copy) {  // the bulk is on its way: only what was staged since (the cumulative lengths)
-    // (this copy and the guide table on the second stream, beside the checks: measured, no gain)
+  // what was staged since the bulk left (the cumulative lengths, unless they already went over
+  // the second stream; the extended lists of a tessellation with holes) -- or everything
+  if (side_done) {
+  } else if (early_copy) {
     CU(cudaMemcpyAsync(c->arena.d + bulk_bytes, c->arena.h + bulk_bytes, c->arena.used - bulk_bytes, cudaMemcpyHostToDevice, c->stream));
   } else {
     if (g_trace) cudaEventRecord(c->ev_tr[0], c->stream);
@@ -821,76 +1052,17 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
     if (g_trace) cudaEventRecord(c->ev_tr[1], c->stream);
   }
   const size_t nSl = n_slots;
-  if (c->pt.alloc(nSl) || c->udir.alloc(nSl) || c->ang.alloc(nSl) || c->len.alloc(nSl) || c->ca.alloc(nSl) ||
-      c->flg.alloc(nSl) || c->slot_he.alloc(nSl) || c->slot_seg.alloc(nSl) ||
-      c->slot_face.alloc(nSl) || c->he_slot.alloc(nH) || c->f_area.alloc(nF) ||
-      c->f_perim.alloc(nF) || c->f_sumang.alloc(nF) || c->f_minang.alloc(nF) || c->pre.alloc(nSl) ||
-      c->plen.alloc(nSl) || c->f_tot2.alloc(nF) || c->sfo.alloc(nSl) || c->stot2.alloc(nSl))
-    return LITE_ECUDA;
-  CU(cudaMemsetAsync(c->he_slot.p, 0xFF, nH * sizeof(int), c->stream));
-  CU(cudaMemsetAsync(c->err.p, 0, sizeof(int), c->stream));
-  CU(cudaMemsetAsync(c->status.p, 0, 2 * sizeof(unsigned long long), c->stream));  // no-exit counters
-  CU(cudaMemsetAsync(c->status.p + 6, 0, sizeof(unsigned long long), c->stream));  // general-face scratch overflows
-  PrepArgs A{};
-  A.vx = c->vx.p; A.vy = c->vy.p; A.he_src = c->he_src.p; A.he_twin = c->he_twin.p;
-  A.he_next = c->he_next.p; A.he_face = c->he_face.p; A.he_seg = c->he_seg.p;
-  A.he_next_hf = c->he_next_hf.p; A.he_dir = c->he_dir.p; A.face_inside = c->face_inside.p;
-  A.f_gen = general ? c->g_fgen.p : nullptr;
-  A.he_length = c->he_length.p; A.face_he_offset = c->f_off.p; A.face_he_count = c->f_cnt.p;
-  A.face_he_list = c->f_list.p; A.n_faces = nF;
-  A.pt = c->pt.p; A.udir = c->udir.p; A.ang = c->ang.p; A.len = c->len.p; A.ca = c->ca.p; A.flg = c->flg.p;
-  A.slot_he = c->slot_he.p; A.slot_seg = c->slot_seg.p; A.slot_face = c->slot_face.p;
-  A.he_slot = c->he_slot.p; A.err = c->err.p;
-  TessDev &T = c->T;
-  T.n_slots = (int)nSl; T.n_faces = nF; T.n_he = nH; T.n_seg = nS; T.err = c->err.p;
-  T.pt = c->pt.p; T.udir = c->udir.p; T.ang = c->ang.p; T.len = c->len.p; T.ca = c->ca.p; T.flg = c->flg.p;
-  T.slot_he = c->slot_he.p; T.slot_seg = c->slot_seg.p; T.slot_face = c->slot_face.p;
-  T.he_slot = c->he_slot.p; T.he_twin = c->he_twin.p; T.he_src = c->he_src.p;
-  T.he_next_hf = c->he_next_hf.p; T.he_prev_hf = c->he_prev_hf.p;
-  T.f_off = c->f_off.p; T.f_cnt = c->f_cnt.p; T.f_gen = general ? c->g_fgen.p : nullptr;
-  T.f_area = c->f_area.p; T.f_perim = c->f_perim.p; T.f_sumang = c->f_sumang.p; T.f_minang = c->f_minang.p;
-  T.seg_n_edges = c->seg_n_edges.p; T.seg_he_start = c->seg_he_start.p; T.seg_he_end = c->seg_he_end.p;
-  T.seg_bnd = c->seg_bnd.p;
-  T.cum = c->cum.p; T.guide = c->guide.p; T.n_cum = (int)cum.size(); T.n_guide = n_guide;
-  T.total_len = cl; T.guide_scale = (double)n_guide / cl;
-  T.sfo = c->sfo.p; T.pre = c->pre.p; T.plen = c->plen.p; T.f_tot2 = c->f_tot2.p; T.stot2 = c->stot2.p;
-  if (general) {
-    gen::Tess &GT = c->GT;
-    GT.n_he = nH; GT.n_faces = nF; GT.vx = c->vx.p; GT.vy = c->vy.p;
-    GT.he_src = c->he_src.p; GT.he_twin = c->he_twin.p; GT.he_next = c->he_next.p; GT.he_face = c->he_face.p;
-    GT.he_seg = c->he_seg.p; GT.he_next_hf = c->he_next_hf.p; GT.he_prev_hf = c->he_prev_hf.p;
-    GT.he_dir = c->he_dir.p; GT.face_inside = c->face_inside.p; GT.seg_bnd = c->seg_bnd.p;
-    GT.seg_n_edges = c->seg_n_edges.p; GT.f_outer = c->g_outer.p; GT.f_hole_off = c->g_hole_off.p;
-    GT.f_hole_cnt = c->g_hole_cnt.p; GT.hole_he = c->g_hole_he.p;
-    if (!c->gen_scratch) {
-      c->gen_blocks = c->sm_count;
-      // two blocks of scratch: the merge/flip kernel runs on the second stream, beside the split kernel
-      CU(cudaMalloc((void **)&c->gen_scratch, 2 * (size_t)c->gen_blocks * LITE_GEN_TB * LITE_GEN_PTS * sizeof(gen::Pt)));
-    }
+  if (!early_prep) {
+    if (alloc_slots(nSl)) return LITE_ECUDA;
+    if (enqueue_prep(nSl, general) != cudaSuccess) return fail(LITE_ECUDA, "preparation kernels: %s", cudaGetErrorString(cudaGetLastError()));
   }
-  {
-    ValidateArgs V{};
-    V.nV = nV; V.nH = nH; V.nF = nF; V.nS = nS; V.nFH = (int)nSl; V.nNB = s->n_non_blocking; V.nB = s->n_blocking;
-    V.he_src = c->he_src.p; V.he_twin = c->he_twin.p; V.he_next = c->he_next.p; V.he_face = c->he_face.p;
-    V.he_seg = c->he_seg.p; V.he_next_hf = c->he_next_hf.p; V.he_prev_hf = c->he_prev_hf.p;
-    V.face_inside = c->face_inside.p; V.seg_bnd = c->seg_bnd.p; V.f_gen = general ? c->g_fgen.p : nullptr;
-    V.f_off = c->f_off.p; V.f_cnt = c->f_cnt.p; V.f_list = c->f_list.p; V.seg_he_start = c->seg_he_start.p;
-    V.seg_he_end = c->seg_he_end.p; V.seg_n_edges = c->seg_n_edges.p; V.nb_list = c->nb_list.p; V.b_list = c->b_list.p;
-    V.err = c->err.p;
-    int most = nH;
-    if (nF > most) most = nF;
-    if (nS > most) most = nS;
-    if ((int)nSl > most) most = (int)nSl;
-    k_validate<<<(most + 255) / 256, 256, 0, c->stream>>>(V);
+  TessDev &T = c->T;
+  T.cum = c->cum.p; T.guide = c->guide.p; T.n_cum = (int)n_cum; T.n_guide = n_guide;
+  T.total_len = cl; T.guide_scale = (double)n_guide / cl;
+  if (!side_done) {
+    k_build_guide<<<(n_guide + 255) / 256, 256, 0, c->stream>>>(c->cum.p, (int)n_cum, cl / (double)n_guide, n_guide, c->guide.p);
     c->launches += 1;
   }
-  int tb = 128, gb = (nF + tb - 1) / tb;
-  k_build_guide<<<(n_guide + 255) / 256, 256, 0, c->stream>>>(c->cum.p, (int)cum.size(), cl / (double)n_guide, n_guide, c->guide.p);
-  k_prep_slots<<<(unsigned)((nSl + 127) / 128), 128, 0, c->stream>>>(A, (int)nSl);
-  // outside faces: count 0 in the device view
-  k_prep_faces<<<gb, tb, 0, c->stream>>>(T, c->ca.p, c->f_area.p, c->f_perim.p, c->f_sumang.p, c->f_minang.p,
-                                         c->pre.p, c->plen.p, c->f_tot2.p, c->sfo.p, c->stot2.p);
-  c->launches += 3;
   CU(cudaEventRecord(c->ev_upload, c->stream));                     // both copies have left the pinned block
   c->upload_inflight = true; c->early_unfenced = false;
   // the merge/flip stream only depends on the tessellation being in place: it forks here,
@@ -1415,16 +1587,23 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
     P.seq = ++c->peer_seq;
     for (int r = 0; r < c->world; r++) P.box[r] = c->peer_box[r];
   }
-  if (A.grid == 0) CU(cudaMemsetAsync(c->red_out.p, 0, 128 * sizeof(double), c->stream));
-  if (nf == 0) CU(cudaMemsetAsync(c->red_out.p + 128, 0, 128 * sizeof(double), c->stream));
-  CU(cudaEventRecord(c->ev[6], c->stream));
+  // timing events only where something separates them: ev[2] also opens the reduce unless a
+  // memset precedes it, ev[7] also closes the evaluation unless NCCL follows
+  cudaEvent_t red0 = c->ev[2], eval1 = c->ev[7];
+  if (A.grid == 0 || nf == 0) {
+    if (A.grid == 0) CU(cudaMemsetAsync(c->red_out.p, 0, 128 * sizeof(double), c->stream));
+    if (nf == 0) CU(cudaMemsetAsync(c->red_out.p + 128, 0, 128 * sizeof(double), c->stream));
+    CU(cudaEventRecord(c->ev[6], c->stream));
+    red0 = c->ev[6];
+  }
   if (A.grid + B.grid > 0) reduce_dispatch(c, d, A, B, th, P);
   CU(cudaEventRecord(c->ev[7], c->stream));
   if (c->world > 1 && !exch) {
     ncclResult_t ne = g_nccl.AllReduce(c->red_out.p, c->red_out.p, (size_t)NT, ncclFloat64, ncclSum, c->comm, c->stream);
     if (ne != 0) return fail(LITE_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(ne) : "?");
+    CU(cudaEventRecord(c->ev[3], c->stream));
+    eval1 = c->ev[3];
   }
-  CU(cudaEventRecord(c->ev[3], c->stream));
   // the sums, the geometric failures of the candidates behind them (no exit edge found, see
   // lite_pl_failures), the exchange's report and the validation word come back in one copy
   CU(cudaMemcpyAsync(c->h_pinned, c->res.p, LITE_RES_WORDS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1436,8 +1615,8 @@ extern "C" int lite_pl_eval(lite_ctx *c, const double *theta, double *lpl, doubl
   }
   c->mf_inflight = false;
   finalize_mf(c);
-  cudaEventElapsedTime(&c->ms_eval, c->ev[2], c->ev[3]);
-  cudaEventElapsedTime(&c->ms_reduce, c->ev[6], c->ev[7]);
+  cudaEventElapsedTime(&c->ms_eval, c->ev[2], eval1);
+  cudaEventElapsedTime(&c->ms_reduce, red0, c->ev[7]);
   c->ms_exchange = 0; c->peer_wait_us = 0;
   if (c->world > 1 && !exch) cudaEventElapsedTime(&c->ms_exchange, c->ev[7], c->ev[3]);
   if (c->ev01) { float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->ms_split = ms; }

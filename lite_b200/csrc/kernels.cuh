@@ -276,7 +276,7 @@ struct PrepArgs {
   const int *face_he_offset, *face_he_count, *face_he_list;
   int n_faces;
   // outputs
-  double2 *pt; double2 *udir; double *ang, *len, *ca; uint32_t *flg;
+  double2 *pt; double2 *udir; double *ang, *len, *ca, *el; uint32_t *flg;
   int *slot_he, *slot_seg, *slot_face, *he_slot;
   double *f_area, *f_perim, *f_sumang, *f_minang;
   int *err;  // consistency errors
@@ -297,6 +297,7 @@ struct ValidateArgs {
   const uint8_t *face_inside, *seg_bnd, *f_gen;
   const int *f_off, *f_cnt, *f_list, *seg_he_start, *seg_he_end, *seg_n_edges, *nb_list, *b_list;
   int *err;
+  int *he_slot;  // set to -1 here (k_prep_slots fills the listed ones behind this kernel)
 };
 enum { LITE_BAD_HALFEDGE = 1, LITE_BAD_FACE = 2, LITE_BAD_FACE_LIST = 3, LITE_BAD_SEGMENT = 4, LITE_BAD_NON_BLOCKING = 5,
        LITE_BAD_BLOCKING = 6 };
@@ -306,6 +307,7 @@ __device__ __forceinline__ void flag_bad(int *err, int code, int elem) {
 __global__ void k_validate(ValidateArgs A) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < A.nH) {  // links in range, twin of twin
+    A.he_slot[i] = -1;
     const int f = A.he_face[i], tw = A.he_twin[i], v = A.he_src[i], sg = A.he_seg[i], nx = A.he_next[i];
     const int nhf = A.he_next_hf[i], phf = A.he_prev_hf[i];
     bool ok = (unsigned)f < (unsigned)A.nF && (unsigned)tw < (unsigned)A.nH && (unsigned)v < (unsigned)A.nV &&
@@ -386,6 +388,19 @@ __global__ void k_prep_slots(PrepArgs A, int n_slots) {
   uint32_t fl = 0;
   int nhf = A.he_next_hf[hp];
   if (nhf < 0 || nhf != A.he_next[hp]) fl |= SF_CORNER;  // face2poly, lib/ttessel.cpp:4325-4327
+  // the two expensive terms of the face features, one slot per thread (k_prep_faces only adds
+  // them up in the reference's order): the edge length from its end points and the interior
+  // angle at the source, angle_between at a corner and pi elsewhere
+  {
+    const double ex = tx - sx, ey = ty - sy;
+    A.el[m] = sqrt(ex * ex + ey * ey);
+    double a = LITE_PI;
+    if (fl & SF_CORNER) {
+      const int vp = A.he_src[hp];
+      a = angle_between(A.vx[vp] - sx, A.vy[vp] - sy, ex, ey);
+    }
+    A.ca[m] = a;
+  }
   if (!A.face_inside[A.he_face[A.he_twin[h]]]) fl |= SF_BND;
   if (A.he_dir[h]) fl |= SF_DIR;
   if (general) fl |= SF_GENERAL;
@@ -395,7 +410,7 @@ __global__ void k_prep_slots(PrepArgs A, int n_slots) {
   A.he_slot[h] = m;
 }
 
-__global__ void k_prep_faces(TessDev T, double *ca, double *f_area, double *f_perim,
+__global__ void k_prep_faces(TessDev T, const double *ca, const double *el, double *f_area, double *f_perim,
                              double *f_sumang, double *f_minang, double *pre, double *plen,
                              double *f_tot2, int2 *sfo, double *stot2) {
   int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -425,24 +440,23 @@ __global__ void k_prep_faces(TessDev T, double *ca, double *f_area, double *f_pe
   // minimum seeded with the turning angle at the first corner.
   {
     const double2 V0 = ldpt(T.pt, off + (1 == n ? 0 : 1));
-    double2 P = ldpt(T.pt, off), C = V0;   // previous and current vertex
+    double2 C = V0;   // current vertex
     double area2 = 0, perim = 0, sumang = 0, minang = CUDART_INF, seed = -1.0;
+    int kc = (1 == n) ? 0 : 1, kn = (kc + 1 == n) ? 0 : kc + 1;   // slot of the current vertex, of the next
     for (int i = 0; i < n; i++) {
-      const int sc = off + ((1 + i) % n);                 // slot whose source is the current vertex
-      const double2 Nx = (i + 1 < n) ? ldpt(T.pt, off + ((2 + i) % n)) : V0;
+      const int sc = off + kc;                            // slot whose source is the current vertex
+      const double2 Nx = (i + 1 < n) ? ldpt(T.pt, off + kn) : V0;
       area2 += cross2(C.x - V0.x, C.y - V0.y, Nx.x - V0.x, Nx.y - V0.y);
-      const double ex = Nx.x - C.x, ey = Nx.y - C.y;
-      perim += sqrt(ex * ex + ey * ey);
-      double a = LITE_PI;
+      perim += __ldg(el + sc);
       if (T.flg[sc] & SF_CORNER) {
-        a = angle_between(P.x - C.x, P.y - C.y, ex, ey);
+        const double a = __ldg(ca + sc);
         if (seed < 0) seed = LITE_PI - a;
         const double q = LITE_HALF_PI - a;
         if (q >= 0) sumang += q;
         minang = fmin(minang, a);
       }
-      ca[sc] = a;
-      P = C; C = Nx;
+      C = Nx;
+      kc = kn; kn = (kn + 1 == n) ? 0 : kn + 1;
     }
     f_area[f] = 0.5 * area2; f_perim[f] = perim; f_sumang[f] = sumang;
     f_minang[f] = (seed >= 0) ? fmin(seed, minang) : 0.0;
