@@ -771,7 +771,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
     k_validate<<<(most + 255) / 256, 256, 0, c->stream>>>(V);
     k_prep_slots<<<(unsigned)((nSl + 127) / 128), 128, 0, c->stream>>>(A, (int)nSl);
     // outside faces: count 0 in the device view
-    const int tb = 128, gb = (nF + tb - 1) / tb;
+    const int tb = 64, gb = (nF + tb - 1) / tb;   // one thread per face, latency bound: small blocks reach every SM at 10^4 faces
     k_prep_faces<<<gb, tb, 0, c->stream>>>(T, c->ca.p, c->el.p, c->f_area.p, c->f_perim.p, c->f_sumang.p, c->f_minang.p,
                                            c->pre.p, c->plen.p, c->f_tot2.p, c->sfo.p, c->stot2.p);
     c->launches += 3;
