@@ -639,26 +639,25 @@ __device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, cons
   int cnt = 0, k2 = -1;
 #ifndef LITE_SCAN_LOOP
   if (n <= 32) {
-    // sign bit of every vertex residual, vertex k at bit 32-n+k; `nz` stays set while no
-    // residual is exactly zero (then a halfedge crosses iff the signs of its ends differ)
-    uint32_t neg = 0;
-    bool nz = true;
+    // sign bit of every vertex residual, shifted in from the right (vertex k ends at bit
+    // n-1-k: one funnel shift per vertex); `zacc` stays non-zero while no residual is exactly
+    // zero (then a halfedge crosses iff the signs of its ends differ)
+    uint32_t neg = 0, zacc = 0xffffffffu;
 #pragma unroll 4
     for (int k = 0; k < n; k++) {
       const double2 V = ldpt(T.pt, off + k);
       const double sv = fma(a, V.x, fma(b, V.y, -w));
       const uint32_t hi = (uint32_t)__double2hiint(sv), lo = (uint32_t)__double2loint(sv);
-      neg = (neg >> 1) | (hi & 0x80000000u);
-      nz = nz && (((hi & 0x7fffffffu) | lo) != 0u);
+      neg = __funnelshift_l(hi, neg, 1);
+      zacc = min(zacc, (hi & 0x7fffffffu) | lo);
     }
-    if (nz) {
-      neg >>= (32 - n);                                        // vertex k at bit k
+    if (zacc != 0u) {
       const uint32_t full = (n == 32) ? 0xffffffffu : ((1u << n) - 1u);
-      const uint32_t nxt = ((neg >> 1) | (neg << (n - 1))) & full;   // sign of vertex k+1 at bit k
-      uint32_t cross = (neg ^ nxt) & full & ~(1u << k1);
-      if (skip1 >= 0) cross &= ~(1u << skip1);
+      const uint32_t nxt = ((neg << 1) | (neg >> (n - 1))) & full;   // sign of vertex k+1 at the bit of vertex k
+      uint32_t cross = (neg ^ nxt) & ~(1u << (n - 1 - k1));          // bit n-1-k: halfedge k crosses
+      if (skip1 >= 0) cross &= ~(1u << (n - 1 - skip1));
       cnt = __popc(cross);
-      k2 = __ffs(cross) - 1;
+      k2 = cross ? n - 32 + __clz(cross) : -1;                       // the first crossing halfedge in slot order
     } else {
       cnt = -1;  // a vertex lies exactly on the line: the general loop below decides
     }
