@@ -608,6 +608,11 @@ __device__ __noinline__ double corner_min(const uint32_t *flg, const double *ca,
 // halfedge's unit direction: for a sampled candidate cos(angle) = 1 - 2U is the draw
 // itself, so neither acos nor sincos is on the path unless an angle feature asks for it
 // (they were 24 % of the kernel's instructions, profiles/r1_k_split.txt).
+#ifndef LITE_SCAN_UNROLL
+#define LITE_SCAN_UNROLL 4
+#endif
+#define LITE_PRAGMA_(x) _Pragma(#x)
+#define LITE_UNROLL(n) LITE_PRAGMA_(unroll n)
 template <bool WITH_STAT, class PG>
 __device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, const SlotData &S, double x,
                                            double angle, double cos_angle, double sin_angle,
@@ -643,7 +648,7 @@ __device__ __forceinline__ void split_eval(const TessDev &T, const Prog &G, cons
     // n-1-k: one funnel shift per vertex); `zacc` stays non-zero while no residual is exactly
     // zero (then a halfedge crosses iff the signs of its ends differ)
     uint32_t neg = 0, zacc = 0xffffffffu;
-#pragma unroll 4
+LITE_UNROLL(LITE_SCAN_UNROLL)
     for (int k = 0; k < n; k++) {
       const double2 V = ldpt(T.pt, off + k);
       const double sv = fma(a, V.x, fma(b, V.y, -w));
