@@ -201,6 +201,7 @@ struct lite_ctx {
   cudaEvent_t ev_fork = nullptr, ev_mf = nullptr;
   cudaEvent_t ev_up0 = nullptr, ev_guide = nullptr;  // upload: the sampler's tables go over the second stream
   bool mf_inflight = false;         // stream must wait for ev_mf before using the flip statistics
+  bool fork_pending = false;        // an upload since the merge/flip stream last waited for ev_fork
   ncclComm_t comm = nullptr;
   // cross-GPU sum over peer memory (kernels.cuh: PeerArgs); off -> ncclAllReduce
   bool peer_on = false;
@@ -1069,6 +1070,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   // not from whatever the main stream is doing when SetEnergy is called (the split kernel,
   // if AddSplits came first: the two then run side by side)
   CU(cudaEventRecord(c->ev_fork, c->stream));
+  c->fork_pending = true;
   if (g_trace) cudaEventRecord(c->ev_tr[2], c->stream);
   t3 = now_ms();
   // no synchronisation: the copy, the checks and the preparation kernels run behind the
@@ -1202,7 +1204,7 @@ static int mf_flush(lite_ctx *c) {
   }
   // fork: the merge/flip kernels are independent of the split kernel and run beside it
   if (c->mf_inflight) CU(cudaStreamSynchronize(c->stream2));
-  CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));  // recorded by lite_tess_upload
+  if (c->fork_pending) { CU(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0)); c->fork_pending = false; }  // recorded by lite_tess_upload
   CU(cudaEventRecord(c->ev[4], c->stream2));
   CU(cudaMemsetAsync(c->status.p + 1, 0, sizeof(unsigned long long), c->stream2));
   if (nm + nf > 0) {
@@ -1314,7 +1316,6 @@ static bool prog_is_acs(const Prog &G) {
 // the sim_acs energy gets the compile-time program, everything else the run-time one
 template <int MODE>
 static void launch_split(lite_ctx *c, const Prog &G, const SplitArgs &A, int grid) {
-  cudaMemsetAsync(A.ticket, 0, sizeof(unsigned long long), c->stream);
   if ((MODE & 4) && prog_is_acs(G)) k_split<MODE, ProgACS><<<grid, LITE_SPLIT_TB, 0, c->stream>>>(c->T, G, A);
   else k_split<MODE, ProgDyn><<<grid, LITE_SPLIT_TB, 0, c->stream>>>(c->T, G, A);
   c->launches += 1;

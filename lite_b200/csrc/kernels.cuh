@@ -889,7 +889,7 @@ struct SplitArgs {
   int *r_e1, *r_e2; double2 *r_p1, *r_p2; double *r_x, *r_angle, *r_u;
   unsigned long long *status;  // [0] no-exit count
   unsigned long long *checksum;  // [0] xor hash, [1] sum of e2
-  unsigned long long *ticket;  // run scheduler of this launch (zeroed before it)
+  unsigned long long *ticket;  // [0] run scheduler of this launch, [1] warps that have left; both zero between launches
   // i.i.d. sampler (LITE_SAMPLER_IID): positions along the cumulative halfedge length drawn
   // independently and sorted (split_sample, lib/ttessel.cpp:1968-1975), with the batch index of
   // each draw; null = the stratified sampler
@@ -955,7 +955,11 @@ __global__ void __launch_bounds__(LITE_SPLIT_TB, LITE_SPLIT_MINB) k_split(TessDe
       beg += n_warps * len; t -= n_warps; len = max(((len >> 1) + 31) & ~31L, 128L);
     }
     beg += (long)t * len;
-    if (beg >= A.n_local) break;
+    if (beg >= A.n_local) {
+      // every warp leaves here exactly once; the last one re-arms the scheduler for the next launch
+      if (lane == 0 && atomicAdd(A.ticket + 1, 1ULL) == (unsigned long long)(n_warps - 1)) { A.ticket[0] = 0ULL; A.ticket[1] = 0ULL; }
+      break;
+    }
     const long end = min(beg + len, A.n_local);
     m = -1;
   // (a contiguous piece of the run per lane instead of this interleaving keeps a lane on its slot
