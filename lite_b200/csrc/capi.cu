@@ -1045,6 +1045,7 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   // what was staged since the bulk left (the cumulative lengths, unless they already went over
   // the second stream; the extended lists of a tessellation with holes) -- or everything
   if (side_done) {
+    // nothing left: the bulk went in groups, the cumulative lengths over the second stream
   } else if (early_copy) {
     CU(cudaMemcpyAsync(c->arena.d + bulk_bytes, c->arena.h + bulk_bytes, c->arena.used - bulk_bytes, cudaMemcpyHostToDevice, c->stream));
   } else {
