@@ -900,6 +900,21 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
   // for the rest of the block.
   double cl = 0.0;
   int bad_list = -1;
+  // Between blocks of the sum this thread looks whether every group of the bulk has been sent
+  // and, once, queues the checks and the preparation behind it -- for a tessellation without
+  // holes, which the count in progress has yet to confirm; if it finds holes, everything is
+  // prepared again below with the extended lists.  (On a 10^5-cell tessellation the sum takes
+  // longer than the copy.)
+  bool prep_tried = false;
+  auto try_prep = [&]() {
+    if (prep_tried || c->validate_host || arrived_pack.load(std::memory_order_acquire) < nt) return;
+    prep_tried = true;
+    if (copy_failed.load(std::memory_order_relaxed)) return;
+    early_copy = true;
+    if (g_trace) cudaEventRecord(c->ev_tr[1], c->stream);
+    early_prep = enqueue_prep((size_t)s->n_face_he, false) == cudaSuccess;
+    if (g_trace) wk_t[2] = now_ms();
+  };
   for (const SlotRun &R : runs) {
     if (!R.inside) {
       for (int k = R.begin; k < R.end; k++) _mm_stream_si64((long long *)(cum_pin + k), (long long)__builtin_bit_cast(int64_t, cl));
@@ -907,42 +922,39 @@ extern "C" int lite_tess_upload(lite_ctx *c, const lite_tess_soa *s) {
     }
     const int32_t *lst = s->face_he_list;
     const double *hl = s->he_length;
-    for (int k = R.begin; k < R.end; k++) {
-      const int h = lst[k];
-      if ((unsigned)h >= (unsigned)nH) { bad_list = k; break; }
-      cl += hl[h];
-      _mm_stream_si64((long long *)(cum_pin + k), (long long)__builtin_bit_cast(int64_t, cl));
+    for (int k0 = R.begin; k0 < R.end && bad_list < 0; k0 += 8192) {
+      const int k1 = (R.end - k0 > 8192) ? k0 + 8192 : R.end;
+      for (int k = k0; k < k1; k++) {
+        const int h = lst[k];
+        if ((unsigned)h >= (unsigned)nH) { bad_list = k; break; }
+        cl += hl[h];
+        _mm_stream_si64((long long *)(cum_pin + k), (long long)__builtin_bit_cast(int64_t, cl));
+      }
+      try_prep();
     }
     if (bad_list >= 0) break;
   }
   _mm_sfence();
   const double t_cum = now_ms();
-  // As soon as every group of the bulk has been sent, this thread queues -- for a tessellation
-  // without holes, which the count in progress has yet to confirm -- the checks and the
-  // preparation behind the bulk, and the cumulative lengths with the guide table on the second
-  // stream, beside them (the preparation does not read them).  If the count finds holes,
-  // everything is prepared again below with the extended lists.
+  // The cumulative lengths and the guide table go over the second stream, beside the
+  // preparation (which does not read them).
   bool side_done = false;
   int n_guide_simple = 1;
   while (n_guide_simple < 2 * s->n_face_he) n_guide_simple <<= 1;
   if (!c->validate_host && bad_list < 0 && cl > 0.0) {
     while (arrived_pack.load(std::memory_order_acquire) < nt) _mm_pause();
-    if (!copy_failed.load(std::memory_order_relaxed) && c->guide.alloc((size_t)n_guide_simple) == 0) {
-      early_copy = true;
-      if (g_trace) cudaEventRecord(c->ev_tr[1], c->stream);
-      early_prep = enqueue_prep((size_t)s->n_face_he, false) == cudaSuccess;
-      if (early_prep) {
-        const size_t cum_bytes = align256((size_t)s->n_face_he * sizeof(double));
-        bool ok = cudaStreamWaitEvent(c->stream2, c->ev_up0, 0) == cudaSuccess &&
-                  cudaMemcpyAsync(c->arena.d + cum_off, c->arena.h + cum_off, cum_bytes, cudaMemcpyHostToDevice, c->stream2) == cudaSuccess;
-        if (ok) {
-          k_build_guide<<<(n_guide_simple + 255) / 256, 256, 0, c->stream2>>>((const double *)(c->arena.d + cum_off), s->n_face_he,
-                                                                             cl / (double)n_guide_simple, n_guide_simple, c->guide.p);
-          c->launches += 1;
-          ok = cudaEventRecord(c->ev_guide, c->stream2) == cudaSuccess;
-        }
-        side_done = ok;
+    try_prep();
+    if (early_prep && c->guide.alloc((size_t)n_guide_simple) == 0) {
+      const size_t cum_bytes = align256((size_t)s->n_face_he * sizeof(double));
+      bool ok = cudaStreamWaitEvent(c->stream2, c->ev_up0, 0) == cudaSuccess &&
+                cudaMemcpyAsync(c->arena.d + cum_off, c->arena.h + cum_off, cum_bytes, cudaMemcpyHostToDevice, c->stream2) == cudaSuccess;
+      if (ok) {
+        k_build_guide<<<(n_guide_simple + 255) / 256, 256, 0, c->stream2>>>((const double *)(c->arena.d + cum_off), s->n_face_he,
+                                                                           cl / (double)n_guide_simple, n_guide_simple, c->guide.p);
+        c->launches += 1;
+        ok = cudaEventRecord(c->ev_guide, c->stream2) == cudaSuccess;
       }
+      side_done = ok;
       if (g_trace) wk_t[2] = now_ms();
     }
   }
