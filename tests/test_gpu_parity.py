@@ -589,6 +589,54 @@ def test_failed_upload_leaves_no_tessellation(lite):
     ctx.close()
 
 
+def test_uploads_back_to_back_without_a_synchronisation(lite):
+    """lite_tess_upload sends the block in groups from its packing threads, queues the checks and
+    the preparation before the host has finished and sends the sampler's tables over the second
+    stream.  None of that may depend on the caller synchronising: tessellations of different
+    sizes and kinds (rectangle, window with holes -- which prepares twice --, rectangle) are
+    uploaded one after the other with split kernels still queued in between, and the last
+    evaluation of each equals a fresh context's, bit for bit."""
+    t100, _ = load_golden("t100")
+    t11, _ = load_golden("t11")
+    holed, _ = load_golden("holed")
+    import os
+    th = np.array([0.3, -0.02, 0.1, -0.5])
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c2_soa.npz"))
+    c2 = {k: z[k] for k in z.files}          # 10 810 cells: 3.8 MB per upload, split kernels of ~50 us
+    c2["int_length"] = float(c2["int_length"])
+    cases = ((t100, 50000, 1), (c2, 2000000, 5), (holed, 20000, 2), (t11, 30000, 3), (c2, 1000000, 6), (t100, 50000, 4))
+
+    def fresh(a, n, seed):
+        c = _ctx(lite, a, ACS, record=False)
+        c.merges_flips()
+        c.add_splits_philox(n, seed, 0)
+        out = c.pl_eval(th)
+        c.close()
+        return out
+
+    want = [fresh(a, n, seed) for a, n, seed in cases]
+    ctx = lite.Context(0)
+    got = []
+    for rep in range(3):   # the second and third round reuse the arena and the slot arrays
+        got = []
+        for a, n, seed in cases:
+            ctx.tess_upload(lite.TessSoA(a))
+            ctx.energy_set(ACS)
+            ctx.merges_flips()
+            ctx.add_splits_philox(n, seed + 100, 0)      # left queued: the next lines do not wait for it
+            ctx.clear_splits()
+            ctx.tess_upload(lite.TessSoA(a))             # again, over the running kernels
+            ctx.energy_set(ACS)
+            ctx.merges_flips()
+            ctx.add_splits_philox(n, seed, 0)
+            got.append(ctx.pl_eval(th))
+    for (v, g, H), (wv, wg, wH) in zip(got, want):
+        assert v == wv
+        np.testing.assert_array_equal(g, wg)
+        np.testing.assert_array_equal(H, wH)
+    ctx.close()
+
+
 @pytest.mark.parametrize("which,seed,n_moves", [("holed", 5, 0), ("holed", 5, 12), ("holed", 11, 60), ("holed", 13, 90),
                                                  ("flips", 4, 25), ("hole_to_hole", 23, 0)])
 def test_windows_with_holes_against_live_oracle(lite, which, seed, n_moves):
