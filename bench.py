@@ -917,7 +917,10 @@ def run_pl(args, rank, local_rank, world, nccl_id, dist, torch):
     e2e_val = per_step_global / (ms_e2e / args.steps * 1e-3)
     d = len(ACS)
     h2d = soa_bytes(soa) + 8 * d + 4 * d
-    d2h = 256 * 8 + 2 * 12 * 8 + 4 + 32
+    # what lite_pl_eval reads back: the result block (two 128-word sums, status words, the
+    # exchange's report, the validation word: 268 doubles, one copy) and the per-block column sums
+    # of the merge/flip kernel (12 doubles per block of 128 candidates), finished on the host
+    d2h = 268 * 8 + ((nm + 127) // 128 + (nf + 127) // 128) * 12 * 8
 
     # ---- N > 1: the sharded evaluation against the same batch on ONE rank ------------
     shard_check = None
