@@ -916,7 +916,9 @@ def run_pl(args, rank, local_rank, world, nccl_id, dist, torch):
     ms_e2e = allmax(ctx.timer_elapsed(2, 3))
     e2e_val = per_step_global / (ms_e2e / args.steps * 1e-3)
     d = len(ACS)
-    h2d = soa_bytes(soa) + 8 * d + 4 * d
+    # the caller's arrays + the cumulative halfedge lengths lite_tess_upload derives from them on the
+    # host and sends along (8 B per listed halfedge) + theta and the feature ids
+    h2d = soa_bytes(soa) + 8 * int(soa.a["face_he_list"].size) + 8 * d + 4 * d
     # what lite_pl_eval reads back: the result block (two 128-word sums, status words, the
     # exchange's report, the validation word: 268 doubles, one copy) and the per-block column sums
     # of the merge/flip kernel (12 doubles per block of 128 candidates), finished on the host
