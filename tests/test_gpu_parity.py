@@ -841,6 +841,92 @@ def test_inconsistent_tessellation_is_caught_on_the_device(lite, what):
     ctx.close()
 
 
+def test_random_sequence_of_good_and_bad_uploads(lite):
+    """Sixty uploads in random order on one context -- consistent rectangles of three sizes, the
+    window with holes, tessellations that fail on the host (offsets that do not tile, wrong
+    int_length) and ones that fail on the device (broken twin, segment out of range) -- with the
+    host-side validation switched on and off at random and nothing synchronised in between except
+    by the calls themselves.  Every good upload evaluates to exactly what a fresh context gives;
+    every bad one is reported, by the upload or by the next synchronising call, and leaves no
+    tessellation behind."""
+    import os
+    rng = np.random.default_rng(20260)
+    t100, _ = load_golden("t100")
+    t11, _ = load_golden("t11")
+    holed, _ = load_golden("holed")
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c2_soa.npz"))
+    c2 = {k: z[k] for k in z.files}
+    c2["int_length"] = float(c2["int_length"])
+    good = {"t100": (t100, 40000), "t11": (t11, 20000), "holed": (holed, 10000), "c2": (c2, 500000)}
+    th = np.array([0.3, -0.02, 0.1, -0.5])
+
+    def evaluate(c, n, seed):
+        c.energy_set(ACS)
+        c.merges_flips()
+        c.add_splits_philox(n, seed, 0)
+        return c.pl_eval(th)
+
+    want = {}
+    for name, (a, n) in good.items():
+        c = lite.Context(0)
+        c.tess_upload(lite.TessSoA(a))
+        want[name] = evaluate(c, n, 7)
+        c.close()
+
+    def broken(kind):
+        base = c2 if rng.random() < 0.5 else t100
+        b = {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in base.items()}
+        if kind == "tiling":
+            b["face_he_offset"][3] += 1
+        elif kind == "length":
+            b["int_length"] = float(b["int_length"]) * 1.5
+        elif kind == "twin":
+            b["he_twin"][5] = b["he_twin"][9]
+        else:
+            b["seg_he_start"][2] = len(b["he_src"]) + 1000
+        return b
+
+    ctx = lite.Context(0)
+    n_good = n_bad = 0
+    for it in range(60):
+        on_host = bool(rng.random() < 0.3)
+        ctx.validate_on_host(on_host)
+        if rng.random() < 0.6:
+            name = ["t100", "t11", "holed", "c2"][int(rng.integers(4))]
+            a, n = good[name]
+            ctx.tess_upload(lite.TessSoA(a))
+            if rng.random() < 0.5:          # leave kernels queued, upload the same thing again
+                ctx.energy_set(ACS)
+                ctx.merges_flips()
+                ctx.add_splits_philox(n, 99, 0)
+                ctx.clear_splits()
+                ctx.tess_upload(lite.TessSoA(a))
+            v, g, H = evaluate(ctx, n, 7)
+            wv, wg, wH = want[name]
+            assert v == wv, (it, name)
+            np.testing.assert_array_equal(g, wg)
+            np.testing.assert_array_equal(H, wH)
+            n_good += 1
+        else:
+            kind = ["tiling", "length", "twin", "segment"][int(rng.integers(4))]
+            b = broken(kind)
+            if kind in ("tiling", "length") or on_host:
+                with pytest.raises(lite.LiteError):
+                    ctx.tess_upload(lite.TessSoA(b))
+            else:
+                ctx.tess_upload(lite.TessSoA(b))        # the device finds it
+                ctx.energy_set(ACS)
+                ctx.merges_flips()
+                ctx.add_splits_philox(1000, 1, 0)
+                with pytest.raises(lite.LiteError, match="inconsistent"):
+                    ctx.pl_eval(th)
+            with pytest.raises(lite.LiteError, match="upload a tessellation"):
+                ctx.merges_flips()
+            n_bad += 1
+    assert n_good > 20 and n_bad > 10
+    ctx.close()
+
+
 def test_holed_window_from_the_text_format_through_the_host_reader(lite):
     """The whole route a user of the reference takes with a tessellation of a window with holes:
     the text file (LineTes::write, lib/ttessel.cpp:1348-1370) -> lite_host_create_from_text ->
