@@ -43,6 +43,27 @@ int lite_host_export(lite_host_tess *t, lite_tess_soa *out);
  * needed size; writes at most cap bytes */
 int64_t lite_host_write_text(lite_host_tess *t, char *buf, int64_t cap);
 
+/* clip_segment_by_polygon(Segment, HPolygons), lib/ttessel.cpp:3762-3786 (and :3696-3760 for one
+ * polygon with holes): the longest piece of seg = (x0, y0, x1, y1) inside the open window of t,
+ * written to out in the direction of seg.  LITE_EINVAL when the segment does not hit the window
+ * (the reference throws std::domain_error). */
+int lite_host_clip_segment(lite_host_tess *t, const double seg[4], double out[4]);
+/* LineTes::insert_segment, lib/ttessel.cpp:904-980: the segment is clipped by the window and
+ * added to the maximal segments of t.  While the segments do not form a T-tessellation (free
+ * ends, crossings, corners: what remove_[ilx]vertices would clean, not built) the arrangement
+ * can be inspected (lite_host_edges), written and inserted into; checks, moves and the export
+ * answer LITE_EINVAL / LITE_ESTATE until they do.  Ids of an earlier export are invalidated.
+ * seg_id (may be null) receives the id of the new segment. */
+int lite_host_insert_segment(lite_host_tess *t, const double seg[4], int32_t *seg_id);
+/* LineTes::is_a_T_tessellation, lib/ttessel.cpp:1307-1329: 1 or 0 */
+int lite_host_is_t_tessellation(lite_host_tess *t);
+/* Every halfedge of the arrangement, T-tessellation or not: end points (source x, y, target x,
+ * y), segment id, next / previous halfedge along its segment (-1 at the segment's ends:
+ * LineTes_halfedge::get_next_hf / get_prev_hf).  Returns the number of halfedges; writes only if
+ * cap holds them all; any array may be null. */
+int64_t lite_host_edges(lite_host_tess *t, int64_t cap, double *xy, int32_t *seg, int32_t *next_hf,
+                        int32_t *prev_hf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,12 @@
  * Deliberate differences from the reference, all documented in DESIGN.md:
  *   - handles are (tessellation, id) pairs, not CGAL iterators; `e->source()->point()`
  *     style access works, CGAL-specific members do not exist;
- *   - windows are single hole-free polygons (the scope of the hot path);
+ *   - the host model's moves need a single hole-free polygon as window; windows with holes or
+ *     of several polygons are read, built by insert_segment, checked, written and evaluated on
+ *     the device;
+ *   - insert_segment rebuilds the arrangement (handles obtained before are invalidated) and
+ *     remove_[ilx]vertices do not exist: an arrangement that is not a T-tessellation can only
+ *     be inspected, written and inserted into;
  *   - `rnd` is a CGAL::Random look-alike over std::mt19937_64 (CGAL's stream is
  *     un-vendored and unpinned by the reference);
  *   - AddSplits() samples on the device with a counter-based Philox stream.
@@ -239,6 +244,12 @@ class LineTes {
 
   virtual void insert_window(Rectangle);
   virtual void insert_window(Polygon &);
+  virtual void insert_window(HPolygons &);  /* :283: read / check / evaluate; no host moves */
+  /* :904-980.  The segment is clipped by the window and joins the maximal segments; every
+   * handle obtained before is invalidated (the arrangement is rebuilt).  While the segments do
+   * not form a T-tessellation the object can be inspected, written and inserted into. */
+  Seg insert_segment(Segment);
+  bool is_a_T_tessellation(bool verbose = false, std::ostream &out = std::cout); /* :1307-1329 */
   Size number_of_vertices() const;
   Size number_of_halfedges() const;
   Size number_of_edges() const { return number_of_halfedges() / 2; }
@@ -262,6 +273,12 @@ class LineTes {
 };
 
 #define NULL_HALFEDGE_HANDLE LineTes::Halfedge_handle()
+
+/* lib/ttessel.cpp:3696-3786: the longest piece of the segment inside the open polygon(s);
+ * std::domain_error when the segment does not hit them */
+Segment clip_segment_by_polygon(Segment, Polygon);
+Segment clip_segment_by_polygon(Segment, HPolygon);
+Segment clip_segment_by_polygon(Segment, HPolygons);
 
 /* include/ttessel.h:489-498 */
 struct ModList {
@@ -330,6 +347,7 @@ class TTessel : public LineTes {
   TTessel();
   virtual void insert_window(Rectangle);
   virtual void insert_window(Polygon &);
+  virtual void insert_window(HPolygons &);
   Halfedge_handle update(Split);
   Face_handle update(Merge);
   Halfedge_handle update(Flip);

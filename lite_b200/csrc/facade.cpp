@@ -120,6 +120,57 @@ void LineTes::insert_window(Polygon &p) {
   window_.push_back(HPolygon(q));
   touch();
 }
+static void boundaries_of(const HPolygons &w, std::vector<std::vector<double>> &bx, std::vector<std::vector<double>> &by) {
+  // outer boundaries counter-clockwise, holes clockwise (the window on the left of every side)
+  for (size_t i = 0; i < w.size(); i++) {
+    std::vector<Polygon> b;
+    b.push_back(w[i].outer_boundary());
+    if (b[0].area() < 0) b[0].reverse_orientation();
+    for (HPolygon::Hole_const_iterator h = w[i].holes_begin(); h != w[i].holes_end(); ++h) {
+      b.push_back(*h);
+      if (b.back().area() > 0) b.back().reverse_orientation();
+    }
+    for (size_t k = 0; k < b.size(); k++) {
+      bx.push_back(std::vector<double>()); by.push_back(std::vector<double>());
+      for (Size j = 0; j < b[k].size(); j++) { bx.back().push_back(b[k][j].x()); by.back().push_back(b[k][j].y()); }
+    }
+  }
+}
+void LineTes::insert_window(HPolygons &w) {
+  if (w.size() == 1 && w[0].number_of_holes() == 0) { Polygon p(w[0].outer_boundary()); insert_window(p); return; }
+  std::vector<std::vector<double>> bx, by;
+  boundaries_of(w, bx, by);
+  std::string err;
+  if (!lite::build_from_boundaries(*impl_, bx, by, std::vector<std::vector<double>>(), err))
+    throw std::domain_error("insert_window: " + err);
+  window_ = w;
+  touch();
+}
+LineTes::Seg LineTes::insert_segment(Segment sg) {
+  const double c[4] = {sg.source().x(), sg.source().y(), sg.target().x(), sg.target().y()};
+  int id = -1;
+  std::string err;
+  if (!lite::insert_segment(*impl_, c, &id, err)) throw std::domain_error("insert_segment: " + err);
+  touch();
+  return Seg(this, id);
+}
+bool LineTes::is_a_T_tessellation(bool verbose, std::ostream &out) {
+  if (impl_->arrangement_only && verbose) out << "not a T-tessellation: " << impl_->not_t_reason << std::endl;
+  return !impl_->arrangement_only;
+}
+Segment clip_segment_by_polygon(Segment sg, HPolygons w) {
+  std::vector<std::vector<double>> bx, by;
+  boundaries_of(w, bx, by);
+  const double c[4] = {sg.source().x(), sg.source().y(), sg.target().x(), sg.target().y()};
+  double o[4];
+  std::string err;
+  if (!lite::clip_segment(bx, by, c, o, err))
+    throw std::domain_error("function clip_segment_by_polygon failed to return a segment: " + err);
+  return Segment(Point2(o[0], o[1]), Point2(o[2], o[3]));
+}
+Segment clip_segment_by_polygon(Segment sg, HPolygon w) { return clip_segment_by_polygon(sg, HPolygons(1, w)); }
+Segment clip_segment_by_polygon(Segment sg, Polygon w) { return clip_segment_by_polygon(sg, HPolygons(1, HPolygon(w))); }
+
 Size LineTes::number_of_vertices() const {
   Size n = 0;
   for (size_t i = 0; i < impl_->v_alive.size(); i++) n += impl_->v_alive[i];
@@ -154,10 +205,22 @@ void LineTes::read(std::istream &is) {
   ss << is.rdbuf();
   std::string err;
   if (!lite::read_text(*impl_, ss.str(), err)) throw std::domain_error("LineTes::read: " + err);
-  Polygon w;
-  for (size_t i = 0; i < impl_->win_x.size(); i++) w.push_back(Point2(impl_->win_x[i], impl_->win_y[i]));
+  // the window as the file gave it: a counter-clockwise boundary opens a polygon, the clockwise
+  // ones that follow are its holes (lib/ttessel.cpp:1395-1415)
   window_.clear();
-  window_.push_back(HPolygon(w));
+  Polygon outer;
+  Polygons holes;
+  for (size_t b = 0; b < impl_->win_bx.size(); b++) {
+    Polygon q;
+    for (size_t i = 0; i < impl_->win_bx[b].size(); i++) q.push_back(Point2(impl_->win_bx[b][i], impl_->win_by[b][i]));
+    if (q.area() > 0) {
+      if (!outer.is_empty()) window_.push_back(HPolygon(outer, holes.begin(), holes.end()));
+      outer = q; holes.clear();
+    } else {
+      holes.push_back(q);
+    }
+  }
+  if (!outer.is_empty()) window_.push_back(HPolygon(outer, holes.begin(), holes.end()));
   touch();
 }
 void LineTes::print_all_segments() const {
@@ -174,9 +237,10 @@ void LineTes::print_all_segments() const {
 TTessel::TTessel() {}
 void TTessel::insert_window(Rectangle r) { LineTes::insert_window(r); }
 void TTessel::insert_window(Polygon &p) { LineTes::insert_window(p); }
+void TTessel::insert_window(HPolygons &w) { LineTes::insert_window(w); }
 void TTessel::clear(bool remove_window) {
   if (remove_window || window_.empty()) { *impl_ = HostTess(); window_.clear(); touch(); return; }
-  Polygon w(window_[0].outer_boundary());
+  HPolygons w(window_);
   LineTes::insert_window(w);
 }
 double TTessel::get_total_internal_length() { return impl_->int_length; }
@@ -447,7 +511,14 @@ ModList TTessel::Flip::modified_elements() {
 }
 
 // ---- moves ----
+static void require_t(const HostTess &h, const char *what, bool moving) {
+  if (h.arrangement_only)
+    throw std::domain_error(std::string(what) + ": the inserted segments do not form a T-tessellation (" + h.not_t_reason + ")");
+  if (moving && h.has_holes)
+    throw std::domain_error(std::string(what) + ": the host model does not move tessellations of windows with holes");
+}
 TTessel::Halfedge_handle TTessel::update(Split s) {  // lib/ttessel.cpp:1580-1597
+  require_t(*impl_, "TTessel::update(Split)", true);
   if (!s.is_valid()) throw std::domain_error("TTessel::update(Split): invalid split");
   lite::SplitMove m;
   m.e1 = s.get_e1().id(); m.e2 = s.get_e2().id();
@@ -458,6 +529,7 @@ TTessel::Halfedge_handle TTessel::update(Split s) {  // lib/ttessel.cpp:1580-159
   return Halfedge_handle(this, e);
 }
 TTessel::Face_handle TTessel::update(Merge m) {  // :1604-1638
+  require_t(*impl_, "TTessel::update(Merge)", true);
   if (!m.is_valid()) throw std::domain_error("TTessel::update(Merge): not a non-blocking segment");
   int e = m.get_e().id();
   const HostTess &h = *impl_;
@@ -472,6 +544,7 @@ TTessel::Face_handle TTessel::update(Merge m) {  // :1604-1638
   return Face_handle();
 }
 TTessel::Halfedge_handle TTessel::update(Flip f) {  // :1644-1701
+  require_t(*impl_, "TTessel::update(Flip)", true);
   if (f.get_e1().is_null() || f.get_e2().is_null()) throw std::domain_error("TTessel::update(Flip): invalid flip");
   lite::FlipMove m = impl_->make_flip(f.get_e1().id());
   if (!m.valid) throw std::domain_error("TTessel::update(Flip): invalid flip");
@@ -830,6 +903,7 @@ static void sync_mirror(lite::DeviceMirror *&M, Energy &E, TTessel *t) {
   if (!M->ctx) ck(lite_ctx_create(&M->ctx, 0, 0, 1, 0), "lite_ctx_create");
   if (M->tes == t && M->version == t->version() && M->prog == prog) return;
   HostTess &h = *t->host();
+  require_t(h, "Energy", false);
   const lite_tess_soa *soa = h.export_soa();
   ck(lite_candidates_clear_splits(M->ctx), "lite_candidates_clear_splits");
   ck(lite_tess_upload(M->ctx, soa), "lite_tess_upload");
@@ -1002,6 +1076,7 @@ void PseudoLikDiscrete::SetEnergy(Energy *e) {  // :3327-3348: all merges, all f
   std::vector<int32_t> prog = e->device_program();
   ensure_ctx();
   HostTess &h = *t->host();
+  require_t(h, "PseudoLikDiscrete::SetEnergy", false);
   ck(lite_candidates_clear_splits(ctx_), "lite_candidates_clear_splits");
   ck(lite_tess_upload(ctx_, h.export_soa()), "lite_tess_upload");
   ck(lite_energy_set(ctx_, (int)prog.size(), prog.data()), "lite_energy_set");

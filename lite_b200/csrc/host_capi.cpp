@@ -14,6 +14,8 @@ struct lite_host_tess {
   std::vector<int> he_ids;  // export id -> internal id of the last export
 };
 
+static const char *NOT_T = "the segments inserted so far do not form a T-tessellation (lite_host_is_t_tessellation): the arrangement can be inspected, written and inserted into, nothing else";
+
 static void remember_ids(lite_host_tess *h) {
   h->he_ids.clear();
   for (size_t i = 0; i < h->t.h_src.size(); i++)
@@ -49,6 +51,7 @@ extern "C" int lite_host_destroy(lite_host_tess *t) {
 
 extern "C" int lite_host_crtt_run(lite_host_tess *h, double tau, uint64_t n_steps, uint64_t seed,
                                   int64_t counts6[6]) {
+  if (h && h->t.arrangement_only) return lite_set_error_(LITE_ESTATE, NOT_T);
   if (h && h->t.has_holes) return lite_set_error_(LITE_ESTATE, "the host model reads, checks, exports and writes tessellations of windows with holes but does not move them");
   if (!h || !(tau > 0)) return lite_set_error_(LITE_EINVAL, "bad argument");
   lite::ChainCounts c = lite::crtt_chain(h->t, tau, n_steps, seed);
@@ -58,6 +61,7 @@ extern "C" int lite_host_crtt_run(lite_host_tess *h, double tau, uint64_t n_step
 }
 
 extern "C" int lite_host_update_split(lite_host_tess *h, int32_t he, double x, double angle) {
+  if (h && h->t.arrangement_only) return lite_set_error_(LITE_ESTATE, NOT_T);
   if (h && h->t.has_holes) return lite_set_error_(LITE_ESTATE, "the host model reads, checks, exports and writes tessellations of windows with holes but does not move them");
   if (!h || he < 0 || he >= (int)h->he_ids.size()) return lite_set_error_(LITE_EINVAL, "bad halfedge id");
   int e = h->he_ids[he];
@@ -70,6 +74,7 @@ extern "C" int lite_host_update_split(lite_host_tess *h, int32_t he, double x, d
 }
 
 extern "C" int lite_host_update_merge(lite_host_tess *h, int32_t i) {
+  if (h && h->t.arrangement_only) return lite_set_error_(LITE_ESTATE, NOT_T);
   if (h && h->t.has_holes) return lite_set_error_(LITE_ESTATE, "the host model reads, checks, exports and writes tessellations of windows with holes but does not move them");
   if (!h || i < 0 || i >= (int)h->t.nb_list.size()) return lite_set_error_(LITE_EINVAL, "bad non-blocking index");
   h->t.update_merge(h->t.s_he[h->t.nb_list[i]]);
@@ -78,6 +83,7 @@ extern "C" int lite_host_update_merge(lite_host_tess *h, int32_t i) {
 }
 
 extern "C" int lite_host_update_flip(lite_host_tess *h, int32_t i, int side) {
+  if (h && h->t.arrangement_only) return lite_set_error_(LITE_ESTATE, NOT_T);
   if (h && h->t.has_holes) return lite_set_error_(LITE_ESTATE, "the host model reads, checks, exports and writes tessellations of windows with holes but does not move them");
   if (!h || i < 0 || i >= (int)h->t.b_list.size()) return lite_set_error_(LITE_EINVAL, "bad blocking index");
   lite::FlipMove f = h->t.make_flip(h->t.flip_halfedge(h->t.b_list[i], side));
@@ -97,6 +103,7 @@ extern "C" int lite_host_counts(lite_host_tess *h, int32_t *n_cells, int32_t *n_
 
 extern "C" int lite_host_check(lite_host_tess *h) {
   if (!h) return lite_set_error_(LITE_EINVAL, "null argument");
+  if (h->t.arrangement_only) return lite_set_error_(LITE_EINVAL, ("not a T-tessellation: " + h->t.not_t_reason).c_str());
   std::string e = h->t.check();
   if (!e.empty()) return lite_set_error_(LITE_EINVAL, e.c_str());
   return 0;
@@ -104,6 +111,7 @@ extern "C" int lite_host_check(lite_host_tess *h) {
 
 extern "C" int lite_host_export(lite_host_tess *h, lite_tess_soa *out) {
   if (!h || !out) return lite_set_error_(LITE_EINVAL, "null argument");
+  if (h->t.arrangement_only) return lite_set_error_(LITE_ESTATE, NOT_T);
   *out = *h->t.export_soa();
   remember_ids(h);
   return 0;
@@ -118,6 +126,49 @@ extern "C" int64_t lite_host_write_text(lite_host_tess *h, char *buf, int64_t ca
     buf[n] = 0;
   }
   return (int64_t)s.size() + 1;
+}
+
+extern "C" int lite_host_clip_segment(lite_host_tess *h, const double seg[4], double out[4]) {
+  if (!h || !seg || !out) return lite_set_error_(LITE_EINVAL, "null argument");
+  std::vector<std::vector<double>> bx = h->t.win_bx, by = h->t.win_by;
+  if (bx.empty() && !h->t.win_x.empty()) { bx = {h->t.win_x}; by = {h->t.win_y}; }
+  std::string err;
+  if (!lite::clip_segment(bx, by, seg, out, err)) return lite_set_error_(LITE_EINVAL, ("clip_segment_by_polygon: " + err).c_str());
+  return 0;
+}
+
+extern "C" int lite_host_insert_segment(lite_host_tess *h, const double seg[4], int32_t *seg_id) {
+  if (!h || !seg) return lite_set_error_(LITE_EINVAL, "null argument");
+  std::string err;
+  int id = -1;
+  if (!lite::insert_segment(h->t, seg, &id, err)) return lite_set_error_(LITE_EINVAL, ("insert_segment: " + err).c_str());
+  if (seg_id) *seg_id = id;
+  remember_ids(h);
+  return 0;
+}
+
+extern "C" int lite_host_is_t_tessellation(lite_host_tess *h) {
+  if (!h) return lite_set_error_(LITE_EINVAL, "null argument");
+  return h->t.arrangement_only ? 0 : 1;
+}
+
+extern "C" int64_t lite_host_edges(lite_host_tess *h, int64_t cap, double *xy, int32_t *seg, int32_t *next_hf,
+                                   int32_t *prev_hf) {
+  if (!h) return -1;
+  const lite::HostTess &t = h->t;
+  std::vector<int> id(t.h_src.size(), -1);
+  int64_t n = 0;
+  for (size_t e = 0; e < t.h_src.size(); e++) if (t.h_alive[e]) id[e] = (int)n++;
+  if (cap < n) return n;
+  for (size_t e = 0; e < t.h_src.size(); e++) {
+    if (!t.h_alive[e]) continue;
+    const int k = id[e], a = t.h_src[e], b = t.h_src[e ^ 1];
+    if (xy) { xy[4 * k] = t.vx[a]; xy[4 * k + 1] = t.vy[a]; xy[4 * k + 2] = t.vx[b]; xy[4 * k + 3] = t.vy[b]; }
+    if (seg) seg[k] = t.h_seg[e];
+    if (next_hf) next_hf[k] = t.h_next_hf[e] >= 0 ? id[t.h_next_hf[e]] : -1;
+    if (prev_hf) prev_hf[k] = t.h_prev_hf[e] >= 0 ? id[t.h_prev_hf[e]] : -1;
+  }
+  return n;
 }
 
 // One SMF chain brought back from the GPU (lite_smf_export, capi.cu) -> host model.

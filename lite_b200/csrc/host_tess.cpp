@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <random>
+#include <set>
 #include <sstream>
 
 namespace lite {
@@ -645,6 +646,12 @@ bool build_from_segments(HostTess &t, const std::vector<double> &wx, const std::
 bool build_from_boundaries(HostTess &t, const std::vector<std::vector<double>> &bx,
                            const std::vector<std::vector<double>> &by,
                            const std::vector<std::vector<double>> &segs, std::string &err) {
+  return build_arrangement(t, bx, by, segs, false, err);
+}
+
+bool build_arrangement(HostTess &t, const std::vector<std::vector<double>> &bx,
+                       const std::vector<std::vector<double>> &by,
+                       const std::vector<std::vector<double>> &segs, bool lenient, std::string &err) {
   if (bx.empty() || bx.size() != by.size()) { err = "no window"; return false; }
   // all boundary vertices in one list; boundary side i runs wfrom[i] -> wto[i] (vertex ids)
   std::vector<double> wx, wy;
@@ -691,7 +698,9 @@ bool build_from_boundaries(HostTess &t, const std::vector<std::vector<double>> &
     }
   }
   // no two segments may cross in their interiors (X-vertex): distances of the ends of one
-  // to the line of the other have opposite signs, both ways
+  // to the line of the other have opposite signs, both ways (a general arrangement keeps the
+  // pairs: each becomes a vertex on both segments)
+  std::set<std::pair<int, int>> crossings;
   {
     auto side = [&](const S &a, double px, double py) {
       const double ex = a.x1 - a.x0, ey = a.y1 - a.y0;
@@ -703,8 +712,11 @@ bool build_from_boundaries(HostTess &t, const std::vector<std::vector<double>> &
         for (size_t q = p + 1; q < cell.size(); q++) {
           const S &a = L[cell[p]], &b = L[cell[q]];
           if (side(a, b.x0, b.y0) * side(a, b.x1, b.y1) < 0 && side(b, a.x0, a.y0) * side(b, a.x1, a.y1) < 0) {
-            err = "two segments cross (X-vertex): not a T-tessellation";
-            return false;
+            if (!lenient) {
+              err = "two segments cross (X-vertex): not a T-tessellation";
+              return false;
+            }
+            crossings.insert({std::min(cell[p], cell[q]), std::max(cell[p], cell[q])});
           }
         }
   }
@@ -716,11 +728,24 @@ bool build_from_boundaries(HostTess &t, const std::vector<std::vector<double>> &
   std::vector<double> vx, vy;
   for (int i = 0; i < nw; i++) { vx.push_back(wx[i]); vy.push_back(wy[i]); }
   for (int i = 0; i < nw; i++) { L[i].on.push_back({0.0, i}); L[i].on.push_back({1.0, wto[i]}); }
+  // general arrangement: ends that coincide (with a window corner or with each other: L-vertices)
+  // share one vertex
+  std::vector<int> end_vertex(2 * (size_t)nL, -1);
+  if (lenient)
+    for (int i = nw; i < nL; i++)
+      for (int e = 0; e < 2; e++) {
+        const double px = e ? L[i].x1 : L[i].x0, py = e ? L[i].y1 : L[i].y0;
+        int v = -1;
+        for (int k = 0; k < (int)vx.size() && v < 0; k++)
+          if (fabs(vx[k] - px) <= eps && fabs(vy[k] - py) <= eps) v = k;
+        if (v < 0) { v = (int)vx.size(); vx.push_back(px); vy.push_back(py); }
+        end_vertex[2 * (size_t)i + e] = v;
+      }
   for (int i = nw; i < nL; i++) {
     for (int e = 0; e < 2; e++) {
       const double px = e ? L[i].x1 : L[i].x0, py = e ? L[i].y1 : L[i].y0;
-      const int v = (int)vx.size();
-      vx.push_back(px); vy.push_back(py);
+      const int v = lenient ? end_vertex[2 * (size_t)i + e] : (int)vx.size();
+      if (!lenient) { vx.push_back(px); vy.push_back(py); }
       L[i].on.push_back({(double)e, v});
       // the segment this end point abuts on
       int host = -1; double best = eps, host_t = 0;
@@ -732,13 +757,37 @@ bool build_from_boundaries(HostTess &t, const std::vector<std::vector<double>> &
         if (tt < 0 || tt > 1) continue;
         const double qx = h.x0 + tt * ex - px, qy = h.y0 + tt * ey - py;
         const double d = sqrt(qx * qx + qy * qy);
+        if (lenient) {
+          // every segment whose interior holds the point gets the vertex (once); a segment that
+          // merely ends there shares it already
+          const double hl = sqrt(l2);
+          if (d > eps || tt * hl <= eps || (1 - tt) * hl <= eps) continue;
+          bool there = false;
+          for (const auto &o : L[j].on) there = there || o.second == v;
+          if (!there) L[j].on.push_back({tt, v});
+          continue;
+        }
         if (d <= best) { best = d; host = j; host_t = tt; }
       }
-      if (host < 0) { err = "a segment end lies on no other segment and not on the window boundary"; return false; }
+      if (host < 0) {
+        if (lenient) continue;  // a free end (I-vertex), or an end shared with other ends only
+        err = "a segment end lies on no other segment and not on the window boundary"; return false;
+      }
       const double hl = sqrt((L[host].x1 - L[host].x0) * (L[host].x1 - L[host].x0) + (L[host].y1 - L[host].y0) * (L[host].y1 - L[host].y0));
       if (host_t * hl <= eps || (1 - host_t) * hl <= eps) { err = "two segments meet at their end points (L- or X-vertex): not a T-tessellation"; return false; }
       L[host].on.push_back({host_t, v});
     }
+  }
+  for (const auto &c : crossings) {   // general arrangement only
+    const S &a = L[c.first], &b = L[c.second];
+    const double ax = a.x1 - a.x0, ay = a.y1 - a.y0, bxx = b.x1 - b.x0, byy = b.y1 - b.y0;
+    const double den = ax * byy - ay * bxx;
+    const double ta = ((b.x0 - a.x0) * byy - (b.y0 - a.y0) * bxx) / den;
+    const double tb = ((b.x0 - a.x0) * ay - (b.y0 - a.y0) * ax) / den;
+    const int v = (int)vx.size();
+    vx.push_back(a.x0 + ta * ax); vy.push_back(a.y0 + ta * ay);
+    L[c.first].on.push_back({ta, v});
+    L[c.second].on.push_back({tb, v});
   }
   // edges along every segment
   struct E { int v0, v1, seg, prev_hf, next_hf; bool bnd; };
@@ -777,7 +826,7 @@ bool build_from_boundaries(HostTess &t, const std::vector<std::vector<double>> &
   // next(): at the head of h, turn to the outgoing halfedge that follows twin(h) clockwise
   for (int v = 0; v < nV; v++) {
     auto &o = out[v];
-    if (o.size() < 2) { err = "dangling vertex"; return false; }
+    if (o.empty() || (o.size() < 2 && !lenient)) { err = "dangling vertex"; return false; }
     std::sort(o.begin(), o.end(), [&](int a, int b) {
       const int ta = t.h_src[a ^ 1], tb = t.h_src[b ^ 1];
       return atan2(vy[ta] - vy[v], vx[ta] - vx[v]) < atan2(vy[tb] - vy[v], vx[tb] - vx[v]);
@@ -809,7 +858,9 @@ bool build_from_boundaries(HostTess &t, const std::vector<std::vector<double>> &
       h = t.h_next[h];
       if (h < 0 || ++guard > 2 * nE) { err = "broken boundary cycle"; return false; }
     } while (h != h0);
-    if (a2 < 0 && !outside_side) {   // inner boundary of an inside face: assigned below
+    // (a general arrangement also has the contours of free-standing groups of segments: trees have
+    // no area, up to rounding)
+    if ((a2 < 0 || (lenient && a2 <= 1e-12 * scale * scale)) && !outside_side) {   // inner boundary of an inside face: assigned below
       cw_cycles.push_back(h0);
       h = h0;
       do { t.h_face[h] = -2; h = t.h_next[h]; } while (h != h0);
@@ -865,8 +916,120 @@ bool build_from_boundaries(HostTess &t, const std::vector<std::vector<double>> &
   for (int i = 0; i < nw; i++)
     if (t.f_inside[t.h_face[t.s_he[i] ^ 1]] || !t.f_inside[t.h_face[t.s_he[i]]]) { err = "window side with the window on the wrong side (outer boundaries counter-clockwise, holes clockwise)"; return false; }
   t.finish_import();
+  if (lenient) {   // links only: the T-tessellation invariants of check() do not apply
+    t.arrangement_only = true;
+    for (size_t h = 0; h < t.h_src.size(); h++)
+      if (t.h_face[h] < 0 || t.h_next[h] < 0 || t.h_prev[t.h_next[h]] != (int)h) { err = "inconsistent arrangement"; return false; }
+    return true;
+  }
   std::string bad = t.check();
   if (!bad.empty()) { err = "inconsistent tessellation: " + bad; return false; }
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// clip_segment_by_polygon (lib/ttessel.cpp:3696-3786): the longest piece of a segment inside
+// the open window (its boundaries cut the segment and are not part of the result)
+// ---------------------------------------------------------------------------
+static bool point_in_open_window(const std::vector<std::vector<double>> &bx, const std::vector<std::vector<double>> &by,
+                                 double px, double py, double eps) {
+  bool in = false;
+  for (size_t b = 0; b < bx.size(); b++) {
+    const size_t n = bx[b].size();
+    for (size_t i = 0; i < n; i++) {
+      const size_t j = (i + 1) % n;
+      const double x0 = bx[b][i], y0 = by[b][i], x1 = bx[b][j], y1 = by[b][j];
+      const double ex = x1 - x0, ey = y1 - y0, l2 = ex * ex + ey * ey;
+      double tt = ((px - x0) * ex + (py - y0) * ey) / l2;
+      tt = fmax(0.0, fmin(1.0, tt));
+      const double qx = x0 + tt * ex - px, qy = y0 + tt * ey - py;
+      if (qx * qx + qy * qy <= eps * eps) return false;   // on a boundary: outside the open set
+      if ((y0 > py) != (y1 > py)) {
+        const double xc = x0 + (py - y0) * ex / ey;
+        if (px < xc) in = !in;
+      }
+    }
+  }
+  return in;   // odd number of boundaries crossed: inside an outer boundary and in none of its holes
+}
+
+bool clip_segment(const std::vector<std::vector<double>> &bx, const std::vector<std::vector<double>> &by,
+                  const double seg[4], double out[4], std::string &err) {
+  if (bx.empty() || bx.size() != by.size()) { err = "no window"; return false; }
+  const double sx = seg[2] - seg[0], sy = seg[3] - seg[1], sl = sqrt(sx * sx + sy * sy);
+  if (!(sl > 0)) { err = "degenerate segment"; return false; }
+  double scale = sl;
+  for (size_t b = 0; b < bx.size(); b++)
+    for (size_t i = 0; i < bx[b].size(); i++) scale = fmax(scale, fmax(fabs(bx[b][i]), fabs(by[b][i])));
+  const double eps = 1e-9 * scale;
+  std::vector<double> cuts = {0.0, 1.0};
+  for (size_t b = 0; b < bx.size(); b++) {
+    const size_t n = bx[b].size();
+    for (size_t i = 0; i < n; i++) {
+      const size_t j = (i + 1) % n;
+      const double x0 = bx[b][i], y0 = by[b][i], ex = bx[b][j] - x0, ey = by[b][j] - y0;
+      const double el = sqrt(ex * ex + ey * ey);
+      const double den = sx * ey - sy * ex;
+      if (fabs(den) > 1e-14 * sl * el) {
+        const double ts = ((x0 - seg[0]) * ey - (y0 - seg[1]) * ex) / den;   // along the segment
+        const double te = ((x0 - seg[0]) * sy - (y0 - seg[1]) * sx) / den;   // along the boundary edge
+        if (ts * sl >= -eps && (1 - ts) * sl >= -eps && te * el >= -eps && (1 - te) * el >= -eps)
+          cuts.push_back(fmax(0.0, fmin(1.0, ts)));
+      } else {
+        // parallel: a boundary edge lying on the segment's line cuts it at the edge's two ends
+        const double d = ((x0 - seg[0]) * sy - (y0 - seg[1]) * sx) / sl;
+        if (fabs(d) > eps) continue;
+        const double ta = ((x0 - seg[0]) * sx + (y0 - seg[1]) * sy) / (sl * sl);
+        const double tb = ((x0 + ex - seg[0]) * sx + (y0 + ey - seg[1]) * sy) / (sl * sl);
+        if (ta > 0 && ta < 1) cuts.push_back(ta);
+        if (tb > 0 && tb < 1) cuts.push_back(tb);
+      }
+    }
+  }
+  std::sort(cuts.begin(), cuts.end());
+  double best = -1, b0 = 0, b1 = 0;
+  for (size_t k = 0; k + 1 < cuts.size(); k++) {
+    const double ta = cuts[k], tb = cuts[k + 1];
+    if ((tb - ta) * sl <= eps) continue;
+    const double tm = 0.5 * (ta + tb);
+    if (!point_in_open_window(bx, by, seg[0] + tm * sx, seg[1] + tm * sy, eps)) continue;
+    if (tb - ta > best) { best = tb - ta; b0 = ta; b1 = tb; }
+  }
+  if (best < 0) { err = "the segment does not hit the window"; return false; }
+  out[0] = b0 == 0.0 ? seg[0] : seg[0] + b0 * sx; out[1] = b0 == 0.0 ? seg[1] : seg[1] + b0 * sy;
+  out[2] = b1 == 1.0 ? seg[2] : seg[0] + b1 * sx; out[3] = b1 == 1.0 ? seg[3] : seg[1] + b1 * sy;
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// LineTes::insert_segment (lib/ttessel.cpp:904-980): the segment, clipped by the window, joins
+// the maximal segments already there and the arrangement is built again from all of them --
+// as a T-tessellation if they form one, else as a general arrangement (free ends, crossings,
+// corners) that can be inspected, written and inserted into further, nothing else.
+// ---------------------------------------------------------------------------
+bool insert_segment(HostTess &t, const double seg[4], int *seg_id, std::string &err) {
+  std::vector<std::vector<double>> bx = t.win_bx, by = t.win_by;
+  if (bx.empty() && !t.win_x.empty()) { bx = {t.win_x}; by = {t.win_y}; }
+  if (bx.empty()) { err = "no window"; return false; }
+  double c[4];
+  if (!clip_segment(bx, by, seg, c, err)) return false;
+  std::vector<std::vector<double>> segs;
+  for (size_t s = 0; s < t.s_he.size(); s++) {
+    if (!t.s_alive[s] || t.s_bnd[s]) continue;
+    const int a = t.seg_start((int)s), b = t.seg_end((int)s);
+    segs.push_back({t.vx[t.h_src[a]], t.vy[t.h_src[a]], t.vx[t.tgt(b)], t.vy[t.tgt(b)]});
+  }
+  segs.push_back({c[0], c[1], c[2], c[3]});
+  size_t nw = 0;
+  for (const auto &b : bx) nw += b.size();
+  HostTess nt;
+  std::string strict_err;
+  if (!build_arrangement(nt, bx, by, segs, false, strict_err)) {
+    if (!build_arrangement(nt, bx, by, segs, true, err)) return false;
+    nt.not_t_reason = strict_err;
+  }
+  t = nt;
+  if (seg_id) *seg_id = (int)(nw + segs.size() - 1);
   return true;
 }
 

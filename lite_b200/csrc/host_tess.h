@@ -63,6 +63,10 @@ class HostTess {
   // every boundary of the window: outer boundaries counter-clockwise, holes clockwise, in file order
   std::vector<std::vector<double>> win_bx, win_by;
   bool has_holes = false;  // window with holes or several polygons: read / check / export / write only (no moves)
+  // built by insert_segment from segments that do not form a T-tessellation (free ends, crossings,
+  // corners): links, lengths and segments are there to be inspected and written; no moves, no export
+  bool arrangement_only = false;
+  std::string not_t_reason;
 
   HostTess();
   void insert_window_polygon(const std::vector<double> &x, const std::vector<double> &y);
@@ -157,6 +161,19 @@ bool build_from_segments(HostTess &t, const std::vector<double> &wx, const std::
 bool build_from_boundaries(HostTess &t, const std::vector<std::vector<double>> &bx,
                            const std::vector<std::vector<double>> &by,
                            const std::vector<std::vector<double>> &segs, std::string &err);
+
+// The same builder, strict (a T-tessellation or an error) or lenient (any arrangement of the
+// segments: sets HostTess::arrangement_only).
+bool build_arrangement(HostTess &t, const std::vector<std::vector<double>> &bx,
+                       const std::vector<std::vector<double>> &by,
+                       const std::vector<std::vector<double>> &segs, bool lenient, std::string &err);
+// clip_segment_by_polygon for a union of polygons with holes (lib/ttessel.cpp:3762-3786): the
+// longest piece of seg (x0 y0 x1 y1) inside the open window; false if it does not hit it.
+bool clip_segment(const std::vector<std::vector<double>> &bx, const std::vector<std::vector<double>> &by,
+                  const double seg[4], double out[4], std::string &err);
+// LineTes::insert_segment (lib/ttessel.cpp:904-980); seg_id receives the id of the new segment.
+// Every handle into t is invalidated (the arrangement is rebuilt).
+bool insert_segment(HostTess &t, const double seg[4], int *seg_id, std::string &err);
 
 // LineTes::read / write text format (lib/ttessel.cpp:1331-1441), double precision
 bool read_text(HostTess &t, const std::string &text, std::string &err);

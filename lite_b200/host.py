@@ -12,7 +12,8 @@ HOST_SYMBOLS = [
     "lite_host_create_rect", "lite_host_create_from_text", "lite_host_destroy",
     "lite_host_crtt_run", "lite_host_update_split", "lite_host_update_merge",
     "lite_host_update_flip", "lite_host_counts", "lite_host_check", "lite_host_export",
-    "lite_host_write_text",
+    "lite_host_write_text", "lite_host_clip_segment", "lite_host_insert_segment",
+    "lite_host_is_t_tessellation", "lite_host_edges",
 ]
 
 _COUNT_OF = dict(vx="n_vertices", vy="n_vertices", he_src="n_halfedges", he_twin="n_halfedges",
@@ -39,6 +40,11 @@ def _lib():
         L.lite_host_export.argtypes = [C.c_void_p, C.POINTER(_SoA)]
         L.lite_host_write_text.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.lite_host_write_text.restype = C.c_int64
+        L.lite_host_clip_segment.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lite_host_insert_segment.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        L.lite_host_is_t_tessellation.argtypes = [C.c_void_p]
+        L.lite_host_edges.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lite_host_edges.restype = C.c_int64
         L._host_ready = True
     return L
 
@@ -103,6 +109,31 @@ class HostTess:
                 arrays[k] = np.frombuffer(buf, dtype=dt, count=n).copy()
         arrays["int_length"] = s.int_length
         return TessSoA(arrays)
+
+    def clip_segment(self, seg):
+        """clip_segment_by_polygon (lib/ttessel.cpp:3762-3786) by this tessellation's window."""
+        a = np.asarray(seg, dtype=np.float64).reshape(4).copy()
+        out = np.zeros(4)
+        _ck(self.L, self.L.lite_host_clip_segment(self.h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def insert_segment(self, seg):
+        """LineTes::insert_segment (lib/ttessel.cpp:904-980); returns the new segment's id."""
+        a = np.asarray(seg, dtype=np.float64).reshape(4).copy()
+        sid = C.c_int32(-1)
+        _ck(self.L, self.L.lite_host_insert_segment(self.h, a.ctypes.data_as(C.c_void_p), C.byref(sid)))
+        return sid.value
+
+    def is_t_tessellation(self):
+        return self.L.lite_host_is_t_tessellation(self.h) == 1
+
+    def edges(self):
+        """Every halfedge: (end points [n,4], segment id, next_hf, prev_hf), T-tessellation or not."""
+        n = self.L.lite_host_edges(self.h, 0, None, None, None, None)
+        xy = np.zeros((n, 4)); seg = np.zeros(n, np.int32); nx = np.zeros(n, np.int32); pv = np.zeros(n, np.int32)
+        self.L.lite_host_edges(self.h, n, xy.ctypes.data_as(C.c_void_p), seg.ctypes.data_as(C.c_void_p),
+                               nx.ctypes.data_as(C.c_void_p), pv.ctypes.data_as(C.c_void_p))
+        return xy, seg, nx, pv
 
     def write_text(self):
         n = self.L.lite_host_write_text(self.h, None, 0)

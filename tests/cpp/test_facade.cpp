@@ -128,6 +128,91 @@ static void test_text_roundtrip(const char *fixture) {
   CHECK(u.number_of_blocking_segments() == t.number_of_blocking_segments());
 }
 
+// tests/check_lite.cpp:129-200
+static HPolygons holed_polygons() {
+  const double o1[][2] = {{0, 0}, {6, 3}, {14, 0}, {9, 10}, {12, 15}, {0, 15}};
+  const double h11[][2] = {{3, 4}, {2, 5}, {3, 7}, {4, 7}};
+  const double h12[][2] = {{7, 4}, {7, 5}, {8, 7}, {8, 5}, {10, 6}, {10, 4}};
+  const double h13[][2] = {{2, 8}, {2, 13}, {6, 13}, {4, 11}, {7, 10}, {7, 9}, {3, 10}};
+  const double o2[][2] = {{14, 3}, {21, 3}, {21, 15}, {14, 15}, {11, 10}, {14, 5}};
+  const double h21[][2] = {{19, 4}, {19, 5}, {20, 5}, {20, 4}};
+  const double h22[][2] = {{15, 6}, {17, 8}, {18, 6}};
+  const double h23[][2] = {{13, 9}, {13, 10}, {14, 10}, {14, 9}};
+  const double h24[][2] = {{17, 10}, {15, 12}, {17, 14}, {17, 12}, {19, 12}};
+  auto poly = [](const double (*c)[2], int n) {
+    Polygon p;
+    for (int i = 0; i < n; i++) p.push_back(Point2(c[i][0], c[i][1]));
+    return p;
+  };
+  Polygons a, b;
+  a.push_back(poly(h11, 4)); a.push_back(poly(h12, 6)); a.push_back(poly(h13, 7));
+  b.push_back(poly(h21, 4)); b.push_back(poly(h22, 3)); b.push_back(poly(h23, 4)); b.push_back(poly(h24, 5));
+  HPolygons r;
+  r.push_back(HPolygon(poly(o1, 6), a.begin(), a.end()));
+  r.push_back(HPolygon(poly(o2, 6), b.begin(), b.end()));
+  return r;
+}
+static LineTes::Halfedge_handle find_halfedge(TTessel &t, Point2 p1, Point2 p2) {  // check_lite.cpp:117-128
+  std::vector<LineTes::Halfedge_handle> hs = t.halfedges();
+  for (size_t i = 0; i < hs.size(); i++)
+    if (close_pt(hs[i]->source()->point(), p1) && close_pt(hs[i]->target()->point(), p2)) return hs[i];
+  return NULL_HALFEDGE_HANDLE;
+}
+static bool same_segment(const Segment &a, const Segment &b) {
+  return (a.source() == b.source() && a.target() == b.target()) || (a.source() == b.target() && a.target() == b.source());
+}
+// tests/check_lite.cpp:544-579
+static void test_clip_segment() {
+  HPolygons dom = holed_polygons();
+  Segment c = clip_segment_by_polygon(Segment(Point2(-1, 8), Point2(3, 12)), dom[0]);
+  CHECK(same_segment(c, Segment(Point2(0, 9), Point2(2, 11))));
+  bool thrown = false;
+  try { clip_segment_by_polygon(Segment(Point2(-1, -1), Point2(-2, -2)), dom[0]); } catch (const std::domain_error &) { thrown = true; }
+  CHECK(thrown);
+  c = clip_segment_by_polygon(Segment(Point2(19 / 2, 9 / 2), Point2(39 / 2, 9 / 2)), dom);  // integer divisions, as there
+  CHECK(same_segment(c, Segment(Point2(14, 9 / 2), Point2(19, 9 / 2))));
+  thrown = false;
+  try { clip_segment_by_polygon(Segment(Point2(-1, -1), Point2(-2, -2)), dom); } catch (const std::domain_error &) { thrown = true; }
+  CHECK(thrown);
+  thrown = false;
+  try { clip_segment_by_polygon(Segment(Point2(19 / 2, 9 / 2), Point2(13, 9 / 2)), dom); } catch (const std::domain_error &) { thrown = true; }
+  CHECK(!thrown);
+}
+// tests/check_lite.cpp:581-624
+static void test_insert_segment() {
+  HPolygons dom = holed_polygons();
+  TTessel tesl;
+  tesl.insert_window(dom);
+  tesl.insert_segment(Segment(Point2(3, 12), Point2(3, 16)));
+  LineTes::Halfedge_handle e = find_halfedge(tesl, Point2(3, 13), Point2(3, 15));
+  CHECK(e != NULL_HALFEDGE_HANDLE);
+  CHECK(e->get_next_hf() == NULL_HALFEDGE_HANDLE);   // does not extend beyond the outer boundary
+  CHECK(e->get_prev_hf() == NULL_HALFEDGE_HANDLE);   // nor into the hole
+  CHECK(tesl.is_a_T_tessellation());
+  tesl.insert_segment(Segment(Point2(1, 2), Point2(5, 2)));
+  e = find_halfedge(tesl, Point2(1, 2), Point2(4, 2));
+  CHECK(e != NULL_HALFEDGE_HANDLE);
+  CHECK(e->get_next_hf() == NULL_HALFEDGE_HANDLE);
+  CHECK(e->get_prev_hf() == NULL_HALFEDGE_HANDLE);
+  CHECK(!tesl.is_a_T_tessellation());                // (1, 2) is a free end
+  bool thrown = false;
+  try { tesl.update(TTessel::Split(tesl.halfedges()[0], 0.5, 1.0)); } catch (const std::domain_error &) { thrown = true; }
+  CHECK(thrown);
+  // LineTes::read's way of building (lib/ttessel.cpp:1417-1437): one segment at a time
+  TTessel sq;
+  sq.insert_window(Rectangle(Point2(0, 0), Point2(1, 1)));
+  sq.insert_segment(Segment(Point2(0.25, -1), Point2(0.25, 2)));
+  sq.insert_segment(Segment(Point2(0.25, 0.5), Point2(3, 0.5)));
+  CHECK(sq.is_a_T_tessellation());
+  CHECK(sq.number_of_non_blocking_segments() == 1 && sq.number_of_blocking_segments() == 1);
+  CHECK(sq.is_valid());
+  CHECK_CLOSE(sq.get_total_internal_length(), 4 + 2 * (1 + 0.75), 1e-15);
+  rnd = new CGAL::Random(3);
+  for (int i = 0; i < 20; i++) sq.update(sq.propose_split());
+  CHECK(sq.is_valid());
+  delete rnd;
+}
+
 static void test_catvector_and_energy_registry() {
   CatVector a, b;
   a.edges.push_back(1); a.faces.push_back(2); a.faces.push_back(3); a.segs.push_back(4);
@@ -381,6 +466,8 @@ int main(int argc, char **argv) {
     test_squared_domain(5, 100, 50);     // tests/check_lite.cpp:1031-1040
     test_squared_domain(11, 40, 400);
     test_text_roundtrip(argc > 2 ? argv[2] : "tests/golden/tessellation_data.txt");
+    test_clip_segment();
+    test_insert_segment();
     test_catvector_and_energy_registry();
     test_unknown_feature_is_refused();
     test_host_features();

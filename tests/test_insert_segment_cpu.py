@@ -1,0 +1,165 @@
+"""LineTes::insert_segment and clip_segment_by_polygon on the host model
+(reference lib/ttessel.cpp:904-980, :3696-3786), against the reference's own known answers
+(tests/check_lite.cpp:544-624) and against the batch reader."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "oracle"))
+sys.path.insert(0, HERE)
+
+import lite_b200
+import lite_oracle as lo
+from lite_b200.capi import LiteError
+from test_oracle_golden import holed_polygons
+
+
+def window_text(window):
+    t = lo.TTessel(lo.Rng(0))
+    t.insert_window(window)
+    return lo.write_text(t)
+
+
+def find_halfedge(h, a, b, tol=1e-8):
+    xy, seg, nx, pv = h.edges()
+    for k in range(len(xy)):
+        if np.allclose(xy[k], [a[0], a[1], b[0], b[1]], rtol=tol, atol=0):
+            return k, seg[k], nx[k], pv[k]
+    return None
+
+
+def test_clip_segment_by_holed_polygon_known_answers():
+    """check_lite.cpp:544-560: one polygon with holes; the piece ends on the outer boundary and on
+    a hole; a segment that misses the polygon is an error (std::domain_error there)."""
+    h = lite_b200.HostTess(text=window_text(holed_polygons()[:1]))
+    c = h.clip_segment([-1, 8, 3, 12])
+    assert np.array_equal(c, [0, 9, 2, 11])
+    with pytest.raises(LiteError, match="does not hit"):
+        h.clip_segment([-1, -1, -2, -2])
+
+
+def test_clip_segment_by_holed_polygons_known_answers():
+    """check_lite.cpp:562-579 (the test's 19/2, 9/2, 39/2 are integer divisions: 9, 4, 19): the
+    segment runs along a hole's side, through the first polygon (a piece of length 2) and into
+    the second (length 5, up to a hole): the longest piece wins."""
+    h = lite_b200.HostTess(text=window_text(holed_polygons()))
+    assert np.array_equal(h.clip_segment([9, 4, 19, 4]), [14, 4, 19, 4])
+    assert np.array_equal(h.clip_segment([19, 4, 9, 4]), [19, 4, 14, 4])   # direction kept
+    with pytest.raises(LiteError, match="does not hit"):
+        h.clip_segment([-1, -1, -2, -2])
+    assert np.array_equal(h.clip_segment([9, 4, 13, 4]), [10, 4, 12, 4])   # hits one polygon only
+
+
+def test_insert_segment_known_answers():
+    """check_lite.cpp:581-624: clipped at both ends (outer boundary, hole) and at one end; the
+    halfedge along the clipped segment has no neighbour along its segment."""
+    h = lite_b200.HostTess(text=window_text(holed_polygons()))
+    n0 = len(h.edges()[0])
+    h.insert_segment([3, 12, 3, 16])
+    e = find_halfedge(h, (3, 13), (3, 15))
+    assert e is not None and e[2] == -1 and e[3] == -1
+    assert h.is_t_tessellation()          # both ends on the window's boundaries
+    h.check()
+    assert len(h.edges()[0]) == n0 + 2 * 3   # two boundary sides split, one new edge
+    h.insert_segment([1, 2, 5, 2])
+    e = find_halfedge(h, (1, 2), (4, 2))
+    assert e is not None and e[2] == -1 and e[3] == -1
+    assert not h.is_t_tessellation()      # (1, 2) is a free end
+    with pytest.raises(LiteError, match="T-tessellation"):
+        h.check()
+    with pytest.raises(LiteError, match="T-tessellation"):
+        h.export()
+
+
+def fixture_text():
+    return open(os.path.join(HERE, "golden", "tessellation_data.txt")).read()
+
+
+def soa_edges(s):
+    out = {}
+    for k in range(len(s["he_src"])):
+        p, q = s["he_src"][k], s["he_src"][s["he_twin"][k]]
+        out[(float(s["vx"][p]), float(s["vy"][p]), float(s["vx"][q]), float(s["vy"][q]))] = (
+            bool(s["face_inside"][s["he_face"][k]]), int(s["seg_n_edges"][s["he_seg"][k]]), bool(s["seg_on_boundary"][s["he_seg"][k]]))
+    return out
+
+
+@pytest.mark.parametrize("order_seed", [0, 1, 2])
+def test_segment_by_segment_equals_the_batch_reader(order_seed):
+    """LineTes::read inserts the file's segments one at a time (lib/ttessel.cpp:1417-1437); a
+    T-tessellation holds cycles of segments each ending on the next, so whatever the order some
+    prefix is not a T-tessellation.  Any order ends on the tessellation the batch reader builds."""
+    text = fixture_text()
+    lines = [l for l in text.splitlines() if l.strip()]
+    win = [l for l in lines if len(l.split()) > 4]
+    segs = [l for l in lines if len(l.split()) == 4]
+    ref = lite_b200.HostTess(text=text)
+    rng = np.random.default_rng(order_seed)
+    h = lite_b200.HostTess(text="\n".join(win) + "\n")
+    was_not_t = False
+    for k in rng.permutation(len(segs)):
+        c = [float(lo.Fr(v)) for v in segs[k].split()]
+        h.insert_segment(c)
+        was_not_t = was_not_t or not h.is_t_tessellation()
+    assert was_not_t
+    assert h.is_t_tessellation()
+    h.check()
+    assert h.counts() == ref.counts()
+    assert soa_edges(h.export().a) == soa_edges(ref.export().a)
+    assert h.export().int_length == pytest.approx(ref.export().int_length, rel=1e-14)
+
+
+def test_crtt_tessellation_rebuilt_by_insertion():
+    """300 cells from the CRTT chain, its segments inserted in a random order (over-long by a
+    tenth on each side where that stays inside the cell structure is not assumed: the ends are
+    exact), then the three moves work on the result."""
+    t, _ = lite_b200.generate_crtt(300, seed=11)
+    text = t.write_text()
+    lines = [l for l in text.splitlines() if l.strip()]
+    h = lite_b200.HostTess((0, 0, 1, 1))
+    segs = [[float(lo.Fr(v)) for v in l.split()] for l in lines if len(l.split()) == 4]
+    for k in np.random.default_rng(3).permutation(len(segs)):
+        h.insert_segment(segs[k])
+    assert h.is_t_tessellation()
+    h.check()
+    assert h.counts() == t.counts()
+    assert soa_edges(h.export().a) == soa_edges(t.export().a)
+    h.update_split(0, 0.4, 1.1)
+    h.update_merge(0)
+    h.check()
+
+
+def test_general_arrangements():
+    """What the reference's arrangement accepts and remove_[ilx]vertices would clean: a crossing
+    (X-vertex), a corner (L-vertex), a free-standing segment, a segment over-running the window."""
+    h = lite_b200.HostTess((0, 0, 4, 4))
+    a = h.insert_segment([-1, 2, 5, 2])          # clipped to the window: (0,2)-(4,2)
+    assert h.is_t_tessellation() and h.counts() == (2, 1, 0)
+    b = h.insert_segment([2, 1, 2, 3])           # crosses it, both ends free
+    assert not h.is_t_tessellation()
+    xy, seg, nx, pv = h.edges()
+    assert len(xy) == 2 * (6 + 2 + 2)            # 4 sides (two of them split), 2 + 2 edges
+    k = find_halfedge(h, (2, 1), (2, 2))
+    assert k is not None and k[1] == b and k[3] == -1 and np.allclose(xy[k[2]], [2, 2, 2, 3])
+    k = find_halfedge(h, (0, 2), (2, 2))
+    assert k is not None and k[1] == a and np.allclose(xy[k[2]], [2, 2, 4, 2])
+    # the free ends closed by two more segments: T again, five cells
+    h.insert_segment([2, 3, 2, 10])              # from the free end (L-vertex, collinear) to the top side
+    assert not h.is_t_tessellation()
+    text = h.write_text()
+    assert len([l for l in text.splitlines() if len(l.split()) == 4]) == 3
+    # a free-standing segment lies in one face as an inner contour
+    g = lite_b200.HostTess((0, 0, 4, 4))
+    g.insert_segment([1, 1, 3, 3])
+    assert not g.is_t_tessellation()
+    xy, seg, nx, pv = g.edges()
+    assert len(xy) == 2 * 5
+    g.insert_segment([1, 3, 3, 1])               # crosses it
+    assert len(g.edges()[0]) == 2 * 8
+    with pytest.raises(LiteError, match="T-tessellation"):
+        g.update_split(0, 0.5, 1.0)
+    with pytest.raises(LiteError, match="does not hit"):
+        g.insert_segment([5, 5, 6, 6])
