@@ -64,6 +64,23 @@ int lite_host_is_t_tessellation(lite_host_tess *t);
 int64_t lite_host_edges(lite_host_tess *t, int64_t cap, double *xy, int32_t *seg, int32_t *next_hf,
                         int32_t *prev_hf);
 
+/* LineTes::remove_ivertices / remove_lvertices / remove_xvertices, lib/ttessel.cpp:982-1296: the
+ * passes that turn what a series of lite_host_insert_segment calls left into a T-tessellation.
+ * Free ends (degree 1) are cut back to the previous vertex or prolonged to the next edge,
+ * whichever changes the smaller length, smallest change first; corners (degree 2, inside the
+ * window) are prolonged likewise; crossings inside the window with no free end next to them are
+ * broken into two T-vertices at most `step` apart.  imax: 0 = all (otherwise imax + 1 removals,
+ * as the reference's loop counts).  The lengths (may be null) are what the verbose mode of the
+ * reference prints.  Ids of an earlier export are invalidated. */
+int lite_host_remove_ivertices(lite_host_tess *t, int64_t imax, double *removed_length, double *added_length);
+int lite_host_remove_lvertices(lite_host_tess *t, int64_t imax, double *added_length);
+int lite_host_remove_xvertices(lite_host_tess *t, double step);
+/* free ends, corners inside the window, crossings (LineTes::number_of_xvertices(false, false),
+ * lib/ttessel.cpp:272-278) and the crossings remove_xvertices would break
+ * (number_of_xvertices(true, true)); any pointer may be null */
+int lite_host_vertex_census(lite_host_tess *t, int32_t *n_free_ends, int32_t *n_corners, int32_t *n_crossings,
+                            int32_t *n_crossings_to_remove);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,9 +24,9 @@
  *   - the host model's moves need a single hole-free polygon as window; windows with holes or
  *     of several polygons are read, built by insert_segment, checked, written and evaluated on
  *     the device;
- *   - insert_segment rebuilds the arrangement (handles obtained before are invalidated) and
- *     remove_[ilx]vertices do not exist: an arrangement that is not a T-tessellation can only
- *     be inspected, written and inserted into;
+ *   - insert_segment and remove_[ilx]vertices rebuild the arrangement (handles obtained before
+ *     are invalidated); an arrangement that is not a T-tessellation can be inspected, written,
+ *     inserted into and cleaned, nothing else;
  *   - `rnd` is a CGAL::Random look-alike over std::mt19937_64 (CGAL's stream is
  *     un-vendored and unpinned by the reference);
  *   - AddSplits() samples on the device with a counter-based Philox stream.
@@ -250,6 +250,12 @@ class LineTes {
    * not form a T-tessellation the object can be inspected, written and inserted into. */
   Seg insert_segment(Segment);
   bool is_a_T_tessellation(bool verbose = false, std::ostream &out = std::cout); /* :1307-1329 */
+  /* :982-1296, the passes that make a T-tessellation of an arrangement of segments */
+  void remove_ivertices(Size imax = 0, bool verbose = false);
+  void remove_lvertices(Size imax = 0, bool verbose = false);
+  void remove_xvertices(double step);
+  Size number_of_xvertices(bool exclude_boundaries = false, bool exclude_ineighbours = false); /* :272-278 */
+  double min_edge_length();                                                                    /* :547-557 */
   Size number_of_vertices() const;
   Size number_of_halfedges() const;
   Size number_of_edges() const { return number_of_halfedges() / 2; }

@@ -158,6 +158,37 @@ bool LineTes::is_a_T_tessellation(bool verbose, std::ostream &out) {
   if (impl_->arrangement_only && verbose) out << "not a T-tessellation: " << impl_->not_t_reason << std::endl;
   return !impl_->arrangement_only;
 }
+void LineTes::remove_ivertices(Size imax, bool verbose) {
+  std::string err;
+  lite::CleanStats st;
+  if (!lite::remove_ivertices(*impl_, imax, &st, err)) throw std::domain_error("remove_ivertices: " + err);
+  if (verbose)
+    std::cout << st.n_removed << " I-vertices removed" << std::endl
+              << "removed length " << st.removed_length << std::endl
+              << "added length " << st.added_length << std::endl;
+  touch();
+}
+void LineTes::remove_lvertices(Size imax, bool verbose) {
+  std::string err;
+  lite::CleanStats st;
+  if (!lite::remove_lvertices(*impl_, imax, &st, err)) throw std::domain_error("remove_lvertices: " + err);
+  if (verbose)
+    std::cout << st.n_removed << " L-vertices removed" << std::endl << "added length " << st.added_length << std::endl;
+  touch();
+}
+void LineTes::remove_xvertices(double step) {
+  std::string err;
+  if (!lite::remove_xvertices(*impl_, step, 0, err)) throw std::domain_error("remove_xvertices: " + err);
+  touch();
+}
+Size LineTes::number_of_xvertices(bool exclude_boundaries, bool exclude_ineighbours) {
+  return (Size)lite::count_xvertices(*impl_, exclude_boundaries, exclude_ineighbours);
+}
+double LineTes::min_edge_length() {
+  double m = HUGE_VAL;
+  for (size_t h = 0; h < impl_->h_src.size(); h += 2) if (impl_->h_alive[h]) m = std::fmin(m, impl_->h_len[h]);
+  return m;
+}
 Segment clip_segment_by_polygon(Segment sg, HPolygons w) {
   std::vector<std::vector<double>> bx, by;
   boundaries_of(w, bx, by);
@@ -195,6 +226,20 @@ std::vector<LineTes::Halfedge_handle> LineTes::halfedges() const {
 }
 bool LineTes::is_on_boundary(Halfedge_handle e) const { return impl_->s_bnd[impl_->h_seg[e.id()]] != 0; }
 bool LineTes::is_valid(bool verbose) {
+  if (impl_->arrangement_only) {   // not a T-tessellation: the links of the arrangement only (:284-300)
+    const HostTess &h = *impl_;
+    for (size_t e = 0; e < h.h_src.size(); e++) {
+      if (!h.h_alive[e]) continue;
+      const int n = h.h_next[e], nf = h.h_next_hf[e];
+      const bool ok = n >= 0 && h.h_prev[n] == (int)e && h.h_src[n] == h.h_src[e ^ 1] && h.h_face[n] == h.h_face[e] &&
+                      (nf < 0 || (h.h_prev_hf[nf] == (int)e && h.h_seg[nf] == h.h_seg[e] && h.h_src[nf] == h.h_src[e ^ 1]));
+      if (!ok) {
+        if (verbose) std::clog << "LineTes::is_valid: broken links at halfedge " << e << std::endl;
+        return false;
+      }
+    }
+    return true;
+  }
   std::string e = impl_->check();
   if (!e.empty() && verbose) std::clog << "LineTes::is_valid: " << e << std::endl;
   return e.empty();

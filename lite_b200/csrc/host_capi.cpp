@@ -171,6 +171,45 @@ extern "C" int64_t lite_host_edges(lite_host_tess *h, int64_t cap, double *xy, i
   return n;
 }
 
+extern "C" int lite_host_remove_ivertices(lite_host_tess *h, int64_t imax, double *removed_length, double *added_length) {
+  if (!h || imax < 0) return lite_set_error_(LITE_EINVAL, "bad argument");
+  std::string err;
+  lite::CleanStats st;
+  if (!lite::remove_ivertices(h->t, (size_t)imax, &st, err)) return lite_set_error_(LITE_EINVAL, ("remove_ivertices: " + err).c_str());
+  if (removed_length) *removed_length = st.removed_length;
+  if (added_length) *added_length = st.added_length;
+  remember_ids(h);
+  return 0;
+}
+
+extern "C" int lite_host_remove_lvertices(lite_host_tess *h, int64_t imax, double *added_length) {
+  if (!h || imax < 0) return lite_set_error_(LITE_EINVAL, "bad argument");
+  std::string err;
+  lite::CleanStats st;
+  if (!lite::remove_lvertices(h->t, (size_t)imax, &st, err)) return lite_set_error_(LITE_EINVAL, ("remove_lvertices: " + err).c_str());
+  if (added_length) *added_length = st.added_length;
+  remember_ids(h);
+  return 0;
+}
+
+extern "C" int lite_host_remove_xvertices(lite_host_tess *h, double step) {
+  if (!h) return lite_set_error_(LITE_EINVAL, "null argument");
+  std::string err;
+  if (!lite::remove_xvertices(h->t, step, nullptr, err)) return lite_set_error_(LITE_EINVAL, ("remove_xvertices: " + err).c_str());
+  remember_ids(h);
+  return 0;
+}
+
+extern "C" int lite_host_vertex_census(lite_host_tess *h, int32_t *n_free_ends, int32_t *n_corners, int32_t *n_crossings,
+                                       int32_t *n_crossings_to_remove) {
+  if (!h) return lite_set_error_(LITE_EINVAL, "null argument");
+  if (n_free_ends) *n_free_ends = lite::count_vertices_of_degree(h->t, 1, false);
+  if (n_corners) *n_corners = lite::count_vertices_of_degree(h->t, 2, true);
+  if (n_crossings) *n_crossings = lite::count_xvertices(h->t, false, false);
+  if (n_crossings_to_remove) *n_crossings_to_remove = lite::count_xvertices(h->t, true, true);
+  return 0;
+}
+
 // One SMF chain brought back from the GPU (lite_smf_export, capi.cu) -> host model.
 // Ids are kept; elements on the chain's free lists stay dead.
 extern "C" int lite_smf_blob_to_host_(char *blob, int cap, lite_host_tess **out) {

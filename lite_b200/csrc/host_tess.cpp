@@ -1033,6 +1033,224 @@ bool insert_segment(HostTess &t, const double seg[4], int *seg_id, std::string &
   return true;
 }
 
+// ---------------------------------------------------------------------------
+// LineTes::remove_ivertices / remove_lvertices / remove_xvertices (lib/ttessel.cpp:982-1296):
+// the passes that turn an arrangement of segments into a T-tessellation.  They work on the
+// list of maximal segments -- move one end, drop a segment, break one in two -- and build the
+// arrangement again after every change (same device as insert_segment).
+// ---------------------------------------------------------------------------
+namespace {
+struct Soup {
+  std::vector<std::vector<double>> bx, by, segs;
+  int nw = 0;
+};
+static bool soup_of(const HostTess &t, Soup &S, std::string &err) {
+  S.bx = t.win_bx; S.by = t.win_by;
+  if (S.bx.empty() && !t.win_x.empty()) { S.bx = {t.win_x}; S.by = {t.win_y}; }
+  if (S.bx.empty()) { err = "no window"; return false; }
+  S.nw = 0;
+  for (const auto &b : S.bx) S.nw += (int)b.size();
+  S.segs.clear();
+  for (size_t s = 0; s < t.s_he.size(); s++) {
+    if (!t.s_alive[s] || t.s_bnd[s]) continue;
+    const int a = t.seg_start((int)s), b = t.seg_end((int)s);
+    S.segs.push_back({t.vx[t.h_src[a]], t.vy[t.h_src[a]], t.vx[t.tgt(b)], t.vy[t.tgt(b)]});
+  }
+  return true;
+}
+// after this the segment ids are nw + (index in S.segs)
+static bool rebuild(HostTess &t, const Soup &S, std::string &err) {
+  HostTess nt;
+  std::string strict_err;
+  if (!build_arrangement(nt, S.bx, S.by, S.segs, false, strict_err)) {
+    if (!build_arrangement(nt, S.bx, S.by, S.segs, true, err)) return false;
+    nt.not_t_reason = strict_err;
+  }
+  t = nt;
+  return true;
+}
+struct Around {   // halfedges arriving at each vertex
+  std::vector<std::vector<int>> in;
+  explicit Around(const HostTess &t) : in(t.vx.size()) {
+    for (size_t h = 0; h < t.h_src.size(); h++) if (t.h_alive[h]) in[t.tgt((int)h)].push_back((int)h);
+  }
+  int degree(int v) const { return (int)in[v].size(); }
+};
+// the first edge met when the edge e is prolonged beyond its target (ray_exit_face on the face
+// ahead, lib/ttessel.cpp:1017-1022, precompute_lengthening :3800-3830): distance and point
+static double prolong(const HostTess &t, int e, double &px, double &py) {
+  const int v = t.tgt(e), u = t.h_src[e];
+  const double ox = t.vx[v], oy = t.vy[v];
+  double dx = ox - t.vx[u], dy = oy - t.vy[u];
+  const double dl = sqrt(dx * dx + dy * dy);
+  dx /= dl; dy /= dl;
+  double best = HUGE_VAL;
+  for (size_t h = 0; h < t.h_src.size(); h += 2) {
+    if (!t.h_alive[h] || (int)h == (e & ~1)) continue;
+    const int a = t.h_src[h], b = t.h_src[h ^ 1];
+    if (a == v || b == v) continue;   // edges that leave the vertex itself
+    const double ex = t.vx[b] - t.vx[a], ey = t.vy[b] - t.vy[a];
+    const double den = dx * ey - dy * ex;
+    if (fabs(den) <= 1e-14 * sqrt(ex * ex + ey * ey)) continue;
+    const double tr = ((t.vx[a] - ox) * ey - (t.vy[a] - oy) * ex) / den;
+    const double te = ((t.vx[a] - ox) * dy - (t.vy[a] - oy) * dx) / den;
+    if (tr > 0 && te >= -1e-12 && te <= 1 + 1e-12 && tr < best) {
+      best = tr;
+      const double tc = fmax(0.0, fmin(1.0, te));
+      px = t.vx[a] + tc * ex; py = t.vy[a] + tc * ey;   // on the edge that is hit
+    }
+  }
+  return best;
+}
+// which end of its maximal segment the target of e is (0: the segment's source, 1: its target)
+static int seg_end_at(const HostTess &t, int e) {
+  const int s = t.h_seg[e];
+  return t.h_src[t.seg_start(s)] == t.tgt(e) ? 0 : 1;
+}
+static bool on_window_boundary(const HostTess &t, const Around &A, int v) {
+  for (int h : A.in[v]) if (t.s_bnd[t.h_seg[h]]) return true;
+  return false;
+}
+static bool is_x_vertex(const HostTess &t, const Around &A, int v) {   // :4058-4067
+  if (A.degree(v) != 4) return false;
+  int through = 0;
+  for (int h : A.in[v]) if (t.h_next_hf[h] >= 0 && t.h_src[t.h_next_hf[h]] == v) through++;
+  int sg[4], n = 0;
+  for (int h : A.in[v]) sg[n++] = t.h_seg[h];
+  std::sort(sg, sg + 4);
+  return through == 4 && sg[0] == sg[1] && sg[2] == sg[3] && sg[1] != sg[2];
+}
+static bool selected_x_vertex(const HostTess &t, const Around &A, int v, bool exclude_boundaries, bool exclude_ineighbours) {
+  if (!is_x_vertex(t, A, v)) return false;
+  if (exclude_boundaries && on_window_boundary(t, A, v)) return false;
+  if (exclude_ineighbours)
+    for (int h : A.in[v]) if (A.degree(t.h_src[h]) == 1) return false;   // :4073-4093
+  return true;
+}
+}  // namespace
+
+int count_xvertices(const HostTess &t, bool exclude_boundaries, bool exclude_ineighbours) {
+  Around A(t);
+  int n = 0;
+  for (size_t v = 0; v < t.vx.size(); v++)
+    if (t.v_alive[v] && selected_x_vertex(t, A, (int)v, exclude_boundaries, exclude_ineighbours)) n++;
+  return n;
+}
+
+int count_vertices_of_degree(const HostTess &t, int degree, bool internal_only) {
+  Around A(t);
+  int n = 0;
+  for (size_t v = 0; v < t.vx.size(); v++)
+    if (t.v_alive[v] && A.degree((int)v) == degree && !(internal_only && on_window_boundary(t, A, (int)v))) n++;
+  return n;
+}
+
+bool remove_ivertices(HostTess &t, size_t imax, CleanStats *st, std::string &err) {
+  if (imax == 0) imax = (size_t)-1;
+  Soup S;
+  if (!soup_of(t, S, err) || !rebuild(t, S, err)) return false;
+  CleanStats loc;
+  for (size_t counter = 1;; counter++) {
+    Around A(t);
+    double best = HUGE_VAL, bx = 0, by = 0;
+    int be = -1;
+    bool shorten = false;
+    for (size_t v = 0; v < t.vx.size(); v++) {
+      if (!t.v_alive[v] || A.degree((int)v) != 1) continue;
+      const int e = A.in[v][0];
+      double px = 0, py = 0;
+      const double lm = t.h_len[e], lp = prolong(t, e, px, py);
+      const double changed = lm <= lp ? lm : lp;   // shortening preferred on a tie (:1026-1032)
+      if (changed < best) { best = changed; be = e; shorten = lm <= lp; bx = px; by = py; }
+    }
+    if (be < 0) break;
+    const int k = t.h_seg[be] - S.nw, end = seg_end_at(t, be);
+    if (shorten) {
+      if (t.s_nedges[t.h_seg[be]] == 1) S.segs.erase(S.segs.begin() + k);
+      else { S.segs[k][2 * end] = t.vx[t.h_src[be]]; S.segs[k][2 * end + 1] = t.vy[t.h_src[be]]; }
+      loc.removed_length += best;
+    } else {
+      S.segs[k][2 * end] = bx; S.segs[k][2 * end + 1] = by;
+      loc.added_length += best;
+    }
+    loc.n_removed++;
+    if (!rebuild(t, S, err)) return false;
+    if (counter > imax) break;   // as written (:1068-1078): imax + 1 removals
+  }
+  if (st) *st = loc;
+  return true;
+}
+
+bool remove_lvertices(HostTess &t, size_t imax, CleanStats *st, std::string &err) {
+  if (imax == 0) imax = (size_t)-1;
+  Soup S;
+  if (!soup_of(t, S, err) || !rebuild(t, S, err)) return false;
+  CleanStats loc;
+  for (size_t counter = 1;; counter++) {
+    Around A(t);
+    double best = HUGE_VAL, bx = 0, by = 0;
+    int be = -1;
+    for (size_t v = 0; v < t.vx.size(); v++) {
+      if (!t.v_alive[v] || A.degree((int)v) != 2 || on_window_boundary(t, A, (int)v)) continue;
+      const int e1 = A.in[v][0], e2 = A.in[v][1];
+      // two aligned edges are one line broken at a vertex, not a corner
+      const double ux = t.vx[v] - t.vx[t.h_src[e1]], uy = t.vy[v] - t.vy[t.h_src[e1]];
+      const double wx = t.vx[v] - t.vx[t.h_src[e2]], wy = t.vy[v] - t.vy[t.h_src[e2]];
+      if (fabs(ux * wy - uy * wx) <= 1e-12 * t.h_len[e1] * t.h_len[e2]) continue;
+      double p1x = 0, p1y = 0, p2x = 0, p2y = 0;
+      const double l1 = prolong(t, e1, p1x, p1y), l2 = prolong(t, e2, p2x, p2y);
+      const bool first = l1 < l2;   // compare_ivertices (:1135)
+      const double l = first ? l1 : l2;
+      if (l < best) { best = l; be = first ? e1 : e2; bx = first ? p1x : p2x; by = first ? p1y : p2y; }
+    }
+    if (be < 0 || best == HUGE_VAL) break;
+    const int k = t.h_seg[be] - S.nw, end = seg_end_at(t, be);
+    S.segs[k][2 * end] = bx; S.segs[k][2 * end + 1] = by;
+    loc.added_length += best;
+    loc.n_removed++;
+    if (!rebuild(t, S, err)) return false;
+    if (counter > imax) break;
+  }
+  if (st) *st = loc;
+  return true;
+}
+
+bool remove_xvertices(HostTess &t, double step, CleanStats *st, std::string &err) {
+  if (!(step > 0)) { err = "the step must be positive"; return false; }
+  Soup S;
+  if (!soup_of(t, S, err) || !rebuild(t, S, err)) return false;
+  CleanStats loc;
+  for (int guard = 0;; guard++) {
+    if (guard > 100000) { err = "remove_xvertices does not terminate"; return false; }
+    Around A(t);
+    int v = -1;
+    for (size_t u = 0; u < t.vx.size() && v < 0; u++)
+      if (t.v_alive[u] && selected_x_vertex(t, A, (int)u, true, true)) v = (int)u;
+    if (v < 0) break;
+    // the segment that is broken: the one with the smaller id; curr arrives at v along its direction
+    int curr = -1;
+    for (int h : A.in[v])
+      if (t.h_dir[h] && (curr < 0 || t.h_seg[h] < t.h_seg[curr])) curr = h;
+    const int s = t.h_seg[curr], k = s - S.nw;
+    const int other = t.h_next[curr] ^ 1;   // the next halfedge arriving at v, clockwise: on the other segment
+    double mel = HUGE_VAL;                   // min_edge_length (:547-557)
+    for (size_t h = 0; h < t.h_src.size(); h += 2) if (t.h_alive[h]) mel = fmin(mel, t.h_len[h]);
+    const double eps = fmin(step, 0.9 * mel);
+    const int q = t.h_src[other];
+    const double ex = t.vx[v] + eps * (t.vx[q] - t.vx[v]) / t.h_len[other];
+    const double ey = t.vy[v] + eps * (t.vy[q] - t.vy[v]) / t.h_len[other];
+    // the first half, from the segment's source, now ends on the other segment a little aside
+    // of the crossing; the second half starts at the crossing (:1233-1252)
+    const std::vector<double> half = {S.segs[k][0], S.segs[k][1], ex, ey};
+    S.segs[k][0] = t.vx[v]; S.segs[k][1] = t.vy[v];
+    S.segs.push_back(half);
+    loc.n_removed++;
+    if (!rebuild(t, S, err)) return false;
+  }
+  if (st) *st = loc;
+  return true;
+}
+
 static bool parse_ratio(const std::string &tok, double &out) {
   size_t sl = tok.find('/');
   std::string num = tok.substr(0, sl), den = sl == std::string::npos ? "1" : tok.substr(sl + 1);

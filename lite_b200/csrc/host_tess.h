@@ -175,6 +175,21 @@ bool clip_segment(const std::vector<std::vector<double>> &bx, const std::vector<
 // Every handle into t is invalidated (the arrangement is rebuilt).
 bool insert_segment(HostTess &t, const double seg[4], int *seg_id, std::string &err);
 
+// LineTes::remove_ivertices / remove_lvertices / remove_xvertices (lib/ttessel.cpp:982-1296) on the
+// arrangement a sequence of insert_segment calls left: free ends are cut back or prolonged to the
+// next edge (whichever changes the smaller length, smallest change first), corners are prolonged,
+// crossings are broken into two T-vertices `step` apart.  imax as in the reference (0: all).
+struct CleanStats {
+  int n_removed = 0;
+  double removed_length = 0, added_length = 0;
+};
+bool remove_ivertices(HostTess &t, size_t imax, CleanStats *st, std::string &err);
+bool remove_lvertices(HostTess &t, size_t imax, CleanStats *st, std::string &err);
+bool remove_xvertices(HostTess &t, double step, CleanStats *st, std::string &err);
+// LineTes::number_of_xvertices (:272-278); vertices of a given degree (1: free ends)
+int count_xvertices(const HostTess &t, bool exclude_boundaries, bool exclude_ineighbours);
+int count_vertices_of_degree(const HostTess &t, int degree, bool internal_only);
+
 // LineTes::read / write text format (lib/ttessel.cpp:1331-1441), double precision
 bool read_text(HostTess &t, const std::string &text, std::string &err);
 std::string write_text(const HostTess &t);

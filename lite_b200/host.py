@@ -13,7 +13,8 @@ HOST_SYMBOLS = [
     "lite_host_crtt_run", "lite_host_update_split", "lite_host_update_merge",
     "lite_host_update_flip", "lite_host_counts", "lite_host_check", "lite_host_export",
     "lite_host_write_text", "lite_host_clip_segment", "lite_host_insert_segment",
-    "lite_host_is_t_tessellation", "lite_host_edges",
+    "lite_host_is_t_tessellation", "lite_host_edges", "lite_host_remove_ivertices",
+    "lite_host_remove_lvertices", "lite_host_remove_xvertices", "lite_host_vertex_census",
 ]
 
 _COUNT_OF = dict(vx="n_vertices", vy="n_vertices", he_src="n_halfedges", he_twin="n_halfedges",
@@ -45,6 +46,10 @@ def _lib():
         L.lite_host_is_t_tessellation.argtypes = [C.c_void_p]
         L.lite_host_edges.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.lite_host_edges.restype = C.c_int64
+        L.lite_host_remove_ivertices.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.lite_host_remove_lvertices.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_double)]
+        L.lite_host_remove_xvertices.argtypes = [C.c_void_p, C.c_double]
+        L.lite_host_vertex_census.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
         L._host_ready = True
     return L
 
@@ -134,6 +139,28 @@ class HostTess:
         self.L.lite_host_edges(self.h, n, xy.ctypes.data_as(C.c_void_p), seg.ctypes.data_as(C.c_void_p),
                                nx.ctypes.data_as(C.c_void_p), pv.ctypes.data_as(C.c_void_p))
         return xy, seg, nx, pv
+
+    def remove_ivertices(self, imax=0):
+        """LineTes::remove_ivertices (lib/ttessel.cpp:982-1086); returns (removed, added) length."""
+        a, b = C.c_double(), C.c_double()
+        _ck(self.L, self.L.lite_host_remove_ivertices(self.h, int(imax), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def remove_lvertices(self, imax=0):
+        """LineTes::remove_lvertices (lib/ttessel.cpp:1088-1179); returns the added length."""
+        a = C.c_double()
+        _ck(self.L, self.L.lite_host_remove_lvertices(self.h, int(imax), C.byref(a)))
+        return a.value
+
+    def remove_xvertices(self, step):
+        """LineTes::remove_xvertices (lib/ttessel.cpp:1181-1296)."""
+        _ck(self.L, self.L.lite_host_remove_xvertices(self.h, float(step)))
+
+    def vertex_census(self):
+        """(free ends, corners inside the window, crossings, crossings remove_xvertices would break)"""
+        v = [C.c_int32() for _ in range(4)]
+        _ck(self.L, self.L.lite_host_vertex_census(self.h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
 
     def write_text(self):
         n = self.L.lite_host_write_text(self.h, None, 0)

@@ -213,6 +213,50 @@ static void test_insert_segment() {
   delete rnd;
 }
 
+// tests/check_lite.cpp:626-669 (its update(Split) on the holed window is the segment the split adds)
+static void test_remove_ivertices() {
+  HPolygons dom = holed_polygons();
+  TTessel tesl;
+  tesl.insert_window(dom);
+  tesl.insert_segment(Segment(Point2(5, 3), Point2(5, 9)));
+  tesl.remove_ivertices();
+  LineTes::Halfedge_handle e = find_halfedge(tesl, Point2(5, 2.5), Point2(5, 9.5));
+  CHECK(e != NULL_HALFEDGE_HANDLE);
+  CHECK(e->get_next_hf() == NULL_HALFEDGE_HANDLE);
+  CHECK(e->get_prev_hf() == NULL_HALFEDGE_HANDLE);
+  tesl.clear();
+  tesl.insert_window(dom);
+  tesl.insert_segment(Segment(Point2(0, 7.5), Point2(10.25, 7.5)));
+  tesl.insert_segment(Segment(Point2(8.5, 15), Point2(8.5, 7)));
+  CHECK(find_halfedge(tesl, Point2(8.5, 7), Point2(8.5, 7.5)) != NULL_HALFEDGE_HANDLE);
+  tesl.remove_ivertices();
+  CHECK(find_halfedge(tesl, Point2(8.5, 7.5), Point2(8.5, 7)) == NULL_HALFEDGE_HANDLE);
+  CHECK(tesl.is_a_T_tessellation());
+}
+// tests/check_lite.cpp:1051-1127
+static void test_remove_xvertices() {
+  LineTes tes;
+  tes.insert_window(Rectangle(Point2(0, 0), Point2(4, 4)));
+  tes.insert_segment(Segment(Point2(2, 0), Point2(2, 4)));
+  tes.insert_segment(Segment(Point2(0, 2), Point2(4, 2)));
+  tes.insert_segment(Segment(Point2(0, 1), Point2(2, 1)));
+  tes.insert_segment(Segment(Point2(1, 0), Point2(1, 2)));
+  CHECK(tes.number_of_xvertices(true, true) == 2);
+  tes.remove_xvertices(0.1);
+  CHECK(tes.number_of_xvertices(true, true) == 0);
+  CHECK(tes.is_valid(true));
+  LineTes rec;
+  rec.insert_window(Rectangle(Point2(0, 0), Point2(8, 8)));
+  const double c[][4] = {{4, 0, 4, 8}, {0, 4, 8, 4}, {0, 2, 2, 2}, {2, 2, 2, 0}, {1, 3.9, 1, 1}, {1, 1, 3.9, 1},
+                         {0, 6, 2, 6}, {2, 6, 2, 8}, {1, 4.1, 1, 7}, {1, 7, 3.9, 7}, {4.1, 7, 7, 7}, {7, 7, 7, 4.1},
+                         {6, 8, 6, 6}, {6, 6, 8, 6}, {4.1, 1, 7, 1}, {7, 1, 7, 3.9}, {6, 0, 6, 2}, {6, 2, 8, 2}};
+  for (int i = 0; i < 18; i++) rec.insert_segment(Segment(Point2(c[i][0], c[i][1]), Point2(c[i][2], c[i][3])));
+  CHECK(rec.number_of_xvertices(true, true) == 1);
+  rec.remove_xvertices(2);
+  CHECK(rec.number_of_xvertices(true, true) == 0);
+  CHECK(rec.is_valid(true));
+}
+
 static void test_catvector_and_energy_registry() {
   CatVector a, b;
   a.edges.push_back(1); a.faces.push_back(2); a.faces.push_back(3); a.segs.push_back(4);
@@ -468,6 +512,8 @@ int main(int argc, char **argv) {
     test_text_roundtrip(argc > 2 ? argv[2] : "tests/golden/tessellation_data.txt");
     test_clip_segment();
     test_insert_segment();
+    test_remove_ivertices();
+    test_remove_xvertices();
     test_catvector_and_energy_registry();
     test_unknown_feature_is_refused();
     test_host_features();

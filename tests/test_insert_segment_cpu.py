@@ -163,3 +163,94 @@ def test_general_arrangements():
         g.update_split(0, 0.5, 1.0)
     with pytest.raises(LiteError, match="does not hit"):
         g.insert_segment([5, 5, 6, 6])
+
+
+def test_remove_ivertices_known_answers():
+    """check_lite.cpp:626-669: a segment with both ends free, close to the boundaries, is
+    prolonged at both ends (outer boundary below, hole above); a short free end past a
+    crossing is cut back."""
+    h = lite_b200.HostTess(text=window_text(holed_polygons()))
+    h.insert_segment([5, 3, 5, 9])
+    assert h.vertex_census()[0] == 2
+    removed, added = h.remove_ivertices()
+    assert (removed, added) == (0.0, pytest.approx(1.0, rel=1e-12))
+    e = find_halfedge(h, (5, 2.5), (5, 9.5))
+    assert e is not None and e[2] == -1 and e[3] == -1
+    assert h.is_t_tessellation()
+    h.check()
+    # the test's Split((0,15)->(0,0), 0.5, pi/2) is the segment (0,7.5)-(10.25,7.5)
+    g = lite_b200.HostTess(text=window_text(holed_polygons()))
+    g.insert_segment([0, 7.5, 10.25, 7.5])
+    assert g.is_t_tessellation()
+    g.insert_segment([8.5, 15, 8.5, 7])
+    assert find_halfedge(g, (8.5, 7), (8.5, 7.5)) is not None
+    assert g.vertex_census()[:3] == (1, 0, 1)
+    removed, added = g.remove_ivertices()
+    assert (removed, added) == (0.5, 0.0)
+    assert find_halfedge(g, (8.5, 7.5), (8.5, 7)) is None
+    assert g.is_t_tessellation() and g.vertex_census() == (0, 0, 0, 0)
+    g.check()
+
+
+def test_remove_xvertices_known_answers():
+    """check_lite.cpp:1051-1074: two crossings inside the window; none left afterwards."""
+    h = lite_b200.HostTess((0, 0, 4, 4))
+    for s in ([2, 0, 2, 4], [0, 2, 4, 2], [0, 1, 2, 1], [1, 0, 1, 2]):
+        h.insert_segment(s)
+    assert h.vertex_census()[3] == 2
+    h.remove_xvertices(0.1)
+    assert h.vertex_census()[3] == 0
+    # breaking the segment (2,0)-(2,4) moved the half on which (0,1)-(2,1) ended: that one now
+    # crosses it with a free end next to the crossing ("this procedure can generate new
+    # I-vertices", lib/ttessel.cpp:1193), which remove_ivertices takes away
+    assert h.vertex_census()[:3] == (1, 0, 1)
+    h.remove_ivertices()
+    assert h.vertex_census() == (0, 0, 0, 0) and h.is_t_tessellation()
+    h.check()
+    assert sum(h.counts()[1:]) == 6   # four segments, two of them broken in two
+
+
+def test_remove_xvertices_recursion_known_answers():
+    """check_lite.cpp:1076-1127: one crossing to remove (the others have a free end next to them);
+    none left after remove_xvertices(2)."""
+    h = lite_b200.HostTess((0, 0, 8, 8))
+    segs = [[4, 0, 4, 8], [0, 4, 8, 4], [0, 2, 2, 2], [2, 2, 2, 0], [1, 3.9, 1, 1], [1, 1, 3.9, 1],
+            [0, 6, 2, 6], [2, 6, 2, 8], [1, 4.1, 1, 7], [1, 7, 3.9, 7], [4.1, 7, 7, 7], [7, 7, 7, 4.1],
+            [6, 8, 6, 6], [6, 6, 8, 6], [4.1, 1, 7, 1], [7, 1, 7, 3.9], [6, 0, 6, 2], [6, 2, 8, 2]]
+    for s in segs:
+        h.insert_segment(s)
+    assert h.vertex_census()[3] == 1
+    h.remove_xvertices(2)
+    assert h.vertex_census()[3] == 0
+    # the arrangement still holds together: every halfedge of a segment chain is linked both ways
+    xy, seg, nx, pv = h.edges()
+    for k in range(len(xy)):
+        if nx[k] >= 0:
+            assert pv[nx[k]] == k and seg[nx[k]] == seg[k] and np.array_equal(xy[nx[k]][:2], xy[k][2:])
+
+
+def test_cleaning_a_random_line_pattern_gives_a_t_tessellation():
+    """The use the three passes are made for (docfiles of the reference, RLiTe's cleaning
+    pipeline): random segments in a window -> crossings broken, free ends and corners removed ->
+    a T-tessellation the device path accepts."""
+    rng = np.random.default_rng(8)
+    h = lite_b200.HostTess((0, 0, 1, 1))
+    for _ in range(25):
+        c = rng.uniform(0.05, 0.95, 2)
+        a = rng.uniform(0, np.pi)
+        l = rng.uniform(0.1, 0.5)
+        d = 0.5 * l * np.array([np.cos(a), np.sin(a)])
+        h.insert_segment([*(c - d), *(c + d)])
+    free, corners, cross, todo = h.vertex_census()
+    assert free > 20 and cross > 5 and not h.is_t_tessellation()
+    for _ in range(20):
+        h.remove_xvertices(0.01)
+        h.remove_ivertices()
+        h.remove_lvertices()
+        if h.is_t_tessellation():
+            break
+    assert h.vertex_census() == (0, 0, 0, 0)
+    assert h.is_t_tessellation()
+    h.check()
+    s = h.export()
+    assert h.counts()[0] == int(np.sum(s.a["face_inside"])) > 5
