@@ -1150,7 +1150,9 @@ bool remove_ivertices(HostTess &t, size_t imax, CleanStats *st, std::string &err
   Soup S;
   if (!soup_of(t, S, err) || !rebuild(t, S, err)) return false;
   CleanStats loc;
+  const size_t guard = 8 * (t.h_src.size() + 16);   // every removal takes a free end away for good
   for (size_t counter = 1;; counter++) {
+    if (counter > guard) { err = "remove_ivertices does not terminate (a prolonged end did not land on its edge)"; return false; }
     Around A(t);
     double best = HUGE_VAL, bx = 0, by = 0;
     int be = -1;
@@ -1186,7 +1188,9 @@ bool remove_lvertices(HostTess &t, size_t imax, CleanStats *st, std::string &err
   Soup S;
   if (!soup_of(t, S, err) || !rebuild(t, S, err)) return false;
   CleanStats loc;
+  const size_t guard = 8 * (t.h_src.size() + 16);
   for (size_t counter = 1;; counter++) {
+    if (counter > guard) { err = "remove_lvertices does not terminate (a prolonged end did not land on its edge)"; return false; }
     Around A(t);
     double best = HUGE_VAL, bx = 0, by = 0;
     int be = -1;
@@ -1235,7 +1239,17 @@ bool remove_xvertices(HostTess &t, double step, CleanStats *st, std::string &err
     const int other = t.h_next[curr] ^ 1;   // the next halfedge arriving at v, clockwise: on the other segment
     double mel = HUGE_VAL;                   // min_edge_length (:547-557)
     for (size_t h = 0; h < t.h_src.size(); h += 2) if (t.h_alive[h]) mel = fmin(mel, t.h_len[h]);
-    const double eps = fmin(step, 0.9 * mel);
+    double eps = fmin(step, 0.9 * mel);
+    // in doubles two ends closer than the builder's tolerance are one vertex: where the shortest
+    // edge is that small the end is moved by half of the edge it moves along instead
+    double xmin = HUGE_VAL, xmax = -HUGE_VAL, ymin = HUGE_VAL, ymax = -HUGE_VAL;
+    for (size_t b = 0; b < S.bx.size(); b++)
+      for (size_t i = 0; i < S.bx[b].size(); i++) {
+        xmin = fmin(xmin, S.bx[b][i]); xmax = fmax(xmax, S.bx[b][i]); ymin = fmin(ymin, S.by[b][i]); ymax = fmax(ymax, S.by[b][i]);
+      }
+    const double tol = 1e-7 * fmax(xmax - xmin, ymax - ymin);
+    if (eps < tol) eps = fmin(step, 0.5 * t.h_len[other]);
+    if (eps < tol) { err = "remove_xvertices: a crossing lies closer to its neighbours than the coordinates resolve"; return false; }
     const int q = t.h_src[other];
     const double ex = t.vx[v] + eps * (t.vx[q] - t.vx[v]) / t.h_len[other];
     const double ey = t.vy[v] + eps * (t.vy[q] - t.vy[v]) / t.h_len[other];
