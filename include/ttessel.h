@@ -169,6 +169,8 @@ class LineTes {
     const Vertex_handle *operator->() const { return this; }
     Point2 point() const;
     Size degree() const;
+    std::vector<Halfedge_handle> incident_halfedges() const;  /* arriving at the vertex, clockwise */
+    const LineTes *tess() const { return t_; }
     int id() const { return id_; }
     bool operator==(const Vertex_handle &o) const { return id_ == o.id_ && t_ == o.t_; }
     bool operator!=(const Vertex_handle &o) const { return !(*this == o); }
@@ -184,6 +186,8 @@ class LineTes {
     bool data() const;          /* true for faces inside the window (:125-127) */
     bool is_unbounded() const { return !data(); }
     Halfedge_handle outer_ccb() const;
+    std::vector<Halfedge_handle> holes() const;  /* one halfedge of each inner boundary */
+    const LineTes *tess() const { return t_; }
     int id() const { return id_; }
     bool operator==(const Face_handle &o) const { return id_ == o.id_ && t_ == o.t_; }
     bool operator!=(const Face_handle &o) const { return !(*this == o); }
@@ -256,6 +260,14 @@ class LineTes {
   void remove_xvertices(double step);
   Size number_of_xvertices(bool exclude_boundaries = false, bool exclude_ineighbours = false); /* :272-278 */
   double min_edge_length();                                                                    /* :547-557 */
+  Size number_of_internal_segments();   /* :256-262 */
+  Size number_of_window_edges();        /* :521-530 */
+  double get_window_perimeter();        /* :533-544 */
+  typedef std::vector<Seg> Seg_list;    /* every segment, window sides first (container order) */
+  typedef Seg_list::const_iterator Seg_list_iterator;
+  Seg_list_iterator segments_begin();
+  Seg_list_iterator segments_end();
+  bool is_on_boundary(Seg) const;
   Size number_of_vertices() const;
   Size number_of_halfedges() const;
   Size number_of_edges() const { return number_of_halfedges() / 2; }
@@ -270,11 +282,14 @@ class LineTes {
   void print_all_segments() const;
   unsigned long version() const { return version_; }
   lite::HostTess *host() const { return impl_; }
+  std::vector<Vertex_handle> vertices() const;
+  std::vector<Face_handle> faces() const;   /* the unbounded face included */
 
  protected:
   lite::HostTess *impl_;
   HPolygons window_;
   unsigned long version_;
+  Seg_list seg_cache_;
   void touch() { version_++; }
 };
 
@@ -373,6 +388,13 @@ class TTessel : public LineTes {
   Size number_of_blocking_segments();
   Size number_of_non_blocking_segments();
   double get_total_internal_length();
+  inline double total_internal_length() { return get_total_internal_length(); }   /* :788 */
+  /* :1932-2010, draws from the global `rnd` */
+  Halfedge_handle random_halfedge();
+  Halfedge_handle length_weighted_random_halfedge();
+  Halfedge_handle alt_length_weighted_random_halfedge();
+  std::vector<Halfedge_handle> alt_length_weighted_random_halfedge(unsigned int);
+  void printRCALI(std::ostream &);   /* :2012-2060, the format califlopp reads */
   bool is_valid(bool verbose = false);
   void print_blocking_segments();
   void print_non_blocking_segments();
@@ -591,6 +613,28 @@ double face_sum_of_angles(HPolygon, TTessel *);
 double min_angle(HPolygon, TTessel *);
 double segment_size_2(std::vector<Point2>, TTessel *);
 double angle_between_vectors(double v1x, double v1y, double v2x, double v2y);
+
+/* ---- helpers of the reference header (:1319-1370) --------------------------- */
+bool are_aligned(Point2 p, Point2 q, Point2 r, bool verbose = false);          /* :3556-3577 */
+bool is_inside(Point2, HPolygon &);                                              /* :3583-3598: strictly inside */
+bool is_inside(Point2, HPolygons &);
+Segment clip_segment_by_convex_polygon(Segment, Polygon);                        /* :3620-3641 */
+LineTes::Halfedge_handle find_halfedge(LineTes &, Point2, Point2);               /* :3955-3969: exact end points */
+bool is_a_T_vertex(LineTes::Vertex_handle, bool verbose = false);                /* :4002-4046 */
+bool is_an_X_vertex(LineTes::Vertex_handle);                                     /* :4058-4067 */
+bool has_an_I_vertex_neighbour(LineTes::Vertex_handle);                          /* :4073-4081 */
+bool is_an_irreducible_X_vertex(LineTes::Vertex_handle);                         /* :4087-4091 */
+unsigned long int number_of_internal_vertices(TTessel &);                        /* :4105-4115 */
+HPolygon face2poly(TTessel::Face_handle, bool simplify = true);                  /* :4314-4336 */
+double sum_of_faces_squared_areas(TTessel *);                                    /* :4372-4382 */
+double sum_of_min_angles(TTessel *);                                             /* :4387-4397 */
+double sum_of_angles_obt(TTessel *);                                             /* :4402-4412 */
+double sum_of_segment_squared_sizes(TTessel *);                                  /* :4440-4445 */
+Polygons boundaries(HPolygon);                                                   /* :4453-4469 */
+Polygon simplify(Polygon);                                                       /* :4474-4492 */
+HPolygon simplify(HPolygon);                                                     /* :4495-4506 */
+bool has_holes(LineTes::Face_handle &);                                          /* :4972-4974 */
+bool has_holes(HPolygon &);                                                      /* :4980-4982 */
 /* EXTENSION (not in the reference): length of internal edges, the evident intent
  * of edge_length's doc comment */
 double edge_length_internal(Segment, TTessel *);

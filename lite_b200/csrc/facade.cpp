@@ -64,6 +64,29 @@ Size LineTes::Vertex_handle::degree() const {
   do { n++; e = h.h_next[e] ^ 1; } while (e != h0);
   return n;
 }
+std::vector<LineTes::Halfedge_handle> LineTes::Vertex_handle::incident_halfedges() const {
+  const HostTess &h = *t_->impl_;
+  std::vector<Halfedge_handle> r;
+  int h0 = h.v_inc[id_], e = h0;
+  do { r.push_back(Halfedge_handle(t_, e)); e = h.h_next[e] ^ 1; } while (e != h0);
+  return r;
+}
+std::vector<LineTes::Halfedge_handle> LineTes::Face_handle::holes() const {
+  // inner boundaries: halfedges that carry the face's id and are not on its outer boundary
+  const HostTess &h = *t_->impl_;
+  std::vector<Halfedge_handle> r;
+  if (!h.has_holes) return r;
+  std::vector<char> seen(h.h_src.size(), 0);
+  int e = h.f_he[id_];
+  do { seen[e] = 1; e = h.h_next[e]; } while (e != h.f_he[id_]);
+  for (size_t k = 0; k < h.h_src.size(); k++) {
+    if (!h.h_alive[k] || seen[k] || h.h_face[k] != id_) continue;
+    r.push_back(Halfedge_handle(t_, (int)k));
+    int q = (int)k;
+    do { seen[q] = 1; q = h.h_next[q]; } while (q != (int)k);
+  }
+  return r;
+}
 bool LineTes::Face_handle::data() const { return t_->impl_->f_inside[id_] != 0; }
 LineTes::Halfedge_handle LineTes::Face_handle::outer_ccb() const { return Halfedge_handle(t_, t_->impl_->f_he[id_]); }
 LineTes::Vertex_handle LineTes::Halfedge_handle::source() const { return Vertex_handle(t_, t_->impl_->h_src[id_]); }
@@ -202,6 +225,45 @@ Segment clip_segment_by_polygon(Segment sg, HPolygons w) {
 Segment clip_segment_by_polygon(Segment sg, HPolygon w) { return clip_segment_by_polygon(sg, HPolygons(1, w)); }
 Segment clip_segment_by_polygon(Segment sg, Polygon w) { return clip_segment_by_polygon(sg, HPolygons(1, HPolygon(w))); }
 
+Size LineTes::number_of_internal_segments() {
+  Size n = 0;
+  for (size_t i = 0; i < impl_->s_alive.size(); i++) n += impl_->s_alive[i] && !impl_->s_bnd[i];
+  return n;
+}
+Size LineTes::number_of_window_edges() {
+  Size n = 0;
+  for (size_t i = 0; i < window_.size(); i++) {
+    Polygons b = boundaries(window_[i]);
+    for (size_t k = 0; k < b.size(); k++) n += b[k].size();
+  }
+  return n;
+}
+double LineTes::get_window_perimeter() {
+  double per = 0;
+  for (size_t i = 0; i < window_.size(); i++) {
+    Polygons b = boundaries(window_[i]);
+    for (size_t k = 0; k < b.size(); k++)
+      for (Size j = 0; j < b[k].size(); j++) per += sqrt(Segment(b[k][j], b[k][(j + 1) % b[k].size()]).squared_length());
+  }
+  return per;
+}
+LineTes::Seg_list_iterator LineTes::segments_begin() {
+  seg_cache_.clear();
+  for (size_t i = 0; i < impl_->s_alive.size(); i++) if (impl_->s_alive[i]) seg_cache_.push_back(Seg(this, (int)i));
+  return seg_cache_.begin();
+}
+LineTes::Seg_list_iterator LineTes::segments_end() { return seg_cache_.end(); }
+bool LineTes::is_on_boundary(Seg s) const { return impl_->s_bnd[s.id()] != 0; }
+std::vector<LineTes::Vertex_handle> LineTes::vertices() const {
+  std::vector<Vertex_handle> r;
+  for (size_t i = 0; i < impl_->v_alive.size(); i++) if (impl_->v_alive[i]) r.push_back(Vertex_handle(this, (int)i));
+  return r;
+}
+std::vector<LineTes::Face_handle> LineTes::faces() const {
+  std::vector<Face_handle> r;
+  for (size_t i = 0; i < impl_->f_alive.size(); i++) if (impl_->f_alive[i]) r.push_back(Face_handle(this, (int)i));
+  return r;
+}
 Size LineTes::number_of_vertices() const {
   Size n = 0;
   for (size_t i = 0; i < impl_->v_alive.size(); i++) n += impl_->v_alive[i];
@@ -329,6 +391,70 @@ static Polygon face_polygon(const HostTess &h, int f, bool simplify) {  // face2
     e = h.h_next[e];
   } while (e != h0);
   return p;
+}
+// ---- random halfedges (lib/ttessel.cpp:1932-2010), from the global `rnd` ----
+TTessel::Halfedge_handle TTessel::random_halfedge() {
+  std::vector<Halfedge_handle> hs = halfedges();
+  for (;;) {
+    Halfedge_handle e = hs[(size_t)the_rnd().get_int(0, (int)hs.size())];
+    if (e->face()->data()) return e;
+  }
+}
+TTessel::Halfedge_handle TTessel::length_weighted_random_halfedge() {  // rejection, :1932-1946
+  const double til = total_internal_length();
+  for (;;) {
+    Halfedge_handle e = random_halfedge();
+    if (the_rnd().get_double(0, til) < e->get_length()) return e;
+  }
+}
+TTessel::Halfedge_handle TTessel::alt_length_weighted_random_halfedge() {  // :1948-1966
+  const double select = the_rnd().get_double(0, total_internal_length());
+  double cumlen = 0;
+  const HostTess &h = *impl_;
+  for (size_t e = 0; e < h.h_src.size(); e++) {
+    if (!h.h_alive[e] || !h.f_inside[h.h_face[e]]) continue;
+    cumlen += h.h_len[e];
+    if (cumlen > select) return Halfedge_handle(this, (int)e);
+  }
+  return Halfedge_handle();
+}
+std::vector<TTessel::Halfedge_handle> TTessel::alt_length_weighted_random_halfedge(unsigned int n) {  // :1968-1991
+  const double til = total_internal_length();
+  std::vector<double> select(n);
+  for (unsigned int i = 0; i != n; i++) select[i] = the_rnd().get_double(0, til);
+  std::sort(select.begin(), select.end(), std::greater<double>());
+  std::vector<Halfedge_handle> res;
+  double cumlen = 0;
+  const HostTess &h = *impl_;
+  for (size_t e = 0; e < h.h_src.size() && !select.empty(); e++) {
+    if (!h.h_alive[e] || !h.f_inside[h.h_face[e]]) continue;
+    cumlen += h.h_len[e];
+    while (!select.empty() && cumlen > select.back()) { res.push_back(Halfedge_handle(this, (int)e)); select.pop_back(); }
+  }
+  return res;
+}
+void TTessel::printRCALI(std::ostream &out) {  // :2012-2060
+  const HostTess &h = *impl_;
+  out << impl_->n_cells() << std::endl;
+  int counter = 0;
+  for (size_t f = 0; f < h.f_alive.size(); f++) {
+    if (!h.f_alive[f] || !h.f_inside[f]) continue;
+    counter++;
+    // the corners after the first halfedge's target, which is always printed (as written)
+    std::vector<int> vs;
+    int e0 = h.f_he[f], e = e0, corners = 0;
+    do {
+      const bool corner = h.h_next_hf[e] < 0 || h.h_next_hf[e] != h.h_next[e];
+      if (corner) corners++;
+      if (e == e0 || corner) vs.push_back(h.h_src[e ^ 1]);
+      e = h.h_next[e];
+    } while (e != e0);
+    out << counter << " " << counter << " " << corners << std::endl;
+    for (size_t k = 0; k < vs.size(); k++) out << (k ? " " : "") << h.vx[vs[k]];
+    out << std::endl;
+    for (size_t k = 0; k < vs.size(); k++) out << (k ? " " : "") << h.vy[vs[k]];
+    out << std::endl;
+  }
 }
 HPolygons TTessel::all_faces() {
   HPolygons r;
@@ -722,6 +848,144 @@ static bool on_seg(const Point2 &p, const Point2 &a, const Point2 &b, double tol
   double t = ((p.x() - a.x()) * ex + (p.y() - a.y()) * ey) / l;
   return t >= -tol && t <= l + tol;
 }
+// ---- helpers of the reference header ----
+bool are_aligned(Point2 p, Point2 q, Point2 r, bool verbose) {  // :3556-3577
+  const double cr = (q.x() - p.x()) * (r.y() - p.y()) - (q.y() - p.y()) * (r.x() - p.x());
+  if (cr != 0.0) { if (verbose) std::clog << "are_aligned function: points are not collinear" << std::endl; return false; }
+  if (p == q || q == r) { if (verbose) std::clog << "are_aligned function: the intermediate point is equal to an end point" << std::endl; return false; }
+  if ((p.x() - q.x()) * (r.x() - q.x()) + (p.y() - q.y()) * (r.y() - q.y()) > 0) {
+    if (verbose) std::clog << "are_aligned function: the intermediate point is not between the end points" << std::endl;
+    return false;
+  }
+  return true;
+}
+// +1 strictly inside, 0 on the boundary, -1 outside (CGAL::bounded_side_2)
+static int bounded_side(const Polygon &poly, const Point2 &pt) {
+  bool in = false;
+  const Size n = poly.size();
+  for (Size i = 0; i < n; i++) {
+    const Point2 &a = poly[i], &b = poly[(i + 1) % n];
+    const double cr = (b.x() - a.x()) * (pt.y() - a.y()) - (b.y() - a.y()) * (pt.x() - a.x());
+    if (cr == 0.0 && std::min(a.x(), b.x()) <= pt.x() && pt.x() <= std::max(a.x(), b.x()) &&
+        std::min(a.y(), b.y()) <= pt.y() && pt.y() <= std::max(a.y(), b.y()))
+      return 0;
+    if ((a.y() > pt.y()) != (b.y() > pt.y())) {
+      const double xc = a.x() + (pt.y() - a.y()) * (b.x() - a.x()) / (b.y() - a.y());
+      if (pt.x() < xc) in = !in;
+    }
+  }
+  return in ? 1 : -1;
+}
+bool is_inside(Point2 pt, HPolygon &poly) {  // :3583-3598
+  if (bounded_side(poly.outer_boundary(), pt) != 1) return false;
+  for (HPolygon::Hole_const_iterator h = poly.holes_begin(); h != poly.holes_end(); ++h)
+    if (bounded_side(*h, pt) != -1) return false;
+  return true;
+}
+bool is_inside(Point2 pt, HPolygons &polys) {
+  for (Size i = 0; i != polys.size(); i++) if (is_inside(pt, polys[i])) return true;
+  return false;
+}
+Segment clip_segment_by_convex_polygon(Segment sg, Polygon w) { return clip_segment_by_polygon(sg, w); }
+LineTes::Halfedge_handle find_halfedge(LineTes &t, Point2 p1, Point2 p2) {  // :3955-3969
+  std::vector<LineTes::Halfedge_handle> hs = t.halfedges();
+  for (size_t i = 0; i < hs.size(); i++)
+    if (hs[i]->source()->point() == p1 && hs[i]->target()->point() == p2) return hs[i];
+  return NULL_HALFEDGE_HANDLE;
+}
+bool is_a_T_vertex(LineTes::Vertex_handle v, bool verbose) {  // :4002-4046
+  if (v->degree() != 3) {
+    if (verbose) std::clog << "is_a_T_vertex function: vertex " << v->point() << " not a T-vertex because its degree not equal to 3" << std::endl;
+    return false;
+  }
+  std::vector<LineTes::Halfedge_handle> in = v->incident_halfedges();
+  int n = 0;
+  for (size_t i = 0; i < in.size(); i++) n += in[i]->get_next_hf() == NULL_HALFEDGE_HANDLE;
+  if (n != 1) {
+    if (verbose) std::clog << "is_a_T_vertex function: vertex " << v->point() << " not a T-vertex because "
+                           << (n == 3 ? "it is a Y-vertex" : "of an unexpected reason") << std::endl;
+    return false;
+  }
+  return true;
+}
+bool is_an_X_vertex(LineTes::Vertex_handle v) {  // :4058-4067
+  if (v->degree() != 4) return false;
+  std::vector<LineTes::Halfedge_handle> e = v->incident_halfedges();
+  return e[0]->get_next_hf() == e[2]->twin() && e[1]->get_next_hf() == e[3]->twin();
+}
+bool has_an_I_vertex_neighbour(LineTes::Vertex_handle v) {  // :4073-4081
+  std::vector<LineTes::Halfedge_handle> e = v->incident_halfedges();
+  for (size_t i = 0; i < e.size(); i++) if (e[i]->source()->degree() == 1) return true;
+  return false;
+}
+bool is_an_irreducible_X_vertex(LineTes::Vertex_handle v) { return is_an_X_vertex(v) && !has_an_I_vertex_neighbour(v); }
+unsigned long int number_of_internal_vertices(TTessel &t) {  // :4105-4115: vertices minus the edges of the window sides
+  unsigned long int compt = 0;
+  LineTes::Seg_list_iterator s = t.segments_begin();
+  for (Size i = 0; i < t.number_of_window_edges() && s != t.segments_end(); i++, ++s) compt += s->number_of_edges();
+  return (unsigned long int)t.number_of_vertices() - compt;
+}
+static Polygon cycle_polygon(const HostTess &h, int h0, bool simplify) {
+  Polygon p;
+  int e = h0;
+  do {
+    if (!simplify || h.h_next_hf[e] < 0 || h.h_next_hf[e] != h.h_next[e]) p.push_back(pt(h, h.h_src[e ^ 1]));
+    e = h.h_next[e];
+  } while (e != h0);
+  return p;
+}
+HPolygon face2poly(TTessel::Face_handle f, bool simplify) {  // :4314-4336
+  const HostTess &h = *f.tess()->host();
+  Polygon outer = cycle_polygon(h, h.f_he[f.id()], simplify);
+  Polygons holes;
+  std::vector<LineTes::Halfedge_handle> hs = f.holes();
+  for (size_t i = 0; i < hs.size(); i++) holes.push_back(cycle_polygon(h, hs[i].id(), simplify));
+  return HPolygon(outer, holes.begin(), holes.end());
+}
+static double sum_over_faces(TTessel *t, double (*feature)(HPolygon, TTessel *)) {
+  double s = 0;
+  std::vector<LineTes::Face_handle> fs = t->faces();
+  for (size_t i = 0; i < fs.size(); i++) if (fs[i].data()) s += feature(face2poly(fs[i]), t);
+  return s;
+}
+double sum_of_faces_squared_areas(TTessel *t) { return sum_over_faces(t, face_area_2); }
+double sum_of_min_angles(TTessel *t) { return sum_over_faces(t, min_angle); }
+double sum_of_angles_obt(TTessel *t) { return sum_over_faces(t, face_sum_of_angles); }
+double sum_of_segment_squared_sizes(TTessel *t) {  // :4440-4445
+  double s4 = 0;
+  for (LineTes::Seg_list_iterator si = t->segments_begin(); si != t->segments_end(); ++si) s4 += segment_size_2(si->list_of_points(), t);
+  return s4;
+}
+Polygons boundaries(HPolygon hp) {  // :4453-4469
+  Polygons b;
+  Polygon ob(hp.outer_boundary());
+  if (ob.area() < 0) ob.reverse_orientation();
+  b.push_back(ob);
+  for (HPolygon::Hole_const_iterator h = hp.holes_begin(); h != hp.holes_end(); ++h) {
+    Polygon q(*h);
+    if (q.area() > 0) q.reverse_orientation();
+    b.push_back(q);
+  }
+  return b;
+}
+Polygon simplify(Polygon p) {  // :4474-4492
+  if (p.is_empty()) throw std::domain_error("simplify(Polygon), input polygon is empty");
+  Polygon sp;
+  const Size n = p.size();
+  for (Size i = 0; i < n; i++) {
+    const Point2 &a = p[(i + n - 1) % n], &b = p[i], &c = p[(i + 1) % n];
+    if ((b.x() - a.x()) * (c.y() - a.y()) - (b.y() - a.y()) * (c.x() - a.x()) != 0.0) sp.push_back(b);
+  }
+  return sp;
+}
+HPolygon simplify(HPolygon p) {  // :4495-4506
+  Polygons b = boundaries(p);
+  for (size_t i = 0; i < b.size(); i++) b[i] = simplify(b[i]);
+  return HPolygon(b[0], b.begin() + 1, b.end());
+}
+bool has_holes(LineTes::Face_handle &f) { return !f.holes().empty(); }
+bool has_holes(HPolygon &p) { return p.number_of_holes() > 0; }
+
 double is_point_inside_window(Point2 p, LineTes *t) {  // :4131-4135
   HPolygons ws = t->get_window();
   for (Size k = 0; k < ws.size(); k++) {

@@ -784,10 +784,18 @@ bool build_arrangement(HostTess &t, const std::vector<std::vector<double>> &bx,
     const double den = ax * byy - ay * bxx;
     const double ta = ((b.x0 - a.x0) * byy - (b.y0 - a.y0) * bxx) / den;
     const double tb = ((b.x0 - a.x0) * ay - (b.y0 - a.y0) * ax) / den;
-    const int v = (int)vx.size();
-    vx.push_back(a.x0 + ta * ax); vy.push_back(a.y0 + ta * ay);
-    L[c.first].on.push_back({ta, v});
-    L[c.second].on.push_back({tb, v});
+    // a segment end may sit on the crossing already: one vertex
+    const double cxp = a.x0 + ta * ax, cyp = a.y0 + ta * ay;
+    int v = -1;
+    for (int k = 0; k < (int)vx.size() && v < 0; k++)
+      if (fabs(vx[k] - cxp) <= eps && fabs(vy[k] - cyp) <= eps) v = k;
+    if (v < 0) { v = (int)vx.size(); vx.push_back(cxp); vy.push_back(cyp); }
+    for (int side = 0; side < 2; side++) {
+      auto &on = L[side ? c.second : c.first].on;
+      bool there = false;
+      for (const auto &o : on) there = there || o.second == v;
+      if (!there) on.push_back({side ? tb : ta, v});
+    }
   }
   // edges along every segment
   struct E { int v0, v1, seg, prev_hf, next_hf; bool bnd; };

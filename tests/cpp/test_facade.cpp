@@ -257,6 +257,99 @@ static void test_remove_xvertices() {
   CHECK(rec.is_valid(true));
 }
 
+// the reference header's helper functions and the sampling / printing members (:1319-1370, :781-794)
+static void test_helpers(const char *fixture) {
+  TTessel t;
+  std::ifstream in(fixture);
+  t.read(in);
+  CHECK(t.is_a_T_tessellation());
+  // sums of features over the faces / segments equal the feature functions applied to all_faces()
+  HPolygons fs = t.all_faces();
+  double a2 = 0, ma = 0, ob = 0;
+  for (size_t i = 0; i < fs.size(); i++) { a2 += face_area_2(fs[i], &t); ma += min_angle(fs[i], &t); ob += face_sum_of_angles(fs[i], &t); }
+  CHECK_CLOSE(sum_of_faces_squared_areas(&t), a2, 1e-14);
+  CHECK_CLOSE(sum_of_min_angles(&t), ma, 1e-14);
+  CHECK_CLOSE(sum_of_angles_obt(&t), ob, 1e-14);
+  double s4 = 0;
+  Size n_int = 0;
+  for (LineTes::Seg_list_iterator si = t.segments_begin(); si != t.segments_end(); ++si) {
+    s4 += segment_size_2(si->list_of_points(), &t);
+    n_int += !t.is_on_boundary(*si);
+  }
+  CHECK_CLOSE(sum_of_segment_squared_sizes(&t), s4, 0);
+  CHECK(n_int == t.number_of_internal_segments());
+  CHECK(n_int == t.number_of_blocking_segments() + t.number_of_non_blocking_segments());
+  CHECK(t.number_of_window_edges() == 4);
+  // every vertex off the window boundary is a T-vertex, none is an X-vertex; the count of
+  // internal vertices is the reference's formula (vertices minus edges of the window sides)
+  std::vector<LineTes::Vertex_handle> vs = t.vertices();
+  unsigned long internal = 0;
+  for (size_t i = 0; i < vs.size(); i++) {
+    if (is_point_inside_window(vs[i].point(), &t) > 0) { internal++; CHECK(is_a_T_vertex(vs[i])); }
+    CHECK(!is_an_X_vertex(vs[i]));
+  }
+  CHECK(number_of_internal_vertices(t) == internal);
+  // window: perimeter, is_inside, boundaries / simplify
+  HPolygons w = t.get_window();
+  Polygons b = boundaries(w[0]);
+  double per = 0;
+  for (Size j = 0; j < b[0].size(); j++) per += sqrt(Segment(b[0][j], b[0][(j + 1) % b[0].size()]).squared_length());
+  CHECK_CLOSE(t.get_window_perimeter(), per, 1e-15);
+  CHECK(b[0].area() > 0 && !has_holes(w[0]));
+  Point2 c((b[0][0].x() + b[0][2].x()) / 2, (b[0][0].y() + b[0][2].y()) / 2);
+  CHECK(is_inside(c, w) && !is_inside(b[0][0], w));
+  Polygon sq;
+  sq.push_back(Point2(0, 0)); sq.push_back(Point2(1, 0)); sq.push_back(Point2(2, 0)); sq.push_back(Point2(2, 2)); sq.push_back(Point2(0, 2));
+  CHECK(simplify(sq).size() == 4);
+  CHECK(are_aligned(Point2(0, 0), Point2(1, 0), Point2(2, 0)) && !are_aligned(Point2(0, 0), Point2(2, 0), Point2(1, 0)) &&
+        !are_aligned(Point2(0, 0), Point2(1, 1), Point2(2, 0)));
+  // face2poly of a face = the polygon all_faces() lists for it
+  std::vector<LineTes::Face_handle> faces = t.faces();
+  size_t k = 0;
+  for (size_t i = 0; i < faces.size(); i++)
+    if (faces[i].data()) { CHECK(close_poly(face2poly(faces[i]).outer_boundary(), fs[k].outer_boundary())); k++; }
+  CHECK(k == fs.size());
+  // sampling of halfedges: inside faces only; the n-sample comes out in container order
+  rnd = new CGAL::Random(7);
+  for (int i = 0; i < 50; i++) {
+    CHECK(t.random_halfedge()->face()->data());
+    CHECK(t.length_weighted_random_halfedge()->face()->data());
+    CHECK(t.alt_length_weighted_random_halfedge()->face()->data());
+  }
+  std::vector<LineTes::Halfedge_handle> smp = t.alt_length_weighted_random_halfedge(500);
+  CHECK(smp.size() == 500);
+  for (size_t i = 0; i < smp.size(); i++) { CHECK(smp[i]->face()->data()); if (i) CHECK(smp[i - 1].id() <= smp[i].id()); }
+  // halfedge frequencies proportional to length: the longest inside halfedge is drawn about n*len/total times
+  std::vector<LineTes::Halfedge_handle> hs = t.halfedges();
+  size_t longest = 0;
+  for (size_t i = 0; i < hs.size(); i++) if (hs[i]->face()->data() && (!hs[longest]->face()->data() || hs[i]->get_length() > hs[longest]->get_length())) longest = i;
+  std::vector<LineTes::Halfedge_handle> big = t.alt_length_weighted_random_halfedge(20000);
+  double hits = 0;
+  for (size_t i = 0; i < big.size(); i++) hits += big[i] == hs[longest];
+  const double expect = 20000 * hs[longest]->get_length() / t.total_internal_length();
+  CHECK(fabs(hits - expect) < 5 * sqrt(expect));
+  delete rnd;
+  // the califlopp print-out: the number of cells, then three lines per cell
+  std::stringstream out;
+  t.printRCALI(out);
+  std::string line;
+  int lines = 0;
+  while (std::getline(out, line)) lines++;
+  CHECK(lines == 1 + 3 * (int)fs.size());
+  // find_halfedge with exact end points; X-vertices of a crossing
+  LineTes x;
+  x.insert_window(Rectangle(Point2(0, 0), Point2(4, 4)));
+  x.insert_segment(Segment(Point2(2, 0), Point2(2, 4)));
+  x.insert_segment(Segment(Point2(0, 2), Point2(4, 2)));
+  LineTes::Halfedge_handle e = find_halfedge(x, Point2(2, 0), Point2(2, 2));
+  CHECK(e != NULL_HALFEDGE_HANDLE && is_an_X_vertex(e->target()) && is_an_irreducible_X_vertex(e->target()));
+  CHECK(!is_a_T_vertex(e->target()) && is_a_T_vertex(e->source()));
+  CHECK(x.number_of_xvertices() == 1);
+  x.insert_segment(Segment(Point2(2, 2), Point2(3, 3)));
+  CHECK(find_halfedge(x, Point2(2, 2), Point2(3, 3)) != NULL_HALFEDGE_HANDLE);
+  CHECK(has_an_I_vertex_neighbour(find_halfedge(x, Point2(3, 3), Point2(2, 2))->target()));
+}
+
 static void test_catvector_and_energy_registry() {
   CatVector a, b;
   a.edges.push_back(1); a.faces.push_back(2); a.faces.push_back(3); a.segs.push_back(4);
@@ -514,6 +607,7 @@ int main(int argc, char **argv) {
     test_insert_segment();
     test_remove_ivertices();
     test_remove_xvertices();
+    test_helpers(argc > 2 ? argv[2] : "tests/golden/tessellation_data.txt");
     test_catvector_and_energy_registry();
     test_unknown_feature_is_refused();
     test_host_features();
