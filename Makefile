@@ -33,6 +33,6 @@ tests/cpp/gen_host: tests/cpp/gen_host.cpp lite_b200/csrc/gen_face.h include/lit
 	g++ -O2 -std=c++17 -o $@ tests/cpp/gen_host.cpp
 
 # the reference's drivers against this library (need a GPU to run)
-examples: examples/pseudo_lik_inference examples/check_acs_ensemble
+examples: examples/pseudo_lik_inference examples/check_acs_ensemble examples/sim_acs
 examples/%: examples/%.cpp include/ttessel.h include/lite_b200.h include/lite_b200_host.h $(LIB)
 	g++ -O1 -std=c++17 -Iinclude -o $@ $< -Llite_b200 -lliteb200 -Wl,-rpath,'$$ORIGIN/../lite_b200' -pthread

@@ -1,4 +1,4 @@
-"""The reference's two drivers, rebuilt against this library (examples/), run end to end."""
+"""The reference's drivers, rebuilt against this library (examples/), run end to end."""
 import os
 import subprocess
 
@@ -37,3 +37,19 @@ def test_check_acs_ensemble_writes_the_reference_columns(tmp_path):
     assert np.all(rows[:, 3] == rows[:, 4] + rows[:, 5])
     text = open(tmp_path / "tessel_chain0.txt").read().strip().split("\n")
     assert len(text) == 1 + int(rows[4, 3])       # window line + one line per internal segment
+
+
+def test_sim_acs_demo_tracks_the_energy():
+    """demos/sim_acs.cpp with both face terms: trace and summary as the reference prints them; the
+    energy accumulated from the device's variations equals the energy recomputed from scratch."""
+    res = subprocess.run([_exe("sim_acs"), "-t", "8", "-f", "0.05", "-g", "1", "-i", "6", "-j", "200"],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    err = res.stderr.split("\n")
+    assert err[0].split() == ["step", "energy", "nb_of_int_segments", "int_length"]
+    trace = np.array([[float(x) for x in ln.split()] for ln in err[1:7]])
+    assert trace.shape == (6, 4) and trace[-1, 2] > 5
+    assert "Sum of squared area of faces" in res.stderr and "Angle statistic" in res.stderr
+    n_seg = int(trace[-1, 2])
+    assert res.stdout.split("\n")[0].startswith("Coordinates of segments")
+    assert len([ln for ln in res.stdout.strip().split("\n")[1:] if ln.strip()]) == n_seg + 4
