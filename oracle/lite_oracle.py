@@ -1586,6 +1586,93 @@ def is_inside(pt, hp):
     return True
 
 
+def clip_segment_by_polygons(seg, window):
+    """clip_segment_by_polygon(Segment, HPolygons), lib/ttessel.cpp:3696-3786, in exact arithmetic:
+    the longest piece of ``seg`` = (p, q) inside the union of the *open* polygons with holes
+    (boundaries cut the segment and are not part of the result).  The reference builds Nef
+    polyhedra; the intersection of a segment with an open polygonal set is what is computed here
+    directly: cut the segment at every boundary edge it meets, keep the pieces whose midpoint
+    is strictly inside.  Returns (a, b) along the direction of seg; ValueError if there is none
+    (std::domain_error there)."""
+    p, q = (Fr(seg[0][0]), Fr(seg[0][1])), (Fr(seg[1][0]), Fr(seg[1][1]))
+    dx, dy = q[0] - p[0], q[1] - p[1]
+    cuts = {Fr(0), Fr(1)}
+    for hp in window:
+        for b in boundaries(hp):
+            n = len(b)
+            for i in range(n):
+                a, c = b[i], b[(i + 1) % n]
+                ex, ey = c[0] - a[0], c[1] - a[1]
+                den = dx * ey - dy * ex
+                if den != 0:
+                    ts = ((a[0] - p[0]) * ey - (a[1] - p[1]) * ex) / den
+                    te = ((a[0] - p[0]) * dy - (a[1] - p[1]) * dx) / den
+                    if 0 <= ts <= 1 and 0 <= te <= 1:
+                        cuts.add(ts)
+                elif (a[0] - p[0]) * dy - (a[1] - p[1]) * dx == 0:   # on the segment's line
+                    for v in (a, c):
+                        t = ((v[0] - p[0]) * dx + (v[1] - p[1]) * dy) / (dx * dx + dy * dy)
+                        if 0 < t < 1:
+                            cuts.add(t)
+    cuts = sorted(cuts)
+    best = None
+    for t0, t1 in zip(cuts[:-1], cuts[1:]):
+        tm = (t0 + t1) / 2
+        m = (p[0] + tm * dx, p[1] + tm * dy)
+        if any(is_inside(m, hp) for hp in window) and (best is None or t1 - t0 > best[1] - best[0]):
+            best = (t0, t1)
+    if best is None:
+        raise ValueError("clip_segment_by_polygon: the segment does not hit the polygons")
+    return ((p[0] + best[0] * dx, p[1] + best[0] * dy), (p[0] + best[1] * dx, p[1] + best[1] * dy))
+
+
+def arrangement_census(window, segs):
+    """What CGAL::insert leaves after LineTes::insert_segment of every segment of ``segs`` (already
+    clipped; lib/ttessel.cpp:904-910), counted exactly: (vertices, edges, proper crossings, ends on
+    another segment or on the window boundary, free ends).  General position is assumed and
+    asserted: no three segments through one point, no overlapping collinear segments, no segment
+    through a window vertex."""
+    sides = []
+    for hp in window:
+        for b in boundaries(hp):
+            sides += [(b[i], b[(i + 1) % len(b)]) for i in range(len(b))]
+    L = sides + [((Fr(s[0][0]), Fr(s[0][1])), (Fr(s[1][0]), Fr(s[1][1]))) for s in segs]
+    nw = len(sides)
+    on = [set() for _ in L]            # points on each segment besides its two ends
+    crossings = 0
+    for i in range(len(L)):
+        for j in range(max(i + 1, nw), len(L)):
+            (a, b), (c, d) = L[i], L[j]
+            r = (b[0] - a[0], b[1] - a[1]); w = (d[0] - c[0], d[1] - c[1])
+            den = _cross(r[0], r[1], w[0], w[1])
+            assert den != 0 or _cross(r[0], r[1], c[0] - a[0], c[1] - a[1]) != 0, "collinear segments"
+            if den == 0:
+                continue
+            t = _cross(c[0] - a[0], c[1] - a[1], w[0], w[1]) / den
+            u = _cross(c[0] - a[0], c[1] - a[1], r[0], r[1]) / den
+            if 0 < t < 1 and 0 < u < 1:
+                crossings += 1
+                x = (a[0] + t * r[0], a[1] + t * r[1])
+                on[i].add(x); on[j].add(x)
+            elif 0 < t < 1 and u in (0, 1):     # an end of j on the interior of i
+                on[i].add(c if u == 0 else d)
+            elif 0 < u < 1 and t in (0, 1):
+                assert i >= nw, "a segment through a window vertex"
+                on[j].add(a if t == 0 else b)
+    pts = set()
+    for k, (a, b) in enumerate(L):
+        pts |= {a, b} | on[k]
+    edges = sum(1 + len(o) for o in on)
+    ends = [e for (a, b) in L[nw:] for e in (a, b)]
+    attached = sum(1 for e in ends if any(e in on[k] for k in range(len(L))))
+    multiplicity = {}
+    for k in range(len(L)):
+        for x in on[k] | set(L[k]):
+            multiplicity[x] = multiplicity.get(x, 0) + 1
+    assert all(m <= 2 for m in multiplicity.values()), "three segments through one point"
+    return len(pts), edges, crossings, attached, len(ends) - attached
+
+
 def is_point_inside_window(pt, t):
     return 1.0 if any(is_inside(pt, hp) for hp in t.window) else 0.0
 

@@ -285,3 +285,58 @@ def test_cleaning_random_patterns_in_plain_and_holed_windows(seed):
     s = h.export()
     assert int(np.sum(s.a["face_inside"])) == h.counts()[0]
     assert lite_b200.HostTess(text=h.write_text()).counts() == h.counts()   # the text round-trips
+
+
+def test_clip_against_the_exact_oracle():
+    """lite::clip_segment (doubles, tolerance 1e-9 of the window) against the oracle's exact
+    clip on 400 random segments over the reference's two holed polygons: same verdict (hit or
+    not), same piece to 1e-12."""
+    win = holed_polygons()
+    h = lite_b200.HostTess(text=window_text(win))
+    rng = np.random.default_rng(21)
+    hits = misses = 0
+    for _ in range(400):
+        a = rng.uniform(-2, 23, 2)
+        if rng.uniform() < 0.5:
+            b = a + rng.uniform(-3, 3, 2)       # short: often wholly inside a hole or outside
+        else:
+            b = rng.uniform(-2, 23, 2)
+        seg = [float(a[0]), float(a[1]), float(b[0]), float(b[1])]
+        try:
+            want = lo.clip_segment_by_polygons(((seg[0], seg[1]), (seg[2], seg[3])), win)
+        except ValueError:
+            with pytest.raises(LiteError, match="does not hit"):
+                h.clip_segment(seg)
+            misses += 1
+            continue
+        got = h.clip_segment(seg)
+        assert np.allclose(got, [float(want[0][0]), float(want[0][1]), float(want[1][0]), float(want[1][1])], rtol=0, atol=1e-12 * 23)
+        hits += 1
+    assert hits > 200 and misses > 20
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_arrangement_against_the_exact_census(seed):
+    """The lenient builder (crossings, free ends, ends on other segments) against exact counting:
+    numbers of vertices, edges, crossings and free ends of the arrangement of random segments in
+    the unit square, some of them over-running the window."""
+    rng = np.random.default_rng(seed)
+    square = [([lo._pt(0, 0), lo._pt(1, 0), lo._pt(1, 1), lo._pt(0, 1)], [])]
+    h = lite_b200.HostTess((0, 0, 1, 1))
+    exact = []
+    for _ in range(int(rng.integers(10, 30))):
+        c = rng.uniform(0.0, 1.0, 2)
+        a = rng.uniform(0, np.pi)
+        d = 0.5 * rng.uniform(0.2, 0.9) * np.array([np.cos(a), np.sin(a)])
+        seg = [float(c[0] - d[0]), float(c[1] - d[1]), float(c[0] + d[0]), float(c[1] + d[1])]
+        try:
+            exact.append(lo.clip_segment_by_polygons(((seg[0], seg[1]), (seg[2], seg[3])), square))
+        except ValueError:
+            continue
+        h.insert_segment(seg)
+    n_v, n_e, n_x, n_attached, n_free = lo.arrangement_census(square, exact)
+    xy, seg, nx, pv = h.edges()
+    assert len(xy) == 2 * n_e
+    assert len({(round(x, 9), round(y, 9)) for x, y, _, _ in xy}) == n_v
+    free, corners, crossings, _ = h.vertex_census()
+    assert (free, corners, crossings) == (n_free, 0, n_x)
