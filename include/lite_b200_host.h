@@ -81,6 +81,12 @@ int lite_host_remove_xvertices(lite_host_tess *t, double step);
 int lite_host_vertex_census(lite_host_tess *t, int32_t *n_free_ends, int32_t *n_corners, int32_t *n_crossings,
                             int32_t *n_crossings_to_remove);
 
+/* The vertices that keep t from being a T-tessellation (is_a_T_vertex per vertex,
+ * lib/ttessel.cpp:1307-1329, :4002-4046): the census above plus what no pass removes (three ends
+ * on one point; two ends on the same point of a third segment).  first_xy (may be null): where
+ * the first one is. */
+int lite_host_non_t_vertices(lite_host_tess *t, int32_t *n, double first_xy[2]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -366,6 +366,7 @@ class TTessel : public LineTes {
   typedef Flip_list::iterator Flip_list_iterator;
 
   TTessel();
+  TTessel(LineTes &);   /* :1506-1540: std::domain_error unless the line tessellation is a T-tessellation */
   virtual void insert_window(Rectangle);
   virtual void insert_window(Polygon &);
   virtual void insert_window(HPolygons &);

@@ -178,7 +178,13 @@ LineTes::Seg LineTes::insert_segment(Segment sg) {
   return Seg(this, id);
 }
 bool LineTes::is_a_T_tessellation(bool verbose, std::ostream &out) {
-  if (impl_->arrangement_only && verbose) out << "not a T-tessellation: " << impl_->not_t_reason << std::endl;
+  if (impl_->arrangement_only && verbose) {
+    double x = 0, y = 0;
+    const int n = lite::count_non_t_vertices(*impl_, &x, &y);
+    out << "not a T-tessellation: " << impl_->not_t_reason;
+    if (n > 0) out << "; " << n << " vertices are not T-vertices, the first at " << Point2(x, y);
+    out << std::endl;
+  }
   return !impl_->arrangement_only;
 }
 void LineTes::remove_ivertices(Size imax, bool verbose) {
@@ -342,6 +348,9 @@ void LineTes::print_all_segments() const {
 // TTessel
 // ---------------------------------------------------------------------------
 TTessel::TTessel() {}
+TTessel::TTessel(LineTes &lt) : LineTes(lt) {  // lib/ttessel.cpp:1506-1540
+  if (!lt.is_a_T_tessellation()) throw std::domain_error("TTessel(LinTes&) input is not a T-tesselation");
+}
 void TTessel::insert_window(Rectangle r) { LineTes::insert_window(r); }
 void TTessel::insert_window(Polygon &p) { LineTes::insert_window(p); }
 void TTessel::insert_window(HPolygons &w) { LineTes::insert_window(w); }

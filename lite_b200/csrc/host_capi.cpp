@@ -210,6 +210,14 @@ extern "C" int lite_host_vertex_census(lite_host_tess *h, int32_t *n_free_ends, 
   return 0;
 }
 
+extern "C" int lite_host_non_t_vertices(lite_host_tess *h, int32_t *n, double first_xy[2]) {
+  if (!h || !n) return lite_set_error_(LITE_EINVAL, "null argument");
+  double x = 0, y = 0;
+  *n = lite::count_non_t_vertices(h->t, &x, &y);
+  if (first_xy) { first_xy[0] = x; first_xy[1] = y; }
+  return 0;
+}
+
 // One SMF chain brought back from the GPU (lite_smf_export, capi.cu) -> host model.
 // Ids are kept; elements on the chain's free lists stay dead.
 extern "C" int lite_smf_blob_to_host_(char *blob, int cap, lite_host_tess **out) {

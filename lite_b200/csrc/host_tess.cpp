@@ -1153,6 +1153,23 @@ int count_vertices_of_degree(const HostTess &t, int degree, bool internal_only) 
   return n;
 }
 
+// LineTes::is_a_T_tessellation, vertex by vertex (lib/ttessel.cpp:1307-1329, is_a_T_vertex
+// :4002-4046): a vertex off the window boundary must have degree 3 with exactly one incident
+// segment ending there; one on the boundary may also have degree 2
+int count_non_t_vertices(const HostTess &t, double *first_x, double *first_y) {
+  Around A(t);
+  int n = 0;
+  for (size_t v = 0; v < t.vx.size(); v++) {
+    if (!t.v_alive[v]) continue;
+    int terminal = 0;
+    for (int h : A.in[v]) terminal += t.h_next_hf[h] < 0;
+    const bool is_t = A.degree((int)v) == 3 && terminal == 1;
+    const bool ok = is_t || (on_window_boundary(t, A, (int)v) && A.degree((int)v) == 2);
+    if (!ok && n++ == 0) { if (first_x) *first_x = t.vx[v]; if (first_y) *first_y = t.vy[v]; }
+  }
+  return n;
+}
+
 bool remove_ivertices(HostTess &t, size_t imax, CleanStats *st, std::string &err) {
   if (imax == 0) imax = (size_t)-1;
   Soup S;

@@ -189,6 +189,10 @@ bool remove_xvertices(HostTess &t, double step, CleanStats *st, std::string &err
 // LineTes::number_of_xvertices (:272-278); vertices of a given degree (1: free ends)
 int count_xvertices(const HostTess &t, bool exclude_boundaries, bool exclude_ineighbours);
 int count_vertices_of_degree(const HostTess &t, int degree, bool internal_only);
+// vertices that keep the arrangement from being a T-tessellation (:1307-1329): free ends, corners
+// and crossings, and also what no cleaning pass removes (three ends on one point, two ends on the
+// same point of a third segment); the first one's position if asked for
+int count_non_t_vertices(const HostTess &t, double *first_x, double *first_y);
 
 // LineTes::read / write text format (lib/ttessel.cpp:1331-1441), double precision
 bool read_text(HostTess &t, const std::string &text, std::string &err);

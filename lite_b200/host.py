@@ -15,6 +15,7 @@ HOST_SYMBOLS = [
     "lite_host_write_text", "lite_host_clip_segment", "lite_host_insert_segment",
     "lite_host_is_t_tessellation", "lite_host_edges", "lite_host_remove_ivertices",
     "lite_host_remove_lvertices", "lite_host_remove_xvertices", "lite_host_vertex_census",
+    "lite_host_non_t_vertices",
 ]
 
 _COUNT_OF = dict(vx="n_vertices", vy="n_vertices", he_src="n_halfedges", he_twin="n_halfedges",
@@ -50,6 +51,7 @@ def _lib():
         L.lite_host_remove_lvertices.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_double)]
         L.lite_host_remove_xvertices.argtypes = [C.c_void_p, C.c_double]
         L.lite_host_vertex_census.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
+        L.lite_host_non_t_vertices.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
         L._host_ready = True
     return L
 
@@ -161,6 +163,13 @@ class HostTess:
         v = [C.c_int32() for _ in range(4)]
         _ck(self.L, self.L.lite_host_vertex_census(self.h, *[C.byref(x) for x in v]))
         return tuple(x.value for x in v)
+
+    def non_t_vertices(self):
+        """(count, position of the first) of the vertices that are not T (nor plain boundary) vertices."""
+        n = C.c_int32()
+        xy = np.zeros(2)
+        _ck(self.L, self.L.lite_host_non_t_vertices(self.h, C.byref(n), xy.ctypes.data_as(C.c_void_p)))
+        return n.value, (float(xy[0]), float(xy[1]))
 
     def write_text(self):
         n = self.L.lite_host_write_text(self.h, None, 0)

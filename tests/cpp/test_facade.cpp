@@ -255,6 +255,26 @@ static void test_remove_xvertices() {
   rec.remove_xvertices(2);
   CHECK(rec.number_of_xvertices(true, true) == 0);
   CHECK(rec.is_valid(true));
+  // the end of the pipeline: LineTes -> cleaning passes -> TTessel(LineTes&) (lib/ttessel.cpp:1506-1540)
+  // (the first pattern: in the second one the free ends at (1,3.9) and (1,4.1) are prolonged onto
+  // the same point of the segment between them, a vertex no pass of the reference removes either)
+  bool thrown = false;
+  try { TTessel bad(tes); } catch (const std::domain_error &) { thrown = true; }
+  CHECK(thrown);   // a free end is left
+  for (int it = 0; it < 10 && !tes.is_a_T_tessellation(); it++) { tes.remove_xvertices(0.1); tes.remove_ivertices(); tes.remove_lvertices(); }
+  CHECK(tes.is_a_T_tessellation());
+  if (!tes.is_a_T_tessellation()) return;
+  TTessel tt(tes);
+  CHECK(tt.is_valid());
+  CHECK(tt.number_of_blocking_segments() + tt.number_of_non_blocking_segments() == tes.number_of_internal_segments());
+  double len = 0;
+  for (LineTes::Seg_list_iterator si = tt.segments_begin(); si != tt.segments_end(); ++si)
+    if (!tt.is_on_boundary(*si)) len += sqrt(Segment(si->pointSource(), si->pointTarget()).squared_length());
+  CHECK_CLOSE(tt.get_total_internal_length(), tt.get_window_perimeter() + 2 * len, 1e-13);   // :1526-1529
+  rnd = new CGAL::Random(1);
+  for (int i = 0; i < 10; i++) tt.update(tt.propose_split());
+  CHECK(tt.is_valid());
+  delete rnd;
 }
 
 // the reference header's helper functions and the sampling / printing members (:1319-1370, :781-794)

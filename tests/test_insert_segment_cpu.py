@@ -222,6 +222,16 @@ def test_remove_xvertices_recursion_known_answers():
     assert h.vertex_census()[3] == 1
     h.remove_xvertices(2)
     assert h.vertex_census()[3] == 0
+    # the free ends at (1, 3.9) and (1, 4.1) are then prolonged onto the same point of the segment
+    # between them: a vertex of degree 4 that is neither T nor X, which no pass removes (in the
+    # reference either); the census is clean and the count of non-T vertices says what is left
+    for _ in range(3):
+        h.remove_ivertices()
+        h.remove_lvertices()
+        h.remove_xvertices(2)
+    assert h.vertex_census() == (0, 0, 0, 0) and not h.is_t_tessellation()
+    n, first = h.non_t_vertices()
+    assert n == 4 and first in [(1.0, 4.0), (4.0, 1.0), (4.0, 7.0), (7.0, 4.0)]
     # the arrangement still holds together: every halfedge of a segment chain is linked both ways
     xy, seg, nx, pv = h.edges()
     for k in range(len(xy)):
