@@ -83,7 +83,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index, period=None):
         if period is None:
-            period = float(os.environ.get("LITE_BENCH_CLOCK_PERIOD", "0.002"))
+            period = float(os.environ.get("LITE_BENCH_CLOCK_PERIOD", "0.003"))
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.sm, self.reasons, self.max_mhz = [], set(), None
