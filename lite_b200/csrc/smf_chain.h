@@ -978,7 +978,29 @@ LITE_HD inline void draw4(const StepRng &R, uint64_t t, uint32_t k, uint32_t out
 
 struct ChainParams {
   double p_split, p_merge;
+  // bit 0: request the lines around e1 as soon as it is known, bit 1: the heads of the free
+  // lists and the tails of the segment lists at the start of a proposal, bit 2: the lines around
+  // e2 when the ray has found it.  Requests only (prefetch_line): the trajectory is unchanged.
+  int prefetch = 0;
 };
+
+// The lines an accepted move reads and writes around halfedge e: its four neighbours on the two
+// faces, its neighbours along the segment, the segment record, its weight.  Their indices sit in
+// e's own 64-byte line, so the requests leave together, one round trip before the DCEL
+// primitives (or, for e1, the ray walk) would ask for them one after the other.
+LITE_HD inline void prefetch_around(const Chain &c, int e) {
+#ifdef __CUDA_ARCH__
+  const HE &a = c.he[e], &b = c.he[e ^ 1];
+  prefetch_line(&c.he[a.next]); prefetch_line(&c.he[a.prev]);
+  prefetch_line(&c.he[b.next]); prefetch_line(&c.he[b.prev]);
+  if (a.nhf != NIL) prefetch_line(&c.he[a.nhf]);
+  if (a.phf != NIL) prefetch_line(&c.he[a.phf]);
+  prefetch_line(&c.seg[a.segd & 0x7FFF]);
+  prefetch_line(&c.w[e >> 1]);
+#else
+  (void)c; (void)e;
+#endif
+}
 
 // Returns false if the chain cannot go on (capacity exhausted / broken state).
 //
@@ -1002,6 +1024,13 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
     tr->p1[0] = tr->p1[1] = tr->p2[0] = tr->p2[1] = 0;
     tr->e2s[0] = tr->e2s[1] = tr->e2t[0] = tr->e2t[1] = 0;
   }
+  if (cp.prefetch & 2) {
+    prefetch_line(&c.he[2 * (c.H->free_p >= 0 ? c.H->free_p : c.H->n_p)]);
+    prefetch_line(&c.f_he[c.H->free_f >= 0 ? c.H->free_f : c.H->n_f]);
+    prefetch_line(&c.seg[c.H->free_s >= 0 ? c.H->free_s : c.H->n_s]);
+    prefetch_line(&c.nb_list[c.H->n_nb]);
+    prefetch_line(&c.b_list[c.H->n_b]);
+  }
   // ---- the candidate (TTessel::propose_split / _merge / _flip, :1755-1777)
   bool have = false;
   int e1 = -1;
@@ -1011,6 +1040,7 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
     if (c.H->n_seg + 1 > c.H->cap) { c.H->status = ST_CAPACITY; return false; }
     draw4(R, t, 1, r4);
     e1 = sample_halfedge(c, u53(r4[0], r4[1]));
+    if (cp.prefetch & 1) prefetch_around(c, e1);
     const double xs = u53(r4[2], r4[3]);
     draw4(R, t, 2, r4);
     // angle = acos(1 - 2U), TTessel::propose_split :1757
@@ -1026,6 +1056,7 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
       int n = (int)(u53(r4[0], r4[1]) * c.H->n_nb);
       if (n >= c.H->n_nb) n = c.H->n_nb - 1;
       e1 = c.seg[c.nb_list[n]].he;
+      if (cp.prefetch & 1) prefetch_around(c, e1);
       have = true;
     }
   } else {
@@ -1036,6 +1067,7 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
       const int sg = c.b_list[n];
       const int side = (u53(r4[2], r4[3]) < 0.5) ? 0 : 1;
       e1 = side == 0 ? (seg_start(c, sg) ^ 1) : seg_end(c, sg);
+      if (cp.prefetch & 1) prefetch_around(c, e1);
       prepare_flip(c, e1, fm, ray);
       have = true;
     }
@@ -1049,6 +1081,7 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
   int e2 = -1;
   Pt p2; p2.x = p2.y = 0;
   if (ray.ok) e2 = ray_exit(c, ray.start, ray.a, ray.b, ray.w, ray.p, ray.dx, ray.dy, ray.skip0, ray.skip1, p2);
+  if ((cp.prefetch & 4) && e2 >= 0) prefetch_around(c, e2);
   bool valid = have && (type == 1 || e2 >= 0);
   if (type == 0) { sm.e2 = e2; sm.p2 = p2; sm.valid = valid; }
   if (type == 2) { fm.e2 = e2; fm.p2 = p2; fm.valid = valid; }
