@@ -317,7 +317,7 @@ void LineTes::read(std::istream &is) {
   std::stringstream ss;
   ss << is.rdbuf();
   std::string err;
-  if (!lite::read_text(*impl_, ss.str(), err)) throw std::domain_error("LineTes::read: " + err);
+  if (!lite::read_text(*impl_, ss.str(), err, /*accept_any=*/true)) throw std::domain_error("LineTes::read: " + err);
   // the window as the file gave it: a counter-clockwise boundary opens a polygon, the clockwise
   // ones that follow are its holes (lib/ttessel.cpp:1395-1415)
   window_.clear();

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <random>
 #include <set>
+#include <unordered_map>
 #include <sstream>
 
 namespace lite {
@@ -731,16 +732,32 @@ bool build_arrangement(HostTess &t, const std::vector<std::vector<double>> &bx,
   // general arrangement: ends that coincide (with a window corner or with each other: L-vertices)
   // share one vertex
   std::vector<int> end_vertex(2 * (size_t)nL, -1);
-  if (lenient)
-    for (int i = nw; i < nL; i++)
-      for (int e = 0; e < 2; e++) {
-        const double px = e ? L[i].x1 : L[i].x0, py = e ? L[i].y1 : L[i].y0;
-        int v = -1;
-        for (int k = 0; k < (int)vx.size() && v < 0; k++)
-          if (fabs(vx[k] - px) <= eps && fabs(vy[k] - py) <= eps) v = k;
-        if (v < 0) { v = (int)vx.size(); vx.push_back(px); vy.push_back(py); }
-        end_vertex[2 * (size_t)i + e] = v;
+  // vertices by cell of a fine grid (cells of 4 eps: a point within eps of another lies in its
+  // cell or in one of the eight around it)
+  std::unordered_map<uint64_t, std::vector<int>> by_cell;
+  auto cell_of = [&](double x, double y, int dx, int dy) {
+    const uint64_t cxq = (uint64_t)(int64_t)floor((x - xmin) / (4 * eps)) + 8 + dx, cyq = (uint64_t)(int64_t)floor((y - ymin) / (4 * eps)) + 8 + dy;
+    return (cxq << 32) ^ cyq;
+  };
+  auto shared_vertex = [&](double px, double py) {   // the vertex within eps of the point, made if there is none
+    for (int dx = -1; dx <= 1; dx++)
+      for (int dy = -1; dy <= 1; dy++) {
+        auto it = by_cell.find(cell_of(px, py, dx, dy));
+        if (it == by_cell.end()) continue;
+        for (int k : it->second)
+          if (fabs(vx[k] - px) <= eps && fabs(vy[k] - py) <= eps) return k;
       }
+    const int v = (int)vx.size();
+    vx.push_back(px); vy.push_back(py);
+    by_cell[cell_of(px, py, 0, 0)].push_back(v);
+    return v;
+  };
+  if (lenient) {
+    for (int k = 0; k < nw; k++) by_cell[cell_of(vx[k], vy[k], 0, 0)].push_back(k);
+    for (int i = nw; i < nL; i++)
+      for (int e = 0; e < 2; e++)
+        end_vertex[2 * (size_t)i + e] = shared_vertex(e ? L[i].x1 : L[i].x0, e ? L[i].y1 : L[i].y0);
+  }
   for (int i = nw; i < nL; i++) {
     for (int e = 0; e < 2; e++) {
       const double px = e ? L[i].x1 : L[i].x0, py = e ? L[i].y1 : L[i].y0;
@@ -786,10 +803,7 @@ bool build_arrangement(HostTess &t, const std::vector<std::vector<double>> &bx,
     const double tb = ((b.x0 - a.x0) * ay - (b.y0 - a.y0) * ax) / den;
     // a segment end may sit on the crossing already: one vertex
     const double cxp = a.x0 + ta * ax, cyp = a.y0 + ta * ay;
-    int v = -1;
-    for (int k = 0; k < (int)vx.size() && v < 0; k++)
-      if (fabs(vx[k] - cxp) <= eps && fabs(vy[k] - cyp) <= eps) v = k;
-    if (v < 0) { v = (int)vx.size(); vx.push_back(cxp); vy.push_back(cyp); }
+    const int v = shared_vertex(cxp, cyp);
     for (int side = 0; side < 2; side++) {
       auto &on = L[side ? c.second : c.first].on;
       bool there = false;
@@ -1313,7 +1327,7 @@ static bool parse_ratio(const std::string &tok, double &out) {
   return true;
 }
 
-bool read_text(HostTess &t, const std::string &text, std::string &err) {
+bool read_text(HostTess &t, const std::string &text, std::string &err, bool accept_any) {
   std::istringstream is(text);
   std::string line;
   std::vector<std::vector<double>> segs, bx, by;
@@ -1343,7 +1357,21 @@ bool read_text(HostTess &t, const std::string &text, std::string &err) {
       segs.push_back(c);
     }
   }
-  return build_from_boundaries(t, bx, by, segs, err);
+  if (build_from_boundaries(t, bx, by, segs, err)) return true;
+  if (!accept_any) return false;
+  // LineTes::read inserts whatever the file holds, one clipped segment at a time
+  // (lib/ttessel.cpp:1417-1437): the arrangement of the segments that hit the window
+  const std::string strict_err = err;
+  std::vector<std::vector<double>> clipped;
+  for (const auto &c : segs) {
+    double o[4];
+    std::string e2;
+    if (clip_segment(bx, by, c.data(), o, e2)) clipped.push_back({o[0], o[1], o[2], o[3]});
+  }
+  err.clear();
+  if (!build_arrangement(t, bx, by, clipped, true, err)) return false;
+  t.not_t_reason = strict_err;
+  return true;
 }
 
 // a double is m*2^e exactly: print it as the rational num/den the format wants

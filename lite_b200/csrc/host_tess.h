@@ -195,7 +195,10 @@ int count_vertices_of_degree(const HostTess &t, int degree, bool internal_only);
 int count_non_t_vertices(const HostTess &t, double *first_x, double *first_y);
 
 // LineTes::read / write text format (lib/ttessel.cpp:1331-1441), double precision
-bool read_text(HostTess &t, const std::string &text, std::string &err);
+// accept_any: a file whose segments do not form a T-tessellation is read as the arrangement of
+// its segments, each clipped by the window (what LineTes::read does with any file); otherwise it
+// is an error
+bool read_text(HostTess &t, const std::string &text, std::string &err, bool accept_any = false);
 std::string write_text(const HostTess &t);
 
 }  // namespace lite

@@ -255,6 +255,23 @@ static void test_remove_xvertices() {
   rec.remove_xvertices(2);
   CHECK(rec.number_of_xvertices(true, true) == 0);
   CHECK(rec.is_valid(true));
+  // LineTes::read takes any file: segments over-running the window are clipped, free ends and
+  // crossings stay (lib/ttessel.cpp:1417-1437); write and read back give the same arrangement
+  {
+    std::stringstream f;
+    f << "0/1 0/1 4/1 0/1 4/1 4/1 0/1 4/1\n" << "2/1 -1/1 2/1 5/1\n" << "1/1 3/1 3/1 1/1\n" << "9/1 9/1 10/1 10/1\n";
+    LineTes any;
+    any.read(f);
+    CHECK(!any.is_a_T_tessellation());
+    CHECK(any.number_of_internal_segments() == 2);   // the third segment misses the window
+    CHECK(any.number_of_xvertices() == 1);
+    CHECK(find_halfedge(any, Point2(2, 0), Point2(2, 2)) != NULL_HALFEDGE_HANDLE);
+    std::stringstream g;
+    any.write(g);
+    LineTes again;
+    again.read(g);
+    CHECK(again.number_of_halfedges() == any.number_of_halfedges() && again.number_of_xvertices() == 1);
+  }
   // the end of the pipeline: LineTes -> cleaning passes -> TTessel(LineTes&) (lib/ttessel.cpp:1506-1540)
   // (the first pattern: in the second one the free ends at (1,3.9) and (1,4.1) are prolonged onto
   // the same point of the segment between them, a vertex no pass of the reference removes either)
