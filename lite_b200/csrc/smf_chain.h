@@ -395,8 +395,9 @@ LITE_HD inline int merge_edge(Chain &c, int e1, int e2) {
   c.he[t1].prev = (idx)t2p; c.he[t2p].next = (idx)t1;
   set_src(c, t1, b);
   const int fe = h_face(c, e2), ft = h_face(c, t2);
-  if (c.f_he[fe] == (idx)e2) c.f_he[fe] = (idx)e1;
-  if (c.f_he[ft] == (idx)t2) c.f_he[ft] = (idx)t1;
+  const idx rep_e = c.f_he[fe], rep_t = c.f_he[ft];   // both requested before either is tested
+  if (rep_e == (idx)e2) c.f_he[fe] = (idx)e1;
+  if (rep_t == (idx)t2) c.f_he[ft] = (idx)t1;
   del_pair(c, e2);
   set_junction(c, hf_before, e1);
   set_junction(c, e1, hf_after);
@@ -493,6 +494,7 @@ LITE_HD inline void remove_edge(Chain &c, int e) {
 SMF_FN void suppress_edge(Chain &c, int e) {
   const int p1 = h_prev(c, e), p2 = h_prev(c, e ^ 1);  // arrive at src(e), tgt(e)
   remove_edge(c, e);
+  prefetch_line(&c.he[h_next(c, p2)]);   // the second end's neighbour travels while the first end is dissolved
   const int ps[2] = {p1, p2};
   for (int k = 0; k < 2; k++) {
     const int p = ps[k];
@@ -1106,8 +1108,9 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
     if (type == 0) {
       int delta_nb = 1;
       const int sa = h_seg(c, e1), sb = h_seg(c, e2);
-      if (c.seg[sa].nedges == 1 && !seg_bnd(sa)) delta_nb--;
-      if (c.seg[sb].nedges == 1 && !seg_bnd(sb)) delta_nb--;
+      const int n_a = c.seg[sa].nedges, n_b2 = c.seg[sb].nedges;
+      if (n_a == 1 && !seg_bnd(sa)) delta_nb--;
+      if (n_b2 == 1 && !seg_bnd(sb)) delta_nb--;
       r = cp.p_merge / cp.p_split;
       r *= (1 / kPi) * c.H->int_length / (c.H->n_nb + delta_nb);
       split_variation(c, G, sm, dv);
@@ -1117,12 +1120,15 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
       merge_variation(c, G, e1, dv);
     } else {
       int db = 0;
-      if (c.seg[h_seg(c, e1)].nedges == 2) db--;
-      if (c.seg[h_seg(c, fm.e3)].nedges == 1) db++;
+      // the four segment records are independent: asked for together, then tested
       const int i_short = h_seg(c, h_next(c, e1)), i_ext = h_seg(c, e2);
+      const int n_e1 = c.seg[h_seg(c, e1)].nedges, n_e3 = c.seg[h_seg(c, fm.e3)].nedges;
+      const int n_short = c.seg[i_short].nedges, n_ext = c.seg[i_ext].nedges;
+      if (n_e1 == 2) db--;
+      if (n_e3 == 1) db++;
       if (i_short != i_ext) {
-        if (c.seg[i_short].nedges == 2 && !seg_bnd(i_short)) db--;
-        if (c.seg[i_ext].nedges == 1 && !seg_bnd(i_ext)) db++;
+        if (n_short == 2 && !seg_bnd(i_short)) db--;
+        if (n_ext == 1 && !seg_bnd(i_ext)) db++;
       }
       const double sb = (double)c.H->n_b;
       r = (c.H->n_b == -db) ? sb : sb / (sb + db);
@@ -1152,8 +1158,9 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
       prev_a = fm.right ? (e1 ^ 1) : h_prev(c, e1);  // split_from_vertex, :161-189
     }
     if (type == 1) {  // TTessel::update(Merge), :1604-1638
-      list_remove(c, h_seg(c, e1));
       const int ends[2] = {h_seg(c, h_next(c, e1)), h_seg(c, h_next(c, e1 ^ 1))};
+      prefetch_line(&c.seg[ends[0]]); prefetch_line(&c.seg[ends[1]]);
+      list_remove(c, h_seg(c, e1));
       for (int k = 0; k < 2; k++) {
         const int sx = ends[k];
         if (!seg_bnd(sx) && c.seg[sx].nedges <= 2 && c.seg[sx].kind == 2) { list_remove(c, sx); list_add(c, sx, 1); }
@@ -1171,8 +1178,9 @@ LITE_HD inline bool smf_step(Chain &c, const Energy &G, const ChainParams &cp, c
     if (type != 1) ne = add_edge(c, type == 0 ? en[0] : prev_a, en[1], type == 0 ? -1 : fm.e3);
     if (type == 0) {  // TTessel::update(Split), :1580-1597
       c.H->int_length += 2 * h_len(c, ne);
-      list_add(c, h_seg(c, ne), 1);
       const int ends[2] = {h_seg(c, h_next(c, ne)), h_seg(c, h_next(c, ne ^ 1))};
+      prefetch_line(&c.seg[ends[0]]); prefetch_line(&c.seg[ends[1]]);
+      list_add(c, h_seg(c, ne), 1);
       for (int k = 0; k < 2; k++) {
         const int s = ends[k];
         if (!seg_bnd(s) && c.seg[s].nedges <= 2 && c.seg[s].kind == 1) { list_remove(c, s); list_add(c, s, 2); }
