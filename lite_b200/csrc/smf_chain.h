@@ -524,33 +524,47 @@ struct FlipMove {
 // forward hit of the line a*X+b*Y=w from p along (dx,dy); strict minimum, first wins
 SMF_FN int ray_exit(const Chain &c, int start_he, double a, double b, double w, Pt p, double dx,
                             double dy, int skip0, int skip1, Pt &hit) {
-  double best = 1.7976931348623157e308;
-  int res = -1;
-  int h = start_he;
-  Pt S = P_src(c, h);
-  double sk = fma(a, S.x, fma(b, S.y, -w));
-  do {
-    const Pt T = P_tgt(c, h);
+  // The window of an ensemble is a rectangle, so every face is convex: the line meets its
+  // boundary once besides the ray's own edge and the first forward hit is the nearest one
+  // (:4563).  The ccb is walked from both ends at once -- `next` from start_he, `prev` from the
+  // halfedge before it -- so that the two pointer chases overlap and the crossed edge is met
+  // after half as many dependent loads.  The front applies the reference's rule as it stands
+  // (first edge in ccb order whose end values s = a*X+b*Y-w straddle or touch zero, forward of
+  // p, not at p).  The back only takes an edge whose end values are non-zero and of opposite
+  // signs: on a convex face no edge before it can qualify then (the values change sign twice
+  // around the face, once on the ray's own edge), so it is the edge the front would have found.
+  // An edge with a zero end value met from the back is left to the front.
+  int hf = start_he, hb = h_prev(c, start_he);
+  Pt Sf = P_src(c, hf);
+  double skf = fma(a, Sf.x, fma(b, Sf.y, -w));
+  Pt Tb = Sf;          // the target of the last halfedge is the source of the first
+  double snb = skf;
+  for (;;) {
+    const Pt T = P_tgt(c, hf);
+    const Pt S = P_src(c, hb);              // both lines requested before either is used
+    const int fn = h_next(c, hf), bp = h_prev(c, hb);
     const double sn = fma(a, T.x, fma(b, T.y, -w));
-    if (h != skip0 && h != skip1) {
-      const bool cr = (sk <= 0.0 && sn >= 0.0) || (sk >= 0.0 && sn <= 0.0);
-      if (cr && sk != sn) {
-        const double sg = sk / (sk - sn);
-        const double X = fma(sg, T.x - S.x, S.x), Y = fma(sg, T.y - S.y, S.y);
+    if (hf != skip0 && hf != skip1) {
+      const bool cr = (skf <= 0.0 && sn >= 0.0) || (skf >= 0.0 && sn <= 0.0);
+      if (cr && skf != sn) {
+        const double sg = skf / (skf - sn);
+        const double X = fma(sg, T.x - Sf.x, Sf.x), Y = fma(sg, T.y - Sf.y, Sf.y);
         const double rx = X - p.x, ry = Y - p.y;
-        if (rx * dx + ry * dy >= 0.0) {
-          const double len = sqrt(rx * rx + ry * ry);
-          // The window of an ensemble is a rectangle, so every face is convex: the line
-          // meets its boundary once besides the ray's own edge and the first forward hit is
-          // the nearest one (:4563).  Stopping here halves the pointer chase on average.
-          if (len != 0.0 && len < best) { hit.x = X; hit.y = Y; return h; }
-        }
+        if (rx * dx + ry * dy >= 0.0 && sqrt(rx * rx + ry * ry) != 0.0) { hit.x = X; hit.y = Y; return hf; }
       }
     }
-    S = T; sk = sn;
-    h = h_next(c, h);
-  } while (h != start_he);
-  return res;
+    if (hf == hb) return -1;
+    const double sk = fma(a, S.x, fma(b, S.y, -w));
+    if (hb != skip0 && hb != skip1 && ((sk < 0.0 && snb > 0.0) || (sk > 0.0 && snb < 0.0))) {
+      const double sg = sk / (sk - snb);
+      const double X = fma(sg, Tb.x - S.x, S.x), Y = fma(sg, Tb.y - S.y, S.y);
+      const double rx = X - p.x, ry = Y - p.y;
+      if (rx * dx + ry * dy >= 0.0 && sqrt(rx * rx + ry * ry) != 0.0) { hit.x = X; hit.y = Y; return hb; }
+    }
+    if (fn == hb) return -1;
+    Sf = T; skf = sn; hf = fn;
+    Tb = S; snb = sk; hb = bp;
+  }
 }
 
 // What ray_exit needs: the supporting line, the ray, where to start the walk and the two
